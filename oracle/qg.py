@@ -65,7 +65,7 @@ class QGModel:
         J = op.arakawa_jacobian(psi, q_total, self.dx, self.dy)
         dq = np.zeros_like(q)
         dq[:, 1:-1, 1:-1] = -J
-        dq[0] += (self.tau0 * self.wind / self.H0).astype(dt)
+        dq[0] += (dt.type(self.tau0) * self.wind.astype(dt)) / dt.type(self.H0)
         dq[-1] += -self.kappa * op.laplacian(psi[-1], self.dx, self.dy)
         dq = dq + self.nu * op.laplacian(q, self.dx, self.dy)
         return dq

@@ -60,8 +60,8 @@ class SWMModel:
         P = ke + p
         du = qU * vhU - op.diff_x_T_to_U(P, dx)
         dv = -qV * uhV - op.diff_y_T_to_V(P, dy)
-        du[0] += (self.tau0 * self.wind_x / self.H0).astype(dt)
-        dv[0] += (self.tau0 * self.wind_y / self.H0).astype(dt)
+        du[0] += (dt.type(self.tau0) * self.wind_x.astype(dt)) / dt.type(self.H0)
+        dv[0] += (dt.type(self.tau0) * self.wind_y.astype(dt)) / dt.type(self.H0)
         du = du + op.diffusion(u, self.nu, dx, dy, sp)
         dv = dv + op.diffusion(v, self.nu, dx, dy, sp)
         du[-1] += -self.kappa * u[-1]

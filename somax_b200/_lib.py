@@ -1,0 +1,98 @@
+"""ctypes binding of ``libsomax_b200.so`` (the C ABI declared in ``include/somax_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``somax_b200._lib.build_library()``
+with ``nvcc -gencode arch=compute_100a,code=sm_100a``.  Loading it needs no GPU; every compute
+entry point fails loudly (``SomaxB200Error``) without one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "lib" / "libsomax_b200.so"
+SOURCES = ["layout.cu", "swm.cu", "qg_solver.cu", "qg.cu"]
+NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+              "-lineinfo", "-O3", "-std=c++17"]
+
+F32, F64 = 0, 1
+BC_PERIODIC, BC_WALL = 0, 1
+SOLVER_AUTO, SOLVER_FFT, SOLVER_DENSE = 0, 1, 2
+SPEC_ADVECTION_REGION2, SPEC_DIFFUSION_FLUX = 1, 2
+DEFAULT_SPEC = SPEC_ADVECTION_REGION2
+
+
+class SomaxB200Error(RuntimeError):
+    pass
+
+
+class ParamsStruct(C.Structure):
+    _fields_ = [("lateral_viscosity", C.c_double), ("bottom_drag", C.c_double),
+                ("wind_amplitude", C.c_double), ("H0", C.c_double)]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check every header symbol.
+_P, _I, _D, _L, _U = C.c_void_p, C.c_int, C.c_double, C.c_long, C.c_uint
+_PP = C.POINTER(ParamsStruct)
+SIGNATURES = {
+    "somax_b200_last_error": (C.c_char_p, []),
+    "somax_b200_abi_version": (_I, []),
+    "somax_b200_launch_count": (C.c_uint64, []),
+    "somax_b200_qg_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _I, _U]),
+    "somax_b200_qg_destroy": (_I, [_P]),
+    "somax_b200_qg_device_bytes": (C.c_size_t, [_P]),
+    "somax_b200_qg_apply_bc": (_I, [_P, _P, _P, _P]),
+    "somax_b200_qg_invert": (_I, [_P, _P, _P, _P]),
+    "somax_b200_qg_rhs": (_I, [_P, _P, _P, _P, _PP, _I, _P]),
+    "somax_b200_qg_steps": (_I, [_P, _P, _L, _D, _D, _PP, _P]),
+    "somax_b200_qg_diag": (_I, [_P, _P, _P, _P]),
+    "somax_b200_swm_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _D, _D, _I, _P, _P, _P, _P, _U]),
+    "somax_b200_swm_destroy": (_I, [_P]),
+    "somax_b200_swm_device_bytes": (C.c_size_t, [_P]),
+    "somax_b200_swm_apply_bc": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "somax_b200_swm_rhs": (_I, [_P, _P, _P, _P, _P, _P, _P, _PP, _I, _P]),
+    "somax_b200_swm_steps": (_I, [_P, _P, _P, _P, _L, _D, _D, _PP, _P]),
+    "somax_b200_swm_diag": (_I, [_P, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def build_library(verbose: bool = False) -> Path:
+    """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
+    srcs = [str(CSRC / s) for s in SOURCES]
+    deps = srcs + [str(p) for p in CSRC.glob("*.cuh")] + [str(PKG_DIR.parent / "include" / "somax_b200.h")]
+    if LIB_PATH.exists() and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", str(LIB_PATH)] + srcs
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """The loaded library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise SomaxB200Error(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (somax_b200 has no CPU fallback)")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().somax_b200_last_error().decode("utf-8", "replace")
+        raise SomaxB200Error(f"libsomax_b200 error {rc}: {msg}")

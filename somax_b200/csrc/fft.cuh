@@ -1,0 +1,124 @@
+// In-place radix-8/4/2 DIF FFT on a (padded) shared-memory line, and the real-odd split that
+// turns a length-n complex FFT into a DST-I of size n-1 (n a power of two).
+//
+//   X_k = sum_{t=1}^{n-1} x_t sin(pi t k / n),  k = 1..n-1
+//
+// Method: z = odd extension of x to length 2n (z_t = x_t, z_{2n-t} = -x_t, z_0 = z_n = 0);
+// c_t = z_{2t} + i z_{2t+1}; C = FFT_n(c); with A = C_k, B = C_{n-k}:
+//   E = (A + conj B)/2, O = (A - conj B)/(2i), Z_k = E + exp(-i pi k/n) O, X_k = -Im(Z_k)/2.
+// The shared array viewed as reals IS z (cf[t] = z_t), so loading is two scalar stores per
+// input element.  Functions are __host__ __device__ so the index algebra is unit-tested on the
+// CPU (tests/test_host_fft.py) without a GPU.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sb {
+
+template <typename T> struct C2 { T x, y; };
+
+template <typename T>
+__host__ __device__ __forceinline__ C2<T> cadd(C2<T> a, C2<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T>
+__host__ __device__ __forceinline__ C2<T> csub(C2<T> a, C2<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T>
+__host__ __device__ __forceinline__ C2<T> cmul(C2<T> a, C2<T> b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+// multiply by -i
+template <typename T>
+__host__ __device__ __forceinline__ C2<T> mul_mi(C2<T> a) { return {a.y, -a.x}; }
+
+// complex index -> padded complex index (one pad slot per 16) to spread late-pass strides
+__host__ __device__ __forceinline__ int fft_pad(int i) { return i + (i >> 4); }
+__host__ __device__ __forceinline__ int fft_padded_len(int n) { return n + (n >> 4) + 1; }
+
+struct FftPlan {
+  int n;          // complex length (power of two)
+  int npass;
+  int radix[8];
+};
+
+inline FftPlan make_fft_plan(int n) {
+  FftPlan p;
+  p.n = n; p.npass = 0;
+  int lg = 0;
+  while ((1 << lg) < n) ++lg;
+  while (lg >= 3) { p.radix[p.npass++] = 8; lg -= 3; }
+  if (lg == 2) p.radix[p.npass++] = 4;
+  if (lg == 1) p.radix[p.npass++] = 2;
+  return p;
+}
+
+// position in the DIF output array of frequency k
+__host__ __device__ __forceinline__ int fft_revpos(const FftPlan& p, int k) {
+  int pos = 0, rem = p.n;
+  for (int i = 0; i < p.npass; ++i) {
+    int R = p.radix[i];
+    rem /= R;
+    pos += (k % R) * rem;
+    k /= R;
+  }
+  return pos;
+}
+
+template <typename T>
+__host__ __device__ __forceinline__ void fft4(C2<T>& a0, C2<T>& a1, C2<T>& a2, C2<T>& a3) {
+  C2<T> t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
+  a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+
+template <typename T>
+__host__ __device__ __forceinline__ void fft8(C2<T>* v) {
+  // even / odd radix-4
+  fft4(v[0], v[2], v[4], v[6]);
+  fft4(v[1], v[3], v[5], v[7]);
+  const T h = (T)0.70710678118654752440;
+  C2<T> o1 = {h * (v[3].x + v[3].y), h * (v[3].y - v[3].x)};       // * exp(-i pi/4)
+  C2<T> o2 = mul_mi(v[5]);                                          // * -i
+  C2<T> o3 = {h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y)};      // * exp(-3i pi/4)
+  C2<T> e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+// One DIF pass of radix R over sub-transform length Lc for the butterflies t = lt, lt+G, ...
+// tw holds exp(-i pi t / n) for t = 0..2n-1 (so w_n^q = tw[2q]).
+template <typename T, int R>
+__host__ __device__ __forceinline__ void fft_dif_pass(C2<T>* s, int n, int Lc, int lt, int G,
+                                                      const C2<T>* __restrict__ tw) {
+  const int M = Lc / R;
+  const int tstride = 2 * (n / Lc);
+  for (int t = lt; t < n / R; t += G) {
+    const int block = t / M, pos = t - block * M;
+    const int base = block * Lc + pos;
+    C2<T> v[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) v[q] = s[fft_pad(base + q * M)];
+    if (R == 8) fft8(v);
+    else if (R == 4) fft4(v[0], v[1], v[2], v[3]);
+    else { C2<T> a = v[0]; v[0] = cadd(a, v[1]); v[1] = csub(a, v[1]); }
+    if (M > 1) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) v[q] = cmul(v[q], tw[(q * pos) * tstride]);
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) s[fft_pad(base + q * M)] = v[q];
+  }
+}
+
+// DST-I post-processing for the pair (k, n-k), 1 <= k <= n/2.
+template <typename T>
+__host__ __device__ __forceinline__ void dst_split(const C2<T>* s, const FftPlan& p, int k,
+                                                   const C2<T>* __restrict__ tw, T& Xk, T& Xnk) {
+  const C2<T> A = s[fft_pad(fft_revpos(p, k))];
+  const C2<T> B = s[fft_pad(fft_revpos(p, p.n - k))];
+  const C2<T> E = {(T)0.5 * (A.x + B.x), (T)0.5 * (A.y - B.y)};
+  const C2<T> O = {(T)0.5 * (A.y + B.y), (T)-0.5 * (A.x - B.x)};
+  const C2<T> wO = cmul(tw[k], O);
+  Xk = (T)-0.5 * (E.y + wO.y);
+  Xnk = (T)0.5 * (E.y - wO.y);
+}
+
+}  // namespace sb

@@ -1,0 +1,398 @@
+// Quasi-geostrophic hot path: fused Arakawa-Jacobian / beta / viscosity / wind / drag stencil
+// with the Tsit5 stage combination in the epilogue, driven around the PV-inversion solver.
+//
+// Replaces BaroclinicQG.{apply_boundary_conditions,_invert_pv,vector_field,diagnose} and
+// BarotropicQG's equivalents plus the diffrax Tsit5 loop (reference qg/baroclinic.py:135-228,
+// qg/barotropic.py:113-183, core/model.py:47-88; Jacobian formula SURVEY.md App. B.3).
+#include "common.cuh"
+#include "qg_solver.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace sb {
+
+constexpr int QTY = 8;             // output rows per CTA
+constexpr int QTXG = 32;           // float4 groups per CTA row
+constexpr int QTW = QTXG * 4 + 2;  // tile width with halo
+constexpr int QTWP = QTW + 2;
+
+template <typename T>
+struct QgArgs {
+  Layout L;
+  int apply_bc;
+  T dx2, dy2, jden;   // dx^2, dy^2, 12 dx dy
+  const T* beta; int b_cp, b_xs;
+  const T* wind; int w_cp, w_xs;
+  T H0, nu, kappa, tau0;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(QTXG* QTY)
+qg_rhs_kernel(QgArgs<T> A, const T* __restrict__ psi, Stage<T> st) {
+  __shared__ T s_q[QTY + 2][QTWP];   // q (BC applied)
+  __shared__ T s_t[QTY + 2][QTWP];   // q + beta_y
+  __shared__ T s_p[QTY + 2][QTWP];   // psi
+  const Layout& L = A.L;
+  const int Ny = L.Ny, Nx = L.Nx, pitch = L.pitch;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * QTXG + tx;
+  const int g0 = blockIdx.x * QTXG, c0 = g0 * 4 - OFF, j0 = blockIdx.y * QTY;
+  const int plane = blockIdx.z, k = plane % L.nl;
+  const size_t po = (size_t)plane * L.plane();
+  const T* pq = st.Yin[0] + po;
+  const T* pp = psi + po;
+
+  for (int e = tid; e < (QTY + 2) * QTW; e += QTXG * QTY) {
+    int r = e / QTW, c = e - r * QTW;
+    int jj = j0 - 1 + r, ii = c0 - 1 + c;
+    T q = 0, t = 0, p = 0;
+    if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
+      const bool ring = (jj == 0 || jj == Ny - 1 || ii == 0 || ii == Nx - 1);
+      size_t o = (size_t)jj * pitch + OFF + ii;
+      q = (A.apply_bc && ring) ? T(0) : pq[o];
+      t = q + A.beta[(size_t)jj * A.b_cp + (size_t)ii * A.b_xs];
+      p = pp[o];
+    }
+    s_q[r][c] = q; s_t[r][c] = t; s_p[r][c] = p;
+  }
+  __syncthreads();
+  const int j = j0 + ty, g = g0 + tx;
+  if (j >= Ny || g >= L.groups()) return;
+  const int r = ty + 1;
+  T out[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = c0 + tx * 4 + e, c = tx * 4 + e + 1;
+    T dq = 0;
+    if (i >= 0 && i < Nx) {
+      const bool interior = (j >= 1 && j <= Ny - 2 && i >= 1 && i <= Nx - 2);
+      if (interior) {
+        auto F = [&](int dr, int dc) { return s_p[r + dr][c + dc]; };
+        auto G = [&](int dr, int dc) { return s_t[r + dr][c + dc]; };
+        const T fE = F(0, 1), fW = F(0, -1), fN = F(1, 0), fS = F(-1, 0);
+        const T fNE = F(1, 1), fNW = F(1, -1), fSE = F(-1, 1), fSW = F(-1, -1);
+        const T gE = G(0, 1), gW = G(0, -1), gN = G(1, 0), gS = G(-1, 0);
+        const T gNE = G(1, 1), gNW = G(1, -1), gSE = G(-1, 1), gSW = G(-1, -1);
+        const T jpp = (fE - fW) * (gN - gS) - (fN - fS) * (gE - gW);
+        const T jpx = fE * (gNE - gSE) - fW * (gNW - gSW) - fN * (gNE - gNW) + fS * (gSE - gSW);
+        const T jxp = gN * (fNE - fNW) - gS * (fSE - fSW) - gE * (fNE - fSE) + gW * (fNW - fSW);
+        dq = -(((jpp + jpx) + jxp) / A.jden);
+      }
+      if (k == 0) dq = dq + (A.tau0 * A.wind[(size_t)j * A.w_cp + (size_t)i * A.w_xs]) / A.H0;
+      if (interior) {
+        if (k == L.nl - 1) {
+          const T pc = s_p[r][c];
+          const T lap = (s_p[r][c + 1] - T(2) * pc + s_p[r][c - 1]) / A.dx2 +
+                        (s_p[r + 1][c] - T(2) * pc + s_p[r - 1][c]) / A.dy2;
+          dq = dq + (-A.kappa * lap);
+        }
+        const T qc = s_q[r][c];
+        const T lapq = (s_q[r][c + 1] - T(2) * qc + s_q[r][c - 1]) / A.dx2 +
+                       (s_q[r + 1][c] - T(2) * qc + s_q[r - 1][c]) / A.dy2;
+        dq = dq + A.nu * lapq;
+      }
+    }
+    out[e] = dq;
+  }
+  const size_t idx = po + (size_t)j * pitch + (size_t)g * 4;
+  const bool need_yin = (st.Yout[0] != nullptr) && (st.y[0] == nullptr);
+  Vec4<T> yin = need_yin ? ld4(st.Yin[0] + idx) : Vec4<T>{0, 0, 0, 0};
+  rk_epilogue4(st, 0, idx, yin, Vec4<T>{out[0], out[1], out[2], out[3]});
+}
+
+// ring := 0 in place on padded planes
+template <typename T>
+__global__ void qg_bc_kernel(T* __restrict__ q, Layout L) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y, p = blockIdx.z;
+  if (i >= L.Nx) return;
+  if (j == 0 || j == L.Ny - 1 || i == 0 || i == L.Nx - 1)
+    q[(size_t)p * L.plane() + (size_t)j * L.pitch + OFF + i] = T(0);
+}
+
+// KE / enstrophy / non-finite count from q (reference layout) and psi (padded layout).
+template <typename T>
+__global__ void qg_diag_kernel(const T* __restrict__ q, const T* __restrict__ psi, Layout L,
+                               double dx, double dy, double* __restrict__ out) {
+  const int plane = blockIdx.z, b = plane / L.nl, k = plane % L.nl;
+  const T* Q = q + (size_t)plane * L.Ny * L.Nx;
+  const T* P = psi + (size_t)plane * L.plane();
+  const int Ny = L.Ny, Nx = L.Nx, pitch = L.pitch;
+  double ke = 0, ens = 0, bad = 0;
+  for (int j = blockIdx.y; j < Ny; j += gridDim.y)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Nx; i += gridDim.x * blockDim.x) {
+      T qv = Q[(size_t)j * Nx + i];
+      if (!isfinite((double)qv)) bad += 1;
+      if (j >= 1 && j <= Ny - 2 && i >= 1 && i <= Nx - 2) {
+        auto PS = [&](int jj, int ii) { return P[(size_t)jj * pitch + OFF + ii]; };
+        // u = -d psi/dy at V points (interior-only, zero ring), v = d psi/dx at U points
+        auto uV = [&](int jj, int ii) -> T {
+          return (jj >= 1 && jj <= Ny - 2 && ii >= 1 && ii <= Nx - 2)
+                     ? -((PS(jj + 1, ii) - PS(jj, ii)) / (T)dy) : T(0); };
+        auto vU = [&](int jj, int ii) -> T {
+          return (jj >= 1 && jj <= Ny - 2 && ii >= 1 && ii <= Nx - 2)
+                     ? (PS(jj, ii + 1) - PS(jj, ii)) / (T)dx : T(0); };
+        T uT = T(0.5) * (uV(j, i) + uV(j - 1, i));
+        T vT = T(0.5) * (vU(j, i) + vU(j, i - 1));
+        ke += (double)(uT * uT + vT * vT);
+        ens += (double)(qv * qv);
+      }
+    }
+  __shared__ double red[3][8];
+  double vals[3] = {ke, ens, bad};
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int qd = 0; qd < 3; ++qd) {
+    double x = vals[qd];
+    for (int s = 16; s > 0; s >>= 1) x += __shfl_down_sync(0xffffffffu, x, s);
+    if (lane == 0) red[qd][w] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double x = 0;
+    for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) x += red[threadIdx.x][ww];
+    double area = dx * dy;
+    double* o = out + (size_t)b * (2 * L.nl + 1);
+    if (threadIdx.x == 0) atomicAdd(o + k, 0.5 * x * area);
+    if (threadIdx.x == 1) atomicAdd(o + L.nl + k, 0.5 * x * area);
+    if (threadIdx.x == 2) atomicAdd(o + 2 * L.nl, x);
+  }
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+struct somax_b200_qg_s {
+  int dtype;
+  Layout L;
+  int ny, nx;
+  double dx, dy;
+  unsigned spec;
+  QgSolver* solver = nullptr;
+  void* beta = nullptr; void* wind = nullptr;
+  bool beta1d = false, wind1d = false;
+  void* y = nullptr; void* Ya = nullptr; void* Yb = nullptr; void* psi = nullptr;
+  void* F[5] = {0, 0, 0, 0, 0};
+  size_t bytes = 0;
+};
+
+namespace {
+
+template <typename T>
+QgArgs<T> make_qargs(somax_b200_qg_t h, const somax_b200_params* p, int apply_bc) {
+  QgArgs<T> A;
+  A.L = h->L; A.apply_bc = apply_bc;
+  A.dx2 = (T)(h->dx * h->dx); A.dy2 = (T)(h->dy * h->dy); A.jden = (T)(12.0 * h->dx * h->dy);
+  A.beta = (const T*)h->beta; A.b_cp = h->beta1d ? 1 : h->L.Nx; A.b_xs = h->beta1d ? 0 : 1;
+  A.wind = (const T*)h->wind; A.w_cp = h->wind1d ? 1 : h->L.Nx; A.w_xs = h->wind1d ? 0 : 1;
+  A.H0 = (T)p->H0; A.nu = (T)p->lateral_viscosity; A.kappa = (T)p->bottom_drag;
+  A.tau0 = (T)p->wind_amplitude;
+  return A;
+}
+
+template <typename T>
+Stage<T> qstage() {
+  Stage<T> st;
+  st.nfields = 1; st.nprev = 0;
+  for (int f = 0; f < MAX_FIELDS; ++f) {
+    st.Yin[f] = nullptr; st.y[f] = nullptr; st.Fout[f] = nullptr; st.Yout[f] = nullptr;
+    for (int j = 0; j < MAX_PREV; ++j) st.Fprev[j][f] = nullptr;
+  }
+  for (int j = 0; j < MAX_PREV; ++j) st.a[j] = 0;
+  st.a_new = 0; st.dt = 0;
+  return st;
+}
+
+// one RHS evaluation: psi = invert(Yin), then the fused stencil + RK epilogue
+template <typename T>
+int eval_rhs(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st, cudaStream_t s) {
+  if (int rc = qg_solver_run<T>(h->solver, st.Yin[0], (T*)h->psi, s)) return rc;
+  const Layout& L = h->L;
+  dim3 block(QTXG, QTY);
+  dim3 grid((L.groups() + QTXG - 1) / QTXG, (L.Ny + QTY - 1) / QTY, L.batch * L.nl);
+  qg_rhs_kernel<T><<<grid, block, 0, s>>>(A, (const T*)h->psi, st);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int qg_bc_inplace(somax_b200_qg_t h, void* q, cudaStream_t s) {
+  const Layout& L = h->L;
+  dim3 b(256), g((L.Nx + 255) / 256, L.Ny, L.batch * L.nl);
+  qg_bc_kernel<T><<<g, b, 0, s>>>((T*)q, L);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int qg_steps_impl(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt_last,
+                  const somax_b200_params* p, cudaStream_t s) {
+  const Layout& L = h->L;
+  void *y = h->y, *Yc = h->Ya, *Yn = h->Yb;
+  if (int rc = pack_field<T>((const T*)q, (T*)y, L, s)) return rc;
+  if (int rc = qg_bc_inplace<T>(h, y, s)) return rc;   // integrate(): BC on state0
+  const long total = n_steps + (dt_last > 0 ? 1 : 0);
+  if (total > 0) {
+    QgArgs<T> A = make_qargs<T>(h, p, 1);
+    auto step_dt = [&](long i) { return (i < n_steps) ? dt : dt_last; };
+    {
+      Stage<T> st = qstage<T>();
+      st.Yin[0] = (const T*)y; st.Fout[0] = (T*)h->F[0]; st.Yout[0] = (T*)Yc;
+      st.a_new = (T)TSIT5_A[0][0]; st.dt = (T)step_dt(0);
+      if (int rc = eval_rhs<T>(h, A, st, s)) return rc;
+    }
+    for (long i = 0; i < total; ++i) {
+      const T hdt = (T)step_dt(i);
+      for (int e = 1; e <= 5; ++e) {
+        Stage<T> st = qstage<T>();
+        st.nprev = e; st.dt = hdt; st.a_new = (T)TSIT5_A[e][e];
+        for (int jj = 0; jj < e; ++jj) { st.a[jj] = (T)TSIT5_A[e][jj]; st.Fprev[jj][0] = (const T*)h->F[jj]; }
+        st.Yin[0] = (const T*)Yc; st.y[0] = (const T*)y; st.Yout[0] = (T*)Yn;
+        st.Fout[0] = (e <= 4) ? (T*)h->F[e] : nullptr;
+        if (int rc = eval_rhs<T>(h, A, st, s)) return rc;
+        std::swap(Yc, Yn);
+      }
+      if (i + 1 < total) {
+        Stage<T> st = qstage<T>();
+        st.dt = (T)step_dt(i + 1); st.a_new = (T)TSIT5_A[0][0];
+        st.Yin[0] = (const T*)Yc; st.Fout[0] = (T*)h->F[0]; st.Yout[0] = (T*)Yn;
+        if (int rc = eval_rhs<T>(h, A, st, s)) return rc;
+        void* oy = y; y = Yc; Yc = Yn; Yn = oy;
+      } else {
+        std::swap(y, Yc);
+      }
+    }
+  }
+  return unpack_field<T>((const T*)y, (T*)q, L, s);
+}
+
+template <typename T>
+int qg_rhs_impl(somax_b200_qg_t h, const void* q, void* dq, void* psi_out,
+                const somax_b200_params* p, int apply_bc, cudaStream_t s) {
+  const Layout& L = h->L;
+  if (int rc = pack_field<T>((const T*)q, (T*)h->Ya, L, s)) return rc;
+  QgArgs<T> A = make_qargs<T>(h, p, apply_bc);
+  Stage<T> st = qstage<T>();
+  st.Yin[0] = (const T*)h->Ya; st.Fout[0] = (T*)h->F[0];
+  if (int rc = eval_rhs<T>(h, A, st, s)) return rc;
+  if (int rc = unpack_field<T>((const T*)h->F[0], (T*)dq, L, s)) return rc;
+  if (psi_out) return unpack_field<T>((const T*)h->psi, (T*)psi_out, L, s);
+  return 0;
+}
+
+template <typename T>
+int qg_invert_impl(somax_b200_qg_t h, const void* q, void* psi, cudaStream_t s) {
+  const Layout& L = h->L;
+  if (int rc = pack_field<T>((const T*)q, (T*)h->Ya, L, s)) return rc;
+  if (int rc = qg_solver_run<T>(h->solver, (const T*)h->Ya, (T*)h->psi, s)) return rc;
+  return unpack_field<T>((const T*)h->psi, (T*)psi, L, s);
+}
+
+template <typename T>
+int qg_bc_impl(somax_b200_qg_t h, const void* q, void* out, cudaStream_t s) {
+  const Layout& L = h->L;
+  if (int rc = pack_field<T>((const T*)q, (T*)h->Ya, L, s)) return rc;
+  if (int rc = qg_bc_inplace<T>(h, h->Ya, s)) return rc;
+  return unpack_field<T>((const T*)h->Ya, (T*)out, L, s);
+}
+
+template <typename T>
+int qg_diag_impl(somax_b200_qg_t h, const void* q, double* out, cudaStream_t s) {
+  const Layout& L = h->L;
+  if (int rc = pack_field<T>((const T*)q, (T*)h->Ya, L, s)) return rc;
+  if (int rc = qg_solver_run<T>(h->solver, (const T*)h->Ya, (T*)h->psi, s)) return rc;
+  SB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * L.batch * (2 * L.nl + 1), s));
+  dim3 b(256), g(std::min((L.Nx + 255) / 256, 64), std::min(L.Ny, 128), L.batch * L.nl);
+  qg_diag_kernel<T><<<g, b, 0, s>>>((const T*)q, (const T*)h->psi, L, h->dx, h->dy, out);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+#define SB_DISPATCH(h, fn, ...) \
+  ((h)->dtype == SOMAX_B200_F32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+
+extern "C" {
+
+int somax_b200_qg_create(somax_b200_qg_t* out, int dtype, int batch, int nl, int ny, int nx,
+                         double dx, double dy, const double* Cl2m, const double* Cm2l,
+                         const double* lambdas, const double* beta_y, const double* wind,
+                         int solver, unsigned spec_flags) {
+  if (!out) return fail(SOMAX_B200_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (dtype != SOMAX_B200_F32 && dtype != SOMAX_B200_F64)
+    return fail(SOMAX_B200_ERR_INVALID, "dtype must be F32 or F64");
+  if (batch < 1 || nl < 1 || ny < 3 || nx < 3)
+    return fail(SOMAX_B200_ERR_INVALID, "need batch>=1, nl>=1, ny>=3, nx>=3");
+  if (!Cl2m || !Cm2l || !lambdas || !beta_y || !wind)
+    return fail(SOMAX_B200_ERR_INVALID, "null coefficient pointer");
+  if ((long)batch * nl > 65535) return fail(SOMAX_B200_ERR_UNSUPPORTED, "batch*nl > 65535");
+  if (int rc = require_device()) return rc;
+  auto* h = new somax_b200_qg_s();
+  h->dtype = dtype; h->L = make_layout(batch, nl, ny, nx); h->ny = ny; h->nx = nx;
+  h->dx = dx; h->dy = dy; h->spec = spec_flags;
+  int rc = qg_solver_create(&h->solver, dtype, batch, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, solver);
+  auto up = [&](const double* src, void** dst, bool* one) {
+    return dtype == SOMAX_B200_F32 ? upload_coef<float>(src, (float**)dst, h->L.Ny, h->L.Nx, one)
+                                   : upload_coef<double>(src, (double**)dst, h->L.Ny, h->L.Nx, one);
+  };
+  if (!rc) rc = up(beta_y, &h->beta, &h->beta1d);
+  if (!rc) rc = up(wind, &h->wind, &h->wind1d);
+  const size_t fb = h->L.count() * (dtype == SOMAX_B200_F32 ? 4 : 8);
+  void** bufs[] = {&h->y, &h->Ya, &h->Yb, &h->psi, &h->F[0], &h->F[1], &h->F[2], &h->F[3], &h->F[4]};
+  for (void** bp : bufs) {
+    if (rc) break;
+    cudaError_t e = cudaMalloc(bp, fb);
+    if (e != cudaSuccess) { rc = fail(SOMAX_B200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); break; }
+    cudaMemset(*bp, 0, fb);
+    h->bytes += fb;
+  }
+  if (rc) { somax_b200_qg_destroy(h); return rc; }
+  h->bytes += qg_solver_bytes(h->solver);
+  *out = h;
+  return 0;
+}
+
+int somax_b200_qg_destroy(somax_b200_qg_t h) {
+  if (!h) return 0;
+  qg_solver_destroy(h->solver);
+  cudaFree(h->beta); cudaFree(h->wind);
+  cudaFree(h->y); cudaFree(h->Ya); cudaFree(h->Yb); cudaFree(h->psi);
+  for (int j = 0; j < 5; ++j) cudaFree(h->F[j]);
+  delete h;
+  return 0;
+}
+
+size_t somax_b200_qg_device_bytes(somax_b200_qg_t h) { return h ? h->bytes : 0; }
+
+int somax_b200_qg_apply_bc(somax_b200_qg_t h, const void* q, void* out, void* stream) {
+  if (!h || !q || !out) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  return SB_DISPATCH(h, qg_bc_impl, h, q, out, (cudaStream_t)stream);
+}
+
+int somax_b200_qg_invert(somax_b200_qg_t h, const void* q, void* psi, void* stream) {
+  if (!h || !q || !psi) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  return SB_DISPATCH(h, qg_invert_impl, h, q, psi, (cudaStream_t)stream);
+}
+
+int somax_b200_qg_rhs(somax_b200_qg_t h, const void* q, void* dq, void* psi_out,
+                      const somax_b200_params* p, int apply_bc, void* stream) {
+  if (!h || !q || !dq || !p) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  return SB_DISPATCH(h, qg_rhs_impl, h, q, dq, psi_out, p, apply_bc, (cudaStream_t)stream);
+}
+
+int somax_b200_qg_steps(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt_last,
+                        const somax_b200_params* p, void* stream) {
+  if (!h || !q || !p) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  if (n_steps < 0 || !(dt > 0) || dt_last < 0) return fail(SOMAX_B200_ERR_INVALID, "need n_steps>=0, dt>0, dt_last>=0");
+  return SB_DISPATCH(h, qg_steps_impl, h, q, n_steps, dt, dt_last, p, (cudaStream_t)stream);
+}
+
+int somax_b200_qg_diag(somax_b200_qg_t h, const void* q, double* out, void* stream) {
+  if (!h || !q || !out) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  return SB_DISPATCH(h, qg_diag_impl, h, q, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,560 @@
+// Shallow-water hot path: single-pass fused RHS (mass flux, PV, Bernoulli, Coriolis
+// interpolation, diffusion, wind, drag) with the Tsit5 stage combination in the epilogue.
+//
+// Replaces MultilayerShallowWater2D.{apply_boundary_conditions,vector_field} and the diffrax
+// Tsit5 loop around them (reference swm/multilayer.py:150-223, core/model.py:47-88; operator
+// semantics SURVEY.md App. B).  One kernel launch per RHS evaluation; every second-level
+// operand (q, uh, vh, ke, P) is recomputed on chip from a shared-memory tile of (h,u,v) with a
+// one-cell halo, reproducing finitevolx's "interior-only, zero ghost ring" intermediates by
+// predicate on the global index.
+#include "common.cuh"
+
+#include <vector>
+
+namespace sb {
+
+constexpr int SWM_MAX_NL = 8;
+constexpr int TY = 8;            // output rows per CTA
+constexpr int TXG = 32;          // float4 groups per CTA row (=> 128 columns)
+constexpr int TW = TXG * 4 + 2;  // tile width incl. halo
+constexpr int TWP = TW + 2;      // padded smem row
+
+template <typename T>
+struct SwmArgs {
+  Layout L;
+  int bc;
+  unsigned spec;
+  int apply_bc;
+  T dx, dy, dx2, dy2;
+  const T* f;  int f_cp, f_xs;
+  const T* wx; int wx_cp, wx_xs;
+  const T* wy; int wy_cp, wy_xs;
+  T gprime[SWM_MAX_NL];
+  T H0, nu, kappa, tau0;
+};
+
+enum { FH = 0, FU = 1, FV = 2 };
+
+// Value of field `kind` at (j,i) after apply_boundary_conditions, read from the raw plane.
+// Periodic: enforce_periodic (rows then columns).  Wall: swm/multilayer.py:386-408.
+template <typename T>
+__device__ __forceinline__ T swm_bc_value(const T* __restrict__ plane, int kind, int bc, int j,
+                                          int i, int Ny, int Nx, int pitch) {
+  if (bc == SOMAX_B200_BC_PERIODIC) {
+    int jj = (j == 0) ? Ny - 2 : (j == Ny - 1 ? 1 : j);
+    int ii = (i == 0) ? Nx - 2 : (i == Nx - 1 ? 1 : i);
+    return plane[(size_t)jj * pitch + OFF + ii];
+  }
+  int jj = (j == 0) ? 1 : (j == Ny - 1 ? Ny - 2 : j);
+  int ii = (i == 0) ? 1 : (i == Nx - 1 ? Nx - 2 : i);
+  if (kind == FU) {
+    if (i == 0 || i >= Nx - 2) return T(0);
+    return plane[(size_t)jj * pitch + OFF + i];
+  }
+  if (kind == FV) {
+    if (j == 0 || j >= Ny - 2) return T(0);
+    return plane[(size_t)j * pitch + OFF + ii];
+  }
+  return plane[(size_t)jj * pitch + OFF + ii];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TXG* TY)
+swm_rhs_kernel(SwmArgs<T> A, Stage<T> st) {
+  __shared__ T s_h[TY + 2][TWP];
+  __shared__ T s_u[TY + 2][TWP];
+  __shared__ T s_v[TY + 2][TWP];
+  __shared__ T s_p[TY + 2][TWP];
+
+  const Layout& L = A.L;
+  const int Ny = L.Ny, Nx = L.Nx, pitch = L.pitch;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TXG + tx;
+  const int g0 = blockIdx.x * TXG;           // first float4 group of the tile
+  const int c0 = g0 * 4 - OFF;               // column of the tile's first slot
+  const int j0 = blockIdx.y * TY;
+  const int b = blockIdx.z;
+  const int j = j0 + ty;
+  const int g = g0 + tx;
+  const bool active = (j < Ny) && (g < L.groups());
+
+  // zero the running pressure sum
+  for (int e = tid; e < (TY + 2) * TWP; e += TXG * TY) (&s_p[0][0])[e] = T(0);
+
+  for (int k = 0; k < L.nl; ++k) {
+    const size_t plane_off = ((size_t)b * L.nl + k) * L.plane();
+    const T* ph = st.Yin[FH] + plane_off;
+    const T* pu = st.Yin[FU] + plane_off;
+    const T* pv = st.Yin[FV] + plane_off;
+    __syncthreads();  // previous layer's compute done before the tiles are overwritten
+    for (int e = tid; e < (TY + 2) * TW; e += TXG * TY) {
+      int r = e / TW, c = e - r * TW;
+      int jj = j0 - 1 + r, ii = c0 - 1 + c;
+      T vh = 0, vu = 0, vv = 0;
+      if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
+        if (A.apply_bc) {
+          vh = swm_bc_value(ph, FH, A.bc, jj, ii, Ny, Nx, pitch);
+          vu = swm_bc_value(pu, FU, A.bc, jj, ii, Ny, Nx, pitch);
+          vv = swm_bc_value(pv, FV, A.bc, jj, ii, Ny, Nx, pitch);
+        } else {
+          size_t o = (size_t)jj * pitch + OFF + ii;
+          vh = ph[o]; vu = pu[o]; vv = pv[o];
+        }
+      }
+      s_h[r][c] = vh; s_u[r][c] = vu; s_v[r][c] = vv;
+      s_p[r][c] = s_p[r][c] + A.gprime[k] * vh;   // p_k = cumsum_k(g'_k h_k), full grid
+    }
+    __syncthreads();
+    if (!active) continue;
+
+    T out_h[4], out_u[4], out_v[4];
+    const int r = ty + 1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = c0 + tx * 4 + e;
+      const int c = tx * 4 + e + 1;
+      T dh = 0, du = 0, dv = 0;
+      if (i >= 0 && i < Nx) {
+        auto H = [&](int dr, int dc) { return s_h[r + dr][c + dc]; };
+        auto U = [&](int dr, int dc) { return s_u[r + dr][c + dc]; };
+        auto V = [&](int dr, int dc) { return s_v[r + dr][c + dc]; };
+        auto P = [&](int dr, int dc) { return s_p[r + dr][c + dc]; };
+        auto inI = [&](int dr, int dc) {
+          int jj = j + dr, ii = i + dc;
+          return jj >= 1 && jj <= Ny - 2 && ii >= 1 && ii <= Nx - 2;
+        };
+        auto Fc = [&](int dr, int dc) {
+          return A.f[(size_t)(j + dr) * A.f_cp + (size_t)(i + dc) * A.f_xs];
+        };
+        const bool interior = inI(0, 0);
+        if (interior) {
+          // --- potential vorticity at X points (interior-only, zero ring) ---
+          auto qX = [&](int dr, int dc) -> T {
+            if (!inI(dr, dc)) return T(0);
+            T zeta = (V(dr, dc + 1) - V(dr, dc)) / A.dx - (U(dr + 1, dc) - U(dr, dc)) / A.dy;
+            T fX = T(0.25) * (Fc(dr, dc) + Fc(dr, dc + 1) + Fc(dr + 1, dc) + Fc(dr + 1, dc + 1));
+            T hX = T(0.25) * (H(dr, dc) + H(dr, dc + 1) + H(dr + 1, dc) + H(dr + 1, dc + 1));
+            return (zeta + fX) / hX;
+          };
+          auto vhV = [&](int dr, int dc) -> T {
+            return inI(dr, dc) ? (T(0.5) * (H(dr, dc) + H(dr + 1, dc))) * V(dr, dc) : T(0);
+          };
+          auto uhU = [&](int dr, int dc) -> T {
+            return inI(dr, dc) ? (T(0.5) * (H(dr, dc) + H(dr, dc + 1))) * U(dr, dc) : T(0);
+          };
+          auto keT = [&](int dr, int dc) -> T {
+            if (!inI(dr, dc)) return T(0);
+            T u2 = T(0.5) * (U(dr, dc) * U(dr, dc) + U(dr, dc - 1) * U(dr, dc - 1));
+            T v2 = T(0.5) * (V(dr, dc) * V(dr, dc) + V(dr - 1, dc) * V(dr - 1, dc));
+            return T(0.5) * (u2 + v2);
+          };
+          const T q00 = qX(0, 0);
+          const T qU = T(0.5) * (q00 + qX(-1, 0));
+          const T qV = T(0.5) * (q00 + qX(0, -1));
+          const T vhU = T(0.25) * (vhV(0, 0) + vhV(0, 1) + vhV(-1, 0) + vhV(-1, 1));
+          const T uhVv = T(0.25) * (uhU(0, 0) + uhU(1, 0) + uhU(0, -1) + uhU(1, -1));
+          const T P00 = keT(0, 0) + P(0, 0);
+          const T P01 = keT(0, 1) + P(0, 1);
+          const T P10 = keT(1, 0) + P(1, 0);
+          du = qU * vhU - (P01 - P00) / A.dx;
+          dv = -qV * uhVv - (P10 - P00) / A.dy;
+          // --- mass: -div(h u), first-order upwind ---
+          auto fe = [&](int dr, int dc) -> T {
+            if (!inI(dr, dc)) return T(0);
+            T uu = U(dr, dc);
+            return uu * (uu > T(0) ? H(dr, dc) : H(dr, dc + 1));
+          };
+          auto fn = [&](int dr, int dc) -> T {
+            if (!inI(dr, dc)) return T(0);
+            T vv = V(dr, dc);
+            return vv * (vv > T(0) ? H(dr, dc) : H(dr + 1, dc));
+          };
+          bool wr = true;
+          if (A.spec & SOMAX_B200_SPEC_ADVECTION_REGION2)
+            wr = (j >= 2 && j <= Ny - 3 && i >= 2 && i <= Nx - 3);
+          if (wr) dh = -((fe(0, 0) - fe(0, -1)) / A.dx + (fn(0, 0) - fn(-1, 0)) / A.dy);
+        }
+        // --- wind (top layer, FULL grid incl. ring) ---
+        if (k == 0) {
+          du = du + (A.tau0 * A.wx[(size_t)j * A.wx_cp + (size_t)i * A.wx_xs]) / A.H0;
+          dv = dv + (A.tau0 * A.wy[(size_t)j * A.wy_cp + (size_t)i * A.wy_xs]) / A.H0;
+        }
+        // --- diffusion (interior-only output) ---
+        if (interior) {
+          T lu, lv;
+          if (A.spec & SOMAX_B200_SPEC_DIFFUSION_FLUX) {
+            auto fxU = [&](int dr, int dc) -> T {
+              return inI(dr, dc) ? A.nu * ((U(dr, dc + 1) - U(dr, dc)) / A.dx) : T(0); };
+            auto fyU = [&](int dr, int dc) -> T {
+              return inI(dr, dc) ? A.nu * ((U(dr + 1, dc) - U(dr, dc)) / A.dy) : T(0); };
+            auto fxV = [&](int dr, int dc) -> T {
+              return inI(dr, dc) ? A.nu * ((V(dr, dc + 1) - V(dr, dc)) / A.dx) : T(0); };
+            auto fyV = [&](int dr, int dc) -> T {
+              return inI(dr, dc) ? A.nu * ((V(dr + 1, dc) - V(dr, dc)) / A.dy) : T(0); };
+            lu = (fxU(0, 0) - fxU(0, -1)) / A.dx + (fyU(0, 0) - fyU(-1, 0)) / A.dy;
+            lv = (fxV(0, 0) - fxV(0, -1)) / A.dx + (fyV(0, 0) - fyV(-1, 0)) / A.dy;
+          } else {
+            lu = A.nu * ((U(0, 1) - T(2) * U(0, 0) + U(0, -1)) / A.dx2 +
+                         (U(1, 0) - T(2) * U(0, 0) + U(-1, 0)) / A.dy2);
+            lv = A.nu * ((V(0, 1) - T(2) * V(0, 0) + V(0, -1)) / A.dx2 +
+                         (V(1, 0) - T(2) * V(0, 0) + V(-1, 0)) / A.dy2);
+          }
+          du = du + lu;
+          dv = dv + lv;
+        }
+        // --- bottom drag (bottom layer, FULL grid incl. ring) ---
+        if (k == L.nl - 1) {
+          du = du + (-A.kappa * U(0, 0));
+          dv = dv + (-A.kappa * V(0, 0));
+        }
+      }
+      out_h[e] = dh; out_u[e] = du; out_v[e] = dv;
+    }
+    const size_t idx = plane_off + (size_t)j * pitch + (size_t)g * 4;
+    Vec4<T> yin;
+    Vec4<T> Fh{out_h[0], out_h[1], out_h[2], out_h[3]};
+    Vec4<T> Fu{out_u[0], out_u[1], out_u[2], out_u[3]};
+    Vec4<T> Fv{out_v[0], out_v[1], out_v[2], out_v[3]};
+    const bool need_yin = (st.Yout[0] != nullptr) && (st.y[0] == nullptr);
+    yin = need_yin ? ld4(st.Yin[FH] + idx) : Vec4<T>{0, 0, 0, 0};
+    rk_epilogue4(st, FH, idx, yin, Fh);
+    yin = need_yin ? ld4(st.Yin[FU] + idx) : Vec4<T>{0, 0, 0, 0};
+    rk_epilogue4(st, FU, idx, yin, Fu);
+    yin = need_yin ? ld4(st.Yin[FV] + idx) : Vec4<T>{0, 0, 0, 0};
+    rk_epilogue4(st, FV, idx, yin, Fv);
+  }
+}
+
+// In-place apply_boundary_conditions on padded planes.
+template <typename T>
+__global__ void swm_bc_kernel(T* __restrict__ h, T* __restrict__ u, T* __restrict__ v, Layout L,
+                              int bc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y;
+  int p = blockIdx.z;
+  if (i >= L.Nx) return;
+  bool ring = (j == 0 || j == L.Ny - 1 || i == 0 || i == L.Nx - 1);
+  bool near_u = (bc == SOMAX_B200_BC_WALL) && (i == L.Nx - 2);
+  bool near_v = (bc == SOMAX_B200_BC_WALL) && (j == L.Ny - 2);
+  if (!ring && !near_u && !near_v) return;
+  size_t po = (size_t)p * L.plane();
+  size_t o = po + (size_t)j * L.pitch + OFF + i;
+  // every value is computed from cells the kernel never writes (see swm_bc_value)
+  if (ring) h[o] = swm_bc_value(h + po, FH, bc, j, i, L.Ny, L.Nx, L.pitch);
+  if (ring || near_u) u[o] = swm_bc_value(u + po, FU, bc, j, i, L.Ny, L.Nx, L.pitch);
+  if (ring || near_v) v[o] = swm_bc_value(v + po, FV, bc, j, i, L.Ny, L.Nx, L.pitch);
+}
+
+// Diagnostics on the reference layout (state as given, no BC): swm/multilayer.py:225-256.
+template <typename T>
+__global__ void swm_diag_kernel(const T* __restrict__ h, const T* __restrict__ u,
+                                const T* __restrict__ v, const T* __restrict__ f, int f_cp,
+                                int f_xs, int nl, int Ny, int Nx, double dx, double dy,
+                                double* __restrict__ out) {
+  const int b = blockIdx.z / nl, k = blockIdx.z % nl;
+  const size_t po = ((size_t)b * nl + k) * Ny * Nx;
+  const T* H = h + po; const T* U = u + po; const T* V = v + po;
+  double ke = 0, h2 = 0, ens = 0, bad = 0;
+  for (int j = blockIdx.y; j < Ny; j += gridDim.y) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Nx; i += gridDim.x * blockDim.x) {
+      size_t o = (size_t)j * Nx + i;
+      T hv = H[o], uv = U[o], vv = V[o];
+      if (!isfinite((double)hv)) bad += 1;
+      if (!isfinite((double)uv)) bad += 1;
+      if (!isfinite((double)vv)) bad += 1;
+      if (j >= 1 && j <= Ny - 2 && i >= 1 && i <= Nx - 2) {
+        T uw = U[o - 1], vs = V[o - Nx];
+        T kev = T(0.5) * (T(0.5) * (uv * uv + uw * uw) + T(0.5) * (vv * vv + vs * vs));
+        T zeta = (T)((V[o + 1] - vv) / (T)dx - (U[o + Nx] - uv) / (T)dy);
+        auto Fc = [&](int jj, int ii) { return f[(size_t)jj * f_cp + (size_t)ii * f_xs]; };
+        T fX = T(0.25) * (Fc(j, i) + Fc(j, i + 1) + Fc(j + 1, i) + Fc(j + 1, i + 1));
+        T hX = T(0.25) * (hv + H[o + 1] + H[o + Nx] + H[o + Nx + 1]);
+        T q = (zeta + fX) / hX;
+        ke += (double)kev;
+        h2 += (double)(hv * hv);
+        ens += (double)(q * q * hX);
+      }
+    }
+  }
+  // block reduce
+  __shared__ double red[4][8];
+  double vals[4] = {ke, h2, ens, bad};
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    double x = vals[q];
+    for (int s = 16; s > 0; s >>= 1) x += __shfl_down_sync(0xffffffffu, x, s);
+    if (lane == 0) red[q][w] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double x = 0;
+    for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) x += red[threadIdx.x][ww];
+    double area = dx * dy;
+    double* o = out + (size_t)b * (3 * nl + 1);
+    if (threadIdx.x == 0) atomicAdd(o + k, x * area);
+    if (threadIdx.x == 1) atomicAdd(o + nl + k, x * area);
+    if (threadIdx.x == 2) atomicAdd(o + 2 * nl + k, 0.5 * x * area);
+    if (threadIdx.x == 3) atomicAdd(o + 3 * nl, x);
+  }
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+struct somax_b200_swm_s {
+  int dtype;
+  Layout L;
+  int ny, nx, bc;
+  unsigned spec;
+  double dx, dy;
+  double gprime[SWM_MAX_NL];
+  void* f = nullptr; void* wx = nullptr; void* wy = nullptr;
+  bool f1d = false, wx1d = false, wy1d = false;
+  void* y[3] = {0, 0, 0};
+  void* Ya[3] = {0, 0, 0};
+  void* Yb[3] = {0, 0, 0};
+  void* F[5][3] = {};
+  size_t bytes = 0;
+};
+
+namespace {
+
+template <typename T>
+SwmArgs<T> make_args(somax_b200_swm_t h, const somax_b200_params* p, int apply_bc) {
+  SwmArgs<T> A;
+  A.L = h->L; A.bc = h->bc; A.spec = h->spec; A.apply_bc = apply_bc;
+  A.dx = (T)h->dx; A.dy = (T)h->dy; A.dx2 = (T)(h->dx * h->dx); A.dy2 = (T)(h->dy * h->dy);
+  A.f = (const T*)h->f;   A.f_cp = h->f1d ? 1 : h->L.Nx;   A.f_xs = h->f1d ? 0 : 1;
+  A.wx = (const T*)h->wx; A.wx_cp = h->wx1d ? 1 : h->L.Nx; A.wx_xs = h->wx1d ? 0 : 1;
+  A.wy = (const T*)h->wy; A.wy_cp = h->wy1d ? 1 : h->L.Nx; A.wy_xs = h->wy1d ? 0 : 1;
+  for (int k = 0; k < SWM_MAX_NL; ++k) A.gprime[k] = (T)h->gprime[k];
+  A.H0 = (T)p->H0; A.nu = (T)p->lateral_viscosity; A.kappa = (T)p->bottom_drag;
+  A.tau0 = (T)p->wind_amplitude;
+  return A;
+}
+
+template <typename T>
+int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A, const Stage<T>& st, cudaStream_t s) {
+  const Layout& L = h->L;
+  dim3 block(TXG, TY);
+  dim3 grid((L.groups() + TXG - 1) / TXG, (L.Ny + TY - 1) / TY, L.batch);
+  swm_rhs_kernel<T><<<grid, block, 0, s>>>(A, st);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+Stage<T> empty_stage() {
+  Stage<T> st;
+  st.nfields = 3; st.nprev = 0;
+  for (int f = 0; f < MAX_FIELDS; ++f) {
+    st.Yin[f] = nullptr; st.y[f] = nullptr; st.Fout[f] = nullptr; st.Yout[f] = nullptr;
+    for (int j = 0; j < MAX_PREV; ++j) st.Fprev[j][f] = nullptr;
+  }
+  for (int j = 0; j < MAX_PREV; ++j) st.a[j] = 0;
+  st.a_new = 0; st.dt = 0;
+  return st;
+}
+
+template <typename T>
+int bc_inplace(somax_b200_swm_t h, void* const f[3], cudaStream_t s) {
+  const Layout& L = h->L;
+  dim3 b(256), g((L.Nx + 255) / 256, L.Ny, L.batch * L.nl);
+  swm_bc_kernel<T><<<g, b, 0, s>>>((T*)f[0], (T*)f[1], (T*)f[2], L, h->bc);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int swm_steps_impl(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps, double dt,
+                   double dt_last, const somax_b200_params* p, cudaStream_t s) {
+  const Layout& L = h->L;
+  void* ext[3] = {hh, u, v};
+  void *y[3], *Yc[3], *Yn[3];
+  for (int f = 0; f < 3; ++f) { y[f] = h->y[f]; Yc[f] = h->Ya[f]; Yn[f] = h->Yb[f]; }
+  for (int f = 0; f < 3; ++f)
+    if (int rc = pack_field<T>((const T*)ext[f], (T*)y[f], L, s)) return rc;
+  if (int rc = bc_inplace<T>(h, y, s)) return rc;   // integrate(): BC on state0
+  const long total = n_steps + (dt_last > 0 ? 1 : 0);
+  if (total > 0) {
+    SwmArgs<T> A = make_args<T>(h, p, 1);
+    auto step_dt = [&](long i) { return (i < n_steps) ? dt : dt_last; };
+    // k1 of the first step: F1 = f(BC(y)), Y2 = y + a21*dt*F1
+    {
+      Stage<T> st = empty_stage<T>();
+      for (int f = 0; f < 3; ++f) {
+        st.Yin[f] = (const T*)y[f]; st.Fout[f] = (T*)h->F[0][f]; st.Yout[f] = (T*)Yc[f];
+      }
+      st.a_new = (T)TSIT5_A[0][0]; st.dt = (T)step_dt(0);
+      if (int rc = launch_rhs<T>(h, A, st, s)) return rc;
+    }
+    for (long i = 0; i < total; ++i) {
+      const T hdt = (T)step_dt(i);
+      for (int e = 1; e <= 5; ++e) {
+        Stage<T> st = empty_stage<T>();
+        st.nprev = e; st.dt = hdt; st.a_new = (T)TSIT5_A[e][e];
+        for (int jj = 0; jj < e; ++jj) st.a[jj] = (T)TSIT5_A[e][jj];
+        for (int f = 0; f < 3; ++f) {
+          st.Yin[f] = (const T*)Yc[f]; st.y[f] = (const T*)y[f]; st.Yout[f] = (T*)Yn[f];
+          st.Fout[f] = (e <= 4) ? (T*)h->F[e][f] : nullptr;
+          for (int jj = 0; jj < e; ++jj) st.Fprev[jj][f] = (const T*)h->F[jj][f];
+        }
+        if (int rc = launch_rhs<T>(h, A, st, s)) return rc;
+        for (int f = 0; f < 3; ++f) { void* t = Yc[f]; Yc[f] = Yn[f]; Yn[f] = t; }
+      }
+      // Yc now holds Y7 = y_{n+1}; Yn is free.
+      if (i + 1 < total) {
+        Stage<T> st = empty_stage<T>();
+        st.dt = (T)step_dt(i + 1); st.a_new = (T)TSIT5_A[0][0];
+        for (int f = 0; f < 3; ++f) {
+          st.Yin[f] = (const T*)Yc[f]; st.Fout[f] = (T*)h->F[0][f]; st.Yout[f] = (T*)Yn[f];
+        }
+        if (int rc = launch_rhs<T>(h, A, st, s)) return rc;
+        for (int f = 0; f < 3; ++f) { void* oy = y[f]; y[f] = Yc[f]; Yc[f] = Yn[f]; Yn[f] = oy; }
+      } else {
+        for (int f = 0; f < 3; ++f) { void* oy = y[f]; y[f] = Yc[f]; Yc[f] = oy; }
+      }
+    }
+  }
+  for (int f = 0; f < 3; ++f)
+    if (int rc = unpack_field<T>((const T*)y[f], (T*)ext[f], L, s)) return rc;
+  return 0;
+}
+
+template <typename T>
+int swm_rhs_impl(somax_b200_swm_t h, const void* hh, const void* u, const void* v, void* dh,
+                 void* du, void* dv, const somax_b200_params* p, int apply_bc, cudaStream_t s) {
+  const Layout& L = h->L;
+  const void* in[3] = {hh, u, v};
+  void* out[3] = {dh, du, dv};
+  for (int f = 0; f < 3; ++f)
+    if (int rc = pack_field<T>((const T*)in[f], (T*)h->Ya[f], L, s)) return rc;
+  SwmArgs<T> A = make_args<T>(h, p, apply_bc);
+  Stage<T> st = empty_stage<T>();
+  for (int f = 0; f < 3; ++f) { st.Yin[f] = (const T*)h->Ya[f]; st.Fout[f] = (T*)h->F[0][f]; }
+  if (int rc = launch_rhs<T>(h, A, st, s)) return rc;
+  for (int f = 0; f < 3; ++f)
+    if (int rc = unpack_field<T>((const T*)h->F[0][f], (T*)out[f], L, s)) return rc;
+  return 0;
+}
+
+template <typename T>
+int swm_bc_impl(somax_b200_swm_t h, const void* hh, const void* u, const void* v, void* ho,
+                void* uo, void* vo, cudaStream_t s) {
+  const Layout& L = h->L;
+  const void* in[3] = {hh, u, v};
+  void* out[3] = {ho, uo, vo};
+  for (int f = 0; f < 3; ++f)
+    if (int rc = pack_field<T>((const T*)in[f], (T*)h->Ya[f], L, s)) return rc;
+  if (int rc = bc_inplace<T>(h, h->Ya, s)) return rc;
+  for (int f = 0; f < 3; ++f)
+    if (int rc = unpack_field<T>((const T*)h->Ya[f], (T*)out[f], L, s)) return rc;
+  return 0;
+}
+
+template <typename T>
+int swm_diag_impl(somax_b200_swm_t h, const void* hh, const void* u, const void* v, double* out,
+                  cudaStream_t s) {
+  const Layout& L = h->L;
+  SB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * L.batch * (3 * L.nl + 1), s));
+  dim3 b(256), g(std::min((L.Nx + 255) / 256, 64), std::min(L.Ny, 128), L.batch * L.nl);
+  swm_diag_kernel<T><<<g, b, 0, s>>>((const T*)hh, (const T*)u, (const T*)v, (const T*)h->f,
+                                     h->f1d ? 1 : L.Nx, h->f1d ? 0 : 1, L.nl, L.Ny, L.Nx, h->dx,
+                                     h->dy, out);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+#define SB_DISPATCH(h, fn, ...) \
+  ((h)->dtype == SOMAX_B200_F32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+
+extern "C" {
+
+int somax_b200_swm_create(somax_b200_swm_t* out, int dtype, int batch, int nl, int ny, int nx,
+                          double dx, double dy, int bc, const double* g_prime,
+                          const double* f_field, const double* wind_x, const double* wind_y,
+                          unsigned spec_flags) {
+  if (!out) return fail(SOMAX_B200_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (dtype != SOMAX_B200_F32 && dtype != SOMAX_B200_F64)
+    return fail(SOMAX_B200_ERR_INVALID, "dtype must be F32 or F64");
+  if (batch < 1 || nl < 1 || nl > SWM_MAX_NL || ny < 3 || nx < 3)
+    return fail(SOMAX_B200_ERR_INVALID, "need batch>=1, 1<=nl<=8, ny>=3, nx>=3");
+  if (bc != SOMAX_B200_BC_PERIODIC && bc != SOMAX_B200_BC_WALL)
+    return fail(SOMAX_B200_ERR_INVALID, "bc must be PERIODIC or WALL");
+  if (!g_prime || !f_field || !wind_x || !wind_y)
+    return fail(SOMAX_B200_ERR_INVALID, "null coefficient pointer");
+  if (int rc = require_device()) return rc;
+  auto* h = new somax_b200_swm_s();
+  h->dtype = dtype; h->L = make_layout(batch, nl, ny, nx); h->ny = ny; h->nx = nx; h->bc = bc;
+  h->spec = spec_flags; h->dx = dx; h->dy = dy;
+  for (int k = 0; k < SWM_MAX_NL; ++k) h->gprime[k] = k < nl ? g_prime[k] : 0.0;
+  const size_t es = dtype == SOMAX_B200_F32 ? 4 : 8;
+  const size_t fb = h->L.count() * es;
+  int rc = 0;
+  auto up = [&](const double* src, void** dst, bool* one) {
+    return dtype == SOMAX_B200_F32 ? upload_coef<float>(src, (float**)dst, h->L.Ny, h->L.Nx, one)
+                                   : upload_coef<double>(src, (double**)dst, h->L.Ny, h->L.Nx, one);
+  };
+  rc = up(f_field, &h->f, &h->f1d);
+  if (!rc) rc = up(wind_x, &h->wx, &h->wx1d);
+  if (!rc) rc = up(wind_y, &h->wy, &h->wy1d);
+  std::vector<void**> bufs;
+  for (int f = 0; f < 3; ++f) {
+    bufs.push_back(&h->y[f]); bufs.push_back(&h->Ya[f]); bufs.push_back(&h->Yb[f]);
+    for (int j = 0; j < 5; ++j) bufs.push_back(&h->F[j][f]);
+  }
+  for (void** bp : bufs) {
+    if (rc) break;
+    cudaError_t e = cudaMalloc(bp, fb);
+    if (e != cudaSuccess) { rc = fail(SOMAX_B200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); break; }
+    cudaMemset(*bp, 0, fb);
+    h->bytes += fb;
+  }
+  if (rc) { somax_b200_swm_destroy(h); return rc; }
+  *out = h;
+  return 0;
+}
+
+int somax_b200_swm_destroy(somax_b200_swm_t h) {
+  if (!h) return 0;
+  cudaFree(h->f); cudaFree(h->wx); cudaFree(h->wy);
+  for (int f = 0; f < 3; ++f) {
+    cudaFree(h->y[f]); cudaFree(h->Ya[f]); cudaFree(h->Yb[f]);
+    for (int j = 0; j < 5; ++j) cudaFree(h->F[j][f]);
+  }
+  delete h;
+  return 0;
+}
+
+size_t somax_b200_swm_device_bytes(somax_b200_swm_t h) { return h ? h->bytes : 0; }
+
+int somax_b200_swm_apply_bc(somax_b200_swm_t h, const void* hh, const void* u, const void* v,
+                            void* ho, void* uo, void* vo, void* stream) {
+  if (!h || !hh || !u || !v || !ho || !uo || !vo) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  return SB_DISPATCH(h, swm_bc_impl, h, hh, u, v, ho, uo, vo, (cudaStream_t)stream);
+}
+
+int somax_b200_swm_rhs(somax_b200_swm_t h, const void* hh, const void* u, const void* v, void* dh,
+                       void* du, void* dv, const somax_b200_params* p, int apply_bc, void* stream) {
+  if (!h || !hh || !u || !v || !dh || !du || !dv || !p) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  return SB_DISPATCH(h, swm_rhs_impl, h, hh, u, v, dh, du, dv, p, apply_bc, (cudaStream_t)stream);
+}
+
+int somax_b200_swm_steps(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps, double dt,
+                         double dt_last, const somax_b200_params* p, void* stream) {
+  if (!h || !hh || !u || !v || !p) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  if (n_steps < 0 || !(dt > 0) || dt_last < 0) return fail(SOMAX_B200_ERR_INVALID, "need n_steps>=0, dt>0, dt_last>=0");
+  return SB_DISPATCH(h, swm_steps_impl, h, hh, u, v, n_steps, dt, dt_last, p, (cudaStream_t)stream);
+}
+
+int somax_b200_swm_diag(somax_b200_swm_t h, const void* hh, const void* u, const void* v,
+                        double* out, void* stream) {
+  if (!h || !hh || !u || !v || !out) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  return SB_DISPATCH(h, swm_diag_impl, h, hh, u, v, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+"""CPU: the C-ABI library loads and exports every symbol include/somax_b200.h declares."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def header_symbols():
+    text = (ROOT / "include" / "somax_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(somax_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = header_symbols()
+    for need in ("somax_b200_qg_create", "somax_b200_qg_rhs", "somax_b200_qg_steps",
+                 "somax_b200_qg_invert", "somax_b200_swm_rhs", "somax_b200_swm_steps",
+                 "somax_b200_last_error"):
+        assert need in syms
+
+
+def test_library_exports_every_header_symbol(built_lib):
+    lib = ctypes.CDLL(str(built_lib))
+    missing = [s for s in header_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_binding_table_matches_header(built_lib):
+    from somax_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+    assert _lib.lib().somax_b200_abi_version() == 1
+
+
+def test_create_fails_loudly_without_gpu(built_lib):
+    """No CPU fallback: on a GPU-less host create() returns NO_DEVICE and a message."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from somax_b200 import _lib
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    one = np.ones(1)
+    f = np.zeros((10, 10))
+    rc = L.somax_b200_qg_create(ctypes.byref(h), 0, 1, 1, 8, 8, 1.0, 1.0, one.ctypes.data,
+                                one.ctypes.data, one.ctypes.data, f.ctypes.data, f.ctypes.data, 0, 1)
+    assert rc == -4
+    assert b"no CPU fallback" in L.somax_b200_last_error() or b"sm_100a" in L.somax_b200_last_error()
+    with pytest.raises(_lib.SomaxB200Error):
+        _lib.check(rc)
+
+
+def test_invalid_arguments_are_rejected(built_lib):
+    from somax_b200 import _lib
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    rc = L.somax_b200_qg_create(ctypes.byref(h), 7, 1, 1, 8, 8, 1.0, 1.0, None, None, None, None, None, 0, 1)
+    assert rc == -1 and b"dtype" in L.somax_b200_last_error()
+    rc = L.somax_b200_swm_create(ctypes.byref(h), 0, 1, 9, 8, 8, 1.0, 1.0, 0, None, None, None, None, 1)
+    assert rc == -1
+
+
+def test_host_fft_dst_matches_scipy(built_lib):
+    """The kernels' FFT pass/split index algebra, run on the CPU through the same code."""
+    import scipy.fft
+    lib = ctypes.CDLL(str(built_lib))
+    f = lib.somax_b200_host_dst1_check
+    f.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    for n in (8, 16, 32, 64, 128, 256, 1024, 8192):
+        x = np.random.default_rng(n).standard_normal(n - 1)
+        X = np.zeros(n - 1)
+        assert f(n, x.ctypes.data, X.ctypes.data) == 0
+        ref = scipy.fft.dst(x, type=1) * 0.5
+        assert np.abs(X - ref).max() <= 1e-13 * np.abs(ref).max()

@@ -1,0 +1,324 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's: relative L2 <= 1e-5 in fp32, <= 1e-12 in fp64 on q/psi or h/u/v
+after 1 and 100 steps; energy / enstrophy within 1e-4.  The fp32 CUDA results are compared with
+the fp64 oracle (the "true" reference trajectory) as well as the fp32 oracle.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float32: 1e-5, np.float64: 1e-12}
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    d = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (d if d > 0 else 1.0)
+
+
+def qg_pair(nx, ny, dtype, solver=0, **kw):
+    from oracle import qg as oqg
+    import somax_b200 as sb
+    args = dict(lateral_viscosity=15.0, bottom_drag=1e-7, wind_amplitude=1.3e-10)
+    args.update(kw)
+    om = oqg.create_baroclinic(nx=nx, ny=ny, **args)
+    gm = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype=np.dtype(dtype).name, solver=solver, **args)
+    return om, gm
+
+
+def qstate(nl, nx, ny, dtype, ring=False):
+    from oracle.testcases import synthetic_qg_state
+    q = synthetic_qg_state(nl, nx, ny, dtype=np.float64)
+    if ring:
+        rng = np.random.default_rng(7)
+        noise = 1e-6 * rng.standard_normal(q.shape)
+        q[:, 0, :] = noise[:, 0, :]; q[:, -1, :] = noise[:, -1, :]
+        q[:, :, 0] = noise[:, :, 0]; q[:, :, -1] = noise[:, :, -1]
+    return q.astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nx,ny,solver", [(16, 16, 1), (16, 16, 2), (64, 48, 1), (24, 20, 2),
+                                          (128, 128, 1), (256, 64, 1)])
+def test_qg_invert_matches_oracle(nx, ny, solver, dtype):
+    om, gm = qg_pair(nx, ny, dtype, solver)
+    q = qstate(3, nx, ny, dtype, ring=True)
+    psi = gm._invert_pv(q)
+    ref = om.invert_pv(q.astype(np.float64))
+    assert psi.dtype == dtype
+    assert np.all(psi[:, 0] == 0) and np.all(psi[:, :, -1] == 0)
+    assert rel(psi, ref) <= (2e-6 if dtype == np.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_qg_invert_white_noise_rhs(dtype):
+    """Every wavenumber excited, positive and negative Helmholtz shifts."""
+    from oracle.elliptic import helmholtz_dst
+    import somax_b200 as sb
+    nx, ny = 64, 64
+    gm = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype=np.dtype(dtype).name)
+    om, _ = qg_pair(nx, ny, dtype)
+    rng = np.random.default_rng(3)
+    q = np.zeros((3, ny + 2, nx + 2))
+    q[:, 1:-1, 1:-1] = 1e-6 * rng.standard_normal((3, ny, nx))
+    psi = gm._invert_pv(q.astype(dtype))
+    ref = om.invert_pv(q)
+    assert rel(psi, ref) <= (5e-6 if dtype == np.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nx,ny,solver", [(32, 32, 1), (32, 32, 2), (64, 40, 1)])
+def test_qg_vector_field_and_bc(nx, ny, solver, dtype):
+    import somax_b200 as sb
+    om, gm = qg_pair(nx, ny, dtype, solver)
+    q = qstate(3, nx, ny, dtype, ring=True)
+    st = sb.BaroclinicQGState(q=q)
+    # raw vector_field (no BC: ring values of q enter the stencils)
+    dq = gm.vector_field(0.0, st).q
+    ref = om.rhs(q.astype(np.float64))
+    assert rel(dq, ref) <= (2e-5 if dtype == np.float32 else 1e-11)
+    # apply_boundary_conditions: exact
+    b = gm.apply_boundary_conditions(st).q
+    assert np.array_equal(b, om.bc(q))
+    # build_terms()._rhs = vector_field(BC(q))
+    dq2 = gm.build_terms().vf(0.0, st).q
+    ref2 = om.rhs(om.bc(q.astype(np.float64)))
+    assert rel(dq2, ref2) <= (2e-5 if dtype == np.float32 else 1e-11)
+    # wind forcing reaches the ghost ring of layer 0 only
+    assert np.all(dq2[1:, 0, :] == 0) and np.any(dq2[0, 0, :] != 0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nx,ny,steps", [(32, 32, 1), (32, 32, 100), (64, 64, 100)])
+def test_qg_integrate_parity(nx, ny, steps, dtype):
+    import somax_b200 as sb
+    om, gm = qg_pair(nx, ny, dtype)
+    q0 = qstate(3, nx, ny, dtype, ring=True)
+    dt = 600.0 * 128 / max(nx, 128) if nx >= 128 else 600.0
+    sol = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, steps * dt, dt, max_steps=None)
+    q = sol.ys.q[0]
+    ref = om.integrate(q0.astype(np.float64), 0.0, steps * dt, dt)
+    assert sol.ys.q.shape == (1,) + q0.shape and q.dtype == dtype
+    assert rel(q[:, 1:-1, 1:-1], ref[:, 1:-1, 1:-1]) <= TOL[dtype]
+    assert rel(q, ref) <= TOL[dtype]           # full array incl. the drifting ghost ring
+    psi = gm._invert_pv(q)
+    assert rel(psi, om.invert_pv(ref)) <= TOL[dtype] * 2
+    d, dref = gm.diagnose(sb.BaroclinicQGState(q=q)), om.diagnose(ref)
+    assert np.allclose(d.kinetic_energy, dref["kinetic_energy"], rtol=1e-4)
+    assert np.allclose(d.enstrophy, dref["enstrophy"], rtol=1e-4)
+    assert d.nonfinite == 0
+
+
+def test_qg_clipped_last_step_and_save_times():
+    import somax_b200 as sb
+    om, gm = qg_pair(32, 32, np.float64)
+    q0 = qstate(3, 32, 32, np.float64)
+    sol = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, 2500.0, 600.0)
+    ref = om.integrate(q0, 0.0, 2500.0, 600.0)
+    assert rel(sol.ys.q[0], ref) <= 1e-12
+    sol = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, 2400.0, 600.0,
+                       saveat=sb.SaveAt(ts=[1200.0, 2400.0]))
+    assert sol.ys.q.shape[0] == 2
+    assert rel(sol.ys.q[1][:, 1:-1, 1:-1], om.integrate(q0, 0.0, 2400.0, 600.0)[:, 1:-1, 1:-1]) <= 1e-12
+    with pytest.raises(RuntimeError):
+        gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, 6000.0, 600.0, max_steps=5)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_barotropic_qg_parity(dtype):
+    from oracle import qg as oqg
+    import somax_b200 as sb
+    kw = dict(nx=64, ny=64, lateral_viscosity=500.0, bottom_drag=1e-7, wind_amplitude=1e-12)
+    om = oqg.create_barotropic(**kw)
+    gm = sb.BarotropicQG.create(dtype=np.dtype(dtype).name, **kw)
+    q0 = (qstate(1, 64, 64, np.float64) * 1e-1).astype(dtype)
+    sol = gm.integrate(sb.BarotropicQGState(q=q0[0]), 0.0, 100 * 600.0, 600.0)
+    ref = om.integrate(q0.astype(np.float64), 0.0, 100 * 600.0, 600.0)[0]
+    assert sol.ys.q.shape == (1, 66, 66)
+    assert rel(sol.ys.q[0], ref) <= TOL[dtype]
+    d = gm.diagnose(sb.BarotropicQGState(q=sol.ys.q[0]))
+    dref = om.diagnose(ref[None])
+    assert np.allclose(d.kinetic_energy, dref["kinetic_energy"][0], rtol=1e-4)
+
+
+def test_qg_reference_property_tests_on_gpu():
+    """tests/models/test_qg_baroclinic.py:79-112,202-223 against the CUDA path."""
+    import somax_b200 as sb
+    m = sb.BaroclinicQG.create(nx=16, ny=16)
+    z = np.zeros((3, 18, 18), np.float32)
+    assert np.abs(m.vector_field(0.0, sb.BaroclinicQGState(q=z)).q).max() < 1e-12
+    m = sb.BaroclinicQG.create(nx=16, ny=16, wind_amplitude=1e-10)
+    dq = m.vector_field(0.0, sb.BaroclinicQGState(q=z)).q
+    assert np.abs(dq[0]).max() > 0 and np.abs(dq[1:]).max() < 1e-20
+    m = sb.BaroclinicQG.create(nx=16, ny=16, lateral_viscosity=100.0, wind_amplitude=1e-5)
+    sol = m.integrate(sb.BaroclinicQGState(q=z), 0.0, 100.0, 1.0)
+    assert np.isfinite(sol.ys.q).all() and np.abs(sol.ys.q[0, 0, 2:-2, 2:-2]).max() > 1e-10
+    with pytest.raises(ValueError):
+        sb.BaroclinicQG.create(nx=16, ny=16, n_layers=3, H=(1.0, 2.0), g_prime=(9.81, 0.02))
+
+
+def test_qg_ensemble_matches_single_members():
+    import somax_b200 as sb
+    _, gm = qg_pair(32, 32, np.float32)
+    qs = np.stack([qstate(3, 32, 32, np.float32) * s for s in (1.0, 0.5, -0.7)])
+    ens = gm.integrate(sb.BaroclinicQGState(q=qs), 0.0, 6000.0, 600.0).ys.q[0]
+    for e in range(3):
+        one = gm.integrate(sb.BaroclinicQGState(q=qs[e]), 0.0, 6000.0, 600.0).ys.q[0]
+        assert np.array_equal(ens[e], one)
+
+
+def test_qg_torch_tensors_stay_on_device():
+    import torch
+    import somax_b200 as sb
+    _, gm = qg_pair(32, 32, np.float32)
+    q = torch.as_tensor(qstate(3, 32, 32, np.float32), device="cuda")
+    q_before = q.clone()
+    out = gm.integrate(sb.BaroclinicQGState(q=q), 0.0, 600.0, 600.0).ys.q
+    assert isinstance(out, torch.Tensor) and out.is_cuda and out.shape == (1, 3, 34, 34)
+    assert torch.equal(q, q_before)          # pure function: the input is not modified
+
+
+# ---------------------------------------------------------------------------- shallow water
+def swm_pair(nx, ny, dtype, bc="periodic", spec=None, **kw):
+    from oracle import swm as oswm
+    from oracle.operators import OperatorSpec
+    import somax_b200 as sb
+    args = dict(Lx=1e6, Ly=1e6, f0=1e-4, beta=1.6e-11, n_layers=2, H=(500.0, 4500.0),
+                g_prime=(9.81, 0.025), lateral_viscosity=100.0, bottom_drag=1e-7,
+                wind_amplitude=1e-6, bc=bc)
+    args.update(kw)
+    ospec = spec or OperatorSpec()
+    om = oswm.create_multilayer(nx=nx, ny=ny, spec=ospec, **args)
+    gm = sb.MultilayerShallowWater2D.create(nx=nx, ny=ny, dtype=np.dtype(dtype).name,
+                                            spec=ospec.flags(), **args)
+    return om, gm
+
+
+def swm_state(nx, ny, dtype, noise=True):
+    from oracle.testcases import baroclinic_instability_swm
+    _, (h, u, v) = baroclinic_instability_swm(nx=nx, ny=ny, dtype=np.float64)
+    if noise:
+        rng = np.random.default_rng(5)
+        h = h + 0.5 * rng.standard_normal(h.shape)
+        u = u + 0.05 * rng.standard_normal(u.shape)
+        v = v + 0.05 * rng.standard_normal(v.shape)
+    return h.astype(dtype), u.astype(dtype), v.astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("bc", ["periodic", "wall"])
+@pytest.mark.parametrize("nx,ny", [(16, 16), (64, 40), (130, 33)])
+def test_swm_bc_and_vector_field(nx, ny, bc, dtype):
+    import somax_b200 as sb
+    om, gm = swm_pair(nx, ny, dtype, bc)
+    h, u, v = swm_state(nx, ny, dtype)
+    st = sb.MultilayerSW2DState(h=h, u=u, v=v)
+    b = gm.apply_boundary_conditions(st)
+    rb = om.bc(h, u, v)
+    for a, r in zip((b.h, b.u, b.v), rb):
+        assert np.array_equal(a, r)
+    tol = 2e-5 if dtype == np.float32 else 1e-11
+    f64 = [a.astype(np.float64) for a in (h, u, v)]
+    t = gm.vector_field(0.0, st)
+    for a, r in zip((t.h, t.u, t.v), om.rhs(*f64)):
+        assert rel(a, r) <= tol
+    t = gm.build_terms().vf(0.0, st)
+    for a, r in zip((t.h, t.u, t.v), om.rhs(*om.bc(*f64))):
+        assert rel(a, r) <= tol
+
+
+@pytest.mark.parametrize("flags", [(True, False), (False, False), (True, True)])
+def test_swm_operator_spec_switches(flags):
+    from oracle.operators import OperatorSpec
+    import somax_b200 as sb
+    spec = OperatorSpec(advection_region2=flags[0], diffusion_flux_form=flags[1])
+    om, gm = swm_pair(32, 32, np.float64, spec=spec)
+    h, u, v = swm_state(32, 32, np.float64)
+    t = gm.build_terms().vf(0.0, sb.MultilayerSW2DState(h=h, u=u, v=v))
+    for a, r in zip((t.h, t.u, t.v), om.rhs(*om.bc(h, u, v))):
+        assert rel(a, r) <= 1e-11
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("bc", ["periodic", "wall"])
+@pytest.mark.parametrize("nx,steps", [(32, 1), (32, 100), (64, 100)])
+def test_swm_integrate_parity(nx, steps, bc, dtype):
+    import somax_b200 as sb
+    om, gm = swm_pair(nx, nx, dtype, bc)
+    h, u, v = swm_state(nx, nx, dtype, noise=False)
+    dt = 20.0 * 64 / max(nx, 64)
+    sol = gm.integrate(sb.MultilayerSW2DState(h=h, u=u, v=v), 0.0, steps * dt, dt)
+    ref = om.integrate(*[a.astype(np.float64) for a in (h, u, v)], 0.0, steps * dt, dt)
+    # h carries a large mean (H = 500 / 4500 m): compare the anomaly too
+    for name, r in zip("huv", ref):
+        a = getattr(sol.ys, name)[0]
+        assert a.dtype == dtype
+        assert rel(a, r) <= TOL[dtype], name
+    hm = np.asarray(om.H)[:, None, None]
+    assert rel(sol.ys.h[0] - hm, ref[0] - hm) <= (2e-3 if dtype == np.float32 else 1e-11)
+    last = sb.MultilayerSW2DState(h=sol.ys.h[0], u=sol.ys.u[0], v=sol.ys.v[0])
+    d, dref = gm.diagnose(last), om.diagnose(*ref)
+    assert np.allclose(d.energy, dref["energy"], rtol=1e-4)
+    assert np.allclose(d.enstrophy, dref["enstrophy"], rtol=1e-4)
+    assert d.nonfinite == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_nonlinear_single_layer_parity(dtype):
+    from oracle import swm as oswm
+    import somax_b200 as sb
+    from somax_b200 import gfd_testcases as g
+    gm, st = g.barotropic_jet_instability(nx=32, ny=32, dtype=np.dtype(dtype).name)
+    om = oswm.create_multilayer(nx=32, ny=32, Lx=1e6, Ly=1e6, f0=1e-4, beta=1.6e-11, n_layers=1,
+                                H=(1.0,), g_prime=(9.81,), lateral_viscosity=100.0)
+    sol = gm.integrate(st, 0.0, 100 * 20.0, 20.0)
+    ref = om.integrate(*[np.asarray(a, np.float64)[None] for a in (st.h, st.u, st.v)], 0.0, 2000.0, 20.0)
+    assert sol.ys.h.shape == (1, 34, 34)
+    for name, r in zip("huv", ref):
+        assert rel(getattr(sol.ys, name)[0], r[0]) <= TOL[dtype]
+
+
+def test_swm_behavioural_pin_jet_diverges():
+    """tests/test_cli_run.py:187-212: swm_jet 64^2 with dt=300 must go non-finite."""
+    from somax_b200 import gfd_testcases as g
+    m, st = g.baroclinic_instability_swm(nx=64, ny=64)
+    sol = m.integrate(st, 0.0, 48 * 300.0, 300.0)
+    last = type(st)(h=sol.ys.h[0], u=sol.ys.u[0], v=sol.ys.v[0])
+    assert m.diagnose(last).nonfinite > 0
+    m, st = g.baroclinic_instability_swm(nx=32, ny=32)
+    sol = m.integrate(st, 0.0, 3600.0, 10.0)
+    assert all(np.isfinite(getattr(sol.ys, n)).all() for n in "huv")
+
+
+def test_swm_rest_state_and_wind():
+    """tests/models/test_swm_multilayer.py:94-113 against the CUDA path."""
+    import somax_b200 as sb
+    m = sb.MultilayerShallowWater2D.create(nx=16, ny=16, n_layers=2, H=(500.0, 4500.0),
+                                           g_prime=(9.81, 0.025), wind_amplitude=1e-5)
+    h = np.ones((2, 18, 18), np.float32) * np.array([500.0, 4500.0], np.float32)[:, None, None]
+    z = np.zeros_like(h)
+    st = m.apply_boundary_conditions(sb.MultilayerSW2DState(h=h, u=z, v=z))
+    t = m.vector_field(0.0, st)
+    assert np.abs(t.h).max() < 1e-10 and np.abs(t.v).max() < 1e-10
+    assert np.abs(t.u[0]).max() > 0 and np.abs(t.u[-1]).max() < 1e-15
+
+
+def test_golden_fixtures():
+    """Frozen oracle outputs (tools/make_golden.py): guards both sides against silent drift."""
+    from pathlib import Path
+    import somax_b200 as sb
+    gdir = Path(__file__).parent / "golden"
+    g = np.load(gdir / "qg3_32x32_f64.npz")
+    _, gm = qg_pair(32, 32, np.float64)
+    out = gm.integrate(sb.BaroclinicQGState(q=g["q0"]), 0.0, float(g["t1"]), float(g["dt"])).ys.q[0]
+    assert rel(out, g["q1"]) <= 1e-12
+    assert rel(gm._invert_pv(g["q0"]), g["psi0"]) <= 1e-12
+    g = np.load(gdir / "swm2_32x32_f64.npz")
+    _, gm = swm_pair(32, 32, np.float64)
+    sol = gm.integrate(sb.MultilayerSW2DState(h=g["h0"], u=g["u0"], v=g["v0"]), 0.0, float(g["t1"]),
+                       float(g["dt"]))
+    for n in "huv":
+        assert rel(getattr(sol.ys, n)[0], g[n + "1"]) <= 1e-12
