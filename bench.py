@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Headline benchmark: Tsit5 stepping of the 3-layer quasi-geostrophic double gyre on B200.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+A "step" is one full Tsit5 step (6 fresh RHS evaluations: PV inversion + fused stencil/RK
+epilogue each) of the whole grid.  One cell-update = one interior cell of one layer advanced by
+one step.  N = 1 runs BASELINE.json's target configuration, the 3-layer QG double gyre at 8192^2
+in fp32 (it fits one B200).  For N > 1 the ensemble shards by member (one 8192^2 member per
+rank, no data-path collective; "weak" scaling) - see DESIGN.md section "multi-GPU".
+
+Rank 0 prints ONE JSON line (keys: see the graft bench contract; `roofline` is for the kernel
+with the largest share of the step, `cpu_baseline` times the numpy/scipy oracle port on the
+host cores, `e2e` goes through the public `model.integrate` API with host numpy buffers).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (kind, nl, nx, ny)
+    "qg3_8192": ("qg", 3, 8192, 8192),
+    "qg3_4096": ("qg", 3, 4096, 4096),
+    "qg3_1024": ("qg", 3, 1024, 1024),
+    "qg3_128": ("qg", 3, 128, 128),
+    "swm2_4096": ("swm", 2, 4096, 4096),
+    "swm2_1024": ("swm", 2, 1024, 1024),
+}
+QG_PARAMS = dict(Lx=4e6, Ly=4e6, f0=9.375e-5, beta=1.754e-11, n_layers=3,
+                 H=(400.0, 1100.0, 2600.0), g_prime=(9.81, 0.025, 0.0125), lateral_viscosity=15.0,
+                 bottom_drag=1e-7, wind_amplitude=1.3e-10)           # configs/_authoring/doublegyre_bc_qg.py:26-36
+SWM_PARAMS = dict(Lx=1e6, Ly=1e6, f0=1e-4, beta=1.6e-11, H=(500.0, 4500.0), g_prime=(9.81, 0.025),
+                  lateral_viscosity=100.0, bottom_drag=1e-7)        # configs/_authoring/swm_jet.py:21-40
+# algorithmic state-sized transfers per Tsit5 step
+TRANSFERS = {"qg": 79, "swm": 111}
+# algorithmic transfers of one launch of each kernel (DESIGN.md "kernels"): arrays it must read+write
+KERNEL_TRANSFERS = {
+    "rowdst_fwd_fft": 2.0, "rowdst_inv_fft": 2.0, "thomas_fwd_0": 2.0, "thomas_bwd_0": 2.0,
+    "thomas_fwd_1": 1.0, "thomas_bwd_1": 3.0, "border_dot": 1.0,
+    "qg_rhs_kernel": (37.0 + 6.0) / 6.0, "swm_rhs_kernel": 111.0 / 6.0 / 3.0 * 3.0,
+}
+
+
+def qg_dt(nx):
+    return 600.0 * (128.0 / nx) if nx >= 128 else 600.0
+
+
+def swm_dt(nx):
+    return 20.0 * (64.0 / nx)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_model(kind, nl, nx, ny, workers):
+    from oracle import qg as oqg
+    from oracle import testcases as ot
+    if kind == "qg":
+        m = oqg.create_baroclinic(nx=nx, ny=ny, **QG_PARAMS)
+        m.workers = workers
+        q0 = ot.synthetic_qg_state(nl, nx, ny, dtype=np.float32)
+        return m, (q0,), qg_dt(nx)
+    m, st = ot.baroclinic_instability_swm(nx=nx, ny=ny, **SWM_PARAMS)
+    return m, st, swm_dt(nx)
+
+
+def time_oracle(kind, nl, nx, ny, steps, warmup, workers):
+    """Oracle port (numpy/scipy) on the host cores.  Returns Gcell-steps/s."""
+    m, st, dt = oracle_model(kind, nl, nx, ny, workers)
+    if warmup:
+        m.integrate(*st, 0.0, warmup * dt, dt)
+    t = time.perf_counter()
+    m.integrate(*st, 0.0, steps * dt, dt)
+    el = time.perf_counter() - t
+    return nl * nx * ny * steps / el / 1e9, el
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host CPU.  The reference itself (JAX)
+    cannot be installed in this image (no jax/jaxlib wheels), so this is the
+    oracle port - numpy/scipy with all host threads - on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, nl, nx, ny = WORKLOADS[args.workload]
+    sn = min(nx, 1024)   # bounded sample: same model and parameters on a 1024^2 grid
+    cores = os.cpu_count()
+    K, W = max(1, min(args.steps, 8)), min(args.warmup, 1)
+    v, el = time_oracle(kind, nl, sn, sn, K, W, cores)
+    sample = (f"{K} Tsit5 steps of the {nl}-layer {kind.upper()} at {sn}^2 fp32 (per-cell cost of the "
+              f"workload's {nx}^2 grid is >= this: FFT work grows as n log n)")
+    line = {
+        "impl": "reference", "metric": "cell_updates_per_s", "value": v, "unit": "Gcell-steps/s",
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": el / K * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": args.workload, "sample_grid": sn},
+        "cpu_baseline": {"value": v, "unit": "Gcell-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Gcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def build_gpu_model(kind, nl, nx, ny):
+    import somax_b200 as sb
+    from somax_b200 import gfd_testcases as g
+    if kind == "qg":
+        model = sb.BaroclinicQG.create(nx=nx, ny=ny, **QG_PARAMS)
+        q0 = g.synthetic_qg_state(nl, nx, ny, dtype="float32")
+        return model, sb.BaroclinicQGState(q=q0), qg_dt(nx)
+    model, st = g.baroclinic_instability_swm(nx=nx, ny=ny, **SWM_PARAMS)
+    return model, st, swm_dt(nx)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from somax_b200 import _lib
+    import somax_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    kind, nl, nx, ny = WORKLOADS[args.workload]
+    K, W = args.steps, max(args.warmup, 3)
+    lib = _lib.lib()
+
+    model, st0, dt = build_gpu_model(kind, nl, nx, ny)
+    fields = [f for f in ("q", "h", "u", "v") if hasattr(st0, f)]
+    dev = {f: torch.as_tensor(getattr(st0, f)).cuda() for f in fields}
+    state_bytes = sum(t.numel() * t.element_size() for t in dev.values())
+    handle = model._engine.handle(1) if kind == "qg" else model._handle(1)
+    p = (sb.models.qg._params_struct(model.params, model._H0) if kind == "qg" else model._pstruct())
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def steps_dev(n):
+        if kind == "qg":
+            _lib.check(lib.somax_b200_qg_steps(handle, dev["q"].data_ptr(), n, dt, 0.0, C.byref(p), stream))
+        else:
+            _lib.check(lib.somax_b200_swm_steps(handle, dev["h"].data_ptr(), dev["u"].data_ptr(),
+                                                dev["v"].data_ptr(), n, dt, 0.0, C.byref(p), stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (untimed) ----
+    steps_dev(W)
+    barrier()
+
+    # ---- timed region: K steps, device resident, CUDA events on the launching stream ----
+    lib.somax_b200_profile_reset()
+    lib.somax_b200_profile_enable(1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = lib.somax_b200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    steps_dev(K)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.somax_b200_launch_count() - n0
+    clocks = sampler.stop()
+    lib.somax_b200_profile_enable(0)
+    buf = C.create_string_buffer(1 << 16)
+    _lib.check(lib.somax_b200_profile_report(buf, len(buf)))
+    prof = json.loads(buf.value.decode())
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    cells = nl * nx * ny
+    value = world * cells * K / (ms_max * 1e-3) / 1e9
+
+    # ---- e2e: public API, host numpy state in -> host numpy state out (pinned staging) ----
+    host_state = type(st0)(**{f: np.ascontiguousarray(getattr(st0, f)) for f in fields})
+    barrier()
+    t0 = time.perf_counter()
+    sol = model.integrate(host_state, 0.0, K * dt, dt, max_steps=None)
+    out_state = type(st0)(**{f: getattr(sol.ys, f)[0] for f in fields})
+    nonfinite = float(np.sum(model.diag_scalars(out_state)[2]))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * cells * K / float(t_e.item()) / 1e9
+    io = model.last_io
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    w = 4
+    padded = nl * (ny + 2) * (nx + 2) * w          # one state-sized array (one field)
+    prof.sort(key=lambda r: -r["total_ms"])
+    total_prof = sum(r["total_ms"] for r in prof) or 1.0
+    top = prof[0]
+    k_tr = KERNEL_TRANSFERS.get(top["kernel"], 2.0)
+    per_launch_ms = top["total_ms"] / top["launches"]
+    achieved = k_tr * padded / (per_launch_ms * 1e-3) / 1e9
+    step_alg_bytes = TRANSFERS[kind] * padded
+    step_frac = step_alg_bytes / (ms_max / K * 1e-3) / 1e9 / peak
+    roofline = {
+        "bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": k_tr * padded, "avg_launch_ms": per_launch_ms,
+        "share_of_step": top["total_ms"] / total_prof,
+        "step": {"algorithmic_bytes": step_alg_bytes, "achieved_gbs": step_alg_bytes / (ms_max / K * 1e-3) / 1e9,
+                 "frac": step_frac, "transfers_per_step": TRANSFERS[kind]},
+        "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "total_ms": round(r["total_ms"], 3),
+                     "share": round(r["total_ms"] / total_prof, 4)} for r in prof],
+    }
+
+    # ---- CPU baseline: oracle port on the host cores, bounded sample ----
+    cores = os.cpu_count()
+    sn = min(nx, 1024)
+    ksteps = 4
+    cpu_v, cpu_el = time_oracle(kind, nl, sn, sn, ksteps, 0, cores)
+    cpu_baseline = {"value": cpu_v, "unit": "Gcell-steps/s", "cores": cores, "kind": "port",
+                    "sample": f"{ksteps} Tsit5 steps of the same model at {sn}^2 fp32, numpy/scipy oracle, "
+                              f"scipy.fft workers={cores} ({cpu_el:.1f} s)"}
+
+    line = {
+        "metric": "cell_updates_per_s", "value": value, "unit": "Gcell-steps/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model": f"{nl}-layer {kind}", "grid": [ny, nx],
+                   "dt": dt, "l2": "working set (>= 7 GB) far larger than the 126 MB L2; no flush needed"
+                   if state_bytes > 5e8 else "small working set: L2 resident by nature of the workload",
+                   "parallelism": "1 member per GPU (ensemble sharded by member)" if world > 1 else "single GPU",
+                   "solver": "fft+bordered+thomas" if kind == "qg" else "n/a",
+                   "device_bytes": int(lib.somax_b200_qg_device_bytes(handle) if kind == "qg"
+                                       else lib.somax_b200_swm_device_bytes(handle))},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Gcell-steps/s", "h2d_bytes_per_step": io.h2d_bytes / K,
+                "d2h_bytes_per_step": io.d2h_bytes / K, "steps_per_call": K,
+                "note": "one model.integrate() call of K steps: pinned H2D of the state, K steps, D2H of "
+                        "the state and of the diagnostics scalars", "nonfinite": nonfinite},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="qg3_8192", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,13 @@ int somax_b200_abi_version(void);
 /* Number of kernels this library has launched in the calling process (bench `gpu_launches`). */
 uint64_t somax_b200_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled every kernel launch of this
+ * library is bracketed by CUDA events on its stream; report() synchronises and writes a JSON
+ * array [{"kernel", "launches", "total_ms"}] into buf. */
+void somax_b200_profile_enable(int on);
+void somax_b200_profile_reset(void);
+int somax_b200_profile_report(char* buf, size_t cap);
+
 /* ------------------------------------------------------------------------------------------
  * Quasi-geostrophic model (barotropic = nl 1 with Cl2m = Cm2l = [[1]], lambda = [0], H0 = 1).
  * ------------------------------------------------------------------------------------------ */

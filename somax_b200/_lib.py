@@ -41,6 +41,9 @@ SIGNATURES = {
     "somax_b200_last_error": (C.c_char_p, []),
     "somax_b200_abi_version": (_I, []),
     "somax_b200_launch_count": (C.c_uint64, []),
+    "somax_b200_profile_enable": (None, [_I]),
+    "somax_b200_profile_reset": (None, []),
+    "somax_b200_profile_report": (_I, [C.c_char_p, C.c_size_t]),
     "somax_b200_qg_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _I, _U]),
     "somax_b200_qg_destroy": (_I, [_P]),
     "somax_b200_qg_device_bytes": (C.c_size_t, [_P]),

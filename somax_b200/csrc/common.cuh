@@ -27,8 +27,14 @@ extern std::atomic<uint64_t> g_launches;
       return ::sb::fail(SOMAX_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// Optional per-kernel CUDA-event timing (somax_b200_profile_*): prof_begin() before a launch,
+// SB_LAUNCH_CHECK() closes the record.  No-ops unless profiling is enabled.
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end();
+
 #define SB_LAUNCH_CHECK()                                                                 \
   do {                                                                                    \
+    ::sb::prof_end();                                                                     \
     ::sb::g_launches.fetch_add(1, std::memory_order_relaxed);                             \
     cudaError_t _e = cudaGetLastError();                                                  \
     if (_e != cudaSuccess)                                                                \

@@ -1,6 +1,8 @@
 // Error plumbing, launch accounting and reference<->padded layout conversion.
 #include "common.cuh"
 
+#include <string.h>
+
 #include <vector>
 
 namespace sb {
@@ -23,6 +25,46 @@ const double TSIT5_A[6][6] = {
      -0.028269050394068383, 0},
     {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081,
      2.324710524099774}};
+
+// ---------------------------------------------------------------------------------------
+// per-kernel event timing
+// ---------------------------------------------------------------------------------------
+namespace {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+struct Prof {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  bool open = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+};
+Prof g_prof;
+}  // namespace
+
+void prof_begin(const char* name, cudaStream_t s) {
+  if (!g_prof.on || g_prof.recs.size() >= 200000) return;
+  ProfRec r{name, g_prof.get(), g_prof.get()};
+  if (!r.a || !r.b) return;
+  cudaEventRecord(r.a, s);
+  g_prof.recs.push_back(r);
+  g_prof.open = true;
+  g_prof.stream = s;
+}
+
+void prof_end() {
+  if (!g_prof.open) return;
+  cudaEventRecord(g_prof.recs.back().b, g_prof.stream);
+  g_prof.open = false;
+}
 
 int require_device() {
   int n = 0;
@@ -70,6 +112,7 @@ int pack_field(const T* ref, T* pad, const Layout& L, cudaStream_t s) {
   int planes = L.batch * L.nl;
   dim3 b(256), g((L.pitch + 255) / 256, L.Ny, planes);
   if (g.z > 65535) return fail(SOMAX_B200_ERR_UNSUPPORTED, "batch*nl > 65535");
+  prof_begin("pack_kernel", s);
   pack_kernel<T><<<g, b, 0, s>>>(ref, pad, planes, L.Ny, L.Nx, L.pitch);
   SB_LAUNCH_CHECK();
   return 0;
@@ -80,6 +123,7 @@ int unpack_field(const T* pad, T* ref, const Layout& L, cudaStream_t s) {
   int planes = L.batch * L.nl;
   dim3 b(256), g((L.Nx + 255) / 256, L.Ny, planes);
   if (g.z > 65535) return fail(SOMAX_B200_ERR_UNSUPPORTED, "batch*nl > 65535");
+  prof_begin("unpack_kernel", s);
   unpack_kernel<T><<<g, b, 0, s>>>(pad, ref, planes, L.Ny, L.Nx, L.pitch);
   SB_LAUNCH_CHECK();
   return 0;
@@ -120,4 +164,34 @@ extern "C" {
 const char* somax_b200_last_error(void) { return sb::t_last_error.c_str(); }
 int somax_b200_abi_version(void) { return SOMAX_B200_ABI_VERSION; }
 uint64_t somax_b200_launch_count(void) { return sb::g_launches.load(); }
+
+void somax_b200_profile_enable(int on) { sb::g_prof.on = on != 0; }
+void somax_b200_profile_reset(void) { sb::g_prof.recs.clear(); sb::g_prof.used = 0; sb::g_prof.open = false; }
+
+// Aggregates the recorded launches by kernel name into JSON:
+// [{"kernel": "...", "launches": n, "total_ms": t}, ...].  Synchronises the device.
+int somax_b200_profile_report(char* buf, size_t cap) {
+  cudaDeviceSynchronize();
+  struct Agg { const char* name; long n; double ms; };
+  std::vector<Agg> aggs;
+  for (auto& r : sb::g_prof.recs) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    Agg* a = nullptr;
+    for (auto& x : aggs) if (std::string(x.name) == r.name) { a = &x; break; }
+    if (!a) { aggs.push_back({r.name, 0, 0.0}); a = &aggs.back(); }
+    a->n += 1; a->ms += ms;
+  }
+  std::string out = "[";
+  for (size_t i = 0; i < aggs.size(); ++i) {
+    char tmp[256];
+    snprintf(tmp, sizeof tmp, "%s{\"kernel\": \"%s\", \"launches\": %ld, \"total_ms\": %.6f}",
+             i ? ", " : "", aggs[i].name, aggs[i].n, aggs[i].ms);
+    out += tmp;
+  }
+  out += "]";
+  if (out.size() + 1 > cap) return sb::fail(SOMAX_B200_ERR_INVALID, "profile buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
 }

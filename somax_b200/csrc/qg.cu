@@ -211,6 +211,7 @@ int eval_rhs(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st, cudaStre
   const Layout& L = h->L;
   dim3 block(QTXG, QTY);
   dim3 grid((L.groups() + QTXG - 1) / QTXG, (L.Ny + QTY - 1) / QTY, L.batch * L.nl);
+  prof_begin("qg_rhs_kernel", s);
   qg_rhs_kernel<T><<<grid, block, 0, s>>>(A, (const T*)h->psi, st);
   SB_LAUNCH_CHECK();
   return 0;
@@ -220,6 +221,7 @@ template <typename T>
 int qg_bc_inplace(somax_b200_qg_t h, void* q, cudaStream_t s) {
   const Layout& L = h->L;
   dim3 b(256), g((L.Nx + 255) / 256, L.Ny, L.batch * L.nl);
+  prof_begin("qg_bc_kernel", s);
   qg_bc_kernel<T><<<g, b, 0, s>>>((T*)q, L);
   SB_LAUNCH_CHECK();
   return 0;
@@ -304,6 +306,7 @@ int qg_diag_impl(somax_b200_qg_t h, const void* q, double* out, cudaStream_t s) 
   if (int rc = qg_solver_run<T>(h->solver, (const T*)h->Ya, (T*)h->psi, s)) return rc;
   SB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * L.batch * (2 * L.nl + 1), s));
   dim3 b(256), g(std::min((L.Nx + 255) / 256, 64), std::min(L.Ny, 128), L.batch * L.nl);
+  prof_begin("qg_diag_kernel", s);
   qg_diag_kernel<T><<<g, b, 0, s>>>((const T*)q, (const T*)h->psi, L, h->dx, h->dy, out);
   SB_LAUNCH_CHECK();
   return 0;

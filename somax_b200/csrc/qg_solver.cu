@@ -635,23 +635,32 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
         smem_set_i = smem;
       }
     }
+    prof_begin("rowdst_fwd_fft", st);
     rowdst_fwd_fft<T><<<blocks, threads, smem, st>>>(Af, q, S);
     SB_LAUNCH_CHECK();
+    prof_begin("thomas_fwd_0", st);
     thomas_fwd<T, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, S);
     SB_LAUNCH_CHECK();
+    prof_begin("thomas_bwd_0", st);
     thomas_bwd<T, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, S);
     SB_LAUNCH_CHECK();
+    prof_begin("border_dot", st);
     border_dot<T><<<dim3(ny, s->planes), 256, 0, st>>>(S, s->sig2n, ny, np, s->ncols, s->rvec);
     SB_LAUNCH_CHECK();
     const double b = 1.0 / (s->dx * s->dx);
+    prof_begin("border_gsolve_a", st);
     border_gsolve_a<T><<<dim3(ny, s->planes), 128, 0, st>>>(S, s->rvec, s->sintab, s->sdiag, ny, np, n, nl, b, s->ghat);
     SB_LAUNCH_CHECK();
+    prof_begin("border_gsolve_b", st);
     border_gsolve_b<T><<<dim3(ny, s->planes), 128, 0, st>>>(s->ghat, s->sintab, ny, np, n, s->gvec, S);
     SB_LAUNCH_CHECK();
+    prof_begin("thomas_fwd_1", st);
     thomas_fwd<T, true><<<tgrid, TH_COLS, 0, st>>>(tb, nullptr, s->gvec, W);
     SB_LAUNCH_CHECK();
+    prof_begin("thomas_bwd_1", st);
     thomas_bwd<T, true><<<tgrid, TH_COLS, 0, st>>>(tb, W, S, s->bsig, S);
     SB_LAUNCH_CHECK();
+    prof_begin("rowdst_inv_fft", st);
     rowdst_inv_fft<T><<<blocks, threads, smem, st>>>(Ai, S, psi);
     SB_LAUNCH_CHECK();
   } else {
@@ -661,12 +670,16 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
       SB_CUDA(cudaFuncSetAttribute(rowdst_dense<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const int threads = std::min(256, ((n + 31) / 32) * 32);
+    prof_begin("rowdst_dense_0", st);
     rowdst_dense<T, false><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->l2m, (const T*)s->dstmat, q, S, 1.0);
     SB_LAUNCH_CHECK();
+    prof_begin("thomas_fwd_0", st);
     thomas_fwd<T, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, S);
     SB_LAUNCH_CHECK();
+    prof_begin("thomas_bwd_0", st);
     thomas_bwd<T, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, S);
     SB_LAUNCH_CHECK();
+    prof_begin("rowdst_dense_1", st);
     rowdst_dense<T, true><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->m2l, (const T*)s->dstmat, S, psi, 2.0 / (n + 1));
     SB_LAUNCH_CHECK();
   }

@@ -339,6 +339,7 @@ int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A, const Stage<T>& st, cuda
   const Layout& L = h->L;
   dim3 block(TXG, TY);
   dim3 grid((L.groups() + TXG - 1) / TXG, (L.Ny + TY - 1) / TY, L.batch);
+  prof_begin("swm_rhs_kernel", s);
   swm_rhs_kernel<T><<<grid, block, 0, s>>>(A, st);
   SB_LAUNCH_CHECK();
   return 0;
@@ -361,6 +362,7 @@ template <typename T>
 int bc_inplace(somax_b200_swm_t h, void* const f[3], cudaStream_t s) {
   const Layout& L = h->L;
   dim3 b(256), g((L.Nx + 255) / 256, L.Ny, L.batch * L.nl);
+  prof_begin("swm_bc_kernel", s);
   swm_bc_kernel<T><<<g, b, 0, s>>>((T*)f[0], (T*)f[1], (T*)f[2], L, h->bc);
   SB_LAUNCH_CHECK();
   return 0;
@@ -459,6 +461,7 @@ int swm_diag_impl(somax_b200_swm_t h, const void* hh, const void* u, const void*
   const Layout& L = h->L;
   SB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * L.batch * (3 * L.nl + 1), s));
   dim3 b(256), g(std::min((L.Nx + 255) / 256, 64), std::min(L.Ny, 128), L.batch * L.nl);
+  prof_begin("swm_diag_kernel", s);
   swm_diag_kernel<T><<<g, b, 0, s>>>((const T*)hh, (const T*)u, (const T*)v, (const T*)h->f,
                                      h->f1d ? 1 : L.Nx, h->f1d ? 0 : 1, L.nl, L.Ny, L.Nx, h->dx,
                                      h->dy, out);
