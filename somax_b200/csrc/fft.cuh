@@ -34,8 +34,9 @@ __host__ __device__ __forceinline__ int fft_padded_len(int n) { return n + (n >>
 
 struct FftPlan {
   int n;          // complex length (power of two)
+  int lgn;
   int npass;
-  int radix[8];
+  int lgr[8];     // log2 of the radix of each pass (3, 2 or 1)
 };
 
 inline FftPlan make_fft_plan(int n) {
@@ -43,20 +44,25 @@ inline FftPlan make_fft_plan(int n) {
   p.n = n; p.npass = 0;
   int lg = 0;
   while ((1 << lg) < n) ++lg;
-  while (lg >= 3) { p.radix[p.npass++] = 8; lg -= 3; }
-  if (lg == 2) p.radix[p.npass++] = 4;
-  if (lg == 1) p.radix[p.npass++] = 2;
+  p.lgn = lg;
+  for (int i = 0; i < 8; ++i) p.lgr[i] = 0;
+  while (lg >= 3) { p.lgr[p.npass++] = 3; lg -= 3; }
+  if (lg == 2) p.lgr[p.npass++] = 2;
+  if (lg == 1) p.lgr[p.npass++] = 1;
   return p;
 }
 
-// position in the DIF output array of frequency k
+// position in the DIF output array of frequency k (mixed-radix digit reversal, shifts only)
 __host__ __device__ __forceinline__ int fft_revpos(const FftPlan& p, int k) {
-  int pos = 0, rem = p.n;
-  for (int i = 0; i < p.npass; ++i) {
-    int R = p.radix[i];
-    rem /= R;
-    pos += (k % R) * rem;
-    k /= R;
+  int pos = 0, sh = p.lgn;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < p.npass) {
+      const int lr = p.lgr[i];
+      sh -= lr;
+      pos += (k & ((1 << lr) - 1)) << sh;
+      k >>= lr;
+    }
   }
   return pos;
 }
@@ -86,13 +92,16 @@ __host__ __device__ __forceinline__ void fft8(C2<T>* v) {
 // One DIF pass of radix R over sub-transform length Lc for the butterflies t = lt, lt+G, ...
 // tw holds exp(-i pi t / n) for t = 0..2n-1 (so w_n^q = tw[2q]).
 template <typename T, int R>
-__host__ __device__ __forceinline__ void fft_dif_pass(C2<T>* s, int n, int Lc, int lt, int G,
+__host__ __device__ __forceinline__ void fft_dif_pass(C2<T>* s, int lgn, int lgLc, int lt, int G,
                                                       const C2<T>* __restrict__ tw) {
-  const int M = Lc / R;
-  const int tstride = 2 * (n / Lc);
-  for (int t = lt; t < n / R; t += G) {
-    const int block = t / M, pos = t - block * M;
-    const int base = block * Lc + pos;
+  constexpr int LGR = R == 8 ? 3 : (R == 4 ? 2 : 1);
+  const int lgM = lgLc - LGR;
+  const int M = 1 << lgM;
+  const int tstride = 2 << (lgn - lgLc);
+  const int nb = 1 << (lgn - LGR);
+  for (int t = lt; t < nb; t += G) {
+    const int block = t >> lgM, pos = t & (M - 1);
+    const int base = (block << lgLc) + pos;
     C2<T> v[R];
 #pragma unroll
     for (int q = 0; q < R; ++q) v[q] = s[fft_pad(base + q * M)];
@@ -114,6 +123,80 @@ __host__ __device__ __forceinline__ void dst_split(const C2<T>* s, const FftPlan
                                                    const C2<T>* __restrict__ tw, T& Xk, T& Xnk) {
   const C2<T> A = s[fft_pad(fft_revpos(p, k))];
   const C2<T> B = s[fft_pad(fft_revpos(p, p.n - k))];
+  const C2<T> E = {(T)0.5 * (A.x + B.x), (T)0.5 * (A.y - B.y)};
+  const C2<T> O = {(T)0.5 * (A.y + B.y), (T)-0.5 * (A.x - B.x)};
+  const C2<T> wO = cmul(tw[k], O);
+  Xk = (T)-0.5 * (E.y + wO.y);
+  Xnk = (T)0.5 * (E.y - wO.y);
+}
+
+// ---- compile-time sized variants used by the row kernels (all index algebra constant-folds) ----
+template <int LGN> struct FftCT {
+  static constexpr int n = 1 << LGN;
+  static constexpr int npass = (LGN + 2) / 3;
+  __host__ __device__ static constexpr int lgr(int i) {
+    return (i < LGN / 3) ? 3 : (LGN % 3);   // radix-8 passes first, then one radix-4 or radix-2
+  }
+  __host__ __device__ static __forceinline__ int revpos(int k) {
+    int pos = 0, sh = LGN;
+#pragma unroll
+    for (int i = 0; i < npass; ++i) {
+      const int lr = lgr(i);
+      sh -= lr;
+      pos += (k & ((1 << lr) - 1)) << sh;
+      k >>= lr;
+    }
+    return pos;
+  }
+};
+
+// DIF pass with compile-time geometry; twiddles w, w^2, w^4 are loaded, the rest are products.
+template <typename T, int LGN, int LGLC, int R, int G>
+__host__ __device__ __forceinline__ void fft_dif_pass_ct(C2<T>* s, int lt, const C2<T>* __restrict__ tw) {
+  constexpr int LGR = R == 8 ? 3 : (R == 4 ? 2 : 1);
+  constexpr int lgM = LGLC - LGR;
+  constexpr int M = 1 << lgM;
+  constexpr int tstride = 2 << (LGN - LGLC);
+  constexpr int nb = 1 << (LGN - LGR);
+#pragma unroll
+  for (int t0 = 0; t0 < nb; t0 += G) {
+    const int t = t0 + lt;
+    if (nb % G != 0 && t >= nb) break;
+    const int block = t >> lgM, pos = t & (M - 1);
+    const int base = (block << LGLC) + pos;
+    C2<T> v[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) v[q] = s[fft_pad(base + q * M)];
+    if (R == 8) fft8(v);
+    else if (R == 4) fft4(v[0], v[1], v[2], v[3]);
+    else { C2<T> a = v[0]; v[0] = cadd(a, v[1]); v[1] = csub(a, v[1]); }
+    if (M > 1) {
+      const C2<T> w1 = tw[pos * tstride];
+      v[1] = cmul(v[1], w1);
+      if (R >= 4) {
+        const C2<T> w2 = tw[2 * pos * tstride];
+        const C2<T> w3 = cmul(w1, w2);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        if (R == 8) {
+          const C2<T> w4 = tw[4 * pos * tstride];
+          v[4] = cmul(v[4], w4);
+          v[5] = cmul(v[5], cmul(w1, w4));
+          v[6] = cmul(v[6], cmul(w2, w4));
+          v[7] = cmul(v[7], cmul(w3, w4));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) s[fft_pad(base + q * M)] = v[q];
+  }
+}
+
+template <typename T, int LGN>
+__host__ __device__ __forceinline__ void dst_split_ct(const C2<T>* s, int k,
+                                                      const C2<T>* __restrict__ tw, T& Xk, T& Xnk) {
+  const C2<T> A = s[fft_pad(FftCT<LGN>::revpos(k))];
+  const C2<T> B = s[fft_pad(FftCT<LGN>::revpos((1 << LGN) - k))];
   const C2<T> E = {(T)0.5 * (A.x + B.x), (T)0.5 * (A.y - B.y)};
   const C2<T> O = {(T)0.5 * (A.y + B.y), (T)-0.5 * (A.x - B.x)};
   const C2<T> wO = cmul(tw[k], O);

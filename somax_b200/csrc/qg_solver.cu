@@ -30,8 +30,6 @@ namespace sb {
 
 constexpr int QG_MAX_NL = 4;
 constexpr int TH_COLS = 64;   // columns (threads) per Thomas CTA
-// cp.async ring depth (rows in flight per column): 16 KB of shared memory per CTA either way
-template <typename T> struct ThDepth { static constexpr int v = sizeof(T) == 4 ? 64 : 32; };
 
 struct Mix { double c[QG_MAX_NL][QG_MAX_NL]; };
 
@@ -41,7 +39,7 @@ struct QgSolver {
   Layout L;
   int np, ncols, planes;
   void* S = nullptr; void* W = nullptr;
-  double* ctab = nullptr; int* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
+  double* ctab = nullptr; long long* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
   int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0; double* dbad = nullptr;
   double* bsig = nullptr; double* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
   double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr;
@@ -94,15 +92,15 @@ __global__ void rowdst_fwd_fft(RowArgs<T> A, const T* __restrict__ q, T* __restr
       if (lt == 0) { z[zi(0)] = 0; z[zi(n)] = 0; }
     }
     __syncthreads();
-    int Lc = n;
+    int lgLc = A.plan.lgn;
     for (int ps = 0; ps < A.plan.npass; ++ps) {
-      const int R = A.plan.radix[ps];
+      const int lr = A.plan.lgr[ps];
       if (valid) {
-        if (R == 8) fft_dif_pass<T, 8>(s, n, Lc, lt, G, A.tw);
-        else if (R == 4) fft_dif_pass<T, 4>(s, n, Lc, lt, G, A.tw);
-        else fft_dif_pass<T, 2>(s, n, Lc, lt, G, A.tw);
+        if (lr == 3) fft_dif_pass<T, 8>(s, A.plan.lgn, lgLc, lt, G, A.tw);
+        else if (lr == 2) fft_dif_pass<T, 4>(s, A.plan.lgn, lgLc, lt, G, A.tw);
+        else fft_dif_pass<T, 2>(s, A.plan.lgn, lgLc, lt, G, A.tw);
       }
-      Lc /= R;
+      lgLc -= lr;
       __syncthreads();
     }
     if (valid) {
@@ -146,15 +144,15 @@ __global__ void rowdst_inv_fft(RowArgs<T> A, const T* __restrict__ S, T* __restr
       if (lt == 0) { z[zi(0)] = 0; z[zi(n)] = 0; }
     }
     __syncthreads();
-    int Lc = n;
+    int lgLc = A.plan.lgn;
     for (int ps = 0; ps < A.plan.npass; ++ps) {
-      const int R = A.plan.radix[ps];
+      const int lr = A.plan.lgr[ps];
       if (valid) {
-        if (R == 8) fft_dif_pass<T, 8>(s, n, Lc, lt, G, A.tw);
-        else if (R == 4) fft_dif_pass<T, 4>(s, n, Lc, lt, G, A.tw);
-        else fft_dif_pass<T, 2>(s, n, Lc, lt, G, A.tw);
+        if (lr == 3) fft_dif_pass<T, 8>(s, A.plan.lgn, lgLc, lt, G, A.tw);
+        else if (lr == 2) fft_dif_pass<T, 4>(s, A.plan.lgn, lgLc, lt, G, A.tw);
+        else fft_dif_pass<T, 2>(s, A.plan.lgn, lgLc, lt, G, A.tw);
       }
-      Lc /= R;
+      lgLc -= lr;
       __syncthreads();
     }
     if (valid) {
@@ -166,6 +164,157 @@ __global__ void rowdst_inv_fft(RowArgs<T> A, const T* __restrict__ S, T* __restr
       }
     }
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// row kernels, FFT path, compile-time sized (the ones actually launched for nx = 2^LGN)
+//   FWD: in = q (padded field), mix = Cl2m, out = S (spectral rows; slot n-1 = raw border column)
+//   INV: in = S, mix = Cm2l (layer mixing commutes with the transform), out = psi (padded field)
+// One CTA row-group per (member, y-row); the nl mixed rows are transformed one after another in
+// the same shared-memory line.  Loads are 128-bit and batched per source layer.
+// ------------------------------------------------------------------------------------------
+template <int LGN> struct RowCfg {
+  static constexpr int n = 1 << LGN;
+  static constexpr int EPT = LGN >= 12 ? 16 : (LGN >= 8 ? 8 : (LGN >= 7 ? 4 : 2));
+  static constexpr int G = n / EPT;                       // threads per row
+  static constexpr int RPB = G >= 128 ? 1 : 128 / G;      // rows per block
+  static constexpr int threads = G * RPB;
+  static constexpr int minblocks = threads >= 512 ? 2 : (threads >= 256 ? 3 : 4);
+};
+
+template <typename T>
+struct RowArgsCT {
+  Layout L;
+  int ny, np, nl, nrows;
+  T mix[QG_MAX_NL][QG_MAX_NL];
+  const C2<T>* tw;
+  T scale;
+};
+
+template <typename T, int LGN, int G, int PASS>
+__device__ __forceinline__ void fft_passes_ct(C2<T>* s, int lt, const C2<T>* __restrict__ tw, bool valid) {
+  if constexpr (PASS < FftCT<LGN>::npass) {
+    constexpr int lr = FftCT<LGN>::lgr(PASS);
+    constexpr int LGLC = LGN - 3 * PASS;      // every earlier pass is radix 8
+    if (valid) fft_dif_pass_ct<T, LGN, LGLC, (1 << lr), G>(s, lt, tw);
+    __syncthreads();
+    fft_passes_ct<T, LGN, G, PASS + 1>(s, lt, tw, valid);
+  }
+}
+
+template <typename T, int LGN, bool INV>
+__global__ void __launch_bounds__(RowCfg<LGN>::threads, RowCfg<LGN>::minblocks)
+rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
+  using Cfg = RowCfg<LGN>;
+  constexpr int n = Cfg::n, G = Cfg::G, EPT = Cfg::EPT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lrow = threadIdx.x / G, lt = threadIdx.x % G;
+  constexpr int plen = n + (n >> 4) + 1;
+  C2<T>* s = reinterpret_cast<C2<T>*>(smem_raw) + (size_t)lrow * plen;
+  T* z = reinterpret_cast<T*>(s);
+  const int row = blockIdx.x * Cfg::RPB + lrow;
+  const bool valid = row < A.nrows;
+  const int b = valid ? row / A.ny : 0, j = valid ? row - b * A.ny : 0;
+  auto zi = [&](int t) { return 2 * fft_pad(t >> 1) + (t & 1); };
+  // source row of layer/mode c and destination row of mode/layer a
+  auto src = [&](int c) -> const T* {
+    return INV ? in + (((size_t)b * A.nl + c) * A.ny + j) * A.np
+               : in + (((size_t)b * A.nl + c) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1;
+  };
+  auto dst = [&](int a) -> T* {
+    return INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1
+               : out + (((size_t)b * A.nl + a) * A.ny + j) * A.np;
+  };
+
+  for (int a = 0; a < A.nl; ++a) {
+    T* o = dst(a);
+    if (valid) {
+      if constexpr (EPT >= 4) {
+        constexpr int NV = EPT / 4;
+        Vec4<T> acc[NV];
+#pragma unroll
+        for (int e = 0; e < NV; ++e) acc[e] = Vec4<T>{0, 0, 0, 0};
+        for (int c = 0; c < A.nl; ++c) {
+          const T* sp = src(c);
+          Vec4<T> v[NV];
+#pragma unroll
+          for (int e = 0; e < NV; ++e) v[e] = ld4(sp + 4 * (lt + e * G));
+          const T mx = A.mix[a][c];
+#pragma unroll
+          for (int e = 0; e < NV; ++e) {
+            acc[e].x += mx * v[e].x; acc[e].y += mx * v[e].y;
+            acc[e].z += mx * v[e].z; acc[e].w += mx * v[e].w;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < NV; ++e) {
+          const int t = 4 * (lt + e * G) + 1;     // x_t .. x_{t+3}
+          const T vals[4] = {acc[e].x, acc[e].y, acc[e].z, acc[e].w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (t + u < n) { z[zi(t + u)] = vals[u]; z[zi(2 * n - t - u)] = -vals[u]; }
+            else o[n - 1] = vals[u];              // border column (x index n)
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const int p = lt + e * G;
+          T val = 0;
+          for (int c = 0; c < A.nl; ++c) val += A.mix[a][c] * src(c)[p];
+          const int t = p + 1;
+          if (t < n) { z[zi(t)] = val; z[zi(2 * n - t)] = -val; }
+          else o[n - 1] = val;
+        }
+      }
+      if (lt == 0) { z[zi(0)] = 0; z[zi(n)] = 0; }
+    }
+    __syncthreads();
+    fft_passes_ct<T, LGN, G, 0>(s, lt, A.tw, valid);
+    if (valid) {
+#pragma unroll
+      for (int k0 = 1; k0 <= n / 2; k0 += G) {
+        const int k = k0 + lt;
+        if (k <= n / 2) {
+          T Xk, Xnk;
+          dst_split_ct<T, LGN>(s, k, A.tw, Xk, Xnk);
+          o[k - 1] = INV ? A.scale * Xk : Xk;
+          if (k != n - k) o[n - k - 1] = INV ? A.scale * Xnk : Xnk;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int LGN, bool INV>
+static int launch_rowdst_ct(const RowArgsCT<T>& A, const T* in, T* out, cudaStream_t st) {
+  using Cfg = RowCfg<LGN>;
+  constexpr size_t smem = (size_t)(Cfg::n + (Cfg::n >> 4) + 1) * sizeof(C2<T>) * Cfg::RPB;
+  static bool attr_done = false;
+  if (smem > 48 * 1024 && !attr_done) {
+    SB_CUDA(cudaFuncSetAttribute(rowdst_fft_ct<T, LGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int blocks = (A.nrows + Cfg::RPB - 1) / Cfg::RPB;
+  prof_begin(INV ? "rowdst_inv_fft" : "rowdst_fwd_fft", st);
+  rowdst_fft_ct<T, LGN, INV><<<blocks, Cfg::threads, smem, st>>>(A, in, out);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, bool INV>
+static int launch_rowdst(int lgn, const RowArgsCT<T>& A, const T* in, T* out, cudaStream_t st) {
+  switch (lgn) {
+#define SB_ROW_CASE(L) case L: return launch_rowdst_ct<T, L, INV>(A, in, out, st);
+    SB_ROW_CASE(3) SB_ROW_CASE(4) SB_ROW_CASE(5) SB_ROW_CASE(6) SB_ROW_CASE(7) SB_ROW_CASE(8)
+    SB_ROW_CASE(9) SB_ROW_CASE(10) SB_ROW_CASE(11) SB_ROW_CASE(12) SB_ROW_CASE(13)
+#undef SB_ROW_CASE
+    case 14:
+      if constexpr (sizeof(T) == 4) return launch_rowdst_ct<T, 14, INV>(A, in, out, st);
+    default:
+      return fail(SOMAX_B200_ERR_UNSUPPORTED, "FFT solver: unsupported nx");
   }
 }
 
@@ -210,124 +359,129 @@ __global__ void rowdst_dense(Layout L, int ny, int n, int np, int nl, Mix mix,
 // Thomas sweeps along y, one thread per x-wavenumber, fp64 carry.
 //   normalised system per column: x_{j-1} + delta x_j + x_{j+1} = dy^2 f_j
 //   c_j = 1/(delta - c_{j-1}),  d_j = (dy^2 f_j - d_{j-1}) c_j,  x_j = d_j - c_j x_{j+1}
+// c_j converges to a fixed point after J rows (J << ny for almost every wavenumber): rows
+// below J read a per-column fp64 table, the rest use the constant.  Rows are processed in
+// batches of TH_RB so that only ONE fp64 FMA per row sits on the loop-carried chain; input rows
+// are prefetched TH_NB batches ahead with cp.async into a per-thread shared-memory ring.
 // ------------------------------------------------------------------------------------------
 struct ThomasTab {
-  const double* ctab; const int* coff; const int* krow; const double* cinf;
+  const double* ctab;        // per-column runs: column (m,c) at ctab[coloff[m*ncols+c] + j], j < J
+  const long long* coloff;
+  const int* J;
+  const double* cinf;
   int kbad[QG_MAX_NL]; int KB; double* dbad;
   int ny, np, ncols, nl;
   double dy2;
 };
 
+constexpr int TH_RB = 8;   // rows per batch
+template <typename T> struct ThNB { static constexpr int v = sizeof(T) == 4 ? 8 : 4; };  // batches in flight
+
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 template <typename T>
 __device__ __forceinline__ void cp_async_elem(T* smem, const T* gmem) {
   if (sizeof(T) == 4) cp_async4(smem, gmem); else cp_async8(smem, gmem);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// FROM_VEC: right-hand side is gvec[plane][j] for every column (second, border solve).
-template <typename T, bool FROM_VEC>
+// DIR = +1: forward elimination (rows ascending); DIR = -1: back substitution (descending).
+// FROM_VEC (forward only): right-hand side is gvec[plane][j] for every column (border solve).
+// COMBINE (backward only): out = V - bsig[c] * x  (second solve applied to the first one's V).
+template <typename T, int DIR, bool FROM_VEC, bool COMBINE>
 __global__ void __launch_bounds__(TH_COLS)
-thomas_fwd(ThomasTab tb, const T* __restrict__ in, const double* __restrict__ gvec,
-           T* __restrict__ out) {
-  constexpr int TH_DEPTH = ThDepth<T>::v;
-  __shared__ T ring[TH_DEPTH][TH_COLS];
-  const int c = blockIdx.x * TH_COLS + threadIdx.x;
+thomas_sweep(ThomasTab tb, const T* __restrict__ in, const T* __restrict__ V,
+             const double* __restrict__ gvec, const double* __restrict__ bsig, T* __restrict__ out) {
+  constexpr int NB = ThNB<T>::v;
+  constexpr int DEPTH = NB * TH_RB;
+  __shared__ T ring[FROM_VEC ? 1 : DEPTH][TH_COLS];
+  __shared__ T ringv[COMBINE ? DEPTH : 1][TH_COLS];
+  const int tid = threadIdx.x;
+  const int c = blockIdx.x * TH_COLS + tid;
   const int plane = blockIdx.y, m = plane % tb.nl;
   const bool act = c < tb.ncols;
   const int cc = act ? c : 0;
-  const size_t base = (size_t)plane * tb.ny * tb.np + cc;
+  const int ny = tb.ny;
+  const size_t base = (size_t)plane * ny * tb.np + cc;
   const double cfix = tb.cinf[m * tb.ncols + cc];
-  const bool bad = act && cc < tb.kbad[m];
-  if (!FROM_VEC) {
-#pragma unroll 1
-    for (int r = 0; r < TH_DEPTH; ++r) {
-      if (r < tb.ny) cp_async_elem(&ring[r][threadIdx.x], in + base + (size_t)r * tb.np);
-      cp_async_commit();
-    }
-  }
-  double d = 0.0;
-#pragma unroll 1
-  for (int j = 0; j < tb.ny; ++j) {
-    double f;
-    if (FROM_VEC) {
-      f = gvec[(size_t)plane * tb.ny + j];
-    } else {
-      cp_async_wait<TH_DEPTH - 1>();
-      f = (double)ring[j % TH_DEPTH][threadIdx.x];
-      if (j + TH_DEPTH < tb.ny)
-        cp_async_elem(&ring[j % TH_DEPTH][threadIdx.x], in + base + (size_t)(j + TH_DEPTH) * tb.np);
-      cp_async_commit();
-    }
-    const int kr = tb.krow[m * tb.ny + j];
-    const double cj = (cc < kr) ? tb.ctab[(size_t)tb.coff[m * tb.ny + j] + cc] : cfix;
-    d = (tb.dy2 * f - d) * cj;
-    if (act) {
-      out[base + (size_t)j * tb.np] = (T)d;
-      if (bad) tb.dbad[((size_t)plane * tb.ny + j) * tb.KB + cc] = d;
-    }
-  }
-}
-
-// COMBINE: out = V - bsig[c] * x   (second solve applied to the first solve's result V)
-template <typename T, bool COMBINE>
-__global__ void __launch_bounds__(TH_COLS)
-thomas_bwd(ThomasTab tb, const T* __restrict__ din, const T* __restrict__ V,
-           const double* __restrict__ bsig, T* __restrict__ out) {
-  constexpr int TH_DEPTH = ThDepth<T>::v;
-  __shared__ T ring[TH_DEPTH][TH_COLS];
-  __shared__ T ringv[COMBINE ? TH_DEPTH : 1][TH_COLS];
-  const int c = blockIdx.x * TH_COLS + threadIdx.x;
-  const int plane = blockIdx.y, m = plane % tb.nl;
-  const bool act = c < tb.ncols;
-  const int cc = act ? c : 0;
-  const size_t base = (size_t)plane * tb.ny * tb.np + cc;
-  const double cfix = tb.cinf[m * tb.ncols + cc];
-  const bool bad = act && cc < tb.kbad[m];
+  const int Jc = tb.J[m * tb.ncols + cc];
+  const double* ctc = tb.ctab + tb.coloff[m * tb.ncols + cc];
+  const bool bad = cc < tb.kbad[m];
+  double* dbc = tb.dbad + ((size_t)plane * ny) * tb.KB + cc;
   const double bs = COMBINE ? bsig[cc] : 0.0;
-#pragma unroll 1
-  for (int r = 0; r < TH_DEPTH; ++r) {
-    const int j = tb.ny - 1 - r;
-    if (j >= 0) {
-      cp_async_elem(&ring[r][threadIdx.x], din + base + (size_t)j * tb.np);
-      if (COMBINE) cp_async_elem(&ringv[r][threadIdx.x], V + base + (size_t)j * tb.np);
+  const int nbatch = (ny + TH_RB - 1) / TH_RB;
+  auto row_of = [&](int b, int r) { int i = b * TH_RB + r; return DIR > 0 ? i : ny - 1 - i; };
+
+  auto issue = [&](int b) {
+    if (b < nbatch) {
+#pragma unroll
+      for (int r = 0; r < TH_RB; ++r) {
+        const int j = row_of(b, r);
+        if (j >= 0 && j < ny) {
+          const int slot = (b % NB) * TH_RB + r;
+          if (!FROM_VEC) cp_async_elem(&ring[slot][tid], in + base + (size_t)j * tb.np);
+          if (COMBINE) cp_async_elem(&ringv[slot][tid], V + base + (size_t)j * tb.np);
+        }
+      }
     }
     cp_async_commit();
-  }
-  double x = 0.0;
+  };
+  if (!FROM_VEC || COMBINE)
+    for (int b = 0; b < NB; ++b) issue(b);
+
+  double carry = 0.0;   // d_{j-1} (forward) or x_{j+1} (backward)
 #pragma unroll 1
-  for (int r = 0; r < tb.ny; ++r) {
-    const int j = tb.ny - 1 - r;
-    cp_async_wait<TH_DEPTH - 1>();
-    double d = (double)ring[r % TH_DEPTH][threadIdx.x];
-    double v = COMBINE ? (double)ringv[r % TH_DEPTH][threadIdx.x] : 0.0;
-    const int jn = j - TH_DEPTH;
-    if (jn >= 0) {
-      cp_async_elem(&ring[r % TH_DEPTH][threadIdx.x], din + base + (size_t)jn * tb.np);
-      if (COMBINE) cp_async_elem(&ringv[r % TH_DEPTH][threadIdx.x], V + base + (size_t)jn * tb.np);
+  for (int b = 0; b < nbatch; ++b) {
+    double f[TH_RB], cj[TH_RB], vv[TH_RB];
+    if (!FROM_VEC || COMBINE) cp_async_wait<NB - 1>();
+#pragma unroll
+    for (int r = 0; r < TH_RB; ++r) {
+      const int j = row_of(b, r);
+      const bool ok = (j >= 0 && j < ny);
+      const int slot = (b % NB) * TH_RB + r;
+      const int jj = ok ? j : 0;
+      if (FROM_VEC) f[r] = ok ? gvec[(size_t)plane * ny + jj] : 0.0;
+      else f[r] = ok ? (double)ring[slot][tid] : 0.0;
+      if (COMBINE) vv[r] = ok ? (double)ringv[slot][tid] : 0.0;
+      cj[r] = (jj < Jc) ? ctc[jj] : cfix;
+      if (DIR < 0 && bad && ok) f[r] = dbc[(size_t)jj * tb.KB];
     }
-    cp_async_commit();
-    if (bad) d = tb.dbad[((size_t)plane * tb.ny + j) * tb.KB + cc];
-    const int kr = tb.krow[m * tb.ny + j];
-    const double cj = (cc < kr) ? tb.ctab[(size_t)tb.coff[m * tb.ny + j] + cc] : cfix;
-    x = d - cj * x;                     // x_{ny+1} = 0
-    if (act) out[base + (size_t)j * tb.np] = COMBINE ? (T)(v - bs * x) : (T)x;
+    if (!FROM_VEC || COMBINE) issue(b + NB);
+    if (DIR > 0) {
+#pragma unroll
+      for (int r = 0; r < TH_RB; ++r) f[r] = cj[r] * (tb.dy2 * f[r]);   // off the carried chain
+    }
+#pragma unroll
+    for (int r = 0; r < TH_RB; ++r) {
+      const int j = row_of(b, r);
+      if (j >= 0 && j < ny) {
+        carry = fma(-cj[r], carry, f[r]);    // d_j = c_j dy^2 f_j - c_j d_{j-1} | x_j = d_j - c_j x_{j+1}
+        if (act) {
+          if (DIR > 0) {
+            out[base + (size_t)j * tb.np] = (T)carry;
+            if (bad) dbc[(size_t)j * tb.KB] = carry;
+          } else {
+            out[base + (size_t)j * tb.np] = COMBINE ? (T)(vv[r] - bs * carry) : (T)carry;
+          }
+        }
+      }
+    }
   }
 }
 
-// r[plane][j] = sum_c sig2n[c] * V[plane][j][c]   (= value of the first solve at column n-1)
+// r[plane][j] = f_n[j] - b * sum_c sig2n[c] * V[plane][j][c]: right-hand side of the border
+// (Schur) system; the sum is the first solve evaluated at column n-1, f_n sits in slot n-1.
 template <typename T>
 __global__ void border_dot(const T* __restrict__ V, const double* __restrict__ sig2n, int ny,
-                           int np, int ncols, double* __restrict__ r) {
+                           int np, int ncols, double b, double* __restrict__ r) {
   const int j = blockIdx.x, plane = blockIdx.y;
   const T* row = V + ((size_t)plane * ny + j) * np;
   double acc = 0;
@@ -339,22 +493,23 @@ __global__ void border_dot(const T* __restrict__ V, const double* __restrict__ s
   if (threadIdx.x == 0) {
     double t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    r[(size_t)plane * ny + j] = t;
+    r[(size_t)plane * ny + j] = (double)row[ncols] - b * t;
   }
 }
 
-// Border Schur solve, stage A: ghat[l] = (sum_j sin(pi j l/N) (f_n[j] - b r[j])) / sdiag[m][l]
+// Border Schur solve, stage A: ghat[l] = (sum_j sin(pi j l/N) r[j]) / sdiag[m][l]
 template <typename T>
-__global__ void border_gsolve_a(const T* __restrict__ S, const double* __restrict__ r,
+__global__ void border_gsolve_a(const double* __restrict__ r,
                                 const double* __restrict__ sintab, const double* __restrict__ sdiag,
-                                int ny, int np, int n, int nl, double b, double* __restrict__ ghat) {
+                                int ny, int nl, double* __restrict__ ghat) {
   const int l = blockIdx.x + 1, plane = blockIdx.y, m = plane % nl;
   const int N2 = 2 * (ny + 1);
   double acc = 0;
+  int idx = (int)(((long long)(threadIdx.x + 1) * l) % N2);
+  const int step = (int)(((long long)blockDim.x * l) % N2);
   for (int j = threadIdx.x + 1; j <= ny; j += blockDim.x) {
-    double rhs = (double)S[((size_t)plane * ny + (j - 1)) * np + (n - 1)] - b * r[(size_t)plane * ny + (j - 1)];
-    int idx = (int)(((long long)j * l) % N2);
-    acc += sintab[idx] * rhs;
+    acc += sintab[idx] * r[(size_t)plane * ny + (j - 1)];
+    idx += step; if (idx >= N2) idx -= N2;
   }
   __shared__ double red[32];
   for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
@@ -374,9 +529,11 @@ __global__ void border_gsolve_b(const double* __restrict__ ghat, const double* _
   const int j = blockIdx.x + 1, plane = blockIdx.y;
   const int N2 = 2 * (ny + 1);
   double acc = 0;
+  int idx = (int)(((long long)(threadIdx.x + 1) * j) % N2);
+  const int step = (int)(((long long)blockDim.x * j) % N2);
   for (int l = threadIdx.x + 1; l <= ny; l += blockDim.x) {
-    int idx = (int)(((long long)j * l) % N2);
     acc += sintab[idx] * ghat[(size_t)plane * ny + (l - 1)];
+    idx += step; if (idx >= N2) idx -= N2;
   }
   __shared__ double red[32];
   for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
@@ -403,9 +560,9 @@ static int dev_upload(const void* src, size_t bytes, void** dst, size_t* total) 
 
 static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
   const int nl = s->nl, ny = s->ny, nc = s->ncols;
-  std::vector<double> cinf((size_t)nl * nc);
-  std::vector<int> J((size_t)nl * nc);       // rows 1..J use the table
-  std::vector<std::vector<double>> cols((size_t)nl * nc);
+  std::vector<double> cinf((size_t)nl * nc), ctab;
+  std::vector<int> J((size_t)nl * nc);
+  std::vector<long long> coloff((size_t)nl * nc);
   const double dy2 = s->dy * s->dy;
   s->KB = 0;
   for (int m = 0; m < nl; ++m) {
@@ -414,50 +571,30 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
       const double sn = sin(M_PI * (c + 1) / (2.0 * Nx_eig));
       const double lam_x = -(4.0 / (s->dx * s->dx)) * sn * sn;
       const double delta = (lam_x - lambdas[m]) * dy2 - 2.0;
-      auto& col = cols[(size_t)m * nc + c];
       const bool definite = delta < -2.0;
       double cstar = 0.0;
       if (definite) cstar = 0.5 * (delta + sqrt(delta * delta - 4.0));
-      else s->kbad[m] = std::max(s->kbad[m], c + 1);
+      else s->kbad[m] = std::max(s->kbad[m], c + 1);   // indefinite (oscillatory) column
       cinf[(size_t)m * nc + c] = cstar;
+      coloff[(size_t)m * nc + c] = (long long)ctab.size();
       double cj = 0.0;
       int jconv = ny;
       for (int j = 1; j <= ny; ++j) {
         cj = 1.0 / (delta - cj);
         if (definite && fabs(cj - cstar) <= 4e-16 * fabs(cstar)) { jconv = j - 1; break; }
-        col.push_back(cj);
+        ctab.push_back(cj);
       }
       J[(size_t)m * nc + c] = jconv;
     }
     s->KB = std::max(s->KB, s->kbad[m]);
   }
-  // row-major ragged table: row j (1-based) of mode m holds columns 0..K-1, K = 1 + max{c: J>=j}
-  std::vector<int> krow((size_t)nl * ny), coff((size_t)nl * ny);
-  std::vector<double> ctab;
-  for (int m = 0; m < nl; ++m) {
-    // K_j is non-increasing in j; compute via suffix sweep
-    std::vector<int> K(ny + 2, 0);
-    for (int c = 0; c < nc; ++c) {
-      int jc = J[(size_t)m * nc + c];
-      if (jc >= 1) K[jc] = std::max(K[jc], c + 1);
-    }
-    for (int j = ny - 1; j >= 1; --j) K[j] = std::max(K[j], K[j + 1]);
-    for (int j = 1; j <= ny; ++j) {
-      krow[(size_t)m * ny + (j - 1)] = K[j];
-      coff[(size_t)m * ny + (j - 1)] = (int)ctab.size();
-      for (int c = 0; c < K[j]; ++c) {
-        const auto& col = cols[(size_t)m * nc + c];
-        ctab.push_back(j <= (int)col.size() ? col[j - 1] : cinf[(size_t)m * nc + c]);
-      }
-    }
-  }
-  if (ctab.size() > (size_t)2000000000) return fail(SOMAX_B200_ERR_UNSUPPORTED, "thomas table too large");
+  if (ctab.empty()) ctab.push_back(0.0);
   if (int rc = dev_upload(ctab.data(), ctab.size() * 8, (void**)&s->ctab, &s->bytes)) return rc;
-  if (int rc = dev_upload(krow.data(), krow.size() * 4, (void**)&s->krow, &s->bytes)) return rc;
-  if (int rc = dev_upload(coff.data(), coff.size() * 4, (void**)&s->coff, &s->bytes)) return rc;
+  if (int rc = dev_upload(J.data(), J.size() * 4, (void**)&s->krow, &s->bytes)) return rc;
+  if (int rc = dev_upload(coloff.data(), coloff.size() * 8, (void**)&s->coff, &s->bytes)) return rc;
   if (int rc = dev_upload(cinf.data(), cinf.size() * 8, (void**)&s->cinf, &s->bytes)) return rc;
-  if (s->KB > 0) {
-    size_t nb = (size_t)s->planes * ny * s->KB * 8;
+  {
+    size_t nb = (size_t)s->planes * ny * std::max(s->KB, 1) * 8;
     SB_CUDA(cudaMalloc((void**)&s->dbad, nb));
     SB_CUDA(cudaMemset(s->dbad, 0, nb));
     s->bytes += nb;
@@ -610,59 +747,44 @@ template <typename T>
 int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
   const int ny = s->ny, n = s->nx, np = s->np, nl = s->nl;
   ThomasTab tb;
-  tb.ctab = s->ctab; tb.coff = s->coff; tb.krow = s->krow; tb.cinf = s->cinf;
+  tb.ctab = s->ctab; tb.coloff = s->coff; tb.J = s->krow; tb.cinf = s->cinf;
   for (int m = 0; m < QG_MAX_NL; ++m) tb.kbad[m] = s->kbad[m];
-  tb.KB = s->KB; tb.dbad = s->dbad; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
+  tb.KB = std::max(s->KB, 1); tb.dbad = s->dbad; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
   tb.dy2 = s->dy * s->dy;
   dim3 tgrid((s->ncols + TH_COLS - 1) / TH_COLS, s->planes);
   T* S = (T*)s->S;
   if (s->kind == SOMAX_B200_SOLVER_FFT) {
     T* W = (T*)s->W;
-    RowArgs<T> Af = make_row_args<T>(s, s->l2m, 1.0);
-    RowArgs<T> Ai = make_row_args<T>(s, s->m2l, 2.0 / n);
-    const size_t smem = (size_t)fft_padded_len(n) * sizeof(C2<T>) * Af.rows_per_block;
-    const int threads = Af.G * Af.rows_per_block;
-    const int nrows = s->batch * ny;
-    const int blocks = (nrows + Af.rows_per_block - 1) / Af.rows_per_block;
-    static thread_local size_t smem_set_f = 0, smem_set_i = 0;
-    if (smem > 48 * 1024) {
-      if (smem_set_f < smem) {
-        SB_CUDA(cudaFuncSetAttribute(rowdst_fwd_fft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set_f = smem;
-      }
-      if (smem_set_i < smem) {
-        SB_CUDA(cudaFuncSetAttribute(rowdst_inv_fft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set_i = smem;
-      }
-    }
-    prof_begin("rowdst_fwd_fft", st);
-    rowdst_fwd_fft<T><<<blocks, threads, smem, st>>>(Af, q, S);
-    SB_LAUNCH_CHECK();
+    RowArgsCT<T> Af, Ai;
+    Af.L = s->L; Af.ny = ny; Af.np = np; Af.nl = nl; Af.nrows = s->batch * ny;
+    Af.tw = (const C2<T>*)s->tw; Af.scale = (T)1;
+    Ai = Af; Ai.scale = (T)(2.0 / n);
+    for (int a = 0; a < QG_MAX_NL; ++a)
+      for (int c = 0; c < QG_MAX_NL; ++c) { Af.mix[a][c] = (T)s->l2m.c[a][c]; Ai.mix[a][c] = (T)s->m2l.c[a][c]; }
+    if (int rc = launch_rowdst<T, false>(s->plan.lgn, Af, q, S, st)) return rc;
     prof_begin("thomas_fwd_0", st);
-    thomas_fwd<T, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, S);
+    thomas_sweep<T, 1, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
     SB_LAUNCH_CHECK();
     prof_begin("thomas_bwd_0", st);
-    thomas_bwd<T, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, S);
-    SB_LAUNCH_CHECK();
-    prof_begin("border_dot", st);
-    border_dot<T><<<dim3(ny, s->planes), 256, 0, st>>>(S, s->sig2n, ny, np, s->ncols, s->rvec);
+    thomas_sweep<T, -1, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
     SB_LAUNCH_CHECK();
     const double b = 1.0 / (s->dx * s->dx);
+    prof_begin("border_dot", st);
+    border_dot<T><<<dim3(ny, s->planes), 256, 0, st>>>(S, s->sig2n, ny, np, s->ncols, b, s->rvec);
+    SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_a", st);
-    border_gsolve_a<T><<<dim3(ny, s->planes), 128, 0, st>>>(S, s->rvec, s->sintab, s->sdiag, ny, np, n, nl, b, s->ghat);
+    border_gsolve_a<T><<<dim3(ny, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, nl, s->ghat);
     SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_b", st);
     border_gsolve_b<T><<<dim3(ny, s->planes), 128, 0, st>>>(s->ghat, s->sintab, ny, np, n, s->gvec, S);
     SB_LAUNCH_CHECK();
     prof_begin("thomas_fwd_1", st);
-    thomas_fwd<T, true><<<tgrid, TH_COLS, 0, st>>>(tb, nullptr, s->gvec, W);
+    thomas_sweep<T, 1, true, false><<<tgrid, TH_COLS, 0, st>>>(tb, nullptr, nullptr, s->gvec, nullptr, W);
     SB_LAUNCH_CHECK();
     prof_begin("thomas_bwd_1", st);
-    thomas_bwd<T, true><<<tgrid, TH_COLS, 0, st>>>(tb, W, S, s->bsig, S);
+    thomas_sweep<T, -1, false, true><<<tgrid, TH_COLS, 0, st>>>(tb, W, S, nullptr, s->bsig, S);
     SB_LAUNCH_CHECK();
-    prof_begin("rowdst_inv_fft", st);
-    rowdst_inv_fft<T><<<blocks, threads, smem, st>>>(Ai, S, psi);
-    SB_LAUNCH_CHECK();
+    if (int rc = launch_rowdst<T, true>(s->plan.lgn, Ai, S, psi, st)) return rc;
   } else {
     const size_t smem = (size_t)nl * n * sizeof(T);
     if (smem > 48 * 1024) {
@@ -674,10 +796,10 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     rowdst_dense<T, false><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->l2m, (const T*)s->dstmat, q, S, 1.0);
     SB_LAUNCH_CHECK();
     prof_begin("thomas_fwd_0", st);
-    thomas_fwd<T, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, S);
+    thomas_sweep<T, 1, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
     SB_LAUNCH_CHECK();
     prof_begin("thomas_bwd_0", st);
-    thomas_bwd<T, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, S);
+    thomas_sweep<T, -1, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
     SB_LAUNCH_CHECK();
     prof_begin("rowdst_dense_1", st);
     rowdst_dense<T, true><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->m2l, (const T*)s->dstmat, S, psi, 2.0 / (n + 1));
@@ -706,15 +828,15 @@ extern "C" int somax_b200_host_dst1_check(int n, const double* x /* n-1 */, doub
   z[zi(0)] = 0; z[zi(n)] = 0;
   for (int t = 1; t < n; ++t) { z[zi(t)] = x[t - 1]; z[zi(2 * n - t)] = -x[t - 1]; }
   const int G = std::max(1, n / 8);
-  int Lc = n;
+  int lgLc = plan.lgn;
   for (int ps = 0; ps < plan.npass; ++ps) {
-    const int R = plan.radix[ps];
+    const int lr = plan.lgr[ps];
     for (int lt = 0; lt < G; ++lt) {
-      if (R == 8) fft_dif_pass<double, 8>(s.data(), n, Lc, lt, G, tw.data());
-      else if (R == 4) fft_dif_pass<double, 4>(s.data(), n, Lc, lt, G, tw.data());
-      else fft_dif_pass<double, 2>(s.data(), n, Lc, lt, G, tw.data());
+      if (lr == 3) fft_dif_pass<double, 8>(s.data(), plan.lgn, lgLc, lt, G, tw.data());
+      else if (lr == 2) fft_dif_pass<double, 4>(s.data(), plan.lgn, lgLc, lt, G, tw.data());
+      else fft_dif_pass<double, 2>(s.data(), plan.lgn, lgLc, lt, G, tw.data());
     }
-    Lc /= R;
+    lgLc -= lr;
   }
   for (int k = 1; k <= n / 2; ++k) {
     double a, b;
