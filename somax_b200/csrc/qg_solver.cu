@@ -42,7 +42,7 @@ struct QgSolver {
   double* ctab = nullptr; long long* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
   int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0; double* dbad = nullptr;
   double* bsig = nullptr; double* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
-  double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr;
+  double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; double* meet = nullptr;
   void* tw = nullptr; void* dstmat = nullptr;
   FftPlan plan;
   Mix l2m, m2l;
@@ -370,6 +370,7 @@ struct ThomasTab {
   const int* J;
   const double* cinf;
   int kbad[QG_MAX_NL]; int KB; double* dbad;
+  double* meet;              // [plane][2][ncols]: last eliminated value of each half (fp64)
   int ny, np, ncols, nl;
   double dy2;
 };
@@ -393,83 +394,159 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// DIR = +1: forward elimination (rows ascending); DIR = -1: back substitution (descending).
-// FROM_VEC (forward only): right-hand side is gvec[plane][j] for every column (border solve).
-// COMBINE (backward only): out = V - bsig[c] * x  (second solve applied to the first one's V).
-template <typename T, int DIR, bool FROM_VEC, bool COMBINE>
+// Two-way ("burn at both ends") Thomas: every column is handled by TWO threads (blockIdx.z):
+// half 0 eliminates rows 0..m1-1 downwards, half 1 eliminates rows ny-1..m1 upwards with the
+// mirrored recurrence (same coefficient table by symmetry of the Toeplitz system).  The halves
+// meet between rows m1-1 and m1 with a 2x2 solve, then substitute outwards.  Twice the
+// parallelism of the classic sweep for the same memory passes.
+//   SUBST = false: elimination  d_s = (dy^2 f_s - d_{s-1}) c_s           (s counts from the end)
+//   SUBST = true : substitution x_s = d_s - c_s x_{s'}  outwards from the meeting point
+// FROM_VEC (elimination only): right-hand side is gvec[plane][j] for every column (border solve).
+// COMBINE (substitution only): out = V - bsig[c] * x (second solve applied to the first one's V).
+//
+// Batches are split warp-uniformly: a batch whose table indices are all >= Jw (max over the
+// warp of the per-column convergence row; ny if the warp holds an indefinite column) takes the
+// FAST path (constant coefficient, pointer increments); others take the GENERAL path whose
+// coefficient loads are software-pipelined one batch ahead.
+template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE>
 __global__ void __launch_bounds__(TH_COLS)
 thomas_sweep(ThomasTab tb, const T* __restrict__ in, const T* __restrict__ V,
              const double* __restrict__ gvec, const double* __restrict__ bsig, T* __restrict__ out) {
   constexpr int NB = ThNB<T>::v;
   constexpr int DEPTH = NB * TH_RB;
-  __shared__ T ring[FROM_VEC ? 1 : DEPTH][TH_COLS];
+  constexpr bool RING = !FROM_VEC;
+  __shared__ T ring[RING ? DEPTH : 1][TH_COLS];
   __shared__ T ringv[COMBINE ? DEPTH : 1][TH_COLS];
   const int tid = threadIdx.x;
   const int c = blockIdx.x * TH_COLS + tid;
   const int plane = blockIdx.y, m = plane % tb.nl;
+  const int half = blockIdx.z;
   const bool act = c < tb.ncols;
   const int cc = act ? c : 0;
   const int ny = tb.ny;
-  const size_t base = (size_t)plane * ny * tb.np + cc;
+  const long long np = tb.np;
+  const size_t base = (size_t)plane * ny * np + cc;
   const double cfix = tb.cinf[m * tb.ncols + cc];
   const int Jc = tb.J[m * tb.ncols + cc];
   const double* ctc = tb.ctab + tb.coloff[m * tb.ncols + cc];
   const bool bad = cc < tb.kbad[m];
   double* dbc = tb.dbad + ((size_t)plane * ny) * tb.KB + cc;
   const double bs = COMBINE ? bsig[cc] : 0.0;
-  const int nbatch = (ny + TH_RB - 1) / TH_RB;
-  auto row_of = [&](int b, int r) { int i = b * TH_RB + r; return DIR > 0 ? i : ny - 1 - i; };
+  const double kfix = cfix * tb.dy2;
+  const int Jw = __reduce_max_sync(0xffffffffu, bad ? ny : Jc);
+  const double* gv = gvec + (FROM_VEC ? (size_t)plane * ny : 0);
+  // geometry of this thread's run: rows j(s) = j0 + dj*s, table index i(s), s = 0..cnt-1
+  const int m1 = ny / 2;
+  const int cnt = half == 0 ? m1 : ny - m1;
+  int j0, dj;
+  if (!SUBST) { j0 = half == 0 ? 0 : ny - 1; dj = half == 0 ? 1 : -1; }
+  else        { j0 = half == 0 ? m1 - 1 : m1; dj = half == 0 ? -1 : 1; }
+  auto tix = [&](int s) { return SUBST ? cnt - 1 - s : s; };
+  auto coef = [&](int i) { return (i >= 0 && i < Jc) ? ctc[i] : cfix; };
+  const int nbatch = (cnt + TH_RB - 1) / TH_RB;
 
   auto issue = [&](int b) {
     if (b < nbatch) {
 #pragma unroll
       for (int r = 0; r < TH_RB; ++r) {
-        const int j = row_of(b, r);
-        if (j >= 0 && j < ny) {
+        const int s = b * TH_RB + r;
+        if (s < cnt) {
           const int slot = (b % NB) * TH_RB + r;
-          if (!FROM_VEC) cp_async_elem(&ring[slot][tid], in + base + (size_t)j * tb.np);
-          if (COMBINE) cp_async_elem(&ringv[slot][tid], V + base + (size_t)j * tb.np);
+          const long long off = (long long)(j0 + dj * s) * np;
+          if (RING) cp_async_elem(&ring[slot][tid], in + base + off);
+          if (COMBINE) cp_async_elem(&ringv[slot][tid], V + base + off);
         }
       }
     }
     cp_async_commit();
   };
-  if (!FROM_VEC || COMBINE)
+  if (RING)
     for (int b = 0; b < NB; ++b) issue(b);
 
-  double carry = 0.0;   // d_{j-1} (forward) or x_{j+1} (backward)
+  double carry = 0.0;
+  if (SUBST && cnt > 0 && m1 > 0) {
+    // meeting point: x_{m1-1} + ca x_{m1} = d_{m1-1};  x_{m1} + cb x_{m1-1} = e_{m1}
+    // (read from the fp64 side buffer: the rows themselves are being overwritten in place)
+    const double ca = coef(m1 - 1), cb = coef(ny - 1 - m1);
+    const double dm = tb.meet[((size_t)plane * 2 + 0) * tb.ncols + cc];
+    const double em = tb.meet[((size_t)plane * 2 + 1) * tb.ncols + cc];
+    const double den = 1.0 / (1.0 - ca * cb);
+    const double xa = (dm - ca * em) * den, xb = (em - cb * dm) * den;
+    carry = half == 0 ? xb : xa;     // the neighbour's value across the meeting point
+  }
+
+  auto general_fast = [&](int b) {
+    const int slo = b * TH_RB, shi = slo + TH_RB - 1;
+    const int imin = SUBST ? cnt - 1 - shi : slo;
+    return (imin >= Jw) && (shi < cnt);
+  };
+  double cjn[TH_RB];
+  auto prefetch = [&](int b) {
+    if (b < nbatch && !general_fast(b)) {
+#pragma unroll
+      for (int r = 0; r < TH_RB; ++r) cjn[r] = coef(tix(b * TH_RB + r));
+    }
+  };
+  prefetch(0);
+
 #pragma unroll 1
   for (int b = 0; b < nbatch; ++b) {
-    double f[TH_RB], cj[TH_RB], vv[TH_RB];
-    if (!FROM_VEC || COMBINE) cp_async_wait<NB - 1>();
+    if (RING) cp_async_wait<NB - 1>();
+    const int sbase = (b % NB) * TH_RB;
+    if (general_fast(b)) {
+      double f[TH_RB], vv[TH_RB];
+      const int jb = j0 + dj * (b * TH_RB);
 #pragma unroll
-    for (int r = 0; r < TH_RB; ++r) {
-      const int j = row_of(b, r);
-      const bool ok = (j >= 0 && j < ny);
-      const int slot = (b % NB) * TH_RB + r;
-      const int jj = ok ? j : 0;
-      if (FROM_VEC) f[r] = ok ? gvec[(size_t)plane * ny + jj] : 0.0;
-      else f[r] = ok ? (double)ring[slot][tid] : 0.0;
-      if (COMBINE) vv[r] = ok ? (double)ringv[slot][tid] : 0.0;
-      cj[r] = (jj < Jc) ? ctc[jj] : cfix;
-      if (DIR < 0 && bad && ok) f[r] = dbc[(size_t)jj * tb.KB];
-    }
-    if (!FROM_VEC || COMBINE) issue(b + NB);
-    if (DIR > 0) {
+      for (int r = 0; r < TH_RB; ++r) {
+        if (FROM_VEC) f[r] = gv[jb + dj * r];
+        else f[r] = (double)ring[sbase + r][tid];
+        if (COMBINE) vv[r] = (double)ringv[sbase + r][tid];
+      }
+      if (RING) issue(b + NB);
+      prefetch(b + 1);
+      T* op = out + base + (long long)jb * np;
+      const long long ostep = dj * np;
 #pragma unroll
-      for (int r = 0; r < TH_RB; ++r) f[r] = cj[r] * (tb.dy2 * f[r]);   // off the carried chain
-    }
+      for (int r = 0; r < TH_RB; ++r) {
+        if (!SUBST) carry = fma(-cfix, carry, kfix * f[r]);
+        else carry = fma(-cfix, carry, f[r]);
+        if (act) *op = COMBINE ? (T)(vv[r] - bs * carry) : (T)carry;
+        op += ostep;
+      }
+      if (!SUBST && act && b == nbatch - 1) tb.meet[((size_t)plane * 2 + half) * tb.ncols + cc] = carry;
+    } else {
+      double f[TH_RB], cj[TH_RB], vv[TH_RB];
 #pragma unroll
-    for (int r = 0; r < TH_RB; ++r) {
-      const int j = row_of(b, r);
-      if (j >= 0 && j < ny) {
-        carry = fma(-cj[r], carry, f[r]);    // d_j = c_j dy^2 f_j - c_j d_{j-1} | x_j = d_j - c_j x_{j+1}
-        if (act) {
-          if (DIR > 0) {
-            out[base + (size_t)j * tb.np] = (T)carry;
-            if (bad) dbc[(size_t)j * tb.KB] = carry;
-          } else {
-            out[base + (size_t)j * tb.np] = COMBINE ? (T)(vv[r] - bs * carry) : (T)carry;
+      for (int r = 0; r < TH_RB; ++r) {
+        const int s = b * TH_RB + r;
+        const bool ok = s < cnt;
+        const int j = ok ? j0 + dj * s : 0;
+        cj[r] = cjn[r];
+        if (FROM_VEC) f[r] = ok ? gv[j] : 0.0;
+        else f[r] = ok ? (double)ring[sbase + r][tid] : 0.0;
+        if (COMBINE) vv[r] = ok ? (double)ringv[sbase + r][tid] : 0.0;
+        if (SUBST && bad && ok) f[r] = dbc[(size_t)j * tb.KB];
+      }
+      if (RING) issue(b + NB);
+      prefetch(b + 1);
+      if (!SUBST) {
+#pragma unroll
+        for (int r = 0; r < TH_RB; ++r) f[r] = cj[r] * (tb.dy2 * f[r]);   // off the carried chain
+      }
+#pragma unroll
+      for (int r = 0; r < TH_RB; ++r) {
+        const int s = b * TH_RB + r;
+        if (s < cnt) {
+          const int j = j0 + dj * s;
+          carry = fma(-cj[r], carry, f[r]);
+          if (act) {
+            if (!SUBST) {
+              out[base + (size_t)j * np] = (T)carry;
+              if (bad) dbc[(size_t)j * tb.KB] = carry;
+              if (s == cnt - 1) tb.meet[((size_t)plane * 2 + half) * tb.ncols + cc] = carry;
+            } else {
+              out[base + (size_t)j * np] = COMBINE ? (T)(vv[r] - bs * carry) : (T)carry;
+            }
           }
         }
       }
@@ -570,18 +647,27 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
     for (int c = 0; c < nc; ++c) {
       const double sn = sin(M_PI * (c + 1) / (2.0 * Nx_eig));
       const double lam_x = -(4.0 / (s->dx * s->dx)) * sn * sn;
-      const double delta = (lam_x - lambdas[m]) * dy2 - 2.0;
-      const bool definite = delta < -2.0;
+      const double eps = (lambdas[m] - lam_x) * dy2;      // |delta| - 2 when the column is definite
+      const double delta = -2.0 - eps;
+      const bool definite = eps > 0.0;
       double cstar = 0.0;
-      if (definite) cstar = 0.5 * (delta + sqrt(delta * delta - 4.0));
-      else s->kbad[m] = std::max(s->kbad[m], c + 1);   // indefinite (oscillatory) column
+      int jconv = ny;
+      if (definite) {
+        // attracting fixed point c* = 2 / (delta - sqrt(delta^2 - 4)), no cancellation; the
+        // recurrence approaches it like exp(-2 j theta), theta = acosh(1 + eps/2)
+        const double sq = sqrt(eps * (4.0 + eps));
+        cstar = 2.0 / (delta - sq);
+        const double theta = log1p(0.5 * eps + 0.5 * sq);
+        const double jr = log((1.0 - exp(-2.0 * theta)) / 1e-17) / (2.0 * theta) + 2.0;
+        if (jr < (double)ny) jconv = (int)ceil(jr);
+      } else {
+        s->kbad[m] = std::max(s->kbad[m], c + 1);   // indefinite (oscillatory) column
+      }
       cinf[(size_t)m * nc + c] = cstar;
       coloff[(size_t)m * nc + c] = (long long)ctab.size();
       double cj = 0.0;
-      int jconv = ny;
-      for (int j = 1; j <= ny; ++j) {
+      for (int j = 1; j <= jconv; ++j) {
         cj = 1.0 / (delta - cj);
-        if (definite && fabs(cj - cstar) <= 4e-16 * fabs(cstar)) { jconv = j - 1; break; }
         ctab.push_back(cj);
       }
       J[(size_t)m * nc + c] = jconv;
@@ -593,6 +679,12 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
   if (int rc = dev_upload(J.data(), J.size() * 4, (void**)&s->krow, &s->bytes)) return rc;
   if (int rc = dev_upload(coloff.data(), coloff.size() * 8, (void**)&s->coff, &s->bytes)) return rc;
   if (int rc = dev_upload(cinf.data(), cinf.size() * 8, (void**)&s->cinf, &s->bytes)) return rc;
+  {
+    size_t mb = (size_t)s->planes * 2 * nc * 8;
+    SB_CUDA(cudaMalloc((void**)&s->meet, mb));
+    SB_CUDA(cudaMemset(s->meet, 0, mb));
+    s->bytes += mb;
+  }
   {
     size_t nb = (size_t)s->planes * ny * std::max(s->KB, 1) * 8;
     SB_CUDA(cudaMalloc((void**)&s->dbad, nb));
@@ -716,7 +808,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
 void qg_solver_destroy(QgSolver* s) {
   if (!s) return;
   void* ptrs[] = {s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->bsig, s->sig2n,
-                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->tw, s->dstmat};
+                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->tw, s->dstmat, s->meet};
   for (void* p : ptrs) cudaFree(p);
   delete s;
 }
@@ -749,9 +841,9 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
   ThomasTab tb;
   tb.ctab = s->ctab; tb.coloff = s->coff; tb.J = s->krow; tb.cinf = s->cinf;
   for (int m = 0; m < QG_MAX_NL; ++m) tb.kbad[m] = s->kbad[m];
-  tb.KB = std::max(s->KB, 1); tb.dbad = s->dbad; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
+  tb.KB = std::max(s->KB, 1); tb.dbad = s->dbad; tb.meet = s->meet; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
   tb.dy2 = s->dy * s->dy;
-  dim3 tgrid((s->ncols + TH_COLS - 1) / TH_COLS, s->planes);
+  dim3 tgrid((s->ncols + TH_COLS - 1) / TH_COLS, s->planes, 2);
   T* S = (T*)s->S;
   if (s->kind == SOMAX_B200_SOLVER_FFT) {
     T* W = (T*)s->W;
@@ -763,10 +855,10 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
       for (int c = 0; c < QG_MAX_NL; ++c) { Af.mix[a][c] = (T)s->l2m.c[a][c]; Ai.mix[a][c] = (T)s->m2l.c[a][c]; }
     if (int rc = launch_rowdst<T, false>(s->plan.lgn, Af, q, S, st)) return rc;
     prof_begin("thomas_fwd_0", st);
-    thomas_sweep<T, 1, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
+    thomas_sweep<T, false, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
     SB_LAUNCH_CHECK();
     prof_begin("thomas_bwd_0", st);
-    thomas_sweep<T, -1, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
+    thomas_sweep<T, true, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
     SB_LAUNCH_CHECK();
     const double b = 1.0 / (s->dx * s->dx);
     prof_begin("border_dot", st);
@@ -779,10 +871,10 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     border_gsolve_b<T><<<dim3(ny, s->planes), 128, 0, st>>>(s->ghat, s->sintab, ny, np, n, s->gvec, S);
     SB_LAUNCH_CHECK();
     prof_begin("thomas_fwd_1", st);
-    thomas_sweep<T, 1, true, false><<<tgrid, TH_COLS, 0, st>>>(tb, nullptr, nullptr, s->gvec, nullptr, W);
+    thomas_sweep<T, false, true, false><<<tgrid, TH_COLS, 0, st>>>(tb, nullptr, nullptr, s->gvec, nullptr, W);
     SB_LAUNCH_CHECK();
     prof_begin("thomas_bwd_1", st);
-    thomas_sweep<T, -1, false, true><<<tgrid, TH_COLS, 0, st>>>(tb, W, S, nullptr, s->bsig, S);
+    thomas_sweep<T, true, false, true><<<tgrid, TH_COLS, 0, st>>>(tb, W, S, nullptr, s->bsig, S);
     SB_LAUNCH_CHECK();
     if (int rc = launch_rowdst<T, true>(s->plan.lgn, Ai, S, psi, st)) return rc;
   } else {
@@ -796,10 +888,10 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     rowdst_dense<T, false><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->l2m, (const T*)s->dstmat, q, S, 1.0);
     SB_LAUNCH_CHECK();
     prof_begin("thomas_fwd_0", st);
-    thomas_sweep<T, 1, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
+    thomas_sweep<T, false, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
     SB_LAUNCH_CHECK();
     prof_begin("thomas_bwd_0", st);
-    thomas_sweep<T, -1, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
+    thomas_sweep<T, true, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
     SB_LAUNCH_CHECK();
     prof_begin("rowdst_dense_1", st);
     rowdst_dense<T, true><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->m2l, (const T*)s->dstmat, S, psi, 2.0 / (n + 1));
