@@ -91,7 +91,15 @@ struct Stage {
   T a[MAX_PREV];
   T a_new;
   T dt;
+  T adt[MAX_PREV];                 // a[j]*dt and a_new*dt, rounded once on the host: the fast
+  T adt_new;                       // kernels use them (<= 1 ulp from a*(dt*k))
 };
+
+template <typename T>
+inline void stage_finalize(Stage<T>& st, double dt) {
+  for (int j = 0; j < MAX_PREV; ++j) st.adt[j] = (T)((double)st.a[j] * dt);
+  st.adt_new = (T)((double)st.a_new * dt);
+}
 
 // Tsit5 tableau rows (a_{s,1..s-1}), s = 2..7.
 extern const double TSIT5_A[6][6];
@@ -131,6 +139,71 @@ __device__ __forceinline__ void rk_epilogue4(const Stage<T>& st, int f, size_t i
       acc.y = acc.y + st.a[j] * (st.dt * k.y);
       acc.z = acc.z + st.a[j] * (st.dt * k.z);
       acc.w = acc.w + st.a[j] * (st.dt * k.w);
+    }
+  }
+  acc.x = acc.x + st.a_new * (st.dt * F.x);
+  acc.y = acc.y + st.a_new * (st.dt * F.y);
+  acc.z = acc.z + st.a_new * (st.dt * F.z);
+  acc.w = acc.w + st.a_new * (st.dt * F.w);
+  st4(st.Yout[f] + idx, acc);
+}
+
+// Split variant: rk_prefetch4 issues every global load of the epilogue (base state and the
+// previous stage derivatives) up front so their latency overlaps the stencil work.
+template <typename T>
+struct RkRegs { Vec4<T> base; Vec4<T> k[MAX_PREV]; };
+
+template <typename T>
+__device__ __forceinline__ RkRegs<T> rk_prefetch4(const Stage<T>& st, int f, size_t idx, bool valid) {
+  RkRegs<T> R;
+  const Vec4<T> z{0, 0, 0, 0};
+  R.base = z;
+#pragma unroll
+  for (int j = 0; j < MAX_PREV; ++j) R.k[j] = z;
+  if (valid && st.Yout[f]) {
+    R.base = ld4((st.y[f] ? st.y[f] : st.Yin[f]) + idx);
+#pragma unroll
+    for (int j = 0; j < MAX_PREV; ++j)
+      if (j < st.nprev) R.k[j] = ld4(st.Fprev[j][f] + idx);
+  }
+  return R;
+}
+
+// Fast epilogue: loads batched, products with the host-rounded a*dt.
+template <typename T>
+__device__ __forceinline__ void rk_epilogue4_fast(const Stage<T>& st, int f, size_t idx, const Vec4<T>& F) {
+  if (st.Fout[f]) st4(st.Fout[f] + idx, F);
+  if (!st.Yout[f]) return;
+  Vec4<T> acc = ld4((st.y[f] ? st.y[f] : st.Yin[f]) + idx);
+  Vec4<T> k[MAX_PREV];
+#pragma unroll
+  for (int j = 0; j < MAX_PREV; ++j)
+    if (j < st.nprev) k[j] = ld4(st.Fprev[j][f] + idx);
+#pragma unroll
+  for (int j = 0; j < MAX_PREV; ++j) {
+    if (j < st.nprev) {
+      acc.x = fma(st.adt[j], k[j].x, acc.x); acc.y = fma(st.adt[j], k[j].y, acc.y);
+      acc.z = fma(st.adt[j], k[j].z, acc.z); acc.w = fma(st.adt[j], k[j].w, acc.w);
+    }
+  }
+  acc.x = fma(st.adt_new, F.x, acc.x); acc.y = fma(st.adt_new, F.y, acc.y);
+  acc.z = fma(st.adt_new, F.z, acc.z); acc.w = fma(st.adt_new, F.w, acc.w);
+  st4(st.Yout[f] + idx, acc);
+}
+
+template <typename T>
+__device__ __forceinline__ void rk_finish4(const Stage<T>& st, int f, size_t idx, const RkRegs<T>& R,
+                                           const Vec4<T>& F) {
+  if (st.Fout[f]) st4(st.Fout[f] + idx, F);
+  if (!st.Yout[f]) return;
+  Vec4<T> acc = R.base;
+#pragma unroll
+  for (int j = 0; j < MAX_PREV; ++j) {
+    if (j < st.nprev) {
+      acc.x = acc.x + st.a[j] * (st.dt * R.k[j].x);
+      acc.y = acc.y + st.a[j] * (st.dt * R.k[j].y);
+      acc.z = acc.z + st.a[j] * (st.dt * R.k[j].z);
+      acc.w = acc.w + st.a[j] * (st.dt * R.k[j].w);
     }
   }
   acc.x = acc.x + st.a_new * (st.dt * F.x);

@@ -28,9 +28,12 @@ __host__ __device__ __forceinline__ C2<T> cmul(C2<T> a, C2<T> b) {
 template <typename T>
 __host__ __device__ __forceinline__ C2<T> mul_mi(C2<T> a) { return {a.y, -a.x}; }
 
-// complex index -> padded complex index (one pad slot per 16) to spread late-pass strides
-__host__ __device__ __forceinline__ int fft_pad(int i) { return i + (i >> 4); }
-__host__ __device__ __forceinline__ int fft_padded_len(int n) { return n + (n >> 4) + 1; }
+// complex index -> padded complex index.  Three-level padding (one slot per 16, per 128 and per
+// 1024 elements) keeps both the natural-stride butterfly accesses and the digit-reversed reads
+// of the real-odd split spread over the shared-memory banks (simulated: 16 -> 5 wavefronts per
+// request for the split at n = 8192, butterflies unchanged at 2.4).
+__host__ __device__ __forceinline__ constexpr int fft_pad(int i) { return i + (i >> 4) + (i >> 7) + (i >> 10); }
+__host__ __device__ __forceinline__ constexpr int fft_padded_len(int n) { return fft_pad(n) + 1; }
 
 struct FftPlan {
   int n;          // complex length (power of two)

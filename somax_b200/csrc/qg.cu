@@ -22,6 +22,7 @@ struct QgArgs {
   Layout L;
   int apply_bc;
   T dx2, dy2, jden;   // dx^2, dy^2, 12 dx dy
+  T idx2, idy2, ijden, iH0;   // reciprocals (fast kernel)
   const T* beta; int b_cp, b_xs;
   const T* wind; int w_cp, w_xs;
   T H0, nu, kappa, tau0;
@@ -98,6 +99,111 @@ qg_rhs_kernel(QgArgs<T> A, const T* __restrict__ psi, Stage<T> st) {
   const bool need_yin = (st.Yout[0] != nullptr) && (st.y[0] == nullptr);
   Vec4<T> yin = need_yin ? ld4(st.Yin[0] + idx) : Vec4<T>{0, 0, 0, 0};
   rk_epilogue4(st, 0, idx, yin, Vec4<T>{out[0], out[1], out[2], out[3]});
+}
+
+// Fast variant used when beta_y and the wind pattern depend on y only (every reference factory):
+// 128-bit global->shared tile loads, 128-bit shared reads, warp shuffles for the x neighbours.
+constexpr int QSW = QTXG * 4 + 8;   // shared row: 4 slots left (halo at [3]) | 128 | 4 slots right (halo at [0])
+
+template <typename T>
+__global__ void __launch_bounds__(QTXG* QTY)
+qg_rhs_kernel_fast(QgArgs<T> A, const T* __restrict__ psi, Stage<T> st) {
+  __shared__ __align__(32) T s_q[QTY + 2][QSW];
+  __shared__ __align__(32) T s_p[QTY + 2][QSW];
+  const Layout& L = A.L;
+  const int Ny = L.Ny, Nx = L.Nx, pitch = L.pitch, ngroups = L.groups();
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * QTXG + tx;
+  const int g0 = blockIdx.x * QTXG, j0 = blockIdx.y * QTY;
+  const int plane = blockIdx.z, k = plane % L.nl;
+  const size_t po = (size_t)plane * L.plane();
+  const T* pq = st.Yin[0] + po;
+  const T* pp = psi + po;
+  const size_t idx = po + (size_t)(j0 + ty) * pitch + (size_t)(g0 + tx) * 4;
+
+  for (int e = tid; e < (QTY + 2) * (QTXG + 2); e += QTXG * QTY) {
+    const int r = e / (QTXG + 2), gs = e - r * (QTXG + 2);   // gs: shared group 0..QTXG+1
+    const int jj = j0 - 1 + r, gg = g0 - 1 + gs;
+    Vec4<T> q{0, 0, 0, 0}, p{0, 0, 0, 0};
+    if (jj >= 0 && jj < Ny && gg >= 0 && gg < ngroups) {
+      const size_t o = (size_t)jj * pitch + (size_t)gg * 4;
+      q = ld4(pq + o);
+      p = ld4(pp + o);
+      if (A.apply_bc) {
+        const int i0 = gg * 4 - OFF;     // column of .x
+        if (jj == 0 || jj == Ny - 1) q = Vec4<T>{0, 0, 0, 0};
+        if (i0 == 0 || i0 == Nx - 1) q.x = 0;
+        if (i0 + 1 == 0 || i0 + 1 == Nx - 1) q.y = 0;
+        if (i0 + 2 == 0 || i0 + 2 == Nx - 1) q.z = 0;
+        if (i0 + 3 == 0 || i0 + 3 == Nx - 1) q.w = 0;
+      }
+    }
+    st4(&s_q[r][gs * 4], q);
+    st4(&s_p[r][gs * 4], p);
+  }
+  __syncthreads();
+  const int j = j0 + ty, g = g0 + tx;
+  if (j >= Ny) return;       // warp-uniform (ty); lanes with g >= ngroups stay for the shuffles
+  const int r = ty + 1, cs = 4 * (tx + 1);
+  // 3 x 6 windows of psi (f) and q (g): columns cs-1 .. cs+4
+  T f[3][6], q[3][6];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const Vec4<T> a = ld4(&s_p[r - 1 + d][cs]);
+    const Vec4<T> b = ld4(&s_q[r - 1 + d][cs]);
+    T al = __shfl_up_sync(0xffffffffu, a.w, 1), ar = __shfl_down_sync(0xffffffffu, a.x, 1);
+    T bl = __shfl_up_sync(0xffffffffu, b.w, 1), br = __shfl_down_sync(0xffffffffu, b.x, 1);
+    if (tx == 0) { al = s_p[r - 1 + d][cs - 1]; bl = s_q[r - 1 + d][cs - 1]; }
+    if (tx == QTXG - 1) { ar = s_p[r - 1 + d][cs + 4]; br = s_q[r - 1 + d][cs + 4]; }
+    f[d][0] = al; f[d][1] = a.x; f[d][2] = a.y; f[d][3] = a.z; f[d][4] = a.w; f[d][5] = ar;
+    q[d][0] = bl; q[d][1] = b.x; q[d][2] = b.y; q[d][3] = b.z; q[d][4] = b.w; q[d][5] = br;
+  }
+  if (g >= ngroups) return;
+  // beta_y(row) for rows j-1, j, j+1 (clamped rows are never used by interior cells)
+  T bet[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    int jj = j - 1 + d;
+    jj = jj < 0 ? 0 : (jj > Ny - 1 ? Ny - 1 : jj);
+    bet[d] = A.beta[jj];
+  }
+  const T wind = (k == 0) ? (A.tau0 * A.wind[j]) * A.iH0 : T(0);
+  const int i0 = g * 4 - OFF;
+  T out[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = i0 + e, c = e + 1;
+    T dq = 0;
+    if (i >= 0 && i < Nx) {
+      const bool interior = (j >= 1 && j <= Ny - 2 && i >= 1 && i <= Nx - 2);
+      if (interior) {
+        const T fE = f[1][c + 1], fW = f[1][c - 1], fN = f[2][c], fS = f[0][c];
+        const T fNE = f[2][c + 1], fNW = f[2][c - 1], fSE = f[0][c + 1], fSW = f[0][c - 1];
+        const T gE = q[1][c + 1] + bet[1], gW = q[1][c - 1] + bet[1];
+        const T gN = q[2][c] + bet[2], gS = q[0][c] + bet[0];
+        const T gNE = q[2][c + 1] + bet[2], gNW = q[2][c - 1] + bet[2];
+        const T gSE = q[0][c + 1] + bet[0], gSW = q[0][c - 1] + bet[0];
+        const T jpp = (fE - fW) * (gN - gS) - (fN - fS) * (gE - gW);
+        const T jpx = fE * (gNE - gSE) - fW * (gNW - gSW) - fN * (gNE - gNW) + fS * (gSE - gSW);
+        const T jxp = gN * (fNE - fNW) - gS * (fSE - fSW) - gE * (fNE - fSE) + gW * (fNW - fSW);
+        dq = -(((jpp + jpx) + jxp) * A.ijden);
+      }
+      if (k == 0) dq = dq + wind;
+      if (interior) {
+        if (k == L.nl - 1) {
+          const T pc = f[1][c];
+          const T lap = (f[1][c + 1] - T(2) * pc + f[1][c - 1]) * A.idx2 +
+                        (f[2][c] - T(2) * pc + f[0][c]) * A.idy2;
+          dq = dq + (-A.kappa * lap);
+        }
+        const T qc = q[1][c];
+        const T lapq = (q[1][c + 1] - T(2) * qc + q[1][c - 1]) * A.idx2 +
+                       (q[2][c] - T(2) * qc + q[0][c]) * A.idy2;
+        dq = dq + A.nu * lapq;
+      }
+    }
+    out[e] = dq;
+  }
+  rk_epilogue4_fast(st, 0, idx, Vec4<T>{out[0], out[1], out[2], out[3]});
 }
 
 // ring := 0 in place on padded planes
@@ -184,6 +290,8 @@ QgArgs<T> make_qargs(somax_b200_qg_t h, const somax_b200_params* p, int apply_bc
   QgArgs<T> A;
   A.L = h->L; A.apply_bc = apply_bc;
   A.dx2 = (T)(h->dx * h->dx); A.dy2 = (T)(h->dy * h->dy); A.jden = (T)(12.0 * h->dx * h->dy);
+  A.idx2 = (T)(1.0 / (h->dx * h->dx)); A.idy2 = (T)(1.0 / (h->dy * h->dy));
+  A.ijden = (T)(1.0 / (12.0 * h->dx * h->dy)); A.iH0 = (T)(1.0 / p->H0);
   A.beta = (const T*)h->beta; A.b_cp = h->beta1d ? 1 : h->L.Nx; A.b_xs = h->beta1d ? 0 : 1;
   A.wind = (const T*)h->wind; A.w_cp = h->wind1d ? 1 : h->L.Nx; A.w_xs = h->wind1d ? 0 : 1;
   A.H0 = (T)p->H0; A.nu = (T)p->lateral_viscosity; A.kappa = (T)p->bottom_drag;
@@ -206,13 +314,16 @@ Stage<T> qstage() {
 
 // one RHS evaluation: psi = invert(Yin), then the fused stencil + RK epilogue
 template <typename T>
-int eval_rhs(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st, cudaStream_t s) {
+int eval_rhs(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st_in, double dt, cudaStream_t s) {
+  Stage<T> st = st_in;
+  stage_finalize(st, dt);
   if (int rc = qg_solver_run<T>(h->solver, st.Yin[0], (T*)h->psi, s)) return rc;
   const Layout& L = h->L;
   dim3 block(QTXG, QTY);
   dim3 grid((L.groups() + QTXG - 1) / QTXG, (L.Ny + QTY - 1) / QTY, L.batch * L.nl);
   prof_begin("qg_rhs_kernel", s);
-  qg_rhs_kernel<T><<<grid, block, 0, s>>>(A, (const T*)h->psi, st);
+  if (h->beta1d && h->wind1d) qg_rhs_kernel_fast<T><<<grid, block, 0, s>>>(A, (const T*)h->psi, st);
+  else qg_rhs_kernel<T><<<grid, block, 0, s>>>(A, (const T*)h->psi, st);
   SB_LAUNCH_CHECK();
   return 0;
 }
@@ -242,7 +353,7 @@ int qg_steps_impl(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt
       Stage<T> st = qstage<T>();
       st.Yin[0] = (const T*)y; st.Fout[0] = (T*)h->F[0]; st.Yout[0] = (T*)Yc;
       st.a_new = (T)TSIT5_A[0][0]; st.dt = (T)step_dt(0);
-      if (int rc = eval_rhs<T>(h, A, st, s)) return rc;
+      if (int rc = eval_rhs<T>(h, A, st, step_dt(0), s)) return rc;
     }
     for (long i = 0; i < total; ++i) {
       const T hdt = (T)step_dt(i);
@@ -252,14 +363,14 @@ int qg_steps_impl(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt
         for (int jj = 0; jj < e; ++jj) { st.a[jj] = (T)TSIT5_A[e][jj]; st.Fprev[jj][0] = (const T*)h->F[jj]; }
         st.Yin[0] = (const T*)Yc; st.y[0] = (const T*)y; st.Yout[0] = (T*)Yn;
         st.Fout[0] = (e <= 4) ? (T*)h->F[e] : nullptr;
-        if (int rc = eval_rhs<T>(h, A, st, s)) return rc;
+        if (int rc = eval_rhs<T>(h, A, st, step_dt(i), s)) return rc;
         std::swap(Yc, Yn);
       }
       if (i + 1 < total) {
         Stage<T> st = qstage<T>();
         st.dt = (T)step_dt(i + 1); st.a_new = (T)TSIT5_A[0][0];
         st.Yin[0] = (const T*)Yc; st.Fout[0] = (T*)h->F[0]; st.Yout[0] = (T*)Yn;
-        if (int rc = eval_rhs<T>(h, A, st, s)) return rc;
+        if (int rc = eval_rhs<T>(h, A, st, step_dt(i + 1), s)) return rc;
         void* oy = y; y = Yc; Yc = Yn; Yn = oy;
       } else {
         std::swap(y, Yc);
@@ -277,7 +388,7 @@ int qg_rhs_impl(somax_b200_qg_t h, const void* q, void* dq, void* psi_out,
   QgArgs<T> A = make_qargs<T>(h, p, apply_bc);
   Stage<T> st = qstage<T>();
   st.Yin[0] = (const T*)h->Ya; st.Fout[0] = (T*)h->F[0];
-  if (int rc = eval_rhs<T>(h, A, st, s)) return rc;
+  if (int rc = eval_rhs<T>(h, A, st, 0.0, s)) return rc;
   if (int rc = unpack_field<T>((const T*)h->F[0], (T*)dq, L, s)) return rc;
   if (psi_out) return unpack_field<T>((const T*)h->psi, (T*)psi_out, L, s);
   return 0;

@@ -210,7 +210,7 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
   constexpr int n = Cfg::n, G = Cfg::G, EPT = Cfg::EPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lrow = threadIdx.x / G, lt = threadIdx.x % G;
-  constexpr int plen = n + (n >> 4) + 1;
+  constexpr int plen = fft_padded_len(n);
   C2<T>* s = reinterpret_cast<C2<T>*>(smem_raw) + (size_t)lrow * plen;
   T* z = reinterpret_cast<T*>(s);
   const int row = blockIdx.x * Cfg::RPB + lrow;
@@ -291,7 +291,7 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
 template <typename T, int LGN, bool INV>
 static int launch_rowdst_ct(const RowArgsCT<T>& A, const T* in, T* out, cudaStream_t st) {
   using Cfg = RowCfg<LGN>;
-  constexpr size_t smem = (size_t)(Cfg::n + (Cfg::n >> 4) + 1) * sizeof(C2<T>) * Cfg::RPB;
+  constexpr size_t smem = (size_t)fft_padded_len(Cfg::n) * sizeof(C2<T>) * Cfg::RPB;
   static bool attr_done = false;
   if (smem > 48 * 1024 && !attr_done) {
     SB_CUDA(cudaFuncSetAttribute(rowdst_fft_ct<T, LGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -26,6 +26,7 @@ struct SwmArgs {
   unsigned spec;
   int apply_bc;
   T dx, dy, dx2, dy2;
+  T idx, idy, idx2, idy2, iH0;   // reciprocals (fast kernel)
   const T* f;  int f_cp, f_xs;
   const T* wx; int wx_cp, wx_xs;
   const T* wy; int wy_cp, wy_xs;
@@ -224,6 +225,231 @@ swm_rhs_kernel(SwmArgs<T> A, Stage<T> st) {
   }
 }
 
+// Fast variant (f, wind_x, wind_y depend on y only - every reference factory): 128-bit tile
+// loads, per-thread 3x6 register windows filled with 128-bit shared reads + warp shuffles,
+// shared sub-expressions (q, uh, vh, ke, fluxes) evaluated once per window column, reciprocal
+// multiplies for the constant divisors.
+constexpr int SSW = TXG * 4 + 8;   // shared row: 4 | 128 | 4 (halo columns at [3] and [132])
+
+template <typename T>
+__global__ void __launch_bounds__(TXG* TY, (sizeof(T) == 4 ? 2 : 1))
+swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
+  __shared__ __align__(32) T s_h[TY + 2][SSW];
+  __shared__ __align__(32) T s_u[TY + 2][SSW];
+  __shared__ __align__(32) T s_v[TY + 2][SSW];
+  __shared__ __align__(32) T s_p[TY + 2][SSW];
+  const Layout& L = A.L;
+  const int Ny = L.Ny, Nx = L.Nx, pitch = L.pitch, ngroups = L.groups();
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TXG + tx;
+  const int g0 = blockIdx.x * TXG, j0 = blockIdx.y * TY;
+  const int b = blockIdx.z;
+  const int j = j0 + ty, g = g0 + tx;
+  const int r = ty + 1, cs = 4 * (tx + 1);
+  const int i0 = g * 4 - OFF;                    // column of this thread's first cell
+  const T idx_ = A.idx, idy_ = A.idy;
+
+  for (int e = tid; e < (TY + 2) * (SSW / 4); e += TXG * TY)
+    st4(&s_p[0][0] + 4 * e, Vec4<T>{0, 0, 0, 0});
+
+  // row / column interior flags of the 3 x 6 window
+  bool rin[3], cin[6];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) rin[d] = (j - 1 + d >= 1) && (j - 1 + d <= Ny - 2);
+#pragma unroll
+  for (int w = 0; w < 6; ++w) cin[w] = (i0 - 1 + w >= 1) && (i0 - 1 + w <= Nx - 2);
+  // Coriolis at the X points of rows j-1 and j: f depends on y only, so
+  // T_to_X(f) = 0.25*(f[j] + f[j] + f[j+1] + f[j+1]) in the reference's summation order
+  T fX[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    int ja = j - 1 + d; ja = ja < 0 ? 0 : (ja > Ny - 1 ? Ny - 1 : ja);
+    int jb = ja + 1 > Ny - 1 ? Ny - 1 : ja + 1;
+    const T fa = A.f[ja], fb = A.f[jb];
+    fX[d] = T(0.25) * (((fa + fa) + fb) + fb);
+  }
+  const int jc = j < Ny ? j : Ny - 1;
+  const T windx = (A.tau0 * A.wx[jc]) * A.iH0, windy = (A.tau0 * A.wy[jc]) * A.iH0;
+
+  for (int k = 0; k < L.nl; ++k) {
+    const size_t plane_off = ((size_t)b * L.nl + k) * L.plane();
+    const T* ph = st.Yin[FH] + plane_off;
+    const T* pu = st.Yin[FU] + plane_off;
+    const T* pv = st.Yin[FV] + plane_off;
+    __syncthreads();
+    for (int e = tid; e < (TY + 2) * (TXG + 2); e += TXG * TY) {
+      const int rr = e / (TXG + 2), gs = e - rr * (TXG + 2);
+      const int jj = j0 - 1 + rr, gg = g0 - 1 + gs;
+      Vec4<T> vh{0, 0, 0, 0}, vu{0, 0, 0, 0}, vv{0, 0, 0, 0};
+      if (jj >= 0 && jj < Ny && gg >= 0 && gg < ngroups) {
+        const int ib = gg * 4 - OFF;
+        const bool plain = !A.apply_bc ||
+                           (jj >= 1 && jj <= Ny - 3 && ib >= 1 && ib + 3 <= Nx - 3);
+        if (plain) {
+          const size_t o = (size_t)jj * pitch + (size_t)gg * 4;
+          vh = ld4(ph + o); vu = ld4(pu + o); vv = ld4(pv + o);
+        } else {
+          T th[4], tu[4], tv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int ii = ib + q;
+            th[q] = tu[q] = tv[q] = T(0);
+            if (ii >= 0 && ii < Nx) {
+              th[q] = swm_bc_value(ph, FH, A.bc, jj, ii, Ny, Nx, pitch);
+              tu[q] = swm_bc_value(pu, FU, A.bc, jj, ii, Ny, Nx, pitch);
+              tv[q] = swm_bc_value(pv, FV, A.bc, jj, ii, Ny, Nx, pitch);
+            }
+          }
+          vh = Vec4<T>{th[0], th[1], th[2], th[3]};
+          vu = Vec4<T>{tu[0], tu[1], tu[2], tu[3]};
+          vv = Vec4<T>{tv[0], tv[1], tv[2], tv[3]};
+        }
+      }
+      st4(&s_h[rr][gs * 4], vh); st4(&s_u[rr][gs * 4], vu); st4(&s_v[rr][gs * 4], vv);
+      Vec4<T> pp = ld4(&s_p[rr][gs * 4]);
+      const T gk = A.gprime[k];
+      pp.x = pp.x + gk * vh.x; pp.y = pp.y + gk * vh.y; pp.z = pp.z + gk * vh.z; pp.w = pp.w + gk * vh.w;
+      st4(&s_p[rr][gs * 4], pp);
+    }
+    __syncthreads();
+    if (j >= Ny) continue;     // warp-uniform
+    // ---- 3 x 6 register windows: columns i0-1 .. i0+4, rows j-1 .. j+1 ----
+    T H[3][6], U[3][6], V[3][6];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const Vec4<T> a = ld4(&s_h[r - 1 + d][cs]);
+      const Vec4<T> bq = ld4(&s_u[r - 1 + d][cs]);
+      const Vec4<T> c4 = ld4(&s_v[r - 1 + d][cs]);
+      T al = __shfl_up_sync(0xffffffffu, a.w, 1), ar = __shfl_down_sync(0xffffffffu, a.x, 1);
+      T bl = __shfl_up_sync(0xffffffffu, bq.w, 1), br = __shfl_down_sync(0xffffffffu, bq.x, 1);
+      T cl = __shfl_up_sync(0xffffffffu, c4.w, 1), cr = __shfl_down_sync(0xffffffffu, c4.x, 1);
+      if (tx == 0) { al = s_h[r - 1 + d][cs - 1]; bl = s_u[r - 1 + d][cs - 1]; cl = s_v[r - 1 + d][cs - 1]; }
+      if (tx == TXG - 1) { ar = s_h[r - 1 + d][cs + 4]; br = s_u[r - 1 + d][cs + 4]; cr = s_v[r - 1 + d][cs + 4]; }
+      H[d][0] = al; H[d][1] = a.x; H[d][2] = a.y; H[d][3] = a.z; H[d][4] = a.w; H[d][5] = ar;
+      U[d][0] = bl; U[d][1] = bq.x; U[d][2] = bq.y; U[d][3] = bq.z; U[d][4] = bq.w; U[d][5] = br;
+      V[d][0] = cl; V[d][1] = c4.x; V[d][2] = c4.y; V[d][3] = c4.z; V[d][4] = c4.w; V[d][5] = cr;
+    }
+    // pressure sum at (j, i..i+4) and (j+1, i..i+3)
+    T P0[5], P1[4];
+    {
+      const Vec4<T> a = ld4(&s_p[r][cs]);
+      T ar = __shfl_down_sync(0xffffffffu, a.x, 1);
+      if (tx == TXG - 1) ar = s_p[r][cs + 4];
+      P0[0] = a.x; P0[1] = a.y; P0[2] = a.z; P0[3] = a.w; P0[4] = ar;
+      const Vec4<T> c4 = ld4(&s_p[r + 1][cs]);
+      P1[0] = c4.x; P1[1] = c4.y; P1[2] = c4.z; P1[3] = c4.w;
+    }
+    if (g >= ngroups) continue;
+    // window index helpers: row d (0..2 <-> dr = d-1), column w (0..5 <-> dc = w-1 from cell 0)
+    // ---- potential vorticity at X points: rows dr = -1 (w 1..4) and 0 (w 0..4) ----
+    T qm[6], q0[6];
+#pragma unroll
+    for (int w = 0; w < 5; ++w) {
+      q0[w] = T(0); qm[w] = T(0);
+      if (rin[1] && cin[w]) {
+        const T zeta = (V[1][w + 1] - V[1][w]) * idx_ - (U[2][w] - U[1][w]) * idy_;
+        const T hX = T(0.25) * (((H[1][w] + H[1][w + 1]) + H[2][w]) + H[2][w + 1]);
+        q0[w] = (zeta + fX[1]) / hX;
+      }
+      if (w >= 1 && rin[0] && cin[w]) {
+        const T zeta = (V[0][w + 1] - V[0][w]) * idx_ - (U[1][w] - U[0][w]) * idy_;
+        const T hX = T(0.25) * (((H[0][w] + H[0][w + 1]) + H[1][w]) + H[1][w + 1]);
+        qm[w] = (zeta + fX[0]) / hX;
+      }
+    }
+    // ---- mass fluxes: vh at rows -1,0 (w 1..5); uh at rows 0,1 (w 0..4) ----
+    T vhm[6], vh0[6], uh0[6], uh1[6];
+#pragma unroll
+    for (int w = 0; w < 6; ++w) {
+      vhm[w] = (rin[0] && cin[w]) ? (T(0.5) * (H[0][w] + H[1][w])) * V[0][w] : T(0);
+      vh0[w] = (rin[1] && cin[w]) ? (T(0.5) * (H[1][w] + H[2][w])) * V[1][w] : T(0);
+      if (w < 5) {
+        uh0[w] = (rin[1] && cin[w]) ? (T(0.5) * (H[1][w] + H[1][w + 1])) * U[1][w] : T(0);
+        uh1[w] = (rin[2] && cin[w]) ? (T(0.5) * (H[2][w] + H[2][w + 1])) * U[2][w] : T(0);
+      }
+    }
+    // ---- kinetic energy: row 0 (w 1..5), row +1 (w 1..4) ----
+    T ke0[6], ke1[6];
+#pragma unroll
+    for (int w = 1; w < 6; ++w) {
+      ke0[w] = T(0); ke1[w] = T(0);
+      if (rin[1] && cin[w]) {
+        const T u2 = T(0.5) * (U[1][w] * U[1][w] + U[1][w - 1] * U[1][w - 1]);
+        const T v2 = T(0.5) * (V[1][w] * V[1][w] + V[0][w] * V[0][w]);
+        ke0[w] = T(0.5) * (u2 + v2);
+      }
+      if (w < 5 && rin[2] && cin[w]) {
+        const T u2 = T(0.5) * (U[2][w] * U[2][w] + U[2][w - 1] * U[2][w - 1]);
+        const T v2 = T(0.5) * (V[2][w] * V[2][w] + V[1][w] * V[1][w]);
+        ke1[w] = T(0.5) * (u2 + v2);
+      }
+    }
+    // ---- upwind mass fluxes: fe at row 0 (w 0..4), fn at rows -1, 0 (w 1..4) ----
+    T fe[6], fnm[6], fn0[6];
+#pragma unroll
+    for (int w = 0; w < 5; ++w) {
+      fe[w] = T(0); fnm[w] = T(0); fn0[w] = T(0);
+      if (rin[1] && cin[w]) {
+        const T uu = U[1][w];
+        fe[w] = uu * (uu > T(0) ? H[1][w] : H[1][w + 1]);
+        const T vv = V[1][w];
+        fn0[w] = vv * (vv > T(0) ? H[1][w] : H[2][w]);
+      }
+      if (rin[0] && cin[w]) {
+        const T vv = V[0][w];
+        fnm[w] = vv * (vv > T(0) ? H[0][w] : H[1][w]);
+      }
+    }
+    T out_h[4], out_u[4], out_v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = i0 + e, w = e + 1;
+      T dh = 0, du = 0, dv = 0;
+      if (i >= 0 && i < Nx) {
+        const bool interior = rin[1] && cin[w];
+        if (interior) {
+          const T qU = T(0.5) * (q0[w] + qm[w]);
+          const T qV = T(0.5) * (q0[w] + q0[w - 1]);
+          const T vhU = T(0.25) * (((vh0[w] + vh0[w + 1]) + vhm[w]) + vhm[w + 1]);
+          const T uhV = T(0.25) * (((uh0[w] + uh1[w]) + uh0[w - 1]) + uh1[w - 1]);
+          const T P00 = ke0[w] + P0[e];
+          const T P01 = ke0[w + 1] + P0[e + 1];
+          const T P10 = ke1[w] + P1[e];
+          du = qU * vhU - (P01 - P00) * idx_;
+          dv = -qV * uhV - (P10 - P00) * idy_;
+          bool wr = true;
+          if (A.spec & SOMAX_B200_SPEC_ADVECTION_REGION2)
+            wr = (j >= 2 && j <= Ny - 3 && i >= 2 && i <= Nx - 3);
+          if (wr) dh = -((fe[w] - fe[w - 1]) * idx_ + (fn0[w] - fnm[w]) * idy_);
+        }
+        if (k == 0) { du = du + windx; dv = dv + windy; }
+        if (interior) {
+          T lu, lv;
+          if (A.spec & SOMAX_B200_SPEC_DIFFUSION_FLUX) {
+            auto fxf = [&](const T (&X)[3][6], int d, int ww) -> T {
+              return (rin[d] && cin[ww]) ? A.nu * ((X[d][ww + 1] - X[d][ww]) * idx_) : T(0); };
+            auto fyf = [&](const T (&X)[3][6], int d, int ww) -> T {
+              return (rin[d] && cin[ww]) ? A.nu * ((X[d + 1][ww] - X[d][ww]) * idy_) : T(0); };
+            lu = (fxf(U, 1, w) - fxf(U, 1, w - 1)) * idx_ + (fyf(U, 1, w) - fyf(U, 0, w)) * idy_;
+            lv = (fxf(V, 1, w) - fxf(V, 1, w - 1)) * idx_ + (fyf(V, 1, w) - fyf(V, 0, w)) * idy_;
+          } else {
+            lu = A.nu * ((U[1][w + 1] - T(2) * U[1][w] + U[1][w - 1]) * A.idx2 +
+                         (U[2][w] - T(2) * U[1][w] + U[0][w]) * A.idy2);
+            lv = A.nu * ((V[1][w + 1] - T(2) * V[1][w] + V[1][w - 1]) * A.idx2 +
+                         (V[2][w] - T(2) * V[1][w] + V[0][w]) * A.idy2);
+          }
+          du = du + lu; dv = dv + lv;
+        }
+        if (k == L.nl - 1) { du = du + (-A.kappa * U[1][w]); dv = dv + (-A.kappa * V[1][w]); }
+      }
+      out_h[e] = dh; out_u[e] = du; out_v[e] = dv;
+    }
+    const size_t idx = plane_off + (size_t)j * pitch + (size_t)g * 4;
+    rk_epilogue4_fast(st, FH, idx, Vec4<T>{out_h[0], out_h[1], out_h[2], out_h[3]});
+    rk_epilogue4_fast(st, FU, idx, Vec4<T>{out_u[0], out_u[1], out_u[2], out_u[3]});
+    rk_epilogue4_fast(st, FV, idx, Vec4<T>{out_v[0], out_v[1], out_v[2], out_v[3]});
+  }
+}
+
 // In-place apply_boundary_conditions on padded planes.
 template <typename T>
 __global__ void swm_bc_kernel(T* __restrict__ h, T* __restrict__ u, T* __restrict__ v, Layout L,
@@ -325,6 +551,8 @@ SwmArgs<T> make_args(somax_b200_swm_t h, const somax_b200_params* p, int apply_b
   SwmArgs<T> A;
   A.L = h->L; A.bc = h->bc; A.spec = h->spec; A.apply_bc = apply_bc;
   A.dx = (T)h->dx; A.dy = (T)h->dy; A.dx2 = (T)(h->dx * h->dx); A.dy2 = (T)(h->dy * h->dy);
+  A.idx = (T)(1.0 / h->dx); A.idy = (T)(1.0 / h->dy); A.idx2 = (T)(1.0 / (h->dx * h->dx));
+  A.idy2 = (T)(1.0 / (h->dy * h->dy)); A.iH0 = (T)(1.0 / p->H0);
   A.f = (const T*)h->f;   A.f_cp = h->f1d ? 1 : h->L.Nx;   A.f_xs = h->f1d ? 0 : 1;
   A.wx = (const T*)h->wx; A.wx_cp = h->wx1d ? 1 : h->L.Nx; A.wx_xs = h->wx1d ? 0 : 1;
   A.wy = (const T*)h->wy; A.wy_cp = h->wy1d ? 1 : h->L.Nx; A.wy_xs = h->wy1d ? 0 : 1;
@@ -335,12 +563,15 @@ SwmArgs<T> make_args(somax_b200_swm_t h, const somax_b200_params* p, int apply_b
 }
 
 template <typename T>
-int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A, const Stage<T>& st, cudaStream_t s) {
+int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A, const Stage<T>& st_in, cudaStream_t s) {
   const Layout& L = h->L;
+  Stage<T> st = st_in;
+  stage_finalize(st, (double)st.dt);
   dim3 block(TXG, TY);
   dim3 grid((L.groups() + TXG - 1) / TXG, (L.Ny + TY - 1) / TY, L.batch);
   prof_begin("swm_rhs_kernel", s);
-  swm_rhs_kernel<T><<<grid, block, 0, s>>>(A, st);
+  if (h->f1d && h->wx1d && h->wy1d) swm_rhs_kernel_fast<T><<<grid, block, 0, s>>>(A, st);
+  else swm_rhs_kernel<T><<<grid, block, 0, s>>>(A, st);
   SB_LAUNCH_CHECK();
   return 0;
 }

@@ -335,3 +335,21 @@ def test_golden_fixtures():
                        float(g["dt"]))
     for n in "huv":
         assert rel(getattr(sol.ys, n)[0], g[n + "1"]) <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_qg_two_dimensional_coefficient_fields(dtype):
+    """beta_y / wind arrays that vary in x take the general stencil kernel (the reference API
+    allows any (Ny, Nx) field; its factories only ever produce y-profiles)."""
+    import somax_b200 as sb
+    om, gm0 = qg_pair(32, 32, dtype)
+    rng = np.random.default_rng(11)
+    om.beta_y = om.beta_y * (1.0 + 0.1 * rng.standard_normal(om.beta_y.shape))
+    om.wind = om.wind * (1.0 + 0.1 * rng.standard_normal(om.wind.shape))
+    gm = sb.BaroclinicQG(gm0.params, gm0.consts, gm0.grid, gm0.modal, gm0.strat, om.beta_y, om.wind,
+                         gm0.helmholtz_lambdas, dtype=np.dtype(dtype).name)
+    q0 = qstate(3, 32, 32, dtype, ring=True)
+    dq = gm.build_terms().vf(0.0, sb.BaroclinicQGState(q=q0)).q
+    assert rel(dq, om.rhs(om.bc(q0.astype(np.float64)))) <= (2e-5 if dtype == np.float32 else 1e-11)
+    q1 = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, 6000.0, 600.0).ys.q[0]
+    assert rel(q1, om.integrate(q0.astype(np.float64), 0.0, 6000.0, 600.0)) <= TOL[dtype]

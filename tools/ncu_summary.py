@@ -1,0 +1,25 @@
+"""Summarise an .ncu-rep (ncu --set full) into a small CSV for profiles/: one row per launch."""
+import csv
+import subprocess
+import sys
+
+WANT = [
+    "Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
+    "launch__grid_size", "launch__block_size",
+]
+rep, out = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+idx = [hdr.index(w) for w in WANT if w in hdr]
+with open(out, "w", newline="") as f:
+    w = csv.writer(f)
+    w.writerow([f"{hdr[i]} [{units[i]}]" if units[i] else hdr[i] for i in idx])
+    for r in rows[2:]:
+        w.writerow([r[i] for i in idx])
+print("wrote", out, len(rows) - 2, "launches")
