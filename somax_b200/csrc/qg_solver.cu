@@ -20,6 +20,7 @@
 #include "qg_solver.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -42,129 +43,19 @@ struct QgSolver {
   double* ctab = nullptr; long long* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
   int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0; double* dbad = nullptr;
   double* bsig = nullptr; double* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
-  double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; double* meet = nullptr;
+  double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; double* meet = nullptr; double* meetc = nullptr;
   void* tw = nullptr; void* dstmat = nullptr;
   FftPlan plan;
   Mix l2m, m2l;
   size_t bytes = 0;
 };
 
-// ------------------------------------------------------------------------------------------
-// row kernels, FFT path
-// ------------------------------------------------------------------------------------------
-template <typename T>
-struct RowArgs {
-  Layout L;          // padded field layout
-  int ny, n, np, nl; // n = nx
-  int G, rows_per_block;
-  FftPlan plan;
-  T mix[QG_MAX_NL][QG_MAX_NL];
-  const C2<T>* tw;
-  T scale;
-};
-
-// forward: q (padded field) -> S[plane][j][0..n-2] = DST-I(n-1) of mode rows, S[..][n-1] = raw
-// border column of the mode.
-template <typename T>
-__global__ void rowdst_fwd_fft(RowArgs<T> A, const T* __restrict__ q, T* __restrict__ S) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = A.n, G = A.G;
-  const int lrow = threadIdx.x / G, lt = threadIdx.x - lrow * G;
-  const int plen = fft_padded_len(n);
-  C2<T>* s = reinterpret_cast<C2<T>*>(smem_raw) + (size_t)lrow * plen;
-  T* z = reinterpret_cast<T*>(s);
-  const int row = blockIdx.x * A.rows_per_block + lrow;   // (b, j) flattened
-  const bool valid = row < A.L.batch * A.ny;
-  const int b = valid ? row / A.ny : 0, j = valid ? row - b * A.ny : 0;
-  auto zi = [&](int t) { return 2 * fft_pad(t >> 1) + (t & 1); };
-
-  for (int m = 0; m < A.nl; ++m) {
-    if (valid) {
-      for (int p = lt; p < n; p += G) {           // p: interior index, x_{p+1}
-        T val = 0;
-        for (int l = 0; l < A.nl; ++l)
-          val += A.mix[m][l] *
-                 q[(((size_t)b * A.nl + l) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1 + p];
-        const int t = p + 1;
-        if (t < n) { z[zi(t)] = val; z[zi(2 * n - t)] = -val; }
-        else S[(((size_t)b * A.nl + m) * A.ny + j) * A.np + (n - 1)] = val;   // border column
-      }
-      if (lt == 0) { z[zi(0)] = 0; z[zi(n)] = 0; }
-    }
-    __syncthreads();
-    int lgLc = A.plan.lgn;
-    for (int ps = 0; ps < A.plan.npass; ++ps) {
-      const int lr = A.plan.lgr[ps];
-      if (valid) {
-        if (lr == 3) fft_dif_pass<T, 8>(s, A.plan.lgn, lgLc, lt, G, A.tw);
-        else if (lr == 2) fft_dif_pass<T, 4>(s, A.plan.lgn, lgLc, lt, G, A.tw);
-        else fft_dif_pass<T, 2>(s, A.plan.lgn, lgLc, lt, G, A.tw);
-      }
-      lgLc -= lr;
-      __syncthreads();
-    }
-    if (valid) {
-      T* out = S + (((size_t)b * A.nl + m) * A.ny + j) * A.np;
-      for (int k = lt + 1; k <= n / 2; k += G) {
-        T Xk, Xnk;
-        dst_split<T>(s, A.plan, k, A.tw, Xk, Xnk);
-        out[k - 1] = Xk;
-        if (k != n - k) out[n - k - 1] = Xnk;
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// inverse: layer rows = (2/n) DST-I(n-1)[ sum_m Cm2l[l][m] U_m ], border column from slot n-1.
-template <typename T>
-__global__ void rowdst_inv_fft(RowArgs<T> A, const T* __restrict__ S, T* __restrict__ psi) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = A.n, G = A.G;
-  const int lrow = threadIdx.x / G, lt = threadIdx.x - lrow * G;
-  const int plen = fft_padded_len(n);
-  C2<T>* s = reinterpret_cast<C2<T>*>(smem_raw) + (size_t)lrow * plen;
-  T* z = reinterpret_cast<T*>(s);
-  const int row = blockIdx.x * A.rows_per_block + lrow;
-  const bool valid = row < A.L.batch * A.ny;
-  const int b = valid ? row / A.ny : 0, j = valid ? row - b * A.ny : 0;
-  auto zi = [&](int t) { return 2 * fft_pad(t >> 1) + (t & 1); };
-
-  for (int l = 0; l < A.nl; ++l) {
-    T* out = psi + (((size_t)b * A.nl + l) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1;
-    if (valid) {
-      for (int p = lt; p < n; p += G) {           // p = k-1 for k = 1..n-1 ; p = n-1 border
-        T val = 0;
-        for (int m = 0; m < A.nl; ++m)
-          val += A.mix[l][m] * S[(((size_t)b * A.nl + m) * A.ny + j) * A.np + p];
-        const int t = p + 1;
-        if (t < n) { z[zi(t)] = val; z[zi(2 * n - t)] = -val; }
-        else out[n - 1] = val;                    // psi at the border column i = n
-      }
-      if (lt == 0) { z[zi(0)] = 0; z[zi(n)] = 0; }
-    }
-    __syncthreads();
-    int lgLc = A.plan.lgn;
-    for (int ps = 0; ps < A.plan.npass; ++ps) {
-      const int lr = A.plan.lgr[ps];
-      if (valid) {
-        if (lr == 3) fft_dif_pass<T, 8>(s, A.plan.lgn, lgLc, lt, G, A.tw);
-        else if (lr == 2) fft_dif_pass<T, 4>(s, A.plan.lgn, lgLc, lt, G, A.tw);
-        else fft_dif_pass<T, 2>(s, A.plan.lgn, lgLc, lt, G, A.tw);
-      }
-      lgLc -= lr;
-      __syncthreads();
-    }
-    if (valid) {
-      for (int k = lt + 1; k <= n / 2; k += G) {
-        T Xk, Xnk;
-        dst_split<T>(s, A.plan, k, A.tw, Xk, Xnk);
-        out[k - 1] = A.scale * Xk;
-        if (k != n - k) out[n - k - 1] = A.scale * Xnk;
-      }
-    }
-    __syncthreads();
-  }
+// Spectral arrays (S, W) are stored BLOCKED in 64-column strips so that the y-sweeps can move a
+// (rows x 64 columns) tile with a single bulk copy: within a plane, element (row j, column k)
+// lives at ((k / 64) * ny + j) * 64 + (k % 64); the plane stride is ny * np, np = roundup(nx, 64).
+constexpr int SP_W = 64;
+__host__ __device__ __forceinline__ size_t sp_off(int ny, int j, int k) {
+  return ((size_t)(k >> 6) * ny + j) * SP_W + (k & (SP_W - 1));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -218,17 +109,18 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
   const int b = valid ? row / A.ny : 0, j = valid ? row - b * A.ny : 0;
   auto zi = [&](int t) { return 2 * fft_pad(t >> 1) + (t & 1); };
   // source row of layer/mode c and destination row of mode/layer a
-  auto src = [&](int c) -> const T* {
-    return INV ? in + (((size_t)b * A.nl + c) * A.ny + j) * A.np
-               : in + (((size_t)b * A.nl + c) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1;
+  // element p of the source row of layer/mode c, and of the destination row of mode/layer a
+  // (field rows are contiguous; spectral rows are blocked in 64-column strips)
+  auto src = [&](int c, int p) -> const T* {
+    return INV ? in + ((size_t)b * A.nl + c) * A.ny * A.np + sp_off(A.ny, j, p)
+               : in + (((size_t)b * A.nl + c) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1 + p;
   };
-  auto dst = [&](int a) -> T* {
-    return INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1
-               : out + (((size_t)b * A.nl + a) * A.ny + j) * A.np;
+  auto dst = [&](int a, int p) -> T* {
+    return INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1 + p
+               : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, p);
   };
 
   for (int a = 0; a < A.nl; ++a) {
-    T* o = dst(a);
     if (valid) {
       if constexpr (EPT >= 4) {
         constexpr int NV = EPT / 4;
@@ -236,10 +128,9 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
 #pragma unroll
         for (int e = 0; e < NV; ++e) acc[e] = Vec4<T>{0, 0, 0, 0};
         for (int c = 0; c < A.nl; ++c) {
-          const T* sp = src(c);
           Vec4<T> v[NV];
 #pragma unroll
-          for (int e = 0; e < NV; ++e) v[e] = ld4(sp + 4 * (lt + e * G));
+          for (int e = 0; e < NV; ++e) v[e] = ld4(src(c, 4 * (lt + e * G)));
           const T mx = A.mix[a][c];
 #pragma unroll
           for (int e = 0; e < NV; ++e) {
@@ -254,7 +145,7 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (t + u < n) { z[zi(t + u)] = vals[u]; z[zi(2 * n - t - u)] = -vals[u]; }
-            else o[n - 1] = vals[u];              // border column (x index n)
+            else *dst(a, n - 1) = vals[u];        // border column (x index n)
           }
         }
       } else {
@@ -262,10 +153,10 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
         for (int e = 0; e < EPT; ++e) {
           const int p = lt + e * G;
           T val = 0;
-          for (int c = 0; c < A.nl; ++c) val += A.mix[a][c] * src(c)[p];
+          for (int c = 0; c < A.nl; ++c) val += A.mix[a][c] * *src(c, p);
           const int t = p + 1;
           if (t < n) { z[zi(t)] = val; z[zi(2 * n - t)] = -val; }
-          else o[n - 1] = val;
+          else *dst(a, n - 1) = val;
         }
       }
       if (lt == 0) { z[zi(0)] = 0; z[zi(n)] = 0; }
@@ -279,8 +170,8 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
         if (k <= n / 2) {
           T Xk, Xnk;
           dst_split_ct<T, LGN>(s, k, A.tw, Xk, Xnk);
-          o[k - 1] = INV ? A.scale * Xk : Xk;
-          if (k != n - k) o[n - k - 1] = INV ? A.scale * Xnk : Xnk;
+          *dst(a, k - 1) = INV ? A.scale * Xk : Xk;
+          if (k != n - k) *dst(a, n - k - 1) = INV ? A.scale * Xnk : Xnk;
         }
       }
     }
@@ -333,7 +224,7 @@ __global__ void rowdst_dense(Layout L, int ny, int n, int np, int nl, Mix mix,
     int a = e / n, i = e - a * n;
     double val = 0;
     for (int c = 0; c < nl; ++c) {
-      T src = INV ? in[(((size_t)b * nl + c) * ny + j) * np + i]
+      T src = INV ? in[((size_t)b * nl + c) * ny * np + sp_off(ny, j, i)]
                   : in[(((size_t)b * nl + c) * L.Ny + (j + 1)) * L.pitch + OFF + 1 + i];
       val += mix.c[a][c] * (double)src;
     }
@@ -350,7 +241,7 @@ __global__ void rowdst_dense(Layout L, int ny, int n, int np, int nl, Mix mix,
     }
     for (int a = 0; a < nl; ++a) {
       if (INV) out[(((size_t)b * nl + a) * L.Ny + (j + 1)) * L.pitch + OFF + 1 + k] = (T)(scale * acc[a]);
-      else out[(((size_t)b * nl + a) * ny + j) * np + k] = (T)(scale * acc[a]);
+      else out[((size_t)b * nl + a) * ny * np + sp_off(ny, j, k)] = (T)(scale * acc[a]);
     }
   }
 }
@@ -365,14 +256,16 @@ __global__ void rowdst_dense(Layout L, int ny, int n, int np, int nl, Mix mix,
 // are prefetched TH_NB batches ahead with cp.async into a per-thread shared-memory ring.
 // ------------------------------------------------------------------------------------------
 struct ThomasTab {
-  const double* ctab;        // per-column runs: column (m,c) at ctab[coloff[m*ncols+c] + j], j < J
-  const long long* coloff;
-  const int* J;
-  const double* cinf;
+  // Coefficient table blocked like the data: for (mode m, strip) the rows i = 0..Js-1 of the
+  // recurrence c_i for the strip's 64 columns, contiguous ([i][64] doubles).  Rows >= Js use cinf.
+  const double* ctabB; const long long* tabOff; const int* Jstrip;
+  const double* cinf;        // [m][np] fixed point per column
+  const double* meetc;       // [m][2][np]: c[m1-1] and c[ny-1-m1] per column (meeting-point solve)
   int kbad[QG_MAX_NL]; int KB; double* dbad;
-  double* meet;              // [plane][2][ncols]: last eliminated value of each half (fp64)
-  int ny, np, ncols, nl;
+  double* meet;              // [plane][2][np]: last eliminated value of each half (fp64)
+  int ny, np, ncols, nl, nstrip;
   double dy2;
+  int dbg;                   // SOMAX_B200_DEBUG bits (experiments only)
 };
 
 constexpr int TH_RB = 8;   // rows per batch
@@ -408,150 +301,226 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // warp of the per-column convergence row; ny if the warp holds an indefinite column) takes the
 // FAST path (constant coefficient, pointer increments); others take the GENERAL path whose
 // coefficient loads are software-pipelined one batch ahead.
+// ---- bulk-async (TMA engine) helpers: 1-D cp.async.bulk + mbarrier, no tensor map needed ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem, const void* smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+               ::"l"(gmem), "r"(smem_u32(smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+constexpr int TH_RT = 16;   // rows per staged tile (one contiguous TH_RT x 64 block of a strip)
+template <typename T, bool COMBINE> struct ThStages { static constexpr int v = 3; };
+
+// Recurrence over one staged tile for one column (thread).  UP: memory rows ascend with the
+// sequence (dj > 0).  MODE 0: full tile, constant coefficient; MODE 1: full tile, every row
+// tabulated (coefficients in Ct); MODE 2: generic (ragged end, tile straddling the convergence
+// row, indefinite columns with their fp64 side buffer).  Phases are explicit (all loads, the
+// carried chain, all stores) so the shared-memory accesses pipeline.
+template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE, bool UP, int MODE>
+__device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_COLS],
+                                            const double (*Ct)[TH_COLS], const double* __restrict__ gv,
+                                            double* __restrict__ dbc, int KB, int tid, int nr, int s0,
+                                            int ilo, int Js, int cnt, int jb, bool act, bool bad,
+                                            double cfix, double dy2, double bs, double& carry) {
+  constexpr int dj = UP ? 1 : -1;
+  double f[TH_RT], cj[TH_RT];
+  T vv[TH_RT];
+#pragma unroll
+  for (int r = 0; r < TH_RT; ++r) {
+    const bool ok = MODE != 2 || r < nr;
+    const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);   // memory row in the tile
+    const int i = SUBST ? cnt - 1 - (s0 + r) : s0 + r;                  // table index of the row
+    if (MODE == 0) cj[r] = cfix;
+    else if (MODE == 1) cj[r] = Ct[i - ilo][tid];
+    else cj[r] = (ok && i < Js) ? Ct[i - ilo][tid] : cfix;
+    if (FROM_VEC) f[r] = ok ? gv[jb + dj * r] : 0.0;
+    else f[r] = ok ? (double)A[ok ? rm : 0][tid] : 0.0;
+    if (COMBINE) vv[r] = ok ? Vt[ok ? rm : 0][tid] : T(0);
+    if (MODE == 2 && SUBST && bad && ok) f[r] = dbc[(size_t)(jb + dj * r) * KB];
+  }
+  if (!SUBST) {
+    if (MODE == 0) {
+      const double kf = cfix * dy2;
+#pragma unroll
+      for (int r = 0; r < TH_RT; ++r) f[r] = kf * f[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < TH_RT; ++r) f[r] = (cj[r] * dy2) * f[r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < TH_RT; ++r)
+    if (MODE != 2 || r < nr) { carry = fma(-cj[r], carry, f[r]); f[r] = carry; }
+#pragma unroll
+  for (int r = 0; r < TH_RT; ++r) {
+    if (MODE != 2 || r < nr) {
+      const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);
+      if (COMBINE) A[rm][tid] = act ? (T)((double)vv[r] - bs * f[r]) : vv[r];
+      else if (act) A[rm][tid] = (T)f[r];
+      else if (FROM_VEC) A[rm][tid] = T(0);
+      if (MODE == 2 && !SUBST && bad) dbc[(size_t)(jb + dj * r) * KB] = f[r];
+    }
+  }
+}
+
+// y-sweep over staged tiles.  Each CTA owns one 64-column strip of one plane and one half
+// (two-way elimination); it streams contiguous TH_RT-row tiles of the strip through an NS-stage
+// shared-memory ring: ONE cp.async.bulk per tile (TMA engine, completes on an mbarrier), the
+// recurrence runs on shared memory only, and the finished tile leaves with one bulk store.
+// Tiles that still need tabulated coefficients (rows below the strip's convergence row Js) get
+// their fp64 coefficient tile through the same ring, so they run at the same speed.
 template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE>
 __global__ void __launch_bounds__(TH_COLS)
 thomas_sweep(ThomasTab tb, const T* __restrict__ in, const T* __restrict__ V,
              const double* __restrict__ gvec, const double* __restrict__ bsig, T* __restrict__ out) {
-  constexpr int NB = ThNB<T>::v;
-  constexpr int DEPTH = NB * TH_RB;
-  constexpr bool RING = !FROM_VEC;
-  __shared__ T ring[RING ? DEPTH : 1][TH_COLS];
-  __shared__ T ringv[COMBINE ? DEPTH : 1][TH_COLS];
+  constexpr int NS = ThStages<T, COMBINE>::v;
+  constexpr bool LOAD = !FROM_VEC;
+  static_assert(TH_COLS == SP_W, "one CTA per 64-column strip");
+  constexpr size_t TILE_B = (size_t)TH_RT * TH_COLS * sizeof(T);
+  constexpr size_t CT_B = (size_t)TH_RT * TH_COLS * sizeof(double);
+  extern __shared__ __align__(128) unsigned char th_smem[];
+  double (*tileC)[TH_RT][TH_COLS] = reinterpret_cast<double (*)[TH_RT][TH_COLS]>(th_smem);
+  T (*tileA)[TH_RT][TH_COLS] = reinterpret_cast<T (*)[TH_RT][TH_COLS]>(th_smem + NS * CT_B);
+  T (*tileV)[TH_RT][TH_COLS] = reinterpret_cast<T (*)[TH_RT][TH_COLS]>(th_smem + NS * CT_B + NS * TILE_B);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(
+      th_smem + NS * CT_B + NS * TILE_B * (COMBINE ? 2 : 1));
   const int tid = threadIdx.x;
-  const int c = blockIdx.x * TH_COLS + tid;
+  const int strip = blockIdx.x;
+  const int c = strip * TH_COLS + tid;
   const int plane = blockIdx.y, m = plane % tb.nl;
   const int half = blockIdx.z;
   const bool act = c < tb.ncols;
-  const int cc = act ? c : 0;
   const int ny = tb.ny;
-  const long long np = tb.np;
-  const size_t base = (size_t)plane * ny * np + cc;
-  const double cfix = tb.cinf[m * tb.ncols + cc];
-  const int Jc = tb.J[m * tb.ncols + cc];
-  const double* ctc = tb.ctab + tb.coloff[m * tb.ncols + cc];
-  const bool bad = cc < tb.kbad[m];
-  double* dbc = tb.dbad + ((size_t)plane * ny) * tb.KB + cc;
-  const double bs = COMBINE ? bsig[cc] : 0.0;
-  const double kfix = cfix * tb.dy2;
-  const int Jw = __reduce_max_sync(0xffffffffu, bad ? ny : Jc);
+  const size_t strip0 = (size_t)plane * ny * tb.np + (size_t)strip * ny * SP_W;   // strip base
+  const double cfix = tb.cinf[(size_t)m * tb.np + c];
+  const int Js = tb.Jstrip[m * tb.nstrip + strip];
+  const double* tabS = tb.ctabB + tb.tabOff[m * tb.nstrip + strip];
+  const bool bad = act && c < tb.kbad[m];
+  double* dbc = tb.dbad + ((size_t)plane * ny) * tb.KB + (bad ? c : 0);
+  const double bs = (COMBINE && act) ? bsig[c] : 0.0;
+  const bool strip_bad = strip * TH_COLS < tb.kbad[m];     // this strip holds indefinite columns
   const double* gv = gvec + (FROM_VEC ? (size_t)plane * ny : 0);
-  // geometry of this thread's run: rows j(s) = j0 + dj*s, table index i(s), s = 0..cnt-1
   const int m1 = ny / 2;
   const int cnt = half == 0 ? m1 : ny - m1;
   int j0, dj;
   if (!SUBST) { j0 = half == 0 ? 0 : ny - 1; dj = half == 0 ? 1 : -1; }
   else        { j0 = half == 0 ? m1 - 1 : m1; dj = half == 0 ? -1 : 1; }
-  auto tix = [&](int s) { return SUBST ? cnt - 1 - s : s; };
-  auto coef = [&](int i) { return (i >= 0 && i < Jc) ? ctc[i] : cfix; };
-  const int nbatch = (cnt + TH_RB - 1) / TH_RB;
-
-  auto issue = [&](int b) {
-    if (b < nbatch) {
-#pragma unroll
-      for (int r = 0; r < TH_RB; ++r) {
-        const int s = b * TH_RB + r;
-        if (s < cnt) {
-          const int slot = (b % NB) * TH_RB + r;
-          const long long off = (long long)(j0 + dj * s) * np;
-          if (RING) cp_async_elem(&ring[slot][tid], in + base + off);
-          if (COMBINE) cp_async_elem(&ringv[slot][tid], V + base + off);
-        }
-      }
-    }
-    cp_async_commit();
+  const int ntile = (cnt + TH_RT - 1) / TH_RT;
+  // tile t covers sequence numbers s0..s0+nr-1, i.e. memory rows jlo..jlo+nr-1 (ascending), and
+  // table indices ilo..ilo+nr-1 (i = s for elimination, cnt-1-s for substitution)
+  auto tile_nr = [&](int t) { return min(TH_RT, cnt - t * TH_RT); };
+  auto tile_jlo = [&](int t) {
+    const int s0 = t * TH_RT, nr = min(TH_RT, cnt - s0);
+    return dj > 0 ? j0 + s0 : j0 - (s0 + nr - 1);
   };
-  if (RING)
-    for (int b = 0; b < NB; ++b) issue(b);
+  auto tile_ilo = [&](int t) {
+    const int s0 = t * TH_RT, nr = min(TH_RT, cnt - s0);
+    return SUBST ? cnt - 1 - (s0 + nr - 1) : s0;
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  auto load_tile = [&](int t) {       // executed by thread 0 only
+    if (t >= ntile) return;
+    const int st = t % NS;
+    const int nr = tile_nr(t), ilo = tile_ilo(t);
+    const int ncoef = max(0, min(ilo + nr, Js) - ilo);      // tabulated rows of this tile
+    const unsigned bytes = (unsigned)(nr * TH_COLS * sizeof(T));
+    const unsigned cbytes = (unsigned)(ncoef * TH_COLS * sizeof(double));
+    const unsigned total = (LOAD ? bytes * (COMBINE ? 2u : 1u) : 0u) + cbytes;
+    if (total == 0) return;
+    const size_t off = strip0 + (size_t)tile_jlo(t) * SP_W;
+    mbar_arrive_expect_tx(&full[st], total);
+    if (LOAD) bulk_g2s(&tileA[st][0][0], in + off, bytes, &full[st]);
+    if (COMBINE) bulk_g2s(&tileV[st][0][0], V + off, bytes, &full[st]);
+    if (cbytes) bulk_g2s(&tileC[st][0][0], tabS + (size_t)ilo * TH_COLS, cbytes, &full[st]);
+  };
+  auto tile_has_load = [&](int t) {
+    return LOAD || tile_ilo(t) < Js;
+  };
+  if (tid == 0)
+    for (int t = 0; t < NS - 1; ++t) load_tile(t);
 
   double carry = 0.0;
   if (SUBST && cnt > 0 && m1 > 0) {
     // meeting point: x_{m1-1} + ca x_{m1} = d_{m1-1};  x_{m1} + cb x_{m1-1} = e_{m1}
-    // (read from the fp64 side buffer: the rows themselves are being overwritten in place)
-    const double ca = coef(m1 - 1), cb = coef(ny - 1 - m1);
-    const double dm = tb.meet[((size_t)plane * 2 + 0) * tb.ncols + cc];
-    const double em = tb.meet[((size_t)plane * 2 + 1) * tb.ncols + cc];
+    const double ca = tb.meetc[((size_t)m * 2 + 0) * tb.np + c], cb = tb.meetc[((size_t)m * 2 + 1) * tb.np + c];
+    const double dm = tb.meet[((size_t)plane * 2 + 0) * tb.np + c];
+    const double em = tb.meet[((size_t)plane * 2 + 1) * tb.np + c];
     const double den = 1.0 / (1.0 - ca * cb);
     const double xa = (dm - ca * em) * den, xb = (em - cb * dm) * den;
     carry = half == 0 ? xb : xa;     // the neighbour's value across the meeting point
   }
 
-  auto general_fast = [&](int b) {
-    const int slo = b * TH_RB, shi = slo + TH_RB - 1;
-    const int imin = SUBST ? cnt - 1 - shi : slo;
-    return (imin >= Jw) && (shi < cnt);
-  };
-  double cjn[TH_RB];
-  auto prefetch = [&](int b) {
-    if (b < nbatch && !general_fast(b)) {
-#pragma unroll
-      for (int r = 0; r < TH_RB; ++r) cjn[r] = coef(tix(b * TH_RB + r));
-    }
-  };
-  prefetch(0);
-
+  unsigned phase_bits = 0;            // per-stage phase parity (stages may be skipped by FROM_VEC tiles)
 #pragma unroll 1
-  for (int b = 0; b < nbatch; ++b) {
-    if (RING) cp_async_wait<NB - 1>();
-    const int sbase = (b % NB) * TH_RB;
-    if (general_fast(b)) {
-      double f[TH_RB], vv[TH_RB];
-      const int jb = j0 + dj * (b * TH_RB);
-#pragma unroll
-      for (int r = 0; r < TH_RB; ++r) {
-        if (FROM_VEC) f[r] = gv[jb + dj * r];
-        else f[r] = (double)ring[sbase + r][tid];
-        if (COMBINE) vv[r] = (double)ringv[sbase + r][tid];
+  for (int t = 0; t < ntile; ++t) {
+    const int st = t % NS;
+    const int nr = tile_nr(t);
+    const int s0 = t * TH_RT;
+    const int ilo = tile_ilo(t);
+    if (tile_has_load(t)) {
+      mbar_wait(&full[st], (phase_bits >> st) & 1u);
+      phase_bits ^= 1u << st;
+    }
+    T (*A)[TH_COLS] = tileA[st];
+    T (*Vt)[TH_COLS] = tileV[st];
+    double (*Ct)[TH_COLS] = tileC[st];
+    const int jb = j0 + dj * s0;
+    // mode: 0 = constant coefficient, 1 = fully tabulated, 2 = generic
+    const int mode = (nr < TH_RT || strip_bad || (ilo < Js && ilo + nr > Js)) ? 2 : (ilo >= Js ? 0 : 1);
+    if (!(tb.dbg & 1)) {
+#define SB_TILE(UPV, MODEV)                                                                     \
+      thomas_tile<T, SUBST, FROM_VEC, COMBINE, UPV, MODEV>(A, Vt, Ct, gv, dbc, tb.KB, tid, nr, s0, ilo, \
+                                                           Js, cnt, jb, act, bad, cfix, tb.dy2, bs, carry)
+      if (dj > 0) {
+        if (mode == 0) SB_TILE(true, 0); else if (mode == 1) SB_TILE(true, 1); else SB_TILE(true, 2);
+      } else {
+        if (mode == 0) SB_TILE(false, 0); else if (mode == 1) SB_TILE(false, 1); else SB_TILE(false, 2);
       }
-      if (RING) issue(b + NB);
-      prefetch(b + 1);
-      T* op = out + base + (long long)jb * np;
-      const long long ostep = dj * np;
-#pragma unroll
-      for (int r = 0; r < TH_RB; ++r) {
-        if (!SUBST) carry = fma(-cfix, carry, kfix * f[r]);
-        else carry = fma(-cfix, carry, f[r]);
-        if (act) *op = COMBINE ? (T)(vv[r] - bs * carry) : (T)carry;
-        op += ostep;
-      }
-      if (!SUBST && act && b == nbatch - 1) tb.meet[((size_t)plane * 2 + half) * tb.ncols + cc] = carry;
-    } else {
-      double f[TH_RB], cj[TH_RB], vv[TH_RB];
-#pragma unroll
-      for (int r = 0; r < TH_RB; ++r) {
-        const int s = b * TH_RB + r;
-        const bool ok = s < cnt;
-        const int j = ok ? j0 + dj * s : 0;
-        cj[r] = cjn[r];
-        if (FROM_VEC) f[r] = ok ? gv[j] : 0.0;
-        else f[r] = ok ? (double)ring[sbase + r][tid] : 0.0;
-        if (COMBINE) vv[r] = ok ? (double)ringv[sbase + r][tid] : 0.0;
-        if (SUBST && bad && ok) f[r] = dbc[(size_t)j * tb.KB];
-      }
-      if (RING) issue(b + NB);
-      prefetch(b + 1);
-      if (!SUBST) {
-#pragma unroll
-        for (int r = 0; r < TH_RB; ++r) f[r] = cj[r] * (tb.dy2 * f[r]);   // off the carried chain
-      }
-#pragma unroll
-      for (int r = 0; r < TH_RB; ++r) {
-        const int s = b * TH_RB + r;
-        if (s < cnt) {
-          const int j = j0 + dj * s;
-          carry = fma(-cj[r], carry, f[r]);
-          if (act) {
-            if (!SUBST) {
-              out[base + (size_t)j * np] = (T)carry;
-              if (bad) dbc[(size_t)j * tb.KB] = carry;
-              if (s == cnt - 1) tb.meet[((size_t)plane * 2 + half) * tb.ncols + cc] = carry;
-            } else {
-              out[base + (size_t)j * np] = COMBINE ? (T)(vv[r] - bs * carry) : (T)carry;
-            }
-          }
-        }
-      }
+#undef SB_TILE
+    }
+    if (!SUBST && t == ntile - 1) tb.meet[((size_t)plane * 2 + half) * tb.np + c] = carry;
+    // finished tile -> global (the bulk store reads shared memory through the async proxy)
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      if (!(tb.dbg & 2))
+        bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &A[0][0], (unsigned)(nr * TH_COLS * sizeof(T)));
+      bulk_commit();
+      // stage (t-1)%NS is free once the store of tile t-1 has finished reading shared memory
+      bulk_wait_read<1>();
+      load_tile(t + NS - 1);
     }
   }
+  if (tid == 0) bulk_wait_read<0>();
 }
 
 // r[plane][j] = f_n[j] - b * sum_c sig2n[c] * V[plane][j][c]: right-hand side of the border
@@ -560,9 +529,9 @@ template <typename T>
 __global__ void border_dot(const T* __restrict__ V, const double* __restrict__ sig2n, int ny,
                            int np, int ncols, double b, double* __restrict__ r) {
   const int j = blockIdx.x, plane = blockIdx.y;
-  const T* row = V + ((size_t)plane * ny + j) * np;
+  const T* pl = V + (size_t)plane * ny * np;
   double acc = 0;
-  for (int c = threadIdx.x; c < ncols; c += blockDim.x) acc += sig2n[c] * (double)row[c];
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) acc += sig2n[c] * (double)pl[sp_off(ny, j, c)];
   __shared__ double red[32];
   for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -570,7 +539,7 @@ __global__ void border_dot(const T* __restrict__ V, const double* __restrict__ s
   if (threadIdx.x == 0) {
     double t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    r[(size_t)plane * ny + j] = (double)row[ncols] - b * t;
+    r[(size_t)plane * ny + j] = (double)pl[sp_off(ny, j, ncols)] - b * t;
   }
 }
 
@@ -621,7 +590,7 @@ __global__ void border_gsolve_b(const double* __restrict__ ghat, const double* _
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     t *= 2.0 / (ny + 1);
     gvec[(size_t)plane * ny + (j - 1)] = t;
-    S[((size_t)plane * ny + (j - 1)) * np + (n - 1)] = (T)t;
+    S[(size_t)plane * ny * np + sp_off(ny, j - 1, n - 1)] = (T)t;
   }
 }
 
@@ -636,51 +605,77 @@ static int dev_upload(const void* src, size_t bytes, void** dst, size_t* total) 
 }
 
 static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
-  const int nl = s->nl, ny = s->ny, nc = s->ncols;
-  std::vector<double> cinf((size_t)nl * nc), ctab;
-  std::vector<int> J((size_t)nl * nc);
-  std::vector<long long> coloff((size_t)nl * nc);
+  const int nl = s->nl, ny = s->ny, nc = s->ncols, np = s->np, nstrip = np / SP_W;
+  const int hcap = ny - ny / 2;                 // longest run of one half (table indices 0..hcap-1)
+  const int m1 = ny / 2;
+  std::vector<double> cinf((size_t)nl * np, 0.0), meetc((size_t)nl * 2 * np, 0.0), ctab;
+  std::vector<int> Jstrip((size_t)nl * nstrip, 0);
+  std::vector<long long> tabOff((size_t)nl * nstrip, 0);
   const double dy2 = s->dy * s->dy;
   s->KB = 0;
   for (int m = 0; m < nl; ++m) {
     s->kbad[m] = 0;
+    std::vector<double> delta(np, -4.0);
+    std::vector<int> J(np, 0);
     for (int c = 0; c < nc; ++c) {
       const double sn = sin(M_PI * (c + 1) / (2.0 * Nx_eig));
       const double lam_x = -(4.0 / (s->dx * s->dx)) * sn * sn;
       const double eps = (lambdas[m] - lam_x) * dy2;      // |delta| - 2 when the column is definite
-      const double delta = -2.0 - eps;
-      const bool definite = eps > 0.0;
-      double cstar = 0.0;
-      int jconv = ny;
-      if (definite) {
+      delta[c] = -2.0 - eps;
+      int jconv = hcap;
+      if (eps > 0.0) {
         // attracting fixed point c* = 2 / (delta - sqrt(delta^2 - 4)), no cancellation; the
         // recurrence approaches it like exp(-2 j theta), theta = acosh(1 + eps/2)
         const double sq = sqrt(eps * (4.0 + eps));
-        cstar = 2.0 / (delta - sq);
+        cinf[(size_t)m * np + c] = 2.0 / (delta[c] - sq);
         const double theta = log1p(0.5 * eps + 0.5 * sq);
         const double jr = log((1.0 - exp(-2.0 * theta)) / 1e-17) / (2.0 * theta) + 2.0;
-        if (jr < (double)ny) jconv = (int)ceil(jr);
+        if (jr < (double)hcap) jconv = (int)ceil(jr);
       } else {
         s->kbad[m] = std::max(s->kbad[m], c + 1);   // indefinite (oscillatory) column
       }
-      cinf[(size_t)m * nc + c] = cstar;
-      coloff[(size_t)m * nc + c] = (long long)ctab.size();
-      double cj = 0.0;
-      for (int j = 1; j <= jconv; ++j) {
-        cj = 1.0 / (delta - cj);
-        ctab.push_back(cj);
+      J[c] = jconv;
+      // coefficients used by the meeting-point solve
+      double cj = 0.0, ca = 0.0, cb = 0.0;
+      const int ia = m1 - 1, ib = ny - 1 - m1, imax = std::max(ia, ib);
+      for (int i = 0; i <= imax && i < jconv; ++i) {
+        cj = 1.0 / (delta[c] - cj);
+        if (i == ia) ca = cj;
+        if (i == ib) cb = cj;
       }
-      J[(size_t)m * nc + c] = jconv;
+      if (ia >= jconv) ca = cinf[(size_t)m * np + c];
+      if (ib >= jconv) cb = cinf[(size_t)m * np + c];
+      meetc[((size_t)m * 2 + 0) * np + c] = ca;
+      meetc[((size_t)m * 2 + 1) * np + c] = cb;
     }
     s->KB = std::max(s->KB, s->kbad[m]);
+    for (int st = 0; st < nstrip; ++st) {
+      int Js = 0;
+      for (int cl = 0; cl < SP_W; ++cl) Js = std::max(Js, J[st * SP_W + cl]);
+      Jstrip[(size_t)m * nstrip + st] = Js;
+      tabOff[(size_t)m * nstrip + st] = (long long)ctab.size();
+      const size_t o = ctab.size();
+      ctab.resize(o + (size_t)Js * SP_W, 0.0);
+      for (int cl = 0; cl < SP_W; ++cl) {
+        const int c = st * SP_W + cl;
+        if (c >= nc) continue;
+        double cj = 0.0;
+        for (int i = 0; i < Js; ++i) {
+          // beyond the column's own convergence row keep the exact fixed point
+          cj = (i < J[c]) ? 1.0 / (delta[c] - cj) : cinf[(size_t)m * np + c];
+          ctab[o + (size_t)i * SP_W + cl] = cj;
+        }
+      }
+    }
   }
   if (ctab.empty()) ctab.push_back(0.0);
   if (int rc = dev_upload(ctab.data(), ctab.size() * 8, (void**)&s->ctab, &s->bytes)) return rc;
-  if (int rc = dev_upload(J.data(), J.size() * 4, (void**)&s->krow, &s->bytes)) return rc;
-  if (int rc = dev_upload(coloff.data(), coloff.size() * 8, (void**)&s->coff, &s->bytes)) return rc;
+  if (int rc = dev_upload(Jstrip.data(), Jstrip.size() * 4, (void**)&s->krow, &s->bytes)) return rc;
+  if (int rc = dev_upload(tabOff.data(), tabOff.size() * 8, (void**)&s->coff, &s->bytes)) return rc;
   if (int rc = dev_upload(cinf.data(), cinf.size() * 8, (void**)&s->cinf, &s->bytes)) return rc;
+  if (int rc = dev_upload(meetc.data(), meetc.size() * 8, (void**)&s->meetc, &s->bytes)) return rc;
   {
-    size_t mb = (size_t)s->planes * 2 * nc * 8;
+    size_t mb = (size_t)s->planes * 2 * np * 8;
     SB_CUDA(cudaMalloc((void**)&s->meet, mb));
     SB_CUDA(cudaMemset(s->meet, 0, mb));
     s->bytes += mb;
@@ -767,7 +762,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
   auto* s = new QgSolver();
   s->dtype = dtype; s->batch = batch; s->nl = nl; s->ny = ny; s->nx = nx; s->kind = kind;
   s->dx = dx; s->dy = dy; s->L = make_layout(batch, nl, ny, nx);
-  s->np = ((nx + 3) / 4) * 4; s->planes = batch * nl;
+  s->np = ((nx + SP_W - 1) / SP_W) * SP_W; s->planes = batch * nl;
   s->ncols = (kind == SOMAX_B200_SOLVER_FFT) ? nx - 1 : nx;
   for (int a = 0; a < QG_MAX_NL; ++a)
     for (int c = 0; c < QG_MAX_NL; ++c) {
@@ -808,7 +803,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
 void qg_solver_destroy(QgSolver* s) {
   if (!s) return;
   void* ptrs[] = {s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->bsig, s->sig2n,
-                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->tw, s->dstmat, s->meet};
+                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->tw, s->dstmat, s->meet, s->meetc};
   for (void* p : ptrs) cudaFree(p);
   delete s;
 }
@@ -816,34 +811,34 @@ void qg_solver_destroy(QgSolver* s) {
 size_t qg_solver_bytes(const QgSolver* s) { return s ? s->bytes : 0; }
 int qg_solver_kind(const QgSolver* s) { return s->kind; }
 
-template <typename T>
-static RowArgs<T> make_row_args(QgSolver* s, const Mix& mix, double scale) {
-  RowArgs<T> A;
-  A.L = s->L; A.ny = s->ny; A.n = s->nx; A.np = s->np; A.nl = s->nl; A.plan = s->plan;
-  const int n = s->nx;
-  int ept = n >= 8192 ? 16 : (n >= 256 ? 8 : (n >= 128 ? 4 : 2));
-  A.G = n / ept;
-  int threads = std::max(A.G, 128);
-  A.rows_per_block = threads / A.G;
-  // keep shared memory of one block within the opt-in limit
-  const size_t row_bytes = (size_t)fft_padded_len(n) * sizeof(C2<T>);
-  while (A.rows_per_block > 1 && row_bytes * A.rows_per_block > 96 * 1024) A.rows_per_block /= 2;
-  for (int a = 0; a < QG_MAX_NL; ++a)
-    for (int c = 0; c < QG_MAX_NL; ++c) A.mix[a][c] = (T)mix.c[a][c];
-  A.tw = (const C2<T>*)s->tw;
-  A.scale = (T)scale;
-  return A;
+template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE>
+static int launch_thomas(const char* tag, const ThomasTab& tb, dim3 grid, const T* in, const T* V,
+                         const double* gvec, const double* bsig, T* out, cudaStream_t st) {
+  constexpr int NS = ThStages<T, COMBINE>::v;
+  constexpr size_t smem = (size_t)NS * TH_RT * TH_COLS * (sizeof(double) + sizeof(T) * (COMBINE ? 2 : 1)) + NS * 8;
+  static bool attr_done = false;
+  if (smem > 48 * 1024 && !attr_done) {
+    SB_CUDA(cudaFuncSetAttribute(thomas_sweep<T, SUBST, FROM_VEC, COMBINE>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  prof_begin(tag, st);
+  thomas_sweep<T, SUBST, FROM_VEC, COMBINE><<<grid, TH_COLS, smem, st>>>(tb, in, V, gvec, bsig, out);
+  SB_LAUNCH_CHECK();
+  return 0;
 }
 
 template <typename T>
 int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
   const int ny = s->ny, n = s->nx, np = s->np, nl = s->nl;
   ThomasTab tb;
-  tb.ctab = s->ctab; tb.coloff = s->coff; tb.J = s->krow; tb.cinf = s->cinf;
+  tb.ctabB = s->ctab; tb.tabOff = s->coff; tb.Jstrip = s->krow; tb.cinf = s->cinf; tb.meetc = s->meetc;
+  tb.nstrip = s->np / SP_W;
   for (int m = 0; m < QG_MAX_NL; ++m) tb.kbad[m] = s->kbad[m];
   tb.KB = std::max(s->KB, 1); tb.dbad = s->dbad; tb.meet = s->meet; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
   tb.dy2 = s->dy * s->dy;
-  dim3 tgrid((s->ncols + TH_COLS - 1) / TH_COLS, s->planes, 2);
+  { const char* e = getenv("SOMAX_B200_DEBUG"); tb.dbg = e ? atoi(e) : 0; }
+  dim3 tgrid(s->np / SP_W, s->planes, 2);
   T* S = (T*)s->S;
   if (s->kind == SOMAX_B200_SOLVER_FFT) {
     T* W = (T*)s->W;
@@ -854,12 +849,8 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     for (int a = 0; a < QG_MAX_NL; ++a)
       for (int c = 0; c < QG_MAX_NL; ++c) { Af.mix[a][c] = (T)s->l2m.c[a][c]; Ai.mix[a][c] = (T)s->m2l.c[a][c]; }
     if (int rc = launch_rowdst<T, false>(s->plan.lgn, Af, q, S, st)) return rc;
-    prof_begin("thomas_fwd_0", st);
-    thomas_sweep<T, false, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
-    SB_LAUNCH_CHECK();
-    prof_begin("thomas_bwd_0", st);
-    thomas_sweep<T, true, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
-    SB_LAUNCH_CHECK();
+    if (int rc = launch_thomas<T, false, false, false>("thomas_fwd_0", tb, tgrid, S, nullptr, nullptr, nullptr, S, st)) return rc;
+    if (int rc = launch_thomas<T, true, false, false>("thomas_bwd_0", tb, tgrid, S, nullptr, nullptr, nullptr, S, st)) return rc;
     const double b = 1.0 / (s->dx * s->dx);
     prof_begin("border_dot", st);
     border_dot<T><<<dim3(ny, s->planes), 256, 0, st>>>(S, s->sig2n, ny, np, s->ncols, b, s->rvec);
@@ -870,12 +861,8 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     prof_begin("border_gsolve_b", st);
     border_gsolve_b<T><<<dim3(ny, s->planes), 128, 0, st>>>(s->ghat, s->sintab, ny, np, n, s->gvec, S);
     SB_LAUNCH_CHECK();
-    prof_begin("thomas_fwd_1", st);
-    thomas_sweep<T, false, true, false><<<tgrid, TH_COLS, 0, st>>>(tb, nullptr, nullptr, s->gvec, nullptr, W);
-    SB_LAUNCH_CHECK();
-    prof_begin("thomas_bwd_1", st);
-    thomas_sweep<T, true, false, true><<<tgrid, TH_COLS, 0, st>>>(tb, W, S, nullptr, s->bsig, S);
-    SB_LAUNCH_CHECK();
+    if (int rc = launch_thomas<T, false, true, false>("thomas_fwd_1", tb, tgrid, nullptr, nullptr, s->gvec, nullptr, W, st)) return rc;
+    if (int rc = launch_thomas<T, true, false, true>("thomas_bwd_1", tb, tgrid, W, S, nullptr, s->bsig, S, st)) return rc;
     if (int rc = launch_rowdst<T, true>(s->plan.lgn, Ai, S, psi, st)) return rc;
   } else {
     const size_t smem = (size_t)nl * n * sizeof(T);
@@ -887,12 +874,8 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     prof_begin("rowdst_dense_0", st);
     rowdst_dense<T, false><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->l2m, (const T*)s->dstmat, q, S, 1.0);
     SB_LAUNCH_CHECK();
-    prof_begin("thomas_fwd_0", st);
-    thomas_sweep<T, false, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
-    SB_LAUNCH_CHECK();
-    prof_begin("thomas_bwd_0", st);
-    thomas_sweep<T, true, false, false><<<tgrid, TH_COLS, 0, st>>>(tb, S, nullptr, nullptr, nullptr, S);
-    SB_LAUNCH_CHECK();
+    if (int rc = launch_thomas<T, false, false, false>("thomas_fwd_0", tb, tgrid, S, nullptr, nullptr, nullptr, S, st)) return rc;
+    if (int rc = launch_thomas<T, true, false, false>("thomas_bwd_0", tb, tgrid, S, nullptr, nullptr, nullptr, S, st)) return rc;
     prof_begin("rowdst_dense_1", st);
     rowdst_dense<T, true><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->m2l, (const T*)s->dstmat, S, psi, 2.0 / (n + 1));
     SB_LAUNCH_CHECK();
