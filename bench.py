@@ -32,13 +32,15 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name: (kind, nl, nx, ny)
-    "qg3_8192": ("qg", 3, 8192, 8192),
-    "qg3_4096": ("qg", 3, 4096, 4096),
-    "qg3_1024": ("qg", 3, 1024, 1024),
-    "qg3_128": ("qg", 3, 128, 128),
-    "swm2_4096": ("swm", 2, 4096, 4096),
-    "swm2_1024": ("swm", 2, 1024, 1024),
+    # name: (kind, nl, nx, ny, ensemble members)
+    "qg3_8192": ("qg", 3, 8192, 8192, 1),        # the headline: BASELINE target configuration
+    "qg3_4096": ("qg", 3, 4096, 4096, 1),
+    "qg3_1024": ("qg", 3, 1024, 1024, 1),
+    "qg3_128": ("qg", 3, 128, 128, 1),           # BASELINE config 2 (launch-latency bound)
+    "qg3_256_ens1024": ("qg", 3, 256, 256, 1024),  # BASELINE config 5: 1024 members x 3 x 256^2
+    "swm2_4096": ("swm", 2, 4096, 4096, 1),      # BASELINE config 3 at its largest size
+    "swm2_1024": ("swm", 2, 1024, 1024, 1),
+    "swm2_64": ("swm", 2, 64, 64, 1),
 }
 QG_PARAMS = dict(Lx=4e6, Ly=4e6, f0=9.375e-5, beta=1.754e-11, n_layers=3,
                  H=(400.0, 1100.0, 2600.0), g_prime=(9.81, 0.025, 0.0125), lateral_viscosity=15.0,
@@ -130,7 +132,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    kind, nl, nx, ny = WORKLOADS[args.workload]
+    kind, nl, nx, ny, _members = WORKLOADS[args.workload]
     sn = min(nx, 1024)   # bounded sample: same model and parameters on a 1024^2 grid
     cores = os.cpu_count()
     K, W = max(1, min(args.steps, 8)), min(args.warmup, 1)
@@ -149,12 +151,18 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def build_gpu_model(kind, nl, nx, ny):
+def build_gpu_model(kind, nl, nx, ny, members=range(1)):
+    """Model + initial state; for ensembles the state gets a leading member axis and member e
+    uses seed 10_000 + e."""
     import somax_b200 as sb
     from somax_b200 import gfd_testcases as g
+    members = list(members)
     if kind == "qg":
         model = sb.BaroclinicQG.create(nx=nx, ny=ny, **QG_PARAMS)
-        q0 = g.synthetic_qg_state(nl, nx, ny, dtype="float32")
+        if len(members) == 1 and members[0] == 0:
+            q0 = g.synthetic_qg_state(nl, nx, ny, dtype="float32")
+        else:
+            q0 = np.stack([g.synthetic_qg_state(nl, nx, ny, seed=10_000 + e, dtype="float32") for e in members])
         return model, sb.BaroclinicQGState(q=q0), qg_dt(nx)
     model, st = g.baroclinic_instability_swm(nx=nx, ny=ny, **SWM_PARAMS)
     return model, st, swm_dt(nx)
@@ -172,15 +180,18 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    kind, nl, nx, ny = WORKLOADS[args.workload]
+    kind, nl, nx, ny, members = WORKLOADS[args.workload]
     K, W = args.steps, max(args.warmup, 3)
     lib = _lib.lib()
-
-    model, st0, dt = build_gpu_model(kind, nl, nx, ny)
+    from somax_b200.parallel import shard_members
+    # ensembles: strong scaling over a fixed member set; single grids: one member per rank (weak)
+    mine = shard_members(members, rank, world) if members > 1 else range(1)
+    nb = len(mine)
+    model, st0, dt = build_gpu_model(kind, nl, nx, ny, mine)
     fields = [f for f in ("q", "h", "u", "v") if hasattr(st0, f)]
     dev = {f: torch.as_tensor(getattr(st0, f)).cuda() for f in fields}
     state_bytes = sum(t.numel() * t.element_size() for t in dev.values())
-    handle = model._engine.handle(1) if kind == "qg" else model._handle(1)
+    handle = model._engine.handle(nb) if kind == "qg" else model._handle(nb)
     p = (sb.models.qg._params_struct(model.params, model._H0) if kind == "qg" else model._pstruct())
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -223,8 +234,8 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
-    cells = nl * nx * ny
-    value = world * cells * K / (ms_max * 1e-3) / 1e9
+    cells = nl * nx * ny * (members if members > 1 else world)   # whole job
+    value = cells * K / (ms_max * 1e-3) / 1e9
 
     # ---- e2e: public API, host numpy state in -> host numpy state out (pinned staging) ----
     host_state = type(st0)(**{f: np.ascontiguousarray(getattr(st0, f)) for f in fields})
@@ -238,7 +249,7 @@ def run_gpu(args):
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * cells * K / float(t_e.item()) / 1e9
+    e2e_value = cells * K / float(t_e.item()) / 1e9
     io = model.last_io
 
     if rank != 0:
@@ -255,7 +266,7 @@ def run_gpu(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     w = 4
-    padded = nl * (ny + 2) * (nx + 2) * w          # one state-sized array (one field)
+    padded = nb * nl * (ny + 2) * (nx + 2) * w     # one state-sized array (one field) on this rank
     prof.sort(key=lambda r: -r["total_ms"])
     total_prof = sum(r["total_ms"] for r in prof) or 1.0
     top = prof[0]
@@ -263,7 +274,7 @@ def run_gpu(args):
     per_launch_ms = top["total_ms"] / top["launches"]
     achieved = k_tr * padded / (per_launch_ms * 1e-3) / 1e9
     step_alg_bytes = TRANSFERS[kind] * padded
-    step_frac = step_alg_bytes / (ms_max / K * 1e-3) / 1e9 / peak
+    step_frac = step_alg_bytes / (ms_max / K * 1e-3) / 1e9 / peak      # per GPU
     roofline = {
         "bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -287,11 +298,12 @@ def run_gpu(args):
     line = {
         "metric": "cell_updates_per_s", "value": value, "unit": "Gcell-steps/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": f"{nl}-layer {kind}", "grid": [ny, nx],
+        "scaling": "strong" if members > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model": f"{nl}-layer {kind}", "grid": [ny, nx], "members": members,
                    "dt": dt, "l2": "working set (>= 7 GB) far larger than the 126 MB L2; no flush needed"
                    if state_bytes > 5e8 else "small working set: L2 resident by nature of the workload",
-                   "parallelism": "1 member per GPU (ensemble sharded by member)" if world > 1 else "single GPU",
+                   "parallelism": (f"{members} members sharded by member over {world} GPU(s)" if members > 1 else
+                                   ("1 member per GPU (ensemble sharded by member)" if world > 1 else "single GPU")),
                    "solver": "fft+bordered+thomas" if kind == "qg" else "n/a",
                    "device_bytes": int(lib.somax_b200_qg_device_bytes(handle) if kind == "qg"
                                        else lib.somax_b200_swm_device_bytes(handle))},

@@ -47,6 +47,9 @@ struct QgSolver {
   void* tw = nullptr; void* dstmat = nullptr;
   FftPlan plan;
   Mix l2m, m2l;
+  int nheavy = 0;
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t bytes = 0;
 };
 
@@ -332,7 +335,11 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 constexpr int TH_RT = 16;   // rows per staged tile (one contiguous TH_RT x 64 block of a strip)
-template <typename T, bool COMBINE> struct ThStages { static constexpr int v = 3; };
+// ring depth: light CTAs stage data only (deep ring); heavy CTAs (strips whose coefficient
+// recurrence converges late) also stage fp64 coefficient tiles
+template <typename T, bool COMBINE, bool TAB> struct ThStages {
+  static constexpr int v = sizeof(T) == 4 ? (COMBINE ? 6 : 8) : (COMBINE ? 3 : (TAB ? 4 : 6));
+};
 
 // Recurrence over one staged tile for one column (thread).  UP: memory rows ascend with the
 // sequence (dj > 0).  MODE 0: full tile, constant coefficient; MODE 1: full tile, every row
@@ -392,15 +399,15 @@ __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_CO
 // recurrence runs on shared memory only, and the finished tile leaves with one bulk store.
 // Tiles that still need tabulated coefficients (rows below the strip's convergence row Js) get
 // their fp64 coefficient tile through the same ring, so they run at the same speed.
-template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE>
+template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE, bool TAB>
 __global__ void __launch_bounds__(TH_COLS)
-thomas_sweep(ThomasTab tb, const T* __restrict__ in, const T* __restrict__ V,
+thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* __restrict__ V,
              const double* __restrict__ gvec, const double* __restrict__ bsig, T* __restrict__ out) {
-  constexpr int NS = ThStages<T, COMBINE>::v;
+  constexpr int NS = ThStages<T, COMBINE, TAB>::v;
   constexpr bool LOAD = !FROM_VEC;
   static_assert(TH_COLS == SP_W, "one CTA per 64-column strip");
   constexpr size_t TILE_B = (size_t)TH_RT * TH_COLS * sizeof(T);
-  constexpr size_t CT_B = (size_t)TH_RT * TH_COLS * sizeof(double);
+  constexpr size_t CT_B = TAB ? (size_t)TH_RT * TH_COLS * sizeof(double) : 0;
   extern __shared__ __align__(128) unsigned char th_smem[];
   double (*tileC)[TH_RT][TH_COLS] = reinterpret_cast<double (*)[TH_RT][TH_COLS]>(th_smem);
   T (*tileA)[TH_RT][TH_COLS] = reinterpret_cast<T (*)[TH_RT][TH_COLS]>(th_smem + NS * CT_B);
@@ -408,7 +415,7 @@ thomas_sweep(ThomasTab tb, const T* __restrict__ in, const T* __restrict__ V,
   unsigned long long* full = reinterpret_cast<unsigned long long*>(
       th_smem + NS * CT_B + NS * TILE_B * (COMBINE ? 2 : 1));
   const int tid = threadIdx.x;
-  const int strip = blockIdx.x;
+  const int strip = strip_first + blockIdx.x;
   const int c = strip * TH_COLS + tid;
   const int plane = blockIdx.y, m = plane % tb.nl;
   const int half = blockIdx.z;
@@ -451,7 +458,7 @@ thomas_sweep(ThomasTab tb, const T* __restrict__ in, const T* __restrict__ V,
     if (t >= ntile) return;
     const int st = t % NS;
     const int nr = tile_nr(t), ilo = tile_ilo(t);
-    const int ncoef = max(0, min(ilo + nr, Js) - ilo);      // tabulated rows of this tile
+    const int ncoef = TAB ? max(0, min(ilo + nr, Js) - ilo) : 0;      // tabulated rows of this tile
     const unsigned bytes = (unsigned)(nr * TH_COLS * sizeof(T));
     const unsigned cbytes = (unsigned)(ncoef * TH_COLS * sizeof(double));
     const unsigned total = (LOAD ? bytes * (COMBINE ? 2u : 1u) : 0u) + cbytes;
@@ -463,7 +470,7 @@ thomas_sweep(ThomasTab tb, const T* __restrict__ in, const T* __restrict__ V,
     if (cbytes) bulk_g2s(&tileC[st][0][0], tabS + (size_t)ilo * TH_COLS, cbytes, &full[st]);
   };
   auto tile_has_load = [&](int t) {
-    return LOAD || tile_ilo(t) < Js;
+    return LOAD || (TAB && tile_ilo(t) < Js);
   };
   if (tid == 0)
     for (int t = 0; t < NS - 1; ++t) load_tile(t);
@@ -492,7 +499,9 @@ thomas_sweep(ThomasTab tb, const T* __restrict__ in, const T* __restrict__ V,
     }
     T (*A)[TH_COLS] = tileA[st];
     T (*Vt)[TH_COLS] = tileV[st];
-    double (*Ct)[TH_COLS] = tileC[st];
+    // coefficient rows of this tile: staged in shared memory (TAB) or read straight from L2
+    const double (*Ct)[TH_COLS] = TAB ? (const double (*)[TH_COLS])tileC[st]
+                                      : (const double (*)[TH_COLS])(tabS + (size_t)ilo * TH_COLS);
     const int jb = j0 + dj * s0;
     // mode: 0 = constant coefficient, 1 = fully tabulated, 2 = generic
     const int mode = (nr < TH_RT || strip_bad || (ilo < Js && ilo + nr > Js)) ? 2 : (ilo >= Js ? 0 : 1);
@@ -509,14 +518,14 @@ thomas_sweep(ThomasTab tb, const T* __restrict__ in, const T* __restrict__ V,
     }
     if (!SUBST && t == ntile - 1) tb.meet[((size_t)plane * 2 + half) * tb.np + c] = carry;
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
-    fence_async_smem();
-    __syncthreads();
+    if (!(tb.dbg & 4)) fence_async_smem();
+    if (!(tb.dbg & 16)) __syncthreads();
     if (tid == 0) {
       if (!(tb.dbg & 2))
         bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &A[0][0], (unsigned)(nr * TH_COLS * sizeof(T)));
       bulk_commit();
       // stage (t-1)%NS is free once the store of tile t-1 has finished reading shared memory
-      bulk_wait_read<1>();
+      if (!(tb.dbg & 8)) bulk_wait_read<1>();
       load_tile(t + NS - 1);
     }
   }
@@ -668,6 +677,10 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
       }
     }
   }
+  s->nheavy = 0;
+  for (int m = 0; m < nl; ++m)
+    for (int st = 0; st < nstrip; ++st)
+      if (Jstrip[(size_t)m * nstrip + st] > 12 * TH_RT) s->nheavy = std::max(s->nheavy, st + 1);
   if (ctab.empty()) ctab.push_back(0.0);
   if (int rc = dev_upload(ctab.data(), ctab.size() * 8, (void**)&s->ctab, &s->bytes)) return rc;
   if (int rc = dev_upload(Jstrip.data(), Jstrip.size() * 4, (void**)&s->krow, &s->bytes)) return rc;
@@ -778,6 +791,12 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
       }
   s->plan = make_fft_plan(nx);
   int rc = 0;
+  if (cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    delete s;
+    return fail(SOMAX_B200_ERR_CUDA, "stream/event creation failed");
+  }
   const size_t sb_ = (size_t)s->planes * ny * s->np * es;
   auto alloc0 = [&](void** p) -> int {
     cudaError_t e = cudaMalloc(p, sb_);
@@ -805,26 +824,50 @@ void qg_solver_destroy(QgSolver* s) {
   void* ptrs[] = {s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->bsig, s->sig2n,
                   s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->tw, s->dstmat, s->meet, s->meetc};
   for (void* p : ptrs) cudaFree(p);
+  if (s->aux) cudaStreamDestroy(s->aux);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
   delete s;
 }
 
 size_t qg_solver_bytes(const QgSolver* s) { return s ? s->bytes : 0; }
 int qg_solver_kind(const QgSolver* s) { return s->kind; }
 
-template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE>
-static int launch_thomas(const char* tag, const ThomasTab& tb, dim3 grid, const T* in, const T* V,
-                         const double* gvec, const double* bsig, T* out, cudaStream_t st) {
-  constexpr int NS = ThStages<T, COMBINE>::v;
-  constexpr size_t smem = (size_t)NS * TH_RT * TH_COLS * (sizeof(double) + sizeof(T) * (COMBINE ? 2 : 1)) + NS * 8;
+template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE, bool TAB>
+static int launch_thomas_one(const char* tag, const ThomasTab& tb, int strip_first, int nstrips, int planes,
+                             const T* in, const T* V, const double* gvec, const double* bsig, T* out,
+                             cudaStream_t st) {
+  if (nstrips <= 0) return 0;
+  constexpr int NS = ThStages<T, COMBINE, TAB>::v;
+  constexpr size_t smem = (size_t)NS * TH_RT * TH_COLS * ((TAB ? sizeof(double) : 0) + sizeof(T) * (COMBINE ? 2 : 1)) + NS * 8;
   static bool attr_done = false;
   if (smem > 48 * 1024 && !attr_done) {
-    SB_CUDA(cudaFuncSetAttribute(thomas_sweep<T, SUBST, FROM_VEC, COMBINE>,
+    SB_CUDA(cudaFuncSetAttribute(thomas_sweep<T, SUBST, FROM_VEC, COMBINE, TAB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   prof_begin(tag, st);
-  thomas_sweep<T, SUBST, FROM_VEC, COMBINE><<<grid, TH_COLS, smem, st>>>(tb, in, V, gvec, bsig, out);
+  thomas_sweep<T, SUBST, FROM_VEC, COMBINE, TAB><<<dim3(nstrips, planes, 2), TH_COLS, smem, st>>>(
+      tb, strip_first, in, V, gvec, bsig, out);
   SB_LAUNCH_CHECK();
+  return 0;
+}
+
+// One sweep = a few "heavy" strips (late-converging coefficient recurrence: coefficient tiles are
+// staged through shared memory) on the auxiliary stream, overlapped with the "light" strips on
+// the caller's stream.
+template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE>
+static int launch_thomas(const char* tag, QgSolver* s, const ThomasTab& tb, const T* in, const T* V,
+                         const double* gvec, const double* bsig, T* out, cudaStream_t st) {
+  const int nstrip = s->np / SP_W, nh = std::min(s->nheavy, nstrip);
+  if (nh > 0) {
+    SB_CUDA(cudaEventRecord(s->ev_fork, st));
+    SB_CUDA(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
+    if (int rc = launch_thomas_one<T, SUBST, FROM_VEC, COMBINE, true>(tag, tb, 0, nh, s->planes, in, V, gvec, bsig, out, s->aux)) return rc;
+    SB_CUDA(cudaEventRecord(s->ev_join, s->aux));
+  }
+  if (int rc = launch_thomas_one<T, SUBST, FROM_VEC, COMBINE, false>(tag, tb, nh, nstrip - nh, s->planes, in, V, gvec, bsig, out, st)) return rc;
+  if (nh > 0) SB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
   return 0;
 }
 
@@ -838,7 +881,6 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
   tb.KB = std::max(s->KB, 1); tb.dbad = s->dbad; tb.meet = s->meet; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
   tb.dy2 = s->dy * s->dy;
   { const char* e = getenv("SOMAX_B200_DEBUG"); tb.dbg = e ? atoi(e) : 0; }
-  dim3 tgrid(s->np / SP_W, s->planes, 2);
   T* S = (T*)s->S;
   if (s->kind == SOMAX_B200_SOLVER_FFT) {
     T* W = (T*)s->W;
@@ -849,8 +891,8 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     for (int a = 0; a < QG_MAX_NL; ++a)
       for (int c = 0; c < QG_MAX_NL; ++c) { Af.mix[a][c] = (T)s->l2m.c[a][c]; Ai.mix[a][c] = (T)s->m2l.c[a][c]; }
     if (int rc = launch_rowdst<T, false>(s->plan.lgn, Af, q, S, st)) return rc;
-    if (int rc = launch_thomas<T, false, false, false>("thomas_fwd_0", tb, tgrid, S, nullptr, nullptr, nullptr, S, st)) return rc;
-    if (int rc = launch_thomas<T, true, false, false>("thomas_bwd_0", tb, tgrid, S, nullptr, nullptr, nullptr, S, st)) return rc;
+    if (int rc = launch_thomas<T, false, false, false>("thomas_fwd_0", s, tb, S, nullptr, nullptr, nullptr, S, st)) return rc;
+    if (int rc = launch_thomas<T, true, false, false>("thomas_bwd_0", s, tb, S, nullptr, nullptr, nullptr, S, st)) return rc;
     const double b = 1.0 / (s->dx * s->dx);
     prof_begin("border_dot", st);
     border_dot<T><<<dim3(ny, s->planes), 256, 0, st>>>(S, s->sig2n, ny, np, s->ncols, b, s->rvec);
@@ -861,8 +903,8 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     prof_begin("border_gsolve_b", st);
     border_gsolve_b<T><<<dim3(ny, s->planes), 128, 0, st>>>(s->ghat, s->sintab, ny, np, n, s->gvec, S);
     SB_LAUNCH_CHECK();
-    if (int rc = launch_thomas<T, false, true, false>("thomas_fwd_1", tb, tgrid, nullptr, nullptr, s->gvec, nullptr, W, st)) return rc;
-    if (int rc = launch_thomas<T, true, false, true>("thomas_bwd_1", tb, tgrid, W, S, nullptr, s->bsig, S, st)) return rc;
+    if (int rc = launch_thomas<T, false, true, false>("thomas_fwd_1", s, tb, nullptr, nullptr, s->gvec, nullptr, W, st)) return rc;
+    if (int rc = launch_thomas<T, true, false, true>("thomas_bwd_1", s, tb, W, S, nullptr, s->bsig, S, st)) return rc;
     if (int rc = launch_rowdst<T, true>(s->plan.lgn, Ai, S, psi, st)) return rc;
   } else {
     const size_t smem = (size_t)nl * n * sizeof(T);
@@ -874,8 +916,8 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     prof_begin("rowdst_dense_0", st);
     rowdst_dense<T, false><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->l2m, (const T*)s->dstmat, q, S, 1.0);
     SB_LAUNCH_CHECK();
-    if (int rc = launch_thomas<T, false, false, false>("thomas_fwd_0", tb, tgrid, S, nullptr, nullptr, nullptr, S, st)) return rc;
-    if (int rc = launch_thomas<T, true, false, false>("thomas_bwd_0", tb, tgrid, S, nullptr, nullptr, nullptr, S, st)) return rc;
+    if (int rc = launch_thomas<T, false, false, false>("thomas_fwd_0", s, tb, S, nullptr, nullptr, nullptr, S, st)) return rc;
+    if (int rc = launch_thomas<T, true, false, false>("thomas_bwd_0", s, tb, S, nullptr, nullptr, nullptr, S, st)) return rc;
     prof_begin("rowdst_dense_1", st);
     rowdst_dense<T, true><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->m2l, (const T*)s->dstmat, S, psi, 2.0 / (n + 1));
     SB_LAUNCH_CHECK();
