@@ -21,6 +21,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -341,6 +342,92 @@ template <typename T, bool COMBINE, bool TAB> struct ThStages {
   static constexpr int v = sizeof(T) == 4 ? (COMBINE ? 6 : 8) : (COMBINE ? 3 : (TAB ? 4 : 6));
 };
 
+// ---- float-float ("double-single") arithmetic: an unevaluated sum h + l of two floats, ~44
+// bits.  Used for the carried recurrence of the fp32 pipeline so that it needs neither the fp64
+// pipe nor fp32<->fp64 conversions (F2F runs at only ~16 lanes/clk/SM on B200; measured in
+// tools/micro/f2f_rate.cu).  Products use FMA for the exact error term.
+struct ff { float h, l; };
+__host__ __device__ __forceinline__ ff ff_from_double(double x) {
+  ff r; r.h = (float)x; r.l = (float)(x - (double)r.h); return r;
+}
+__device__ __forceinline__ double ff_to_double(ff a) { return (double)a.h + (double)a.l; }
+// (h,l) * f, f a plain float.  __fmul_rn / __fadd_rn / __fsub_rn are never contracted into FMAs
+// by the compiler, which the error-free transformations rely on.
+__device__ __forceinline__ ff ff_mul_f(ff a, float f) {
+  ff r; r.h = __fmul_rn(a.h, f);
+  const float e = fmaf(a.h, f, -r.h);
+  r.l = fmaf(a.l, f, e);
+  return r;
+}
+// (h,l) * (h,l), dropping the l*l term
+__device__ __forceinline__ ff ff_mul(ff a, ff b) {
+  ff r; r.h = __fmul_rn(a.h, b.h);
+  const float e = fmaf(a.h, b.h, -r.h);
+  r.l = fmaf(a.h, b.l, fmaf(a.l, b.h, e));
+  return r;
+}
+// t - p, normalised (TwoSum + FastTwoSum)
+__device__ __forceinline__ ff ff_sub(ff t, ff p) {
+  const float s = __fsub_rn(t.h, p.h);
+  const float bb = __fsub_rn(s, t.h);
+  const float se = __fadd_rn(__fsub_rn(t.h, __fsub_rn(s, bb)), __fsub_rn(-p.h, bb));
+  const float sl = __fadd_rn(se, __fsub_rn(t.l, p.l));
+  ff r; r.h = __fadd_rn(s, sl); r.l = __fsub_rn(sl, __fsub_rn(r.h, s));
+  return r;
+}
+
+// float-float version of thomas_tile for T = float (same modes / phases).  Coefficient tiles and
+// the indefinite-column side buffer hold (hi, lo) float pairs in their 8-byte slots.
+template <bool SUBST, bool FROM_VEC, bool COMBINE, bool UP, int MODE>
+__device__ __forceinline__ void thomas_tile_ff(float (*A)[TH_COLS], const float (*Vt)[TH_COLS],
+                                               const ff (*Ct)[TH_COLS], const ff* __restrict__ gv,
+                                               ff* __restrict__ dbc, int KB, int tid, int nr, int s0,
+                                               int ilo, int Js, int cnt, int jb, bool act, bool bad,
+                                               ff cfix, ff kfix, ff dy2, ff bs, ff& carry) {
+  constexpr int dj = UP ? 1 : -1;
+  ff t[TH_RT], cj[TH_RT];
+  float vv[TH_RT];
+#pragma unroll
+  for (int r = 0; r < TH_RT; ++r) {
+    const bool ok = MODE != 2 || r < nr;
+    const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);
+    const int i = SUBST ? cnt - 1 - (s0 + r) : s0 + r;
+    if (MODE == 0) cj[r] = cfix;
+    else if (MODE == 1) cj[r] = Ct[i - ilo][tid];
+    else cj[r] = (ok && i < Js) ? Ct[i - ilo][tid] : cfix;
+    ff f; f.l = 0.f;
+    if (FROM_VEC) { if (ok) f = gv[jb + dj * r]; else f.h = 0.f; }
+    else f.h = ok ? A[ok ? rm : 0][tid] : 0.f;
+    if (COMBINE) vv[r] = ok ? Vt[ok ? rm : 0][tid] : 0.f;
+    if (MODE == 2 && SUBST && bad && ok) f = dbc[(size_t)(jb + dj * r) * KB];
+    if (!SUBST) {
+      // t = c * dy^2 * f   (off the carried chain)
+      if (MODE == 0 && !FROM_VEC) t[r] = ff_mul_f(kfix, f.h);
+      else if (MODE == 0) t[r] = ff_mul(kfix, f);
+      else t[r] = ff_mul(cj[r], FROM_VEC ? ff_mul(dy2, f) : ff_mul_f(dy2, f.h));
+    } else {
+      t[r] = f;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < TH_RT; ++r)
+    if (MODE != 2 || r < nr) { carry = ff_sub(t[r], ff_mul(cj[r], carry)); t[r] = carry; }
+#pragma unroll
+  for (int r = 0; r < TH_RT; ++r) {
+    if (MODE != 2 || r < nr) {
+      const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);
+      if (COMBINE) {
+        float o = fmaf(-bs.h, t[r].h, vv[r]);
+        o = fmaf(-bs.h, t[r].l, o);
+        o = fmaf(-bs.l, t[r].h, o);
+        A[rm][tid] = act ? o : vv[r];
+      } else if (act) A[rm][tid] = t[r].h;
+      else if (FROM_VEC) A[rm][tid] = 0.f;
+      if (MODE == 2 && !SUBST && bad) dbc[(size_t)(jb + dj * r) * KB] = t[r];
+    }
+  }
+}
+
 // Recurrence over one staged tile for one column (thread).  UP: memory rows ascend with the
 // sequence (dj > 0).  MODE 0: full tile, constant coefficient; MODE 1: full tile, every row
 // tabulated (coefficients in Ct); MODE 2: generic (ragged end, tile straddling the convergence
@@ -428,6 +515,14 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   const bool bad = act && c < tb.kbad[m];
   double* dbc = tb.dbad + ((size_t)plane * ny) * tb.KB + (bad ? c : 0);
   const double bs = (COMBINE && act) ? bsig[c] : 0.0;
+  constexpr bool FF = sizeof(T) == 4;          // fp32 pipeline: float-float carried recurrence
+  ff cfix_f = {0.f, 0.f}, kfix_f = {0.f, 0.f}, bs_f = {0.f, 0.f}, dy2_f = {0.f, 0.f}, carry_f = {0.f, 0.f};
+  if (FF) {
+    cfix_f = reinterpret_cast<const ff*>(tb.cinf)[(size_t)m * tb.np + c];   // tables pre-split on the host
+    kfix_f = ff_from_double(ff_to_double(cfix_f) * tb.dy2);
+    bs_f = ff_from_double(bs);
+    dy2_f = ff_from_double(tb.dy2);
+  }
   const bool strip_bad = strip * TH_COLS < tb.kbad[m];     // this strip holds indefinite columns
   const double* gv = gvec + (FROM_VEC ? (size_t)plane * ny : 0);
   const int m1 = ny / 2;
@@ -479,11 +574,16 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   if (SUBST && cnt > 0 && m1 > 0) {
     // meeting point: x_{m1-1} + ca x_{m1} = d_{m1-1};  x_{m1} + cb x_{m1-1} = e_{m1}
     const double ca = tb.meetc[((size_t)m * 2 + 0) * tb.np + c], cb = tb.meetc[((size_t)m * 2 + 1) * tb.np + c];
-    const double dm = tb.meet[((size_t)plane * 2 + 0) * tb.np + c];
-    const double em = tb.meet[((size_t)plane * 2 + 1) * tb.np + c];
+    double dm = tb.meet[((size_t)plane * 2 + 0) * tb.np + c];
+    double em = tb.meet[((size_t)plane * 2 + 1) * tb.np + c];
+    if (FF) {   // the fp32 pipeline keeps (hi, lo) float pairs in the 8-byte slots
+      dm = ff_to_double(reinterpret_cast<const ff*>(tb.meet)[((size_t)plane * 2 + 0) * tb.np + c]);
+      em = ff_to_double(reinterpret_cast<const ff*>(tb.meet)[((size_t)plane * 2 + 1) * tb.np + c]);
+    }
     const double den = 1.0 / (1.0 - ca * cb);
     const double xa = (dm - ca * em) * den, xb = (em - cb * dm) * den;
     carry = half == 0 ? xb : xa;     // the neighbour's value across the meeting point
+    carry_f = ff_from_double(carry);
   }
 
   unsigned phase_bits = 0;            // per-stage phase parity (stages may be skipped by FROM_VEC tiles)
@@ -507,8 +607,17 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     const int mode = (nr < TH_RT || strip_bad || (ilo < Js && ilo + nr > Js)) ? 2 : (ilo >= Js ? 0 : 1);
     if (!(tb.dbg & 1)) {
 #define SB_TILE(UPV, MODEV)                                                                     \
-      thomas_tile<T, SUBST, FROM_VEC, COMBINE, UPV, MODEV>(A, Vt, Ct, gv, dbc, tb.KB, tid, nr, s0, ilo, \
-                                                           Js, cnt, jb, act, bad, cfix, tb.dy2, bs, carry)
+      do {                                                                                      \
+        if constexpr (FF)                                                                       \
+          thomas_tile_ff<SUBST, FROM_VEC, COMBINE, UPV, MODEV>(                                 \
+              reinterpret_cast<float (*)[TH_COLS]>(A), reinterpret_cast<const float (*)[TH_COLS]>(Vt), \
+              reinterpret_cast<const ff (*)[TH_COLS]>(Ct), reinterpret_cast<const ff*>(gv),     \
+              reinterpret_cast<ff*>(dbc), tb.KB, tid, nr, s0, ilo, Js, cnt, jb, act, bad, cfix_f, kfix_f, \
+              dy2_f, bs_f, carry_f);                                                            \
+        else                                                                                    \
+          thomas_tile<T, SUBST, FROM_VEC, COMBINE, UPV, MODEV>(A, Vt, Ct, gv, dbc, tb.KB, tid, nr, s0, ilo, \
+                                                               Js, cnt, jb, act, bad, cfix, tb.dy2, bs, carry); \
+      } while (0)
       if (dj > 0) {
         if (mode == 0) SB_TILE(true, 0); else if (mode == 1) SB_TILE(true, 1); else SB_TILE(true, 2);
       } else {
@@ -516,7 +625,10 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
       }
 #undef SB_TILE
     }
-    if (!SUBST && t == ntile - 1) tb.meet[((size_t)plane * 2 + half) * tb.np + c] = carry;
+    if (!SUBST && t == ntile - 1) {
+      if (FF) reinterpret_cast<ff*>(tb.meet)[((size_t)plane * 2 + half) * tb.np + c] = carry_f;
+      else tb.meet[((size_t)plane * 2 + half) * tb.np + c] = carry;
+    }
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
     if (!(tb.dbg & 4)) fence_async_smem();
     if (!(tb.dbg & 16)) __syncthreads();
@@ -598,7 +710,8 @@ __global__ void border_gsolve_b(const double* __restrict__ ghat, const double* _
     double t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     t *= 2.0 / (ny + 1);
-    gvec[(size_t)plane * ny + (j - 1)] = t;
+    if (sizeof(T) == 4) reinterpret_cast<ff*>(gvec)[(size_t)plane * ny + (j - 1)] = ff_from_double(t);
+    else gvec[(size_t)plane * ny + (j - 1)] = t;
     S[(size_t)plane * ny * np + sp_off(ny, j - 1, n - 1)] = (T)t;
   }
 }
@@ -676,6 +789,15 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
         }
       }
     }
+  }
+  if (s->dtype == SOMAX_B200_F32) {
+    // fp32 pipeline: the sweeps read coefficients as (hi, lo) float pairs (same 8-byte slots);
+    // meetc stays fp64 (used once per thread, in double)
+    auto split = [](std::vector<double>& v) {
+      for (double& x : v) { ff p = ff_from_double(x); memcpy(&x, &p, sizeof(double)); }
+    };
+    split(ctab);
+    split(cinf);
   }
   s->nheavy = 0;
   for (int m = 0; m < nl; ++m)
