@@ -153,36 +153,64 @@ template <int LGN> struct FftCT {
   }
 };
 
+// Compact per-pass twiddle table: for the pass whose butterflies span Lc = 2^LGLC (M = Lc/R) the
+// records {w^pos, w^(2 pos), w^(4 pos)}, w = exp(-2 pi i / Lc), pos = 0..M-1, are contiguous, so a
+// warp (consecutive pos) reads them coalesced instead of gathering from the length-2n table at
+// stride n/Lc.  Every pass before the last is radix 8, so the record offset of a pass is
+// 3 * sum of the M of the earlier passes.
+__host__ __device__ constexpr int twc_offset(int LGN, int LGLC) {
+  int off = 0;
+  for (int l = LGN; l > LGLC; l -= 3) off += 3 * (1 << (l - 3));
+  return off;
+}
+__host__ __device__ constexpr int twc_size(int LGN) {
+  int off = 0;
+  for (int l = LGN; l > 0; l -= (l >= 3 ? 3 : l)) off += 3 * (1 << (l - (l >= 3 ? 3 : l)));
+  return off;
+}
+
 // DIF pass with compile-time geometry; twiddles w, w^2, w^4 are loaded, the rest are products.
 template <typename T, int LGN, int LGLC, int R, int G>
-__host__ __device__ __forceinline__ void fft_dif_pass_ct(C2<T>* s, int lt, const C2<T>* __restrict__ tw) {
+__host__ __device__ __forceinline__ void fft_dif_pass_ct(C2<T>* s, int lt, const C2<T>* __restrict__ twc) {
   constexpr int LGR = R == 8 ? 3 : (R == 4 ? 2 : 1);
   constexpr int lgM = LGLC - LGR;
   constexpr int M = 1 << lgM;
-  constexpr int tstride = 2 << (LGN - LGLC);
   constexpr int nb = 1 << (LGN - LGR);
+  // The butterfly's elements sit at base + q*M.  When, for every pad period 2^s (s = 4, 7, 10),
+  // M is a multiple of the period or the whole butterfly span Lc fits inside one period, the
+  // padding terms of fft_pad distribute over q and the padded addresses are pad(base) + q*MP
+  // with a compile-time MP (true for every pass of the 8192-point transform); otherwise each
+  // address is padded individually.
+  constexpr int Lc = 1 << LGLC;
+  constexpr bool D4 = (M % 16 == 0) || (Lc <= 16);
+  constexpr bool D7 = (M % 128 == 0) || (Lc <= 128);
+  constexpr bool D10 = (M % 1024 == 0) || (Lc <= 1024);
+  constexpr bool DIST = D4 && D7 && D10;
+  constexpr int MP = M + (M % 16 == 0 ? M >> 4 : 0) + (M % 128 == 0 ? M >> 7 : 0) + (M % 1024 == 0 ? M >> 10 : 0);
 #pragma unroll
   for (int t0 = 0; t0 < nb; t0 += G) {
     const int t = t0 + lt;
     if (nb % G != 0 && t >= nb) break;
     const int block = t >> lgM, pos = t & (M - 1);
     const int base = (block << LGLC) + pos;
+    const int pb = fft_pad(base);
     C2<T> v[R];
 #pragma unroll
-    for (int q = 0; q < R; ++q) v[q] = s[fft_pad(base + q * M)];
+    for (int q = 0; q < R; ++q) v[q] = s[DIST ? pb + q * MP : fft_pad(base + q * M)];
     if (R == 8) fft8(v);
     else if (R == 4) fft4(v[0], v[1], v[2], v[3]);
     else { C2<T> a = v[0]; v[0] = cadd(a, v[1]); v[1] = csub(a, v[1]); }
     if (M > 1) {
-      const C2<T> w1 = tw[pos * tstride];
+      const C2<T>* rec = twc + twc_offset(LGN, LGLC) + 3 * pos;
+      const C2<T> w1 = rec[0];
       v[1] = cmul(v[1], w1);
       if (R >= 4) {
-        const C2<T> w2 = tw[2 * pos * tstride];
+        const C2<T> w2 = rec[1];
         const C2<T> w3 = cmul(w1, w2);
         v[2] = cmul(v[2], w2);
         v[3] = cmul(v[3], w3);
         if (R == 8) {
-          const C2<T> w4 = tw[4 * pos * tstride];
+          const C2<T> w4 = rec[2];
           v[4] = cmul(v[4], w4);
           v[5] = cmul(v[5], cmul(w1, w4));
           v[6] = cmul(v[6], cmul(w2, w4));
@@ -191,7 +219,7 @@ __host__ __device__ __forceinline__ void fft_dif_pass_ct(C2<T>* s, int lt, const
       }
     }
 #pragma unroll
-    for (int q = 0; q < R; ++q) s[fft_pad(base + q * M)] = v[q];
+    for (int q = 0; q < R; ++q) s[DIST ? pb + q * MP : fft_pad(base + q * M)] = v[q];
   }
 }
 

@@ -45,7 +45,7 @@ struct QgSolver {
   int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0; double* dbad = nullptr;
   double* bsig = nullptr; double* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
   double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; double* meet = nullptr; double* meetc = nullptr;
-  void* tw = nullptr; void* dstmat = nullptr;
+  void* tw = nullptr; void* twc = nullptr; void* dstmat = nullptr;
   FftPlan plan;
   Mix l2m, m2l;
   int nheavy = 0;
@@ -83,7 +83,8 @@ struct RowArgsCT {
   Layout L;
   int ny, np, nl, nrows;
   T mix[QG_MAX_NL][QG_MAX_NL];
-  const C2<T>* tw;
+  const C2<T>* tw;    // exp(-i pi t / n), t = 0..2n-1 (real-odd split)
+  const C2<T>* twc;   // compact per-pass butterfly twiddles (fft.cuh: twc_offset)
   T scale;
 };
 
@@ -166,7 +167,7 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
       if (lt == 0) { z[zi(0)] = 0; z[zi(n)] = 0; }
     }
     __syncthreads();
-    fft_passes_ct<T, LGN, G, 0>(s, lt, A.tw, valid);
+    fft_passes_ct<T, LGN, G, 0>(s, lt, A.twc, valid);
     if (valid) {
 #pragma unroll
       for (int k0 = 1; k0 <= n / 2; k0 += G) {
@@ -834,6 +835,21 @@ static int build_fft_tables(QgSolver* s, const double* lambdas) {
     tw[t].x = (T)cos(a); tw[t].y = (T)sin(a);
   }
   if (int rc = dev_upload(tw.data(), tw.size() * sizeof(C2<T>), &s->tw, &s->bytes)) return rc;
+  {
+    // compact per-pass butterfly twiddles (layout: fft.cuh twc_offset)
+    std::vector<C2<T>> twc;
+    int lgLc = s->plan.lgn;
+    for (int ps = 0; ps < s->plan.npass; ++ps) {
+      const int lr = s->plan.lgr[ps], Lc = 1 << lgLc, M = Lc >> lr;
+      for (int pos = 0; pos < M; ++pos)
+        for (int q = 1; q <= 4; q *= 2) {
+          const double a = -2.0 * M_PI * (double)q * (double)pos / (double)Lc;
+          twc.push_back({(T)cos(a), (T)sin(a)});
+        }
+      lgLc -= lr;
+    }
+    if (int rc = dev_upload(twc.data(), twc.size() * sizeof(C2<T>), &s->twc, &s->bytes)) return rc;
+  }
   std::vector<double> sig(nc), lamx(nc), bsig(nc), sig2n(nc);
   for (int c = 0; c < nc; ++c) {
     const int k = c + 1;
@@ -944,7 +960,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
 void qg_solver_destroy(QgSolver* s) {
   if (!s) return;
   void* ptrs[] = {s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->bsig, s->sig2n,
-                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->tw, s->dstmat, s->meet, s->meetc};
+                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->tw, s->twc, s->dstmat, s->meet, s->meetc};
   for (void* p : ptrs) cudaFree(p);
   if (s->aux) cudaStreamDestroy(s->aux);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -1008,7 +1024,7 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     T* W = (T*)s->W;
     RowArgsCT<T> Af, Ai;
     Af.L = s->L; Af.ny = ny; Af.np = np; Af.nl = nl; Af.nrows = s->batch * ny;
-    Af.tw = (const C2<T>*)s->tw; Af.scale = (T)1;
+    Af.tw = (const C2<T>*)s->tw; Af.twc = (const C2<T>*)s->twc; Af.scale = (T)1;
     Ai = Af; Ai.scale = (T)(2.0 / n);
     for (int a = 0; a < QG_MAX_NL; ++a)
       for (int c = 0; c < QG_MAX_NL; ++c) { Af.mix[a][c] = (T)s->l2m.c[a][c]; Ai.mix[a][c] = (T)s->m2l.c[a][c]; }
