@@ -119,6 +119,25 @@ qg_rhs_kernel_fast(QgArgs<T> A, const T* __restrict__ psi, Stage<T> st) {
   const T* pq = st.Yin[0] + po;
   const T* pp = psi + po;
   const size_t idx = po + (size_t)(j0 + ty) * pitch + (size_t)(g0 + tx) * 4;
+  // fp32: the epilogue's operands (step start state and the previous stage derivatives) are
+  // prefetched with 16-byte cp.async into per-thread shared slots right away, so their HBM
+  // latency overlaps the tile load, the barrier and the stencil arithmetic without holding
+  // registers.
+  constexpr bool STAGE_EPI = sizeof(T) == 4;
+  __shared__ __align__(16) T s_epi[STAGE_EPI ? MAX_PREV + 1 : 1][QTXG * QTY][STAGE_EPI ? 4 : 1];
+  const bool epi_valid = (j0 + ty) < Ny && (g0 + tx) < ngroups && st.Yout[0] != nullptr;
+  if (STAGE_EPI && epi_valid) {
+    const T* base = (st.y[0] ? st.y[0] : st.Yin[0]) + idx;
+    unsigned sa = (unsigned)__cvta_generic_to_shared(&s_epi[MAX_PREV][tid][0]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(base) : "memory");
+#pragma unroll
+    for (int jj = 0; jj < MAX_PREV; ++jj)
+      if (jj < st.nprev) {
+        sa = (unsigned)__cvta_generic_to_shared(&s_epi[jj][tid][0]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(st.Fprev[jj][0] + idx) : "memory");
+      }
+  }
+  if (STAGE_EPI) asm volatile("cp.async.commit_group;\n" ::: "memory");
 
   for (int e = tid; e < (QTY + 2) * (QTXG + 2); e += QTXG * QTY) {
     const int r = e / (QTXG + 2), gs = e - r * (QTXG + 2);   // gs: shared group 0..QTXG+1
@@ -203,7 +222,23 @@ qg_rhs_kernel_fast(QgArgs<T> A, const T* __restrict__ psi, Stage<T> st) {
     }
     out[e] = dq;
   }
-  rk_epilogue4_fast(st, 0, idx, Vec4<T>{out[0], out[1], out[2], out[3]});
+  const Vec4<T> F{out[0], out[1], out[2], out[3]};
+  if (!STAGE_EPI) { rk_epilogue4_fast(st, 0, idx, F); return; }
+  if (st.Fout[0]) st4(st.Fout[0] + idx, F);
+  if (!st.Yout[0]) return;
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  Vec4<T> acc = ld4(&s_epi[MAX_PREV][tid][0]);
+#pragma unroll
+  for (int jj = 0; jj < MAX_PREV; ++jj) {
+    if (jj < st.nprev) {
+      const Vec4<T> kk = ld4(&s_epi[jj][tid][0]);
+      acc.x = fma(st.adt[jj], kk.x, acc.x); acc.y = fma(st.adt[jj], kk.y, acc.y);
+      acc.z = fma(st.adt[jj], kk.z, acc.z); acc.w = fma(st.adt[jj], kk.w, acc.w);
+    }
+  }
+  acc.x = fma(st.adt_new, F.x, acc.x); acc.y = fma(st.adt_new, F.y, acc.y);
+  acc.z = fma(st.adt_new, F.z, acc.z); acc.w = fma(st.adt_new, F.w, acc.w);
+  st4(st.Yout[0] + idx, acc);
 }
 
 // ring := 0 in place on padded planes

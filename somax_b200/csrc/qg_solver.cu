@@ -647,13 +647,21 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
 
 // r[plane][j] = f_n[j] - b * sum_c sig2n[c] * V[plane][j][c]: right-hand side of the border
 // (Schur) system; the sum is the first solve evaluated at column n-1, f_n sits in slot n-1.
+// One CTA per (row, plane); 128-bit loads over the 64-column strips of the blocked layout.
 template <typename T>
-__global__ void border_dot(const T* __restrict__ V, const double* __restrict__ sig2n, int ny,
-                           int np, int ncols, double b, double* __restrict__ r) {
+__global__ void __launch_bounds__(256)
+border_dot(const T* __restrict__ V, const double* __restrict__ sig2n, int ny,
+           int np, int ncols, double b, double* __restrict__ r) {
   const int j = blockIdx.x, plane = blockIdx.y;
   const T* pl = V + (size_t)plane * ny * np;
   double acc = 0;
-  for (int c = threadIdx.x; c < ncols; c += blockDim.x) acc += sig2n[c] * (double)pl[sp_off(ny, j, c)];
+  for (int c4 = threadIdx.x * 4; c4 < np; c4 += blockDim.x * 4) {
+    const Vec4<T> v = ld4(pl + sp_off(ny, j, c4));
+    if (c4 + 0 < ncols) acc += sig2n[c4 + 0] * (double)v.x;
+    if (c4 + 1 < ncols) acc += sig2n[c4 + 1] * (double)v.y;
+    if (c4 + 2 < ncols) acc += sig2n[c4 + 2] * (double)v.z;
+    if (c4 + 3 < ncols) acc += sig2n[c4 + 3] * (double)v.w;
+  }
   __shared__ double red[32];
   for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -665,55 +673,53 @@ __global__ void border_dot(const T* __restrict__ V, const double* __restrict__ s
   }
 }
 
-// Border Schur solve, stage A: ghat[l] = (sum_j sin(pi j l/N) r[j]) / sdiag[m][l]
-template <typename T>
-__global__ void border_gsolve_a(const double* __restrict__ r,
-                                const double* __restrict__ sintab, const double* __restrict__ sdiag,
-                                int ny, int nl, double* __restrict__ ghat) {
-  const int l = blockIdx.x + 1, plane = blockIdx.y, m = plane % nl;
-  const int N2 = 2 * (ny + 1);
+// Border Schur solve = dense DST-I in y of one column per plane (length ny, N = ny + 1), brute
+// force in fp64: out[a] = scale(a) * sum_{t=1..ny} sin(pi a t / N) in[t].  Each thread owns the
+// terms t = t0, t0 + B, t0 + 2B, ... and advances sin/cos(pi a t / N) by the fixed angle
+// pi a B / N with a rotation (4 FMAs) instead of gathering from the sine table; the start and
+// step values come exactly from the table.  STAGE_A divides by the Schur diagonal; stage B
+// scales by 2/N and also writes the result where the sweeps / inverse transform read it.
+template <typename T, bool STAGE_A>
+__global__ void __launch_bounds__(128)
+border_gsolve(const double* __restrict__ in, const double* __restrict__ sintab,
+              const double* __restrict__ sdiag, int ny, int np, int n, int nl,
+              double* __restrict__ out, double* __restrict__ gvec, T* __restrict__ S) {
+  const int a = blockIdx.x + 1, plane = blockIdx.y, m = plane % nl;
+  const int N = ny + 1, N2 = 2 * N, B = blockDim.x;
+  auto sn = [&](long long k) { return sintab[(int)(k % N2)]; };          // sin(pi k / N)
+  const int t0 = threadIdx.x + 1;
+  // cos(pi k / N) = sin(pi (k + N/2) / N) needs N even; use the identity through the table of
+  // size 2N only when N is even, otherwise evaluate with cospi (N odd <=> ny even)
+  double s = sn((long long)a * t0), c, ds = sn((long long)a * B), dc;
+  if ((N & 1) == 0) {
+    c = sintab[(int)(((long long)a * t0 + N / 2) % N2)];
+    dc = sintab[(int)(((long long)a * B + N / 2) % N2)];
+  } else {
+    c = cospi((double)(((long long)a * t0) % N2) / (double)N);
+    dc = cospi((double)(((long long)a * B) % N2) / (double)N);
+  }
   double acc = 0;
-  int idx = (int)(((long long)(threadIdx.x + 1) * l) % N2);
-  const int step = (int)(((long long)blockDim.x * l) % N2);
-  for (int j = threadIdx.x + 1; j <= ny; j += blockDim.x) {
-    acc += sintab[idx] * r[(size_t)plane * ny + (j - 1)];
-    idx += step; if (idx >= N2) idx -= N2;
+  const double* x = in + (size_t)plane * ny;
+  for (int t = t0; t <= ny; t += B) {
+    acc = fma(s, x[t - 1], acc);
+    const double s2 = fma(s, dc, c * ds), c2 = fma(c, dc, -(s * ds));   // rotate by pi a B / N
+    s = s2; c = c2;
   }
   __shared__ double red[32];
-  for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
+  for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, sh);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    ghat[(size_t)plane * ny + (l - 1)] = t / sdiag[(size_t)m * ny + (l - 1)];
-  }
-}
-
-// stage B: g[j] = (2/N) sum_l sin(pi j l/N) ghat[l]; stored to gvec (fp64) and the border slot.
-template <typename T>
-__global__ void border_gsolve_b(const double* __restrict__ ghat, const double* __restrict__ sintab,
-                                int ny, int np, int n, double* __restrict__ gvec, T* __restrict__ S) {
-  const int j = blockIdx.x + 1, plane = blockIdx.y;
-  const int N2 = 2 * (ny + 1);
-  double acc = 0;
-  int idx = (int)(((long long)(threadIdx.x + 1) * j) % N2);
-  const int step = (int)(((long long)blockDim.x * j) % N2);
-  for (int l = threadIdx.x + 1; l <= ny; l += blockDim.x) {
-    acc += sintab[idx] * ghat[(size_t)plane * ny + (l - 1)];
-    idx += step; if (idx >= N2) idx -= N2;
-  }
-  __shared__ double red[32];
-  for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    t *= 2.0 / (ny + 1);
-    if (sizeof(T) == 4) reinterpret_cast<ff*>(gvec)[(size_t)plane * ny + (j - 1)] = ff_from_double(t);
-    else gvec[(size_t)plane * ny + (j - 1)] = t;
-    S[(size_t)plane * ny * np + sp_off(ny, j - 1, n - 1)] = (T)t;
+    if (STAGE_A) {
+      out[(size_t)plane * ny + (a - 1)] = t / sdiag[(size_t)m * ny + (a - 1)];
+    } else {
+      t *= 2.0 / N;
+      if (sizeof(T) == 4) reinterpret_cast<ff*>(gvec)[(size_t)plane * ny + (a - 1)] = ff_from_double(t);
+      else gvec[(size_t)plane * ny + (a - 1)] = t;
+      S[(size_t)plane * ny * np + sp_off(ny, a - 1, n - 1)] = (T)t;
+    }
   }
 }
 
@@ -1036,10 +1042,10 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     border_dot<T><<<dim3(ny, s->planes), 256, 0, st>>>(S, s->sig2n, ny, np, s->ncols, b, s->rvec);
     SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_a", st);
-    border_gsolve_a<T><<<dim3(ny, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, nl, s->ghat);
+    border_gsolve<T, true><<<dim3(ny, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr);
     SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_b", st);
-    border_gsolve_b<T><<<dim3(ny, s->planes), 128, 0, st>>>(s->ghat, s->sintab, ny, np, n, s->gvec, S);
+    border_gsolve<T, false><<<dim3(ny, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, S);
     SB_LAUNCH_CHECK();
     if (int rc = launch_thomas<T, false, true, false>("thomas_fwd_1", s, tb, nullptr, nullptr, s->gvec, nullptr, W, st)) return rc;
     if (int rc = launch_thomas<T, true, false, true>("thomas_bwd_1", s, tb, W, S, nullptr, s->bsig, S, st)) return rc;
