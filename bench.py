@@ -212,8 +212,12 @@ def run_gpu(args):
     barrier()
 
     # ---- timed region: K steps, device resident, CUDA events on the launching stream ----
+    # Per-launch CUDA events ride inside the timed region, except where the library replays a captured
+    # CUDA graph (small grids, K >= 9): per-launch events would force the eager path, so those
+    # workloads are timed clean and profiled in a second, identical pass of K steps.
+    graphed = nb * nl * (ny + 2) * (nx + 2) <= (1 << 21) and K >= 9
     lib.somax_b200_profile_reset()
-    lib.somax_b200_profile_enable(1)
+    lib.somax_b200_profile_enable(0 if graphed else 1)
     sampler = ClockSampler(local)
     sampler.start()
     n0 = lib.somax_b200_launch_count()
@@ -226,6 +230,10 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     launches = lib.somax_b200_launch_count() - n0
     clocks = sampler.stop()
+    if graphed:
+        lib.somax_b200_profile_enable(1)
+        steps_dev(K)
+        barrier()
     lib.somax_b200_profile_enable(0)
     buf = C.create_string_buffer(1 << 16)
     _lib.check(lib.somax_b200_profile_report(buf, len(buf)))
@@ -280,6 +288,8 @@ def run_gpu(args):
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": k_tr * padded, "avg_launch_ms": per_launch_ms,
         "share_of_step": top["total_ms"] / total_prof,
+        "events": "second pass of K eager steps (the timed region replays a CUDA graph)" if graphed
+                  else "per-launch CUDA events inside the timed region",
         "step": {"algorithmic_bytes": step_alg_bytes, "achieved_gbs": step_alg_bytes / (ms_max / K * 1e-3) / 1e9,
                  "frac": step_frac, "transfers_per_step": TRANSFERS[kind]},
         "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "total_ms": round(r["total_ms"], 3),

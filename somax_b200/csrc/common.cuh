@@ -31,6 +31,22 @@ extern std::atomic<uint64_t> g_launches;
 // SB_LAUNCH_CHECK() closes the record.  No-ops unless profiling is enabled.
 void prof_begin(const char* name, cudaStream_t s);
 void prof_end();
+bool prof_enabled();
+
+// CUDA-graph replay of the stepping loop for launch-bound (small) grids.  The stage buffers
+// rotate with period 2 steps, so two consecutive full steps (12 RHS evaluations, including the
+// two-stream fork/join of the y-sweeps) are captured once per (dt, params) and replayed.
+struct StepGraph {
+  cudaGraphExec_t exec = nullptr;
+  double key[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t nlaunch = 0;            // kernels per replay
+  cudaStream_t stream = nullptr;   // capture / replay stream (the legacy stream cannot capture)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  int init();
+  void destroy();
+};
+// grids at or below this many cells per handle use the graph path
+constexpr size_t GRAPH_MAX_CELLS = (size_t)1 << 21;
 
 #define SB_LAUNCH_CHECK()                                                                 \
   do {                                                                                    \

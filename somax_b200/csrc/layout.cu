@@ -60,6 +60,25 @@ void prof_begin(const char* name, cudaStream_t s) {
   g_prof.stream = s;
 }
 
+bool prof_enabled() { return g_prof.on; }
+
+int StepGraph::init() {
+  if (stream) return 0;
+  if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming) != cudaSuccess)
+    return fail(SOMAX_B200_ERR_CUDA, "graph stream/event creation failed");
+  return 0;
+}
+
+void StepGraph::destroy() {
+  if (exec) cudaGraphExecDestroy(exec);
+  if (stream) cudaStreamDestroy(stream);
+  if (ev_in) cudaEventDestroy(ev_in);
+  if (ev_out) cudaEventDestroy(ev_out);
+  exec = nullptr; stream = nullptr; ev_in = ev_out = nullptr;
+}
+
 void prof_end() {
   if (!g_prof.open) return;
   cudaEventRecord(g_prof.recs.back().b, g_prof.stream);

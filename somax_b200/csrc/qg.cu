@@ -315,6 +315,7 @@ struct somax_b200_qg_s {
   bool beta1d = false, wind1d = false;
   void* y = nullptr; void* Ya = nullptr; void* Yb = nullptr; void* psi = nullptr;
   void* F[5] = {0, 0, 0, 0, 0};
+  StepGraph graph;
   size_t bytes = 0;
 };
 
@@ -375,12 +376,21 @@ int qg_bc_inplace(somax_b200_qg_t h, void* q, cudaStream_t s) {
 
 template <typename T>
 int qg_steps_impl(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt_last,
-                  const somax_b200_params* p, cudaStream_t s) {
+                  const somax_b200_params* p, cudaStream_t caller) {
   const Layout& L = h->L;
+  const long total = n_steps + (dt_last > 0 ? 1 : 0);
+  // launch-bound grids: replay two-step CUDA graphs on an internal stream
+  const bool use_graph = !prof_enabled() && L.count() <= GRAPH_MAX_CELLS && n_steps >= 9 &&
+                         h->graph.init() == 0;
+  cudaStream_t s = caller;
+  if (use_graph) {
+    s = h->graph.stream;
+    SB_CUDA(cudaEventRecord(h->graph.ev_in, caller));
+    SB_CUDA(cudaStreamWaitEvent(s, h->graph.ev_in, 0));
+  }
   void *y = h->y, *Yc = h->Ya, *Yn = h->Yb;
   if (int rc = pack_field<T>((const T*)q, (T*)y, L, s)) return rc;
   if (int rc = qg_bc_inplace<T>(h, y, s)) return rc;   // integrate(): BC on state0
-  const long total = n_steps + (dt_last > 0 ? 1 : 0);
   if (total > 0) {
     QgArgs<T> A = make_qargs<T>(h, p, 1);
     auto step_dt = [&](long i) { return (i < n_steps) ? dt : dt_last; };
@@ -390,29 +400,68 @@ int qg_steps_impl(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt
       st.a_new = (T)TSIT5_A[0][0]; st.dt = (T)step_dt(0);
       if (int rc = eval_rhs<T>(h, A, st, step_dt(0), s)) return rc;
     }
-    for (long i = 0; i < total; ++i) {
-      const T hdt = (T)step_dt(i);
+    // stages 2..6 of a step (evaluations at Y2..Y6, forming Y7 = y_{n+1} in Yc)
+    auto stages = [&](double hd) -> int {
       for (int e = 1; e <= 5; ++e) {
         Stage<T> st = qstage<T>();
-        st.nprev = e; st.dt = hdt; st.a_new = (T)TSIT5_A[e][e];
+        st.nprev = e; st.dt = (T)hd; st.a_new = (T)TSIT5_A[e][e];
         for (int jj = 0; jj < e; ++jj) { st.a[jj] = (T)TSIT5_A[e][jj]; st.Fprev[jj][0] = (const T*)h->F[jj]; }
         st.Yin[0] = (const T*)Yc; st.y[0] = (const T*)y; st.Yout[0] = (T*)Yn;
         st.Fout[0] = (e <= 4) ? (T*)h->F[e] : nullptr;
-        if (int rc = eval_rhs<T>(h, A, st, step_dt(i), s)) return rc;
+        if (int rc = eval_rhs<T>(h, A, st, hd, s)) return rc;
         std::swap(Yc, Yn);
       }
-      if (i + 1 < total) {
-        Stage<T> st = qstage<T>();
-        st.dt = (T)step_dt(i + 1); st.a_new = (T)TSIT5_A[0][0];
-        st.Yin[0] = (const T*)Yc; st.Fout[0] = (T*)h->F[0]; st.Yout[0] = (T*)Yn;
-        if (int rc = eval_rhs<T>(h, A, st, step_dt(i + 1), s)) return rc;
-        void* oy = y; y = Yc; Yc = Yn; Yn = oy;
-      } else {
-        std::swap(y, Yc);
+      return 0;
+    };
+    // a step followed by another one: also the FSAL evaluation f(Y7) = next step's F1 and Y2
+    auto full_step = [&](double hd, double hnext) -> int {
+      if (int rc = stages(hd)) return rc;
+      Stage<T> st = qstage<T>();
+      st.dt = (T)hnext; st.a_new = (T)TSIT5_A[0][0];
+      st.Yin[0] = (const T*)Yc; st.Fout[0] = (T*)h->F[0]; st.Yout[0] = (T*)Yn;
+      if (int rc = eval_rhs<T>(h, A, st, hnext, s)) return rc;
+      void* oy = y; y = Yc; Yc = Yn; Yn = oy;
+      return 0;
+    };
+    long i = 0;
+    if (use_graph) {
+      StepGraph& G = h->graph;
+      const double key[6] = {dt, p->lateral_viscosity, p->bottom_drag, p->wind_amplitude, p->H0, 1.0};
+      bool same = G.exec != nullptr;
+      for (int k = 0; k < 6; ++k) same = same && (G.key[k] == key[k]);
+      if (!same) {
+        if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+        const uint64_t n0 = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        SB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        int rc = full_step(dt, dt);
+        if (!rc) rc = full_step(dt, dt);          // buffers are back in their starting roles
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(SOMAX_B200_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&G.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(SOMAX_B200_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+        G.nlaunch = g_launches.load() - n0;
+        g_launches.fetch_sub(G.nlaunch);          // captured, not executed
+        for (int k = 0; k < 6; ++k) G.key[k] = key[k];
       }
+      const long pairs = (n_steps - 1) / 2;       // steps 0 .. n_steps-2 have dt before and after
+      for (long r = 0; r < pairs; ++r) SB_CUDA(cudaGraphLaunch(G.exec, s));
+      g_launches.fetch_add(G.nlaunch * (uint64_t)pairs);
+      i = 2 * pairs;
     }
+    for (; i + 1 < total; ++i)
+      if (int rc = full_step(step_dt(i), step_dt(i + 1))) return rc;
+    if (int rc = stages(step_dt(total - 1))) return rc;
+    std::swap(y, Yc);
   }
-  return unpack_field<T>((const T*)y, (T*)q, L, s);
+  if (int rc = unpack_field<T>((const T*)y, (T*)q, L, s)) return rc;
+  if (use_graph) {
+    SB_CUDA(cudaEventRecord(h->graph.ev_out, s));
+    SB_CUDA(cudaStreamWaitEvent(caller, h->graph.ev_out, 0));
+  }
+  return 0;
 }
 
 template <typename T>
@@ -506,6 +555,7 @@ int somax_b200_qg_create(somax_b200_qg_t* out, int dtype, int batch, int nl, int
 
 int somax_b200_qg_destroy(somax_b200_qg_t h) {
   if (!h) return 0;
+  h->graph.destroy();
   qg_solver_destroy(h->solver);
   cudaFree(h->beta); cudaFree(h->wind);
   cudaFree(h->y); cudaFree(h->Ya); cudaFree(h->Yb); cudaFree(h->psi);

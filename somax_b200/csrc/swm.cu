@@ -541,6 +541,7 @@ struct somax_b200_swm_s {
   void* Ya[3] = {0, 0, 0};
   void* Yb[3] = {0, 0, 0};
   void* F[5][3] = {};
+  StepGraph graph;
   size_t bytes = 0;
 };
 
@@ -601,15 +602,23 @@ int bc_inplace(somax_b200_swm_t h, void* const f[3], cudaStream_t s) {
 
 template <typename T>
 int swm_steps_impl(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps, double dt,
-                   double dt_last, const somax_b200_params* p, cudaStream_t s) {
+                   double dt_last, const somax_b200_params* p, cudaStream_t caller) {
   const Layout& L = h->L;
+  const long total = n_steps + (dt_last > 0 ? 1 : 0);
+  const bool use_graph = !prof_enabled() && L.count() <= GRAPH_MAX_CELLS && n_steps >= 9 &&
+                         h->graph.init() == 0;
+  cudaStream_t s = caller;
+  if (use_graph) {
+    s = h->graph.stream;
+    SB_CUDA(cudaEventRecord(h->graph.ev_in, caller));
+    SB_CUDA(cudaStreamWaitEvent(s, h->graph.ev_in, 0));
+  }
   void* ext[3] = {hh, u, v};
   void *y[3], *Yc[3], *Yn[3];
   for (int f = 0; f < 3; ++f) { y[f] = h->y[f]; Yc[f] = h->Ya[f]; Yn[f] = h->Yb[f]; }
   for (int f = 0; f < 3; ++f)
     if (int rc = pack_field<T>((const T*)ext[f], (T*)y[f], L, s)) return rc;
   if (int rc = bc_inplace<T>(h, y, s)) return rc;   // integrate(): BC on state0
-  const long total = n_steps + (dt_last > 0 ? 1 : 0);
   if (total > 0) {
     SwmArgs<T> A = make_args<T>(h, p, 1);
     auto step_dt = [&](long i) { return (i < n_steps) ? dt : dt_last; };
@@ -622,11 +631,10 @@ int swm_steps_impl(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps,
       st.a_new = (T)TSIT5_A[0][0]; st.dt = (T)step_dt(0);
       if (int rc = launch_rhs<T>(h, A, st, s)) return rc;
     }
-    for (long i = 0; i < total; ++i) {
-      const T hdt = (T)step_dt(i);
+    auto stages = [&](double hd) -> int {
       for (int e = 1; e <= 5; ++e) {
         Stage<T> st = empty_stage<T>();
-        st.nprev = e; st.dt = hdt; st.a_new = (T)TSIT5_A[e][e];
+        st.nprev = e; st.dt = (T)hd; st.a_new = (T)TSIT5_A[e][e];
         for (int jj = 0; jj < e; ++jj) st.a[jj] = (T)TSIT5_A[e][jj];
         for (int f = 0; f < 3; ++f) {
           st.Yin[f] = (const T*)Yc[f]; st.y[f] = (const T*)y[f]; st.Yout[f] = (T*)Yn[f];
@@ -636,22 +644,58 @@ int swm_steps_impl(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps,
         if (int rc = launch_rhs<T>(h, A, st, s)) return rc;
         for (int f = 0; f < 3; ++f) { void* t = Yc[f]; Yc[f] = Yn[f]; Yn[f] = t; }
       }
-      // Yc now holds Y7 = y_{n+1}; Yn is free.
-      if (i + 1 < total) {
-        Stage<T> st = empty_stage<T>();
-        st.dt = (T)step_dt(i + 1); st.a_new = (T)TSIT5_A[0][0];
-        for (int f = 0; f < 3; ++f) {
-          st.Yin[f] = (const T*)Yc[f]; st.Fout[f] = (T*)h->F[0][f]; st.Yout[f] = (T*)Yn[f];
-        }
-        if (int rc = launch_rhs<T>(h, A, st, s)) return rc;
-        for (int f = 0; f < 3; ++f) { void* oy = y[f]; y[f] = Yc[f]; Yc[f] = Yn[f]; Yn[f] = oy; }
-      } else {
-        for (int f = 0; f < 3; ++f) { void* oy = y[f]; y[f] = Yc[f]; Yc[f] = oy; }
+      return 0;
+    };
+    auto full_step = [&](double hd, double hnext) -> int {
+      if (int rc = stages(hd)) return rc;
+      Stage<T> st = empty_stage<T>();
+      st.dt = (T)hnext; st.a_new = (T)TSIT5_A[0][0];
+      for (int f = 0; f < 3; ++f) {
+        st.Yin[f] = (const T*)Yc[f]; st.Fout[f] = (T*)h->F[0][f]; st.Yout[f] = (T*)Yn[f];
       }
+      if (int rc = launch_rhs<T>(h, A, st, s)) return rc;
+      for (int f = 0; f < 3; ++f) { void* oy = y[f]; y[f] = Yc[f]; Yc[f] = Yn[f]; Yn[f] = oy; }
+      return 0;
+    };
+    long i = 0;
+    if (use_graph) {
+      StepGraph& G = h->graph;
+      const double key[6] = {dt, p->lateral_viscosity, p->bottom_drag, p->wind_amplitude, p->H0, 2.0};
+      bool same = G.exec != nullptr;
+      for (int k = 0; k < 6; ++k) same = same && (G.key[k] == key[k]);
+      if (!same) {
+        if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+        const uint64_t n0 = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        SB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        int rc = full_step(dt, dt);
+        if (!rc) rc = full_step(dt, dt);          // buffers are back in their starting roles
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(SOMAX_B200_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&G.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(SOMAX_B200_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+        G.nlaunch = g_launches.load() - n0;
+        g_launches.fetch_sub(G.nlaunch);          // captured, not executed
+        for (int k = 0; k < 6; ++k) G.key[k] = key[k];
+      }
+      const long pairs = (n_steps - 1) / 2;
+      for (long r = 0; r < pairs; ++r) SB_CUDA(cudaGraphLaunch(G.exec, s));
+      g_launches.fetch_add(G.nlaunch * (uint64_t)pairs);
+      i = 2 * pairs;
     }
+    for (; i + 1 < total; ++i)
+      if (int rc = full_step(step_dt(i), step_dt(i + 1))) return rc;
+    if (int rc = stages(step_dt(total - 1))) return rc;
+    for (int f = 0; f < 3; ++f) { void* oy = y[f]; y[f] = Yc[f]; Yc[f] = oy; }
   }
   for (int f = 0; f < 3; ++f)
     if (int rc = unpack_field<T>((const T*)y[f], (T*)ext[f], L, s)) return rc;
+  if (use_graph) {
+    SB_CUDA(cudaEventRecord(h->graph.ev_out, s));
+    SB_CUDA(cudaStreamWaitEvent(caller, h->graph.ev_out, 0));
+  }
   return 0;
 }
 
@@ -755,6 +799,7 @@ int somax_b200_swm_create(somax_b200_swm_t* out, int dtype, int batch, int nl, i
 
 int somax_b200_swm_destroy(somax_b200_swm_t h) {
   if (!h) return 0;
+  h->graph.destroy();
   cudaFree(h->f); cudaFree(h->wx); cudaFree(h->wy);
   for (int f = 0; f < 3; ++f) {
     cudaFree(h->y[f]); cudaFree(h->Ya[f]); cudaFree(h->Yb[f]);
