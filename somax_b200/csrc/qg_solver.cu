@@ -44,7 +44,7 @@ struct QgSolver {
   double* ctab = nullptr; long long* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
   int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0; double* dbad = nullptr;
   double* bsig = nullptr; double* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
-  double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; double* meet = nullptr; double* meetc = nullptr;
+  double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; float* gvecf = nullptr; double* meet = nullptr; double* meetc = nullptr;
   void* tw = nullptr; void* twc = nullptr; void* dstmat = nullptr;
   FftPlan plan;
   Mix l2m, m2l;
@@ -252,13 +252,14 @@ __global__ void rowdst_dense(Layout L, int ny, int n, int np, int nl, Mix mix,
 }
 
 // ------------------------------------------------------------------------------------------
-// Thomas sweeps along y, one thread per x-wavenumber, fp64 carry.
+// Thomas sweeps along y, one thread per x-wavenumber.
 //   normalised system per column: x_{j-1} + delta x_j + x_{j+1} = dy^2 f_j
 //   c_j = 1/(delta - c_{j-1}),  d_j = (dy^2 f_j - d_{j-1}) c_j,  x_j = d_j - c_j x_{j+1}
-// c_j converges to a fixed point after J rows (J << ny for almost every wavenumber): rows
-// below J read a per-column fp64 table, the rest use the constant.  Rows are processed in
-// batches of TH_RB so that only ONE fp64 FMA per row sits on the loop-carried chain; input rows
-// are prefetched TH_NB batches ahead with cp.async into a per-thread shared-memory ring.
+// c_j is a property of the grid only: it is tabulated on the host in fp64 and converges to a
+// fixed point after J rows (J << ny for almost every wavenumber), so rows below J read a
+// per-strip table and the rest use the constant.  With exact coefficients the recurrence error
+// of a column grows like (n / k pi) eps: the few low-k strips carry the recurrence in fp64 in
+// both pipelines, everything else runs in the pipeline's own precision.
 // ------------------------------------------------------------------------------------------
 struct ThomasTab {
   // Coefficient table blocked like the data: for (mode m, strip) the rows i = 0..Js-1 of the
@@ -270,27 +271,8 @@ struct ThomasTab {
   double* meet;              // [plane][2][np]: last eliminated value of each half (fp64)
   int ny, np, ncols, nl, nstrip;
   double dy2;
-  int dbg;                   // SOMAX_B200_DEBUG bits (experiments only)
 };
 
-constexpr int TH_RB = 8;   // rows per batch
-template <typename T> struct ThNB { static constexpr int v = sizeof(T) == 4 ? 8 : 4; };  // batches in flight
-
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-template <typename T>
-__device__ __forceinline__ void cp_async_elem(T* smem, const T* gmem) {
-  if (sizeof(T) == 4) cp_async4(smem, gmem); else cp_async8(smem, gmem);
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // Two-way ("burn at both ends") Thomas: every column is handled by TWO threads (blockIdx.z):
 // half 0 eliminates rows 0..m1-1 downwards, half 1 eliminates rows ny-1..m1 upwards with the
@@ -301,11 +283,6 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   SUBST = true : substitution x_s = d_s - c_s x_{s'}  outwards from the meeting point
 // FROM_VEC (elimination only): right-hand side is gvec[plane][j] for every column (border solve).
 // COMBINE (substitution only): out = V - bsig[c] * x (second solve applied to the first one's V).
-//
-// Batches are split warp-uniformly: a batch whose table indices are all >= Jw (max over the
-// warp of the per-column convergence row; ny if the warp holds an indefinite column) takes the
-// FAST path (constant coefficient, pointer increments); others take the GENERAL path whose
-// coefficient loads are software-pipelined one batch ahead.
 // ---- bulk-async (TMA engine) helpers: 1-D cp.async.bulk + mbarrier, no tensor map needed ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -336,58 +313,31 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-constexpr int TH_RT = 16;   // rows per staged tile (one contiguous TH_RT x 64 block of a strip)
-// ring depth: light CTAs stage data only (deep ring); heavy CTAs (strips whose coefficient
-// recurrence converges late) also stage fp64 coefficient tiles
-template <typename T, bool COMBINE, bool TAB> struct ThStages {
-  static constexpr int v = sizeof(T) == 4 ? (COMBINE ? 6 : 8) : (COMBINE ? 3 : (TAB ? 4 : 6));
+constexpr int TH_RT = 16;   // rows per register block of the recurrence
+// Launch classes of a sweep.  LOWK (TAB = true): the few strips of near-singular low x-wavenumbers
+// (and late-converging coefficient recurrences): fp64 carried recurrence for both pipelines,
+// coefficient tiles staged through shared memory, big staged tiles because only a handful of
+// CTAs exist and each is a serial chain over ny/2 rows.  PLAIN (TAB = false): everything else, in
+// the pipeline's own precision, coefficients (needed for the first rows only) read from L2.
+template <typename T, bool TAB> struct ThRows {      // rows per staged tile
+  static constexpr int v = TAB ? (sizeof(T) == 4 ? 64 : 32) : TH_RT;
+};
+template <typename T, bool COMBINE, bool TAB> struct ThStages {   // ring depth
+  static constexpr int v = TAB ? (COMBINE ? 3 : 4) : (sizeof(T) == 4 ? (COMBINE ? 6 : 8) : (COMBINE ? 3 : 6));
 };
 
-// ---- float-float ("double-single") arithmetic: an unevaluated sum h + l of two floats, ~44
-// bits.  Used for the carried recurrence of the fp32 pipeline so that it needs neither the fp64
-// pipe nor fp32<->fp64 conversions (F2F runs at only ~16 lanes/clk/SM on B200; measured in
-// tools/micro/f2f_rate.cu).  Products use FMA for the exact error term.
-struct ff { float h, l; };
-__host__ __device__ __forceinline__ ff ff_from_double(double x) {
-  ff r; r.h = (float)x; r.l = (float)(x - (double)r.h); return r;
-}
-__device__ __forceinline__ double ff_to_double(ff a) { return (double)a.h + (double)a.l; }
-// (h,l) * f, f a plain float.  __fmul_rn / __fadd_rn / __fsub_rn are never contracted into FMAs
-// by the compiler, which the error-free transformations rely on.
-__device__ __forceinline__ ff ff_mul_f(ff a, float f) {
-  ff r; r.h = __fmul_rn(a.h, f);
-  const float e = fmaf(a.h, f, -r.h);
-  r.l = fmaf(a.l, f, e);
-  return r;
-}
-// (h,l) * (h,l), dropping the l*l term
-__device__ __forceinline__ ff ff_mul(ff a, ff b) {
-  ff r; r.h = __fmul_rn(a.h, b.h);
-  const float e = fmaf(a.h, b.h, -r.h);
-  r.l = fmaf(a.h, b.l, fmaf(a.l, b.h, e));
-  return r;
-}
-// t - p, normalised (TwoSum + FastTwoSum)
-__device__ __forceinline__ ff ff_sub(ff t, ff p) {
-  const float s = __fsub_rn(t.h, p.h);
-  const float bb = __fsub_rn(s, t.h);
-  const float se = __fadd_rn(__fsub_rn(t.h, __fsub_rn(s, bb)), __fsub_rn(-p.h, bb));
-  const float sl = __fadd_rn(se, __fsub_rn(t.l, p.l));
-  ff r; r.h = __fadd_rn(s, sl); r.l = __fsub_rn(sl, __fsub_rn(r.h, s));
-  return r;
-}
-
-// float-float version of thomas_tile for T = float (same modes / phases).  Coefficient tiles and
-// the indefinite-column side buffer hold (hi, lo) float pairs in their 8-byte slots.
+// Plain fp32 recurrence over one register block, for the well-conditioned strips of the fp32
+// pipeline: for x-wavenumbers k >~ n/32 the fp32 recurrence error stays at the rounding level
+// (~1e-7 per column; the error of a column grows like (n / k pi) eps with exact coefficients),
+// only the low-k strips need the fp64 carry.  Coefficient rows are plain floats.
 template <bool SUBST, bool FROM_VEC, bool COMBINE, bool UP, int MODE>
-__device__ __forceinline__ void thomas_tile_ff(float (*A)[TH_COLS], const float (*Vt)[TH_COLS],
-                                               const ff (*Ct)[TH_COLS], const ff* __restrict__ gv,
-                                               ff* __restrict__ dbc, int KB, int tid, int nr, int s0,
-                                               int ilo, int Js, int cnt, int jb, bool act, bool bad,
-                                               ff cfix, ff kfix, ff dy2, ff bs, ff& carry) {
+__device__ __forceinline__ void thomas_tile_f32(float (*A)[TH_COLS], const float (*Vt)[TH_COLS],
+                                                const float (*Ct)[TH_COLS], const float* __restrict__ gv,
+                                                int tid, int nr, int s0, int ilo, int Js, int cnt, int jb,
+                                                bool act, float cfix, float kfix, float dy2, float bs,
+                                                float& carry) {
   constexpr int dj = UP ? 1 : -1;
-  ff t[TH_RT], cj[TH_RT];
-  float vv[TH_RT];
+  float f[TH_RT], cj[TH_RT], vv[TH_RT];
 #pragma unroll
   for (int r = 0; r < TH_RT; ++r) {
     const bool ok = MODE != 2 || r < nr;
@@ -396,42 +346,31 @@ __device__ __forceinline__ void thomas_tile_ff(float (*A)[TH_COLS], const float 
     if (MODE == 0) cj[r] = cfix;
     else if (MODE == 1) cj[r] = Ct[i - ilo][tid];
     else cj[r] = (ok && i < Js) ? Ct[i - ilo][tid] : cfix;
-    ff f; f.l = 0.f;
-    if (FROM_VEC) { if (ok) f = gv[jb + dj * r]; else f.h = 0.f; }
-    else f.h = ok ? A[ok ? rm : 0][tid] : 0.f;
+    if (FROM_VEC) f[r] = ok ? gv[jb + dj * r] : 0.f;
+    else f[r] = ok ? A[ok ? rm : 0][tid] : 0.f;
     if (COMBINE) vv[r] = ok ? Vt[ok ? rm : 0][tid] : 0.f;
-    if (MODE == 2 && SUBST && bad && ok) f = dbc[(size_t)(jb + dj * r) * KB];
-    if (!SUBST) {
-      // t = c * dy^2 * f   (off the carried chain)
-      if (MODE == 0 && !FROM_VEC) t[r] = ff_mul_f(kfix, f.h);
-      else if (MODE == 0) t[r] = ff_mul(kfix, f);
-      else t[r] = ff_mul(cj[r], FROM_VEC ? ff_mul(dy2, f) : ff_mul_f(dy2, f.h));
-    } else {
-      t[r] = f;
-    }
+  }
+  if (!SUBST) {
+#pragma unroll
+    for (int r = 0; r < TH_RT; ++r) f[r] = (MODE == 0 ? kfix : cj[r] * dy2) * f[r];
   }
 #pragma unroll
   for (int r = 0; r < TH_RT; ++r)
-    if (MODE != 2 || r < nr) { carry = ff_sub(t[r], ff_mul(cj[r], carry)); t[r] = carry; }
+    if (MODE != 2 || r < nr) { carry = fmaf(-cj[r], carry, f[r]); f[r] = carry; }
 #pragma unroll
   for (int r = 0; r < TH_RT; ++r) {
     if (MODE != 2 || r < nr) {
       const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);
-      if (COMBINE) {
-        float o = fmaf(-bs.h, t[r].h, vv[r]);
-        o = fmaf(-bs.h, t[r].l, o);
-        o = fmaf(-bs.l, t[r].h, o);
-        A[rm][tid] = act ? o : vv[r];
-      } else if (act) A[rm][tid] = t[r].h;
+      if (COMBINE) A[rm][tid] = act ? fmaf(-bs, f[r], vv[r]) : vv[r];
+      else if (act) A[rm][tid] = f[r];
       else if (FROM_VEC) A[rm][tid] = 0.f;
-      if (MODE == 2 && !SUBST && bad) dbc[(size_t)(jb + dj * r) * KB] = t[r];
     }
   }
 }
 
-// Recurrence over one staged tile for one column (thread).  UP: memory rows ascend with the
-// sequence (dj > 0).  MODE 0: full tile, constant coefficient; MODE 1: full tile, every row
-// tabulated (coefficients in Ct); MODE 2: generic (ragged end, tile straddling the convergence
+// fp64 recurrence over one register block for one column (thread).  UP: memory rows ascend with
+// the sequence (dj > 0).  MODE 0: full block, constant coefficient; MODE 1: full block, every row
+// tabulated (coefficients in Ct); MODE 2: generic (ragged end, block straddling the convergence
 // row, indefinite columns with their fp64 side buffer).  Phases are explicit (all loads, the
 // carried chain, all stores) so the shared-memory accesses pipeline.
 template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE, bool UP, int MODE>
@@ -439,14 +378,15 @@ __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_CO
                                             const double (*Ct)[TH_COLS], const double* __restrict__ gv,
                                             double* __restrict__ dbc, int KB, int tid, int nr, int s0,
                                             int ilo, int Js, int cnt, int jb, bool act, bool bad,
-                                            double cfix, double dy2, double bs, double& carry) {
+                                            double cfix, double dy2, double bs, double& carry,
+                                            double (&dpre)[TH_RT]) {
   constexpr int dj = UP ? 1 : -1;
   double f[TH_RT], cj[TH_RT];
   T vv[TH_RT];
 #pragma unroll
   for (int r = 0; r < TH_RT; ++r) {
     const bool ok = MODE != 2 || r < nr;
-    const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);   // memory row in the tile
+    const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);   // memory row in the block
     const int i = SUBST ? cnt - 1 - (s0 + r) : s0 + r;                  // table index of the row
     if (MODE == 0) cj[r] = cfix;
     else if (MODE == 1) cj[r] = Ct[i - ilo][tid];
@@ -454,7 +394,16 @@ __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_CO
     if (FROM_VEC) f[r] = ok ? gv[jb + dj * r] : 0.0;
     else f[r] = ok ? (double)A[ok ? rm : 0][tid] : 0.0;
     if (COMBINE) vv[r] = ok ? Vt[ok ? rm : 0][tid] : T(0);
-    if (MODE == 2 && SUBST && bad && ok) f[r] = dbc[(size_t)(jb + dj * r) * KB];
+  }
+  if (MODE != 0 && SUBST && bad) {
+    // indefinite column: the eliminated right-hand side lives in the fp64 side buffer; this
+    // block's values were prefetched while the previous block ran, now fetch the next block's
+#pragma unroll
+    for (int r = 0; r < TH_RT; ++r)
+      if (MODE != 2 || r < nr) f[r] = dpre[r];
+#pragma unroll
+    for (int r = 0; r < TH_RT; ++r)
+      dpre[r] = (s0 + TH_RT + r < cnt) ? dbc[(size_t)(jb + dj * (TH_RT + r)) * KB] : 0.0;
   }
   if (!SUBST) {
     if (MODE == 0) {
@@ -476,30 +425,33 @@ __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_CO
       if (COMBINE) A[rm][tid] = act ? (T)((double)vv[r] - bs * f[r]) : vv[r];
       else if (act) A[rm][tid] = (T)f[r];
       else if (FROM_VEC) A[rm][tid] = T(0);
-      if (MODE == 2 && !SUBST && bad) dbc[(size_t)(jb + dj * r) * KB] = f[r];
+      if (MODE != 0 && !SUBST && bad) dbc[(size_t)(jb + dj * r) * KB] = f[r];
     }
   }
 }
 
 // y-sweep over staged tiles.  Each CTA owns one 64-column strip of one plane and one half
-// (two-way elimination); it streams contiguous TH_RT-row tiles of the strip through an NS-stage
+// (two-way elimination); it streams contiguous RT-row tiles of the strip through an NS-stage
 // shared-memory ring: ONE cp.async.bulk per tile (TMA engine, completes on an mbarrier), the
-// recurrence runs on shared memory only, and the finished tile leaves with one bulk store.
-// Tiles that still need tabulated coefficients (rows below the strip's convergence row Js) get
-// their fp64 coefficient tile through the same ring, so they run at the same speed.
+// recurrence runs on shared memory only (register blocks of TH_RT rows), and the finished tile
+// leaves with one bulk store.
 template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE, bool TAB>
 __global__ void __launch_bounds__(TH_COLS)
 thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* __restrict__ V,
-             const double* __restrict__ gvec, const double* __restrict__ bsig, T* __restrict__ out) {
+             const double* __restrict__ gvec, const float* __restrict__ gvecf,
+             const double* __restrict__ bsig, T* __restrict__ out) {
   constexpr int NS = ThStages<T, COMBINE, TAB>::v;
+  constexpr int RT = ThRows<T, TAB>::v;
   constexpr bool LOAD = !FROM_VEC;
+  constexpr bool PLAIN = sizeof(T) == 4 && !TAB;     // fp32 arithmetic, float coefficient rows
   static_assert(TH_COLS == SP_W, "one CTA per 64-column strip");
-  constexpr size_t TILE_B = (size_t)TH_RT * TH_COLS * sizeof(T);
-  constexpr size_t CT_B = TAB ? (size_t)TH_RT * TH_COLS * sizeof(double) : 0;
+  static_assert(RT % TH_RT == 0, "staged tile = whole register blocks");
+  constexpr size_t TILE_B = (size_t)RT * TH_COLS * sizeof(T);
+  constexpr size_t CT_B = TAB ? (size_t)RT * TH_COLS * sizeof(double) : 0;
   extern __shared__ __align__(128) unsigned char th_smem[];
-  double (*tileC)[TH_RT][TH_COLS] = reinterpret_cast<double (*)[TH_RT][TH_COLS]>(th_smem);
-  T (*tileA)[TH_RT][TH_COLS] = reinterpret_cast<T (*)[TH_RT][TH_COLS]>(th_smem + NS * CT_B);
-  T (*tileV)[TH_RT][TH_COLS] = reinterpret_cast<T (*)[TH_RT][TH_COLS]>(th_smem + NS * CT_B + NS * TILE_B);
+  double (*tileC)[RT][TH_COLS] = reinterpret_cast<double (*)[RT][TH_COLS]>(th_smem);
+  T (*tileA)[RT][TH_COLS] = reinterpret_cast<T (*)[RT][TH_COLS]>(th_smem + NS * CT_B);
+  T (*tileV)[RT][TH_COLS] = reinterpret_cast<T (*)[RT][TH_COLS]>(th_smem + NS * CT_B + NS * TILE_B);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(
       th_smem + NS * CT_B + NS * TILE_B * (COMBINE ? 2 : 1));
   const int tid = threadIdx.x;
@@ -516,31 +468,25 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   const bool bad = act && c < tb.kbad[m];
   double* dbc = tb.dbad + ((size_t)plane * ny) * tb.KB + (bad ? c : 0);
   const double bs = (COMBINE && act) ? bsig[c] : 0.0;
-  constexpr bool FF = sizeof(T) == 4;          // fp32 pipeline: float-float carried recurrence
-  ff cfix_f = {0.f, 0.f}, kfix_f = {0.f, 0.f}, bs_f = {0.f, 0.f}, dy2_f = {0.f, 0.f}, carry_f = {0.f, 0.f};
-  if (FF) {
-    cfix_f = reinterpret_cast<const ff*>(tb.cinf)[(size_t)m * tb.np + c];   // tables pre-split on the host
-    kfix_f = ff_from_double(ff_to_double(cfix_f) * tb.dy2);
-    bs_f = ff_from_double(bs);
-    dy2_f = ff_from_double(tb.dy2);
-  }
-  const bool strip_bad = strip * TH_COLS < tb.kbad[m];     // this strip holds indefinite columns
+  const float cfix_f = (float)cfix, kfix_f = (float)(cfix * tb.dy2), dy2_f = (float)tb.dy2, bs_f = (float)bs;
+  float carry_f = 0.f;
   const double* gv = gvec + (FROM_VEC ? (size_t)plane * ny : 0);
+  const float* gvf = gvecf + (FROM_VEC ? (size_t)plane * ny : 0);
   const int m1 = ny / 2;
   const int cnt = half == 0 ? m1 : ny - m1;
   int j0, dj;
   if (!SUBST) { j0 = half == 0 ? 0 : ny - 1; dj = half == 0 ? 1 : -1; }
   else        { j0 = half == 0 ? m1 - 1 : m1; dj = half == 0 ? -1 : 1; }
-  const int ntile = (cnt + TH_RT - 1) / TH_RT;
+  const int ntile = (cnt + RT - 1) / RT;
   // tile t covers sequence numbers s0..s0+nr-1, i.e. memory rows jlo..jlo+nr-1 (ascending), and
   // table indices ilo..ilo+nr-1 (i = s for elimination, cnt-1-s for substitution)
-  auto tile_nr = [&](int t) { return min(TH_RT, cnt - t * TH_RT); };
+  auto tile_nr = [&](int t) { return min(RT, cnt - t * RT); };
   auto tile_jlo = [&](int t) {
-    const int s0 = t * TH_RT, nr = min(TH_RT, cnt - s0);
+    const int s0 = t * RT, nr = min(RT, cnt - s0);
     return dj > 0 ? j0 + s0 : j0 - (s0 + nr - 1);
   };
   auto tile_ilo = [&](int t) {
-    const int s0 = t * TH_RT, nr = min(TH_RT, cnt - s0);
+    const int s0 = t * RT, nr = min(RT, cnt - s0);
     return SUBST ? cnt - 1 - (s0 + nr - 1) : s0;
   };
 
@@ -575,70 +521,78 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   if (SUBST && cnt > 0 && m1 > 0) {
     // meeting point: x_{m1-1} + ca x_{m1} = d_{m1-1};  x_{m1} + cb x_{m1-1} = e_{m1}
     const double ca = tb.meetc[((size_t)m * 2 + 0) * tb.np + c], cb = tb.meetc[((size_t)m * 2 + 1) * tb.np + c];
-    double dm = tb.meet[((size_t)plane * 2 + 0) * tb.np + c];
-    double em = tb.meet[((size_t)plane * 2 + 1) * tb.np + c];
-    if (FF) {   // the fp32 pipeline keeps (hi, lo) float pairs in the 8-byte slots
-      dm = ff_to_double(reinterpret_cast<const ff*>(tb.meet)[((size_t)plane * 2 + 0) * tb.np + c]);
-      em = ff_to_double(reinterpret_cast<const ff*>(tb.meet)[((size_t)plane * 2 + 1) * tb.np + c]);
-    }
+    const double dm = tb.meet[((size_t)plane * 2 + 0) * tb.np + c];
+    const double em = tb.meet[((size_t)plane * 2 + 1) * tb.np + c];
     const double den = 1.0 / (1.0 - ca * cb);
     const double xa = (dm - ca * em) * den, xb = (em - cb * dm) * den;
     carry = half == 0 ? xb : xa;     // the neighbour's value across the meeting point
-    carry_f = ff_from_double(carry);
+    carry_f = (float)carry;
+  }
+  double dpre[TH_RT];                // indefinite columns: side-buffer values of the next block
+  if (!PLAIN && SUBST && bad) {
+#pragma unroll
+    for (int r = 0; r < TH_RT; ++r) dpre[r] = (r < cnt) ? dbc[(size_t)(j0 + dj * r) * tb.KB] : 0.0;
   }
 
   unsigned phase_bits = 0;            // per-stage phase parity (stages may be skipped by FROM_VEC tiles)
 #pragma unroll 1
   for (int t = 0; t < ntile; ++t) {
     const int st = t % NS;
-    const int nr = tile_nr(t);
-    const int s0 = t * TH_RT;
-    const int ilo = tile_ilo(t);
+    const int nrt = tile_nr(t);
+    const int ilot = tile_ilo(t);
     if (tile_has_load(t)) {
       mbar_wait(&full[st], (phase_bits >> st) & 1u);
       phase_bits ^= 1u << st;
     }
-    T (*A)[TH_COLS] = tileA[st];
-    T (*Vt)[TH_COLS] = tileV[st];
-    // coefficient rows of this tile: staged in shared memory (TAB) or read straight from L2
-    const double (*Ct)[TH_COLS] = TAB ? (const double (*)[TH_COLS])tileC[st]
-                                      : (const double (*)[TH_COLS])(tabS + (size_t)ilo * TH_COLS);
-    const int jb = j0 + dj * s0;
-    // mode: 0 = constant coefficient, 1 = fully tabulated, 2 = generic
-    const int mode = (nr < TH_RT || strip_bad || (ilo < Js && ilo + nr > Js)) ? 2 : (ilo >= Js ? 0 : 1);
-    if (!(tb.dbg & 1)) {
-#define SB_TILE(UPV, MODEV)                                                                     \
-      do {                                                                                      \
-        if constexpr (FF)                                                                       \
-          thomas_tile_ff<SUBST, FROM_VEC, COMBINE, UPV, MODEV>(                                 \
-              reinterpret_cast<float (*)[TH_COLS]>(A), reinterpret_cast<const float (*)[TH_COLS]>(Vt), \
-              reinterpret_cast<const ff (*)[TH_COLS]>(Ct), reinterpret_cast<const ff*>(gv),     \
-              reinterpret_cast<ff*>(dbc), tb.KB, tid, nr, s0, ilo, Js, cnt, jb, act, bad, cfix_f, kfix_f, \
-              dy2_f, bs_f, carry_f);                                                            \
-        else                                                                                    \
-          thomas_tile<T, SUBST, FROM_VEC, COMBINE, UPV, MODEV>(A, Vt, Ct, gv, dbc, tb.KB, tid, nr, s0, ilo, \
-                                                               Js, cnt, jb, act, bad, cfix, tb.dy2, bs, carry); \
-      } while (0)
-      if (dj > 0) {
-        if (mode == 0) SB_TILE(true, 0); else if (mode == 1) SB_TILE(true, 1); else SB_TILE(true, 2);
-      } else {
-        if (mode == 0) SB_TILE(false, 0); else if (mode == 1) SB_TILE(false, 1); else SB_TILE(false, 2);
-      }
+#pragma unroll 1
+    for (int b0 = 0; b0 < nrt; b0 += TH_RT) {       // register blocks, in sequence order
+      const int nr = min(TH_RT, nrt - b0);
+      const int s0 = t * RT + b0;
+      const int ilo = SUBST ? cnt - 1 - (s0 + nr - 1) : s0;
+      const int row0 = dj > 0 ? b0 : nrt - b0 - nr;   // first memory row of the block inside the tile
+      T (*A)[TH_COLS] = tileA[st] + row0;
+      T (*Vt)[TH_COLS] = tileV[st] + row0;
+      const int jb = j0 + dj * s0;
+      // mode: 0 = constant coefficient, 1 = fully tabulated, 2 = generic
+      const int mode = (nr < TH_RT || (ilo < Js && ilo + nr > Js)) ? 2 : (ilo >= Js ? 0 : 1);
+      if constexpr (PLAIN) {
+        // float coefficient rows, read straight from L2 (only the first Js rows of a half)
+        const float (*Ct)[TH_COLS] = reinterpret_cast<const float (*)[TH_COLS]>(tabS) + ilo;
+#define SB_TILE(UPV, MODEV)                                                                        \
+        thomas_tile_f32<SUBST, FROM_VEC, COMBINE, UPV, MODEV>(                                     \
+            reinterpret_cast<float (*)[TH_COLS]>(A), reinterpret_cast<const float (*)[TH_COLS]>(Vt), Ct, gvf, \
+            tid, nr, s0, ilo, Js, cnt, jb, act, cfix_f, kfix_f, dy2_f, bs_f, carry_f)
+        if (dj > 0) {
+          if (mode == 0) SB_TILE(true, 0); else if (mode == 1) SB_TILE(true, 1); else SB_TILE(true, 2);
+        } else {
+          if (mode == 0) SB_TILE(false, 0); else if (mode == 1) SB_TILE(false, 1); else SB_TILE(false, 2);
+        }
 #undef SB_TILE
+      } else {
+        // coefficient rows of this block: staged in shared memory (TAB) or read straight from L2
+        const double (*Ct)[TH_COLS] = TAB ? (const double (*)[TH_COLS])(tileC[st] + (ilo - ilot))
+                                          : (const double (*)[TH_COLS])(tabS + (size_t)ilo * TH_COLS);
+#define SB_TILE(UPV, MODEV)                                                                        \
+        thomas_tile<T, SUBST, FROM_VEC, COMBINE, UPV, MODEV>(A, Vt, Ct, gv, dbc, tb.KB, tid, nr, s0, ilo, Js, \
+                                                             cnt, jb, act, bad, cfix, tb.dy2, bs, carry, dpre)
+        if (dj > 0) {
+          if (mode == 0) SB_TILE(true, 0); else if (mode == 1) SB_TILE(true, 1); else SB_TILE(true, 2);
+        } else {
+          if (mode == 0) SB_TILE(false, 0); else if (mode == 1) SB_TILE(false, 1); else SB_TILE(false, 2);
+        }
+#undef SB_TILE
+      }
     }
-    if (!SUBST && t == ntile - 1) {
-      if (FF) reinterpret_cast<ff*>(tb.meet)[((size_t)plane * 2 + half) * tb.np + c] = carry_f;
-      else tb.meet[((size_t)plane * 2 + half) * tb.np + c] = carry;
-    }
+    if (!SUBST && t == ntile - 1)
+      tb.meet[((size_t)plane * 2 + half) * tb.np + c] = PLAIN ? (double)carry_f : carry;
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
-    if (!(tb.dbg & 4)) fence_async_smem();
-    if (!(tb.dbg & 16)) __syncthreads();
+    fence_async_smem();
+    __syncthreads();
     if (tid == 0) {
-      if (!(tb.dbg & 2))
-        bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &A[0][0], (unsigned)(nr * TH_COLS * sizeof(T)));
+      bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &tileA[st][0][0], (unsigned)(nrt * TH_COLS * sizeof(T)));
       bulk_commit();
       // stage (t-1)%NS is free once the store of tile t-1 has finished reading shared memory
-      if (!(tb.dbg & 8)) bulk_wait_read<1>();
+      bulk_wait_read<1>();
       load_tile(t + NS - 1);
     }
   }
@@ -683,7 +637,8 @@ template <typename T, bool STAGE_A>
 __global__ void __launch_bounds__(128)
 border_gsolve(const double* __restrict__ in, const double* __restrict__ sintab,
               const double* __restrict__ sdiag, int ny, int np, int n, int nl,
-              double* __restrict__ out, double* __restrict__ gvec, T* __restrict__ S) {
+              double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
+              T* __restrict__ S) {
   const int a = blockIdx.x + 1, plane = blockIdx.y, m = plane % nl;
   const int N = ny + 1, N2 = 2 * N, B = blockDim.x;
   auto sn = [&](long long k) { return sintab[(int)(k % N2)]; };          // sin(pi k / N)
@@ -716,8 +671,8 @@ border_gsolve(const double* __restrict__ in, const double* __restrict__ sintab,
       out[(size_t)plane * ny + (a - 1)] = t / sdiag[(size_t)m * ny + (a - 1)];
     } else {
       t *= 2.0 / N;
-      if (sizeof(T) == 4) reinterpret_cast<ff*>(gvec)[(size_t)plane * ny + (a - 1)] = ff_from_double(t);
-      else gvec[(size_t)plane * ny + (a - 1)] = t;
+      gvec[(size_t)plane * ny + (a - 1)] = t;
+      if (sizeof(T) == 4) gvecf[(size_t)plane * ny + (a - 1)] = (float)t;
       S[(size_t)plane * ny * np + sp_off(ny, a - 1, n - 1)] = (T)t;
     }
   }
@@ -797,19 +752,26 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
       }
     }
   }
-  if (s->dtype == SOMAX_B200_F32) {
-    // fp32 pipeline: the sweeps read coefficients as (hi, lo) float pairs (same 8-byte slots);
-    // meetc stays fp64 (used once per thread, in double)
-    auto split = [](std::vector<double>& v) {
-      for (double& x : v) { ff p = ff_from_double(x); memcpy(&x, &p, sizeof(double)); }
-    };
-    split(ctab);
-    split(cinf);
-  }
+  // Launch classes (see ThRows): strips [0, nheavy) form the low-k launch.  A strip is low-k when
+  // its coefficient recurrence converges late (many tabulated rows) and, for the fp32 pipeline,
+  // when it holds columns k < max(64, n/32) -- near-singular enough to need the fp64 carry -- or
+  // an indefinite column.
   s->nheavy = 0;
   for (int m = 0; m < nl; ++m)
     for (int st = 0; st < nstrip; ++st)
       if (Jstrip[(size_t)m * nstrip + st] > 12 * TH_RT) s->nheavy = std::max(s->nheavy, st + 1);
+  if (s->dtype == SOMAX_B200_F32) {
+    const int klow = std::max(std::max(64, nc / 32), s->KB);
+    s->nheavy = std::min(nstrip, std::max(s->nheavy, (klow + SP_W - 1) / SP_W));
+    // plain strips read their (few) tabulated rows as floats: repack in place, [i][64] floats
+    for (int m = 0; m < nl; ++m)
+      for (int st = s->nheavy; st < nstrip; ++st) {
+        double* base = ctab.data() + tabOff[(size_t)m * nstrip + st];
+        const size_t cnt = (size_t)Jstrip[(size_t)m * nstrip + st] * SP_W;
+        float* fb = reinterpret_cast<float*>(base);
+        for (size_t i = 0; i < cnt; ++i) { const float v = (float)base[i]; fb[i] = v; }
+      }
+  }
   if (ctab.empty()) ctab.push_back(0.0);
   if (int rc = dev_upload(ctab.data(), ctab.size() * 8, (void**)&s->ctab, &s->bytes)) return rc;
   if (int rc = dev_upload(Jstrip.data(), Jstrip.size() * 4, (void**)&s->krow, &s->bytes)) return rc;
@@ -884,7 +846,8 @@ static int build_fft_tables(QgSolver* s, const double* lambdas) {
   SB_CUDA(cudaMalloc((void**)&s->rvec, vb));
   SB_CUDA(cudaMalloc((void**)&s->ghat, vb));
   SB_CUDA(cudaMalloc((void**)&s->gvec, vb));
-  s->bytes += 3 * vb;
+  SB_CUDA(cudaMalloc((void**)&s->gvecf, vb / 2));
+  s->bytes += 3 * vb + vb / 2;
   return 0;
 }
 
@@ -966,7 +929,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
 void qg_solver_destroy(QgSolver* s) {
   if (!s) return;
   void* ptrs[] = {s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->bsig, s->sig2n,
-                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->tw, s->twc, s->dstmat, s->meet, s->meetc};
+                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->gvecf, s->tw, s->twc, s->dstmat, s->meet, s->meetc};
   for (void* p : ptrs) cudaFree(p);
   if (s->aux) cudaStreamDestroy(s->aux);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -979,11 +942,13 @@ int qg_solver_kind(const QgSolver* s) { return s->kind; }
 
 template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE, bool TAB>
 static int launch_thomas_one(const char* tag, const ThomasTab& tb, int strip_first, int nstrips, int planes,
-                             const T* in, const T* V, const double* gvec, const double* bsig, T* out,
-                             cudaStream_t st) {
+                             const T* in, const T* V, const double* gvec, const float* gvecf,
+                             const double* bsig, T* out, cudaStream_t st) {
   if (nstrips <= 0) return 0;
   constexpr int NS = ThStages<T, COMBINE, TAB>::v;
-  constexpr size_t smem = (size_t)NS * TH_RT * TH_COLS * ((TAB ? sizeof(double) : 0) + sizeof(T) * (COMBINE ? 2 : 1)) + NS * 8;
+  constexpr int RT = ThRows<T, TAB>::v;
+  constexpr size_t smem = (size_t)NS * RT * TH_COLS * ((TAB ? sizeof(double) : 0) + sizeof(T) * (COMBINE ? 2 : 1)) + NS * 8;
+  static_assert(smem <= 227 * 1024, "sweep ring exceeds shared memory");
   static bool attr_done = false;
   if (smem > 48 * 1024 && !attr_done) {
     SB_CUDA(cudaFuncSetAttribute(thomas_sweep<T, SUBST, FROM_VEC, COMBINE, TAB>,
@@ -992,26 +957,38 @@ static int launch_thomas_one(const char* tag, const ThomasTab& tb, int strip_fir
   }
   prof_begin(tag, st);
   thomas_sweep<T, SUBST, FROM_VEC, COMBINE, TAB><<<dim3(nstrips, planes, 2), TH_COLS, smem, st>>>(
-      tb, strip_first, in, V, gvec, bsig, out);
+      tb, strip_first, in, V, gvec, gvecf, bsig, out);
   SB_LAUNCH_CHECK();
   return 0;
 }
 
-// One sweep = a few "heavy" strips (late-converging coefficient recurrence: coefficient tiles are
-// staged through shared memory) on the auxiliary stream, overlapped with the "light" strips on
-// the caller's stream.
-template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE>
-static int launch_thomas(const char* tag, QgSolver* s, const ThomasTab& tb, const T* in, const T* V,
-                         const double* gvec, const double* bsig, T* out, cudaStream_t st) {
+// One solve = elimination + substitution sweeps.  Strips are independent of each other, so the
+// low-k launch class runs its two sweeps back to back on the auxiliary stream while the plain
+// class runs its two on the caller's stream; the streams join after the pair.
+//   SECOND = false: S <- A^-1 S.   SECOND = true: S <- S - bsig * A^-1 (gvec x 1), W scratch.
+template <typename T, bool SECOND>
+static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream_t st) {
   const int nstrip = s->np / SP_W, nh = std::min(s->nheavy, nstrip);
-  if (nh > 0) {
+  const char* tf = SECOND ? "thomas_fwd_1" : "thomas_fwd_0";
+  const char* tbk = SECOND ? "thomas_bwd_1" : "thomas_bwd_0";
+  const char* tfl = SECOND ? "thomas_fwd_1_lowk" : "thomas_fwd_0_lowk";
+  const char* tbl = SECOND ? "thomas_bwd_1_lowk" : "thomas_bwd_0_lowk";
+  const T* fin = SECOND ? nullptr : S;      // elimination input
+  T* fout = SECOND ? W : S;                 // eliminated right-hand side
+  const T* Vv = SECOND ? S : nullptr;
+  const double* bs = SECOND ? s->bsig : nullptr;
+  const bool two = nh > 0 && nh < nstrip;
+  cudaStream_t lo = two ? s->aux : st;
+  if (two) {
     SB_CUDA(cudaEventRecord(s->ev_fork, st));
     SB_CUDA(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
-    if (int rc = launch_thomas_one<T, SUBST, FROM_VEC, COMBINE, true>(tag, tb, 0, nh, s->planes, in, V, gvec, bsig, out, s->aux)) return rc;
-    SB_CUDA(cudaEventRecord(s->ev_join, s->aux));
   }
-  if (int rc = launch_thomas_one<T, SUBST, FROM_VEC, COMBINE, false>(tag, tb, nh, nstrip - nh, s->planes, in, V, gvec, bsig, out, st)) return rc;
-  if (nh > 0) SB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+  if (int rc = launch_thomas_one<T, false, SECOND, false, true>(tfl, tb, 0, nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, lo)) return rc;
+  if (int rc = launch_thomas_one<T, true, false, SECOND, true>(tbl, tb, 0, nh, s->planes, fout, Vv, nullptr, nullptr, bs, S, lo)) return rc;
+  if (two) SB_CUDA(cudaEventRecord(s->ev_join, s->aux));
+  if (int rc = launch_thomas_one<T, false, SECOND, false, false>(tf, tb, nh, nstrip - nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, st)) return rc;
+  if (int rc = launch_thomas_one<T, true, false, SECOND, false>(tbk, tb, nh, nstrip - nh, s->planes, fout, Vv, nullptr, nullptr, bs, S, st)) return rc;
+  if (two) SB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
   return 0;
 }
 
@@ -1024,7 +1001,6 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
   for (int m = 0; m < QG_MAX_NL; ++m) tb.kbad[m] = s->kbad[m];
   tb.KB = std::max(s->KB, 1); tb.dbad = s->dbad; tb.meet = s->meet; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
   tb.dy2 = s->dy * s->dy;
-  { const char* e = getenv("SOMAX_B200_DEBUG"); tb.dbg = e ? atoi(e) : 0; }
   T* S = (T*)s->S;
   if (s->kind == SOMAX_B200_SOLVER_FFT) {
     T* W = (T*)s->W;
@@ -1035,20 +1011,18 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     for (int a = 0; a < QG_MAX_NL; ++a)
       for (int c = 0; c < QG_MAX_NL; ++c) { Af.mix[a][c] = (T)s->l2m.c[a][c]; Ai.mix[a][c] = (T)s->m2l.c[a][c]; }
     if (int rc = launch_rowdst<T, false>(s->plan.lgn, Af, q, S, st)) return rc;
-    if (int rc = launch_thomas<T, false, false, false>("thomas_fwd_0", s, tb, S, nullptr, nullptr, nullptr, S, st)) return rc;
-    if (int rc = launch_thomas<T, true, false, false>("thomas_bwd_0", s, tb, S, nullptr, nullptr, nullptr, S, st)) return rc;
+    if (int rc = launch_solve<T, false>(s, tb, S, nullptr, st)) return rc;
     const double b = 1.0 / (s->dx * s->dx);
     prof_begin("border_dot", st);
     border_dot<T><<<dim3(ny, s->planes), 256, 0, st>>>(S, s->sig2n, ny, np, s->ncols, b, s->rvec);
     SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_a", st);
-    border_gsolve<T, true><<<dim3(ny, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr);
+    border_gsolve<T, true><<<dim3(ny, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
     SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_b", st);
-    border_gsolve<T, false><<<dim3(ny, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, S);
+    border_gsolve<T, false><<<dim3(ny, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
     SB_LAUNCH_CHECK();
-    if (int rc = launch_thomas<T, false, true, false>("thomas_fwd_1", s, tb, nullptr, nullptr, s->gvec, nullptr, W, st)) return rc;
-    if (int rc = launch_thomas<T, true, false, true>("thomas_bwd_1", s, tb, W, S, nullptr, s->bsig, S, st)) return rc;
+    if (int rc = launch_solve<T, true>(s, tb, S, W, st)) return rc;
     if (int rc = launch_rowdst<T, true>(s->plan.lgn, Ai, S, psi, st)) return rc;
   } else {
     const size_t smem = (size_t)nl * n * sizeof(T);
@@ -1060,8 +1034,7 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     prof_begin("rowdst_dense_0", st);
     rowdst_dense<T, false><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->l2m, (const T*)s->dstmat, q, S, 1.0);
     SB_LAUNCH_CHECK();
-    if (int rc = launch_thomas<T, false, false, false>("thomas_fwd_0", s, tb, S, nullptr, nullptr, nullptr, S, st)) return rc;
-    if (int rc = launch_thomas<T, true, false, false>("thomas_bwd_0", s, tb, S, nullptr, nullptr, nullptr, S, st)) return rc;
+    if (int rc = launch_solve<T, false>(s, tb, S, nullptr, st)) return rc;
     prof_begin("rowdst_dense_1", st);
     rowdst_dense<T, true><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->m2l, (const T*)s->dstmat, S, psi, 2.0 / (n + 1));
     SB_LAUNCH_CHECK();

@@ -85,6 +85,29 @@ def test_qg_invert_white_noise_rhs(dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nx,ny,white", [(512, 512, True), (1024, 768, False), (2048, 1024, True),
+                                         (4096, 256, False)])
+def test_qg_invert_large_grids(nx, ny, white, dtype):
+    """Sizes where the fp32 y-sweeps mix float-float (low-k strips) and plain fp32 strips."""
+    om, gm = qg_pair(nx, ny, dtype)
+    if white:
+        rng = np.random.default_rng(11)
+        q = np.zeros((3, ny + 2, nx + 2))
+        q[:, 1:-1, 1:-1] = 1e-6 * rng.standard_normal((3, ny, nx))
+    else:
+        q = qstate(3, nx, ny, np.float64, ring=True)
+    psi = gm._invert_pv(q.astype(dtype))
+    ref = om.invert_pv(q.astype(dtype).astype(np.float64))
+    # fp64: the y-direction is a tridiagonal solve whose conditioning grows like (ny/pi)^2 for
+    # the lowest x-wavenumbers, which white noise excites fully
+    tol64 = max(1e-12, 0.5 * (ny / np.pi) ** 2 * 2.2e-16) if white else 1e-12
+    assert rel(psi, ref) <= (2e-6 if dtype == np.float32 else tol64)
+    # per-layer too: the baroclinic layers are not hidden behind the barotropic amplitude
+    for l in range(3):
+        assert rel(psi[l], ref[l]) <= (4e-6 if dtype == np.float32 else tol64)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("nx,ny,solver", [(32, 32, 1), (32, 32, 2), (64, 40, 1)])
 def test_qg_vector_field_and_bc(nx, ny, solver, dtype):
     import somax_b200 as sb
