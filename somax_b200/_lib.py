@@ -72,7 +72,8 @@ def build_library(verbose: bool = False) -> Path:
     if LIB_PATH.exists() and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", str(LIB_PATH)] + srcs
+    extra = os.environ.get("SOMAX_B200_NVCC_EXTRA", "").split()     # e.g. -DSB_TH_DEBUG (experiments)
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", str(LIB_PATH)] + srcs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -42,7 +42,7 @@ struct QgSolver {
   int np, ncols, planes;
   void* S = nullptr; void* W = nullptr;
   double* ctab = nullptr; long long* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
-  int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0; double* dbad = nullptr;
+  int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0, KBs = 2; double* dbad = nullptr;
   double* bsig = nullptr; double* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
   double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; float* gvecf = nullptr; double* meet = nullptr; double* meetc = nullptr;
   void* tw = nullptr; void* twc = nullptr; void* dstmat = nullptr;
@@ -323,7 +323,7 @@ template <typename T, bool TAB> struct ThRows {      // rows per staged tile
   static constexpr int v = TAB ? (sizeof(T) == 4 ? 64 : 32) : TH_RT;
 };
 template <typename T, bool COMBINE, bool TAB> struct ThStages {   // ring depth
-  static constexpr int v = TAB ? (COMBINE ? 3 : 4) : (sizeof(T) == 4 ? (COMBINE ? 6 : 8) : (COMBINE ? 3 : 6));
+  static constexpr int v = TAB ? 3 : (sizeof(T) == 4 ? (COMBINE ? 6 : 8) : (COMBINE ? 3 : 6));
 };
 
 // Plain fp32 recurrence over one register block, for the well-conditioned strips of the fp32
@@ -376,10 +376,9 @@ __device__ __forceinline__ void thomas_tile_f32(float (*A)[TH_COLS], const float
 template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE, bool UP, int MODE>
 __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_COLS],
                                             const double (*Ct)[TH_COLS], const double* __restrict__ gv,
-                                            double* __restrict__ dbc, int KB, int tid, int nr, int s0,
+                                            double* __restrict__ Dt, int KB, int tid, int nr, int s0,
                                             int ilo, int Js, int cnt, int jb, bool act, bool bad,
-                                            double cfix, double dy2, double bs, double& carry,
-                                            double (&dpre)[TH_RT]) {
+                                            double cfix, double dy2, double bs, double& carry) {
   constexpr int dj = UP ? 1 : -1;
   double f[TH_RT], cj[TH_RT];
   T vv[TH_RT];
@@ -396,14 +395,12 @@ __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_CO
     if (COMBINE) vv[r] = ok ? Vt[ok ? rm : 0][tid] : T(0);
   }
   if (MODE != 0 && SUBST && bad) {
-    // indefinite column: the eliminated right-hand side lives in the fp64 side buffer; this
-    // block's values were prefetched while the previous block ran, now fetch the next block's
+    // indefinite column: the eliminated right-hand side comes from the staged fp64 side tile
 #pragma unroll
-    for (int r = 0; r < TH_RT; ++r)
-      if (MODE != 2 || r < nr) f[r] = dpre[r];
-#pragma unroll
-    for (int r = 0; r < TH_RT; ++r)
-      dpre[r] = (s0 + TH_RT + r < cnt) ? dbc[(size_t)(jb + dj * (TH_RT + r)) * KB] : 0.0;
+    for (int r = 0; r < TH_RT; ++r) {
+      const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);
+      if (MODE != 2 || r < nr) f[r] = Dt[rm * KB];
+    }
   }
   if (!SUBST) {
     if (MODE == 0) {
@@ -425,7 +422,7 @@ __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_CO
       if (COMBINE) A[rm][tid] = act ? (T)((double)vv[r] - bs * f[r]) : vv[r];
       else if (act) A[rm][tid] = (T)f[r];
       else if (FROM_VEC) A[rm][tid] = T(0);
-      if (MODE != 0 && !SUBST && bad) dbc[(size_t)(jb + dj * r) * KB] = f[r];
+      if (MODE != 0 && !SUBST && bad) Dt[rm * KB] = f[r];
     }
   }
 }
@@ -452,8 +449,11 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   double (*tileC)[RT][TH_COLS] = reinterpret_cast<double (*)[RT][TH_COLS]>(th_smem);
   T (*tileA)[RT][TH_COLS] = reinterpret_cast<T (*)[RT][TH_COLS]>(th_smem + NS * CT_B);
   T (*tileV)[RT][TH_COLS] = reinterpret_cast<T (*)[RT][TH_COLS]>(th_smem + NS * CT_B + NS * TILE_B);
+  // fp64 side tiles [RT][KB] for the indefinite columns (low-k class only; KB even)
+  double* tileD = reinterpret_cast<double*>(th_smem + NS * CT_B + NS * TILE_B * (COMBINE ? 2 : 1));
+  const size_t SIDE_B = TAB ? (size_t)RT * tb.KB * sizeof(double) : 0;
   unsigned long long* full = reinterpret_cast<unsigned long long*>(
-      th_smem + NS * CT_B + NS * TILE_B * (COMBINE ? 2 : 1));
+      th_smem + NS * CT_B + NS * TILE_B * (COMBINE ? 2 : 1) + NS * SIDE_B);
   const int tid = threadIdx.x;
   const int strip = strip_first + blockIdx.x;
   const int c = strip * TH_COLS + tid;
@@ -465,8 +465,9 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   const double cfix = tb.cinf[(size_t)m * tb.np + c];
   const int Js = tb.Jstrip[m * tb.nstrip + strip];
   const double* tabS = tb.ctabB + tb.tabOff[m * tb.nstrip + strip];
-  const bool bad = act && c < tb.kbad[m];
-  double* dbc = tb.dbad + ((size_t)plane * ny) * tb.KB + (bad ? c : 0);
+  const bool bad = TAB && act && c < tb.kbad[m];
+  const bool strip_bad = TAB && strip * TH_COLS < tb.kbad[m];     // this strip holds indefinite columns
+  double* sideG = tb.dbad + ((size_t)plane * ny) * tb.KB;         // [j][KB] of this plane
   const double bs = (COMBINE && act) ? bsig[c] : 0.0;
   const float cfix_f = (float)cfix, kfix_f = (float)(cfix * tb.dy2), dy2_f = (float)tb.dy2, bs_f = (float)bs;
   float carry_f = 0.f;
@@ -503,16 +504,18 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     const int ncoef = TAB ? max(0, min(ilo + nr, Js) - ilo) : 0;      // tabulated rows of this tile
     const unsigned bytes = (unsigned)(nr * TH_COLS * sizeof(T));
     const unsigned cbytes = (unsigned)(ncoef * TH_COLS * sizeof(double));
-    const unsigned total = (LOAD ? bytes * (COMBINE ? 2u : 1u) : 0u) + cbytes;
+    const unsigned dbytes = (TAB && SUBST && strip_bad) ? (unsigned)(nr * tb.KB * sizeof(double)) : 0u;
+    const unsigned total = (LOAD ? bytes * (COMBINE ? 2u : 1u) : 0u) + cbytes + dbytes;
     if (total == 0) return;
     const size_t off = strip0 + (size_t)tile_jlo(t) * SP_W;
     mbar_arrive_expect_tx(&full[st], total);
+    if (dbytes) bulk_g2s(tileD + (size_t)st * RT * tb.KB, sideG + (size_t)tile_jlo(t) * tb.KB, dbytes, &full[st]);
     if (LOAD) bulk_g2s(&tileA[st][0][0], in + off, bytes, &full[st]);
     if (COMBINE) bulk_g2s(&tileV[st][0][0], V + off, bytes, &full[st]);
     if (cbytes) bulk_g2s(&tileC[st][0][0], tabS + (size_t)ilo * TH_COLS, cbytes, &full[st]);
   };
   auto tile_has_load = [&](int t) {
-    return LOAD || (TAB && tile_ilo(t) < Js);
+    return LOAD || (TAB && tile_ilo(t) < Js) || (TAB && SUBST && strip_bad);
   };
   if (tid == 0)
     for (int t = 0; t < NS - 1; ++t) load_tile(t);
@@ -528,20 +531,24 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     carry = half == 0 ? xb : xa;     // the neighbour's value across the meeting point
     carry_f = (float)carry;
   }
-  double dpre[TH_RT];                // indefinite columns: side-buffer values of the next block
-  if (!PLAIN && SUBST && bad) {
-#pragma unroll
-    for (int r = 0; r < TH_RT; ++r) dpre[r] = (r < cnt) ? dbc[(size_t)(j0 + dj * r) * tb.KB] : 0.0;
-  }
-
   unsigned phase_bits = 0;            // per-stage phase parity (stages may be skipped by FROM_VEC tiles)
+#ifdef SB_TH_DEBUG
+  long long tdbg0 = clock64(), twait = 0, tsync = 0, tmode[3] = {0, 0, 0};
+  int nmode[3] = {0, 0, 0};
+#endif
 #pragma unroll 1
   for (int t = 0; t < ntile; ++t) {
     const int st = t % NS;
     const int nrt = tile_nr(t);
     const int ilot = tile_ilo(t);
     if (tile_has_load(t)) {
+#ifdef SB_TH_DEBUG
+      long long w0 = clock64();
+#endif
       mbar_wait(&full[st], (phase_bits >> st) & 1u);
+#ifdef SB_TH_DEBUG
+      twait += clock64() - w0;
+#endif
       phase_bits ^= 1u << st;
     }
 #pragma unroll 1
@@ -555,6 +562,9 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
       const int jb = j0 + dj * s0;
       // mode: 0 = constant coefficient, 1 = fully tabulated, 2 = generic
       const int mode = (nr < TH_RT || (ilo < Js && ilo + nr > Js)) ? 2 : (ilo >= Js ? 0 : 1);
+#ifdef SB_TH_DEBUG
+      long long b0clk = clock64();
+#endif
       if constexpr (PLAIN) {
         // float coefficient rows, read straight from L2 (only the first Js rows of a half)
         const float (*Ct)[TH_COLS] = reinterpret_cast<const float (*)[TH_COLS]>(tabS) + ilo;
@@ -572,9 +582,10 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
         // coefficient rows of this block: staged in shared memory (TAB) or read straight from L2
         const double (*Ct)[TH_COLS] = TAB ? (const double (*)[TH_COLS])(tileC[st] + (ilo - ilot))
                                           : (const double (*)[TH_COLS])(tabS + (size_t)ilo * TH_COLS);
+        double* Dt = tileD + ((size_t)st * RT + row0) * tb.KB + (bad ? c : 0);
 #define SB_TILE(UPV, MODEV)                                                                        \
-        thomas_tile<T, SUBST, FROM_VEC, COMBINE, UPV, MODEV>(A, Vt, Ct, gv, dbc, tb.KB, tid, nr, s0, ilo, Js, \
-                                                             cnt, jb, act, bad, cfix, tb.dy2, bs, carry, dpre)
+        thomas_tile<T, SUBST, FROM_VEC, COMBINE, UPV, MODEV>(A, Vt, Ct, gv, Dt, tb.KB, tid, nr, s0, ilo, Js, \
+                                                             cnt, jb, act, bad, cfix, tb.dy2, bs, carry)
         if (dj > 0) {
           if (mode == 0) SB_TILE(true, 0); else if (mode == 1) SB_TILE(true, 1); else SB_TILE(true, 2);
         } else {
@@ -582,14 +593,26 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
         }
 #undef SB_TILE
       }
+#ifdef SB_TH_DEBUG
+      tmode[mode] += clock64() - b0clk; nmode[mode]++;
+#endif
     }
     if (!SUBST && t == ntile - 1)
       tb.meet[((size_t)plane * 2 + half) * tb.np + c] = PLAIN ? (double)carry_f : carry;
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
+#ifdef SB_TH_DEBUG
+    long long y0 = clock64();
+#endif
     fence_async_smem();
     __syncthreads();
+#ifdef SB_TH_DEBUG
+    tsync += clock64() - y0;
+#endif
     if (tid == 0) {
       bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &tileA[st][0][0], (unsigned)(nrt * TH_COLS * sizeof(T)));
+      if (TAB && !SUBST && strip_bad)
+        bulk_s2g(sideG + (size_t)tile_jlo(t) * tb.KB, tileD + (size_t)st * RT * tb.KB,
+                 (unsigned)(nrt * tb.KB * sizeof(double)));
       bulk_commit();
       // stage (t-1)%NS is free once the store of tile t-1 has finished reading shared memory
       bulk_wait_read<1>();
@@ -597,6 +620,11 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     }
   }
   if (tid == 0) bulk_wait_read<0>();
+#ifdef SB_TH_DEBUG
+  if (TAB && (tid == 0 || tid == 32) && plane < tb.nl)
+    printf("TH %d%d%d strip %d plane %d half %d tid %d Js %d total %lld wait %lld sync %lld m0 %d %lld m1 %d %lld m2 %d %lld\n", (int)SUBST, (int)FROM_VEC,
+           (int)COMBINE, strip, plane, half, tid, Js, clock64() - tdbg0, twait, tsync, nmode[0], tmode[0], nmode[1], tmode[1], nmode[2], tmode[2]);
+#endif
 }
 
 // r[plane][j] = f_n[j] - b * sum_c sig2n[c] * V[plane][j][c]: right-hand side of the border
@@ -760,6 +788,7 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
   for (int m = 0; m < nl; ++m)
     for (int st = 0; st < nstrip; ++st)
       if (Jstrip[(size_t)m * nstrip + st] > 12 * TH_RT) s->nheavy = std::max(s->nheavy, st + 1);
+  s->nheavy = std::min(nstrip, std::max(s->nheavy, (s->KB + SP_W - 1) / SP_W));   // indefinite columns
   if (s->dtype == SOMAX_B200_F32) {
     const int klow = std::max(std::max(64, nc / 32), s->KB);
     s->nheavy = std::min(nstrip, std::max(s->nheavy, (klow + SP_W - 1) / SP_W));
@@ -785,7 +814,8 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
     s->bytes += mb;
   }
   {
-    size_t nb = (size_t)s->planes * ny * std::max(s->KB, 1) * 8;
+    s->KBs = std::max(2, (s->KB + 1) & ~1);      // side-buffer row length: even (16-byte bulk copies)
+    size_t nb = (size_t)s->planes * ny * s->KBs * 8;
     SB_CUDA(cudaMalloc((void**)&s->dbad, nb));
     SB_CUDA(cudaMemset(s->dbad, 0, nb));
     s->bytes += nb;
@@ -947,13 +977,16 @@ static int launch_thomas_one(const char* tag, const ThomasTab& tb, int strip_fir
   if (nstrips <= 0) return 0;
   constexpr int NS = ThStages<T, COMBINE, TAB>::v;
   constexpr int RT = ThRows<T, TAB>::v;
-  constexpr size_t smem = (size_t)NS * RT * TH_COLS * ((TAB ? sizeof(double) : 0) + sizeof(T) * (COMBINE ? 2 : 1)) + NS * 8;
-  static_assert(smem <= 227 * 1024, "sweep ring exceeds shared memory");
-  static bool attr_done = false;
-  if (smem > 48 * 1024 && !attr_done) {
+  constexpr size_t smem0 = (size_t)NS * RT * TH_COLS * ((TAB ? sizeof(double) : 0) + sizeof(T) * (COMBINE ? 2 : 1)) + NS * 8;
+  static_assert(smem0 <= 227 * 1024, "sweep ring exceeds shared memory");
+  const size_t smem = smem0 + (TAB ? (size_t)NS * RT * tb.KB * sizeof(double) : 0);
+  if (smem > 227 * 1024)
+    return fail(SOMAX_B200_ERR_UNSUPPORTED, "too many indefinite Helmholtz columns for the staged side buffer");
+  static size_t attr_done = 0;
+  if (smem > 48 * 1024 && attr_done < smem) {
     SB_CUDA(cudaFuncSetAttribute(thomas_sweep<T, SUBST, FROM_VEC, COMBINE, TAB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done = smem;
   }
   prof_begin(tag, st);
   thomas_sweep<T, SUBST, FROM_VEC, COMBINE, TAB><<<dim3(nstrips, planes, 2), TH_COLS, smem, st>>>(
@@ -999,7 +1032,7 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
   tb.ctabB = s->ctab; tb.tabOff = s->coff; tb.Jstrip = s->krow; tb.cinf = s->cinf; tb.meetc = s->meetc;
   tb.nstrip = s->np / SP_W;
   for (int m = 0; m < QG_MAX_NL; ++m) tb.kbad[m] = s->kbad[m];
-  tb.KB = std::max(s->KB, 1); tb.dbad = s->dbad; tb.meet = s->meet; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
+  tb.KB = s->KBs; tb.dbad = s->dbad; tb.meet = s->meet; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
   tb.dy2 = s->dy * s->dy;
   T* S = (T*)s->S;
   if (s->kind == SOMAX_B200_SOLVER_FFT) {
