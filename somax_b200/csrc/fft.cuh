@@ -235,4 +235,79 @@ __host__ __device__ __forceinline__ void dst_split_ct(const C2<T>* s, int k,
   Xnk = (T)0.5 * (E.y - wO.y);
 }
 
+// ---- register-resident radix-16/32 butterflies (three-pass transform for n >= 4096) ----
+// w_32^m = exp(-2 pi i m / 32) = (FFT_COS32[m], -FFT_SIN32[m]); indices are compile-time after
+// unrolling, so the values fold into immediates.
+template <typename T>
+__host__ __device__ __forceinline__ C2<T> cmul_w32(C2<T> a, int m) {
+  constexpr double COS32[32] = {
+      1, 0.98078528040323043, 0.92387953251128674, 0.83146961230254524, 0.70710678118654757,
+      0.55557023301960229, 0.38268343236508984, 0.19509032201612833, 0, -0.19509032201612819,
+      -0.38268343236508973, -0.55557023301960196, -0.70710678118654746, -0.83146961230254535,
+      -0.92387953251128674, -0.98078528040323043, -1, -0.98078528040323043, -0.92387953251128685,
+      -0.83146961230254546, -0.70710678118654768, -0.55557023301960218, -0.38268343236509034,
+      -0.19509032201612866, 0, 0.1950903220161283, 0.38268343236509, 0.55557023301960184,
+      0.70710678118654735, 0.83146961230254524, 0.92387953251128652, 0.98078528040323032};
+  constexpr double SIN32[32] = {
+      0, 0.19509032201612825, 0.38268343236508978, 0.55557023301960218, 0.70710678118654746,
+      0.83146961230254524, 0.92387953251128674, 0.98078528040323043, 1, 0.98078528040323043,
+      0.92387953251128674, 0.83146961230254546, 0.70710678118654757, 0.55557023301960218,
+      0.38268343236508989, 0.19509032201612861, 0, -0.19509032201612836, -0.38268343236508967,
+      -0.55557023301960196, -0.70710678118654746, -0.83146961230254524, -0.92387953251128652,
+      -0.98078528040323032, -1, -0.98078528040323043, -0.92387953251128663, -0.83146961230254546,
+      -0.70710678118654768, -0.55557023301960218, -0.38268343236509039, -0.19509032201612872};
+  m &= 31;
+  if (m == 0) return a;
+  if (m == 8) return mul_mi(a);
+  if (m == 16) return {-a.x, -a.y};
+  if (m == 24) return {-a.y, a.x};
+  const T c = (T)COS32[m], sn = (T)SIN32[m];
+  return {a.x * c + a.y * sn, a.y * c - a.x * sn};
+}
+
+// In-register DIF FFT of R = 4 * Rb points (R = 8, 16, 32), natural-order input in v[0..R-1].
+// Output frequency k ends up in v[fft_reg_pos<R>(k)].
+template <int R>
+__host__ __device__ __forceinline__ constexpr int fft_reg_pos(int k) { return (R / 4) * (k & 3) + (k >> 2); }
+
+template <typename T, int R>
+__host__ __device__ __forceinline__ void fft_reg(C2<T>* v) {
+  constexpr int Rb = R / 4;
+  static_assert(R == 8 || R == 16 || R == 32, "radix 8, 16 or 32");
+#pragma unroll
+  for (int j = 0; j < Rb; ++j) fft4(v[j], v[j + Rb], v[j + 2 * Rb], v[j + 3 * Rb]);
+#pragma unroll
+  for (int j = 1; j < Rb; ++j)
+#pragma unroll
+    for (int t = 1; t < 4; ++t) v[j + Rb * t] = cmul_w32(v[j + Rb * t], j * t * (32 / R));
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if constexpr (Rb == 8) fft8(&v[8 * t]);
+    else if constexpr (Rb == 4) fft4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+    else { C2<T> a = v[2 * t]; v[2 * t] = cadd(a, v[2 * t + 1]); v[2 * t + 1] = csub(a, v[2 * t + 1]); }
+  }
+}
+
+// Multiply output frequency q' (q' = 1..R-1, held in v[fft_reg_pos<R>(q')]) by W^{q'} given the
+// powers wp[j] = W^(2^j), j < log2 R; the rest are products (at most two per element).
+template <typename T, int R>
+__host__ __device__ __forceinline__ void fft_reg_twiddle(C2<T>* v, const C2<T>* wp) {
+  constexpr int LG = R == 32 ? 5 : (R == 16 ? 4 : 3);
+  C2<T> lo[8];
+  lo[1] = wp[0]; lo[2] = wp[1]; lo[3] = cmul(lo[1], lo[2]); lo[4] = wp[2];
+  lo[5] = cmul(lo[1], lo[4]); lo[6] = cmul(lo[2], lo[4]); lo[7] = cmul(lo[3], lo[4]);
+#pragma unroll
+  for (int q = 1; q < 8; ++q) v[fft_reg_pos<R>(q)] = cmul(v[fft_reg_pos<R>(q)], lo[q]);
+  if constexpr (LG >= 4) {
+#pragma unroll
+    for (int h = 1; h < R / 8; ++h) {
+      C2<T> wh = (h == 1) ? wp[3] : (h == 2 ? wp[LG >= 5 ? 4 : 3] : cmul(wp[3], wp[LG >= 5 ? 4 : 3]));
+      v[fft_reg_pos<R>(8 * h)] = cmul(v[fft_reg_pos<R>(8 * h)], wh);
+#pragma unroll
+      for (int l = 1; l < 8; ++l)
+        v[fft_reg_pos<R>(8 * h + l)] = cmul(v[fft_reg_pos<R>(8 * h + l)], cmul(wh, lo[l]));
+    }
+  }
+}
+
 }  // namespace sb

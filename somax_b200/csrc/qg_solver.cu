@@ -45,7 +45,7 @@ struct QgSolver {
   int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0, KBs = 2; double* dbad = nullptr;
   double* bsig = nullptr; double* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
   double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; float* gvecf = nullptr; double* meet = nullptr; double* meetc = nullptr;
-  void* tw = nullptr; void* twc = nullptr; void* dstmat = nullptr;
+  void* tw = nullptr; void* twc = nullptr; void* twb = nullptr; void* dstmat = nullptr;
   FftPlan plan;
   Mix l2m, m2l;
   int nheavy = 0;
@@ -85,6 +85,7 @@ struct RowArgsCT {
   T mix[QG_MAX_NL][QG_MAX_NL];
   const C2<T>* tw;    // exp(-i pi t / n), t = 0..2n-1 (real-odd split)
   const C2<T>* twc;   // compact per-pass butterfly twiddles (fft.cuh: twc_offset)
+  const C2<T>* twb;   // three-pass kernel: [LG1][G] pass-1 and [LG2][R3] pass-2 twiddle powers (or null)
   T scale;
 };
 
@@ -200,8 +201,212 @@ static int launch_rowdst_ct(const RowArgsCT<T>& A, const T* in, T* out, cudaStre
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// row kernels, FFT path, large rows (n = 4096 / 8192 / 16384, fp32): three radix-16/32 passes with
+// the butterflies held in registers.  The shared-memory line is crossed 6 times per transform
+// (write after pass 1, read + write in passes 2 and 3, read in the real-odd split) instead of 12
+// for the radix-8 kernel above, which is bound by shared-memory wavefronts:
+//   pass 1 (radix R1, stride G = n/R1): thread lt owns complex elements lt + G q, loaded straight
+//     from global memory (layer mixing and the odd extension happen in registers: element k is
+//     (x_2k, x_2k+1) for k < n/2 and -(x_2n-2k, x_2n-2k-1) above), result to s[q' G + lt];
+//   pass 2 (radix R2 inside blocks of G): butterfly (b, pos) reads s[b G + pos + R3 q], writes the
+//     transposed layout s[pos P2 + b R2 + q'], P2 = n/R3 + 1, so that
+//   pass 3 (radix R3) reads s[q P2 + t3] with consecutive lanes on consecutive words, and writes
+//     frequency k = b + R1 (q2' + R2 q3') in natural order at s[k + (k >> LG1)];
+//   split: pairs (k, n-k) are read in natural order, conflict-free.
+// Every layout change is a read-all / barrier / write-all on the same line.
+// ------------------------------------------------------------------------------------------
+template <int LGN> struct BigCfg {
+  static constexpr int LG1 = LGN >= 13 ? 5 : 4;
+  static constexpr int LG2 = LGN >= 14 ? 5 : 4;
+  static constexpr int LG3 = LGN - LG1 - LG2;
+  static_assert(LG3 == 4, "supported: n = 4096, 8192, 16384");
+  static constexpr int n = 1 << LGN, R1 = 1 << LG1, R2 = 1 << LG2, R3 = 1 << LG3;
+  static constexpr int G = n / R1;                 // threads per row = butterflies of pass 1
+  static constexpr int B2 = R1 / R2, B3 = R1 / R3; // butterflies per thread in passes 2, 3
+  static constexpr int P2 = n / R3 + 1;
+  static constexpr int slen = (R3 * P2 > n + (n >> LG1) + 1) ? R3 * P2 : n + (n >> LG1) + 1;
+  static constexpr int minblocks = LGN >= 14 ? 1 : 2;
+};
+
+template <int LGN, bool INV>
+__global__ void __launch_bounds__(BigCfg<LGN>::G, BigCfg<LGN>::minblocks)
+rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restrict__ out) {
+  using Cfg = BigCfg<LGN>;
+  using C = C2<float>;
+  constexpr int n = Cfg::n, G = Cfg::G, R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3;
+  constexpr int LG1 = Cfg::LG1, LG2 = Cfg::LG2, LG3 = Cfg::LG3, P2 = Cfg::P2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* s = reinterpret_cast<C*>(smem_raw);
+  const int lt = threadIdx.x, lane = lt & 31;
+  const int row = blockIdx.x;
+  const int b = row / A.ny, j = row - b * A.ny;
+  const C* __restrict__ tw1 = A.twb;               // [LG1][G]: exp(-2 pi i lt 2^jj / n)
+  const C* __restrict__ tw2 = A.twb + LG1 * G;     // [LG2][R3]: exp(-2 pi i pos 2^jj / G)
+
+  for (int a = 0; a < A.nl; ++a) {
+    // ---- stage the mixed, odd-extended row: z_t at word t of the line (128-bit, conflict-free).
+    // A thread's vector holds x_{4i+1..4i+4}; the lower half needs x_{4i..4i+3} (x_4i comes from
+    // the lane below), the mirrored upper half is the own vector reversed and negated.
+    {
+      float* z = reinterpret_cast<float*>(s);
+      constexpr int NV = n / 4 / G;
+      Vec4<float> acc[NV];
+      float x0[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) { acc[e] = Vec4<float>{0.f, 0.f, 0.f, 0.f}; x0[e] = 0.f; }
+      for (int c = 0; c < A.nl; ++c) {
+        const float mx = A.mix[a][c];
+        const float* base = INV ? in + ((size_t)b * A.nl + c) * A.ny * A.np
+                                : in + (((size_t)b * A.nl + c) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1;
+        auto xp = [&](int p) -> const float* { return INV ? base + sp_off(A.ny, j, p) : base + p; };
+        Vec4<float> w[NV];
+#pragma unroll
+        for (int e = 0; e < NV; ++e) w[e] = ld4(xp(4 * (lt + e * G)));
+        if (lane == 0) {
+#pragma unroll
+          for (int e = 0; e < NV; ++e) {
+            const int i = lt + e * G;
+            if (i > 0) x0[e] = fmaf(mx, *xp(4 * i - 1), x0[e]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < NV; ++e) {
+          acc[e].x = fmaf(mx, w[e].x, acc[e].x); acc[e].y = fmaf(mx, w[e].y, acc[e].y);
+          acc[e].z = fmaf(mx, w[e].z, acc[e].z); acc[e].w = fmaf(mx, w[e].w, acc[e].w);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        const int i = lt + e * G;
+        float lo = __shfl_up_sync(0xffffffffu, acc[e].w, 1);
+        if (lane == 0) lo = x0[e];
+        float hi = -acc[e].w;
+        if (i == n / 4 - 1) {
+          // x_n is the border column, not part of the transform: z_n = 0
+          *(INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + n
+                : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, n - 1)) = acc[e].w;
+          hi = 0.f;
+        }
+        st4(z + 4 * i, Vec4<float>{lo, acc[e].x, acc[e].y, acc[e].z});
+        st4(z + 2 * n - 4 * i - 4, Vec4<float>{hi, -acc[e].z, -acc[e].y, -acc[e].x});
+      }
+    }
+    __syncthreads();
+    // ---- pass 1
+    C v[R1];
+#pragma unroll
+    for (int q = 0; q < R1; ++q) v[q] = s[lt + G * q];
+    __syncthreads();
+    fft_reg<float, R1>(v);
+    {
+      C wp[LG1];
+#pragma unroll
+      for (int jj = 0; jj < LG1; ++jj) wp[jj] = tw1[jj * G + lt];
+      fft_reg_twiddle<float, R1>(v, wp);
+    }
+#pragma unroll
+    for (int q = 0; q < R1; ++q) s[q * G + lt] = v[fft_reg_pos<R1>(q)];
+    __syncthreads();
+
+    // ---- pass 2
+    {
+      C u[Cfg::B2][R2];
+#pragma unroll
+      for (int i = 0; i < Cfg::B2; ++i) {
+        const int t2 = lt + G * i, b2 = t2 >> LG3, pos = t2 & (R3 - 1);
+#pragma unroll
+        for (int q = 0; q < R2; ++q) u[i][q] = s[b2 * G + pos + R3 * q];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < Cfg::B2; ++i) {
+        const int t2 = lt + G * i, b2 = t2 >> LG3, pos = t2 & (R3 - 1);
+        fft_reg<float, R2>(u[i]);
+        C wp[LG2];
+#pragma unroll
+        for (int jj = 0; jj < LG2; ++jj) wp[jj] = tw2[jj * R3 + pos];
+        fft_reg_twiddle<float, R2>(u[i], wp);
+#pragma unroll
+        for (int q = 0; q < R2; ++q) s[pos * P2 + b2 * R2 + q] = u[i][fft_reg_pos<R2>(q)];
+      }
+    }
+    __syncthreads();
+
+    // ---- pass 3
+    {
+      C u[Cfg::B3][R3];
+#pragma unroll
+      for (int i = 0; i < Cfg::B3; ++i) {
+        const int t3 = lt + G * i;
+#pragma unroll
+        for (int q = 0; q < R3; ++q) u[i][q] = s[q * P2 + t3];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < Cfg::B3; ++i) {
+        const int t3 = lt + G * i, b3 = t3 >> LG2, q2 = t3 & (R2 - 1);
+        fft_reg<float, R3>(u[i]);
+#pragma unroll
+        for (int q = 0; q < R3; ++q) {
+          const int k = b3 + R1 * (q2 + R2 * q);
+          s[k + (k >> LG1)] = u[i][fft_reg_pos<R3>(q)];
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- real-odd split, pairs (k, n-k)
+    float* orow = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF
+                      : out + ((size_t)b * A.nl + a) * A.ny * A.np;
+#pragma unroll 4
+    for (int k0 = 1; k0 <= n / 2; k0 += G) {
+      const int k = k0 + lt;
+      if (k <= n / 2) {
+        const C Ak = s[k + (k >> LG1)];
+        const C Bk = s[(n - k) + ((n - k) >> LG1)];
+        const C E = {0.5f * (Ak.x + Bk.x), 0.5f * (Ak.y - Bk.y)};
+        const C O = {0.5f * (Ak.y + Bk.y), -0.5f * (Ak.x - Bk.x)};
+        const C wO = cmul(A.tw[k], O);
+        const float Xk = -0.5f * (E.y + wO.y), Xnk = 0.5f * (E.y - wO.y);
+        // X_k is element p = k-1 of the destination row (x_t at p = t-1)
+        if (INV) {
+          orow[k] = A.scale * Xk;
+          if (k != n - k) orow[n - k] = A.scale * Xnk;
+        } else {
+          orow[sp_off(A.ny, j, k - 1)] = Xk;
+          if (k != n - k) orow[sp_off(A.ny, j, n - k - 1)] = Xnk;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int LGN, bool INV>
+static int launch_rowdst_big(const RowArgsCT<float>& A, const float* in, float* out, cudaStream_t st) {
+  using Cfg = BigCfg<LGN>;
+  constexpr size_t smem = (size_t)Cfg::slen * sizeof(C2<float>);
+  static bool attr_done = false;
+  if (!attr_done) {
+    SB_CUDA(cudaFuncSetAttribute(rowdst_fft_big<LGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  prof_begin(INV ? "rowdst_inv_fft" : "rowdst_fwd_fft", st);
+  rowdst_fft_big<LGN, INV><<<A.nrows, Cfg::G, smem, st>>>(A, in, out);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T, bool INV>
 static int launch_rowdst(int lgn, const RowArgsCT<T>& A, const T* in, T* out, cudaStream_t st) {
+  if constexpr (sizeof(T) == 4) {
+    if (A.twb) {
+      if (lgn == 12) return launch_rowdst_big<12, INV>(A, in, out, st);
+      if (lgn == 13) return launch_rowdst_big<13, INV>(A, in, out, st);
+      if (lgn == 14) return launch_rowdst_big<14, INV>(A, in, out, st);
+    }
+  }
   switch (lgn) {
 #define SB_ROW_CASE(L) case L: return launch_rowdst_ct<T, L, INV>(A, in, out, st);
     SB_ROW_CASE(3) SB_ROW_CASE(4) SB_ROW_CASE(5) SB_ROW_CASE(6) SB_ROW_CASE(7) SB_ROW_CASE(8)
@@ -847,6 +1052,23 @@ static int build_fft_tables(QgSolver* s, const double* lambdas) {
       lgLc -= lr;
     }
     if (int rc = dev_upload(twc.data(), twc.size() * sizeof(C2<T>), &s->twc, &s->bytes)) return rc;
+    if (sizeof(T) == 4 && s->plan.lgn >= 12 && s->plan.lgn <= 14 && !getenv("SOMAX_B200_FFT_RADIX8")) {
+      // three-pass kernel (BigCfg): powers W^(2^jj) of the pass-1 and pass-2 twiddles
+      const int lgn = s->plan.lgn, lg1 = lgn >= 13 ? 5 : 4, lg2 = lgn >= 14 ? 5 : 4, r3 = 16;
+      const int G = n >> lg1;
+      std::vector<C2<T>> twb;
+      for (int jj = 0; jj < lg1; ++jj)
+        for (int lt = 0; lt < G; ++lt) {
+          const double a = -2.0 * M_PI * (double)(((long long)lt << jj) % n) / (double)n;
+          twb.push_back({(T)cos(a), (T)sin(a)});
+        }
+      for (int jj = 0; jj < lg2; ++jj)
+        for (int pos = 0; pos < r3; ++pos) {
+          const double a = -2.0 * M_PI * (double)((pos << jj) % G) / (double)G;
+          twb.push_back({(T)cos(a), (T)sin(a)});
+        }
+      if (int rc = dev_upload(twb.data(), twb.size() * sizeof(C2<T>), &s->twb, &s->bytes)) return rc;
+    }
   }
   std::vector<double> sig(nc), lamx(nc), bsig(nc), sig2n(nc);
   for (int c = 0; c < nc; ++c) {
@@ -959,7 +1181,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
 void qg_solver_destroy(QgSolver* s) {
   if (!s) return;
   void* ptrs[] = {s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->bsig, s->sig2n,
-                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->gvecf, s->tw, s->twc, s->dstmat, s->meet, s->meetc};
+                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->gvecf, s->tw, s->twc, s->twb, s->dstmat, s->meet, s->meetc};
   for (void* p : ptrs) cudaFree(p);
   if (s->aux) cudaStreamDestroy(s->aux);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -1039,7 +1261,7 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     T* W = (T*)s->W;
     RowArgsCT<T> Af, Ai;
     Af.L = s->L; Af.ny = ny; Af.np = np; Af.nl = nl; Af.nrows = s->batch * ny;
-    Af.tw = (const C2<T>*)s->tw; Af.twc = (const C2<T>*)s->twc; Af.scale = (T)1;
+    Af.tw = (const C2<T>*)s->tw; Af.twc = (const C2<T>*)s->twc; Af.twb = (const C2<T>*)s->twb; Af.scale = (T)1;
     Ai = Af; Ai.scale = (T)(2.0 / n);
     for (int a = 0; a < QG_MAX_NL; ++a)
       for (int c = 0; c < QG_MAX_NL; ++c) { Af.mix[a][c] = (T)s->l2m.c[a][c]; Ai.mix[a][c] = (T)s->m2l.c[a][c]; }

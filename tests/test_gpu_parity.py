@@ -86,9 +86,13 @@ def test_qg_invert_white_noise_rhs(dtype):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("nx,ny,white", [(512, 512, True), (1024, 768, False), (2048, 1024, True),
-                                         (4096, 256, False)])
+                                         (4096, 256, False), (4096, 64, True), (8192, 96, True),
+                                         (8192, 40, False), (16384, 24, True)])
 def test_qg_invert_large_grids(nx, ny, white, dtype):
-    """Sizes where the fp32 y-sweeps mix float-float (low-k strips) and plain fp32 strips."""
+    """Sizes where the fp32 y-sweeps mix fp64-carry (low-k) and plain strips, and where the row
+    transform switches to the three-pass register-resident kernel (nx >= 4096, fp32)."""
+    if nx > 8192 and dtype == np.float64:
+        pytest.skip("fp64 rows are limited to nx <= 8192 (one row must fit in shared memory)")
     om, gm = qg_pair(nx, ny, dtype)
     if white:
         rng = np.random.default_rng(11)
