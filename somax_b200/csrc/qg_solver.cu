@@ -246,30 +246,25 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
 
   for (int a = 0; a < A.nl; ++a) {
     // ---- stage the mixed, odd-extended row: z_t at word t of the line (128-bit, conflict-free).
-    // A thread's vector holds x_{4i+1..4i+4}; the lower half needs x_{4i..4i+3} (x_4i comes from
-    // the lane below), the mirrored upper half is the own vector reversed and negated.
+    // A thread's vector holds x_{4i+1..4i+4}; the lower half needs x_{4i..4i+3}: x_4i comes from
+    // the lane below by shuffle, and across a warp boundary lane 31 stores it for its neighbour
+    // (lane 0 then writes only its three own words).  The mirrored upper half is the own vector
+    // reversed and negated, which is aligned as it is.
     {
       float* z = reinterpret_cast<float*>(s);
       constexpr int NV = n / 4 / G;
       Vec4<float> acc[NV];
-      float x0[NV];
 #pragma unroll
-      for (int e = 0; e < NV; ++e) { acc[e] = Vec4<float>{0.f, 0.f, 0.f, 0.f}; x0[e] = 0.f; }
+      for (int e = 0; e < NV; ++e) acc[e] = Vec4<float>{0.f, 0.f, 0.f, 0.f};
       for (int c = 0; c < A.nl; ++c) {
         const float mx = A.mix[a][c];
-        const float* base = INV ? in + ((size_t)b * A.nl + c) * A.ny * A.np
-                                : in + (((size_t)b * A.nl + c) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1;
-        auto xp = [&](int p) -> const float* { return INV ? base + sp_off(A.ny, j, p) : base + p; };
+        // element p = 4 lt + 4 G e: field rows are contiguous, spectral rows advance 4G/64 strips
+        const float* src = INV ? in + ((size_t)b * A.nl + c) * A.ny * A.np + sp_off(A.ny, j, 4 * lt)
+                               : in + (((size_t)b * A.nl + c) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1 + 4 * lt;
+        const size_t estride = INV ? (size_t)(4 * G / SP_W) * A.ny * SP_W : (size_t)4 * G;
         Vec4<float> w[NV];
 #pragma unroll
-        for (int e = 0; e < NV; ++e) w[e] = ld4(xp(4 * (lt + e * G)));
-        if (lane == 0) {
-#pragma unroll
-          for (int e = 0; e < NV; ++e) {
-            const int i = lt + e * G;
-            if (i > 0) x0[e] = fmaf(mx, *xp(4 * i - 1), x0[e]);
-          }
-        }
+        for (int e = 0; e < NV; ++e) w[e] = ld4(src + e * estride);
 #pragma unroll
         for (int e = 0; e < NV; ++e) {
           acc[e].x = fmaf(mx, w[e].x, acc[e].x); acc[e].y = fmaf(mx, w[e].y, acc[e].y);
@@ -279,16 +274,22 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
 #pragma unroll
       for (int e = 0; e < NV; ++e) {
         const int i = lt + e * G;
-        float lo = __shfl_up_sync(0xffffffffu, acc[e].w, 1);
-        if (lane == 0) lo = x0[e];
+        const float lo = __shfl_up_sync(0xffffffffu, acc[e].w, 1);
         float hi = -acc[e].w;
         if (i == n / 4 - 1) {
           // x_n is the border column, not part of the transform: z_n = 0
           *(INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + n
                 : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, n - 1)) = acc[e].w;
           hi = 0.f;
+        } else if (lane == 31) {
+          z[4 * i + 4] = acc[e].w;           // x_{4(i+1)} for lane 0 of the next warp
         }
-        st4(z + 4 * i, Vec4<float>{lo, acc[e].x, acc[e].y, acc[e].z});
+        if (lane == 0) {
+          if (i == 0) z[0] = 0.f;            // z_0
+          z[4 * i + 1] = acc[e].x; z[4 * i + 2] = acc[e].y; z[4 * i + 3] = acc[e].z;
+        } else {
+          st4(z + 4 * i, Vec4<float>{lo, acc[e].x, acc[e].y, acc[e].z});
+        }
         st4(z + 2 * n - 4 * i - 4, Vec4<float>{hi, -acc[e].z, -acc[e].y, -acc[e].x});
       }
     }
@@ -356,26 +357,33 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
     }
     __syncthreads();
 
-    // ---- real-odd split, pairs (k, n-k)
-    float* orow = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF
-                      : out + ((size_t)b * A.nl + a) * A.ny * A.np;
-#pragma unroll 4
-    for (int k0 = 1; k0 <= n / 2; k0 += G) {
-      const int k = k0 + lt;
-      if (k <= n / 2) {
-        const C Ak = s[k + (k >> LG1)];
-        const C Bk = s[(n - k) + ((n - k) >> LG1)];
-        const C E = {0.5f * (Ak.x + Bk.x), 0.5f * (Ak.y - Bk.y)};
-        const C O = {0.5f * (Ak.y + Bk.y), -0.5f * (Ak.x - Bk.x)};
-        const C wO = cmul(A.tw[k], O);
-        const float Xk = -0.5f * (E.y + wO.y), Xnk = 0.5f * (E.y - wO.y);
-        // X_k is element p = k-1 of the destination row (x_t at p = t-1)
-        if (INV) {
-          orow[k] = A.scale * Xk;
-          if (k != n - k) orow[n - k] = A.scale * Xnk;
-        } else {
-          orow[sp_off(A.ny, j, k - 1)] = Xk;
-          if (k != n - k) orow[sp_off(A.ny, j, n - k - 1)] = Xnk;
+    // ---- real-odd split, pairs (k, n-k), k = 1 + lt + G m.  X_k is element p = k-1 of the
+    // destination row; both destinations move by a constant stride per m (G columns = G/64 strips)
+    {
+      float* orow = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF
+                        : out + ((size_t)b * A.nl + a) * A.ny * A.np;
+      const int k1 = 1 + lt;
+      float* pk = INV ? orow + k1 : orow + sp_off(A.ny, j, k1 - 1);
+      float* pnk = INV ? orow + (n - k1) : orow + sp_off(A.ny, j, n - k1 - 1);
+      const ptrdiff_t dstride = INV ? (ptrdiff_t)G : (ptrdiff_t)(G / SP_W) * A.ny * SP_W;
+      constexpr int NK = (n / 2) / G;      // k = n/2 (thread G-1, last m) pairs with itself: both stores agree
+      constexpr int KB = 8;
+#pragma unroll 1
+      for (int m0 = 0; m0 < NK; m0 += KB) {
+        C w[KB];
+#pragma unroll
+        for (int u = 0; u < KB; ++u) w[u] = A.tw[k1 + (m0 + u) * G];
+#pragma unroll
+        for (int u = 0; u < KB; ++u) {
+          const int k = k1 + (m0 + u) * G;
+          const C Ak = s[k + (k >> LG1)];
+          const C Bk = s[(n - k) + ((n - k) >> LG1)];
+          const C E = {0.5f * (Ak.x + Bk.x), 0.5f * (Ak.y - Bk.y)};
+          const C O = {0.5f * (Ak.y + Bk.y), -0.5f * (Ak.x - Bk.x)};
+          const C wO = cmul(w[u], O);
+          const float Xk = -0.5f * (E.y + wO.y), Xnk = 0.5f * (E.y - wO.y);
+          pk[(m0 + u) * dstride] = INV ? A.scale * Xk : Xk;
+          pnk[-(m0 + u) * dstride] = INV ? A.scale * Xnk : Xnk;
         }
       }
     }
