@@ -7,6 +7,9 @@
 #include "common.cuh"
 #include "qg_solver.cuh"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -26,6 +29,7 @@ struct QgArgs {
   const T* beta; int b_cp, b_xs;
   const T* wind; int w_cp, w_xs;
   T H0, nu, kappa, tau0;
+  unsigned nl_magic;   // ceil(2^32 / nl): plane / nl = umulhi(plane, nl_magic) for plane < 2^16
 };
 
 template <typename T>
@@ -241,6 +245,185 @@ qg_rhs_kernel_fast(QgArgs<T> A, const T* __restrict__ psi, Stage<T> st) {
   st4(st.Yout[0] + idx, acc);
 }
 
+// ------------------------------------------------------------------------------------------
+// fp32 stencil with TMA tile loads (cp.async.bulk.tensor, one elected thread): the q and psi
+// halo tiles and the Tsit5 epilogue operands (step-start state + previous stage derivatives)
+// arrive in shared memory through 3-D tensor maps over the padded (pitch, Ny, plane) arrays --
+// out-of-range boxes are zero-filled by the hardware, so the loader has no per-thread address
+// arithmetic or bounds checks at all.  Each thread computes 2 rows x 4 columns from a 4 x 6
+// register window; CTAs that touch the domain ring take the predicated EDGE path (~3% of CTAs).
+// Same arithmetic (operation order) as qg_rhs_kernel_fast.
+// ------------------------------------------------------------------------------------------
+constexpr int QFR = 2;                    // rows per thread
+constexpr int QFY = QTY * QFR;            // output rows per CTA
+constexpr int QHW = (QTXG + 2) * 4;       // halo tile width (floats): one group either side
+constexpr int QHR = QFY + 2;              // halo tile rows
+constexpr size_t QG_TMA_HALO_B = ((size_t)QHR * QHW * 4 + 127) / 128 * 128;
+constexpr size_t QG_TMA_EPI_B = (size_t)QFY * QTXG * 4 * 4;
+constexpr size_t QG_TMA_SMEM = 2 * QG_TMA_HALO_B + (MAX_PREV + 1) * QG_TMA_EPI_B + 16;
+
+struct QgTmaps { CUtensorMap q, psi, base, f[MAX_PREV]; };
+
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* tm, int x, int y, int z,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+      ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(tm), "r"(x), "r"(y), "r"(z),
+        "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void qg_tma_compute(const QgArgs<float>& A, const Stage<float>& st,
+                                               const float (*s_q)[QHW], const float (*s_p)[QHW],
+                                               const float (*s_epi)[QFY][QTXG * 4], int g0, int j0,
+                                               int plane, int k) {
+  const Layout& L = A.L;
+  const int Ny = L.Ny, Nx = L.Nx;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int jA = j0 + QFR * ty, g = g0 + tx;
+  const int r0 = QFR * ty, cs = 4 * (tx + 1);      // window rows r0 .. r0+3 of the halo tile
+  float f[QFR + 2][6], q[QFR + 2][6];
+#pragma unroll
+  for (int d = 0; d < QFR + 2; ++d) {
+    const Vec4<float> a = ld4(&s_p[r0 + d][cs]);
+    const Vec4<float> b = ld4(&s_q[r0 + d][cs]);
+    float al = __shfl_up_sync(0xffffffffu, a.w, 1), ar = __shfl_down_sync(0xffffffffu, a.x, 1);
+    float bl = __shfl_up_sync(0xffffffffu, b.w, 1), br = __shfl_down_sync(0xffffffffu, b.x, 1);
+    if (tx == 0) { al = s_p[r0 + d][cs - 1]; bl = s_q[r0 + d][cs - 1]; }
+    if (tx == QTXG - 1) { ar = s_p[r0 + d][cs + 4]; br = s_q[r0 + d][cs + 4]; }
+    f[d][0] = al; f[d][1] = a.x; f[d][2] = a.y; f[d][3] = a.z; f[d][4] = a.w; f[d][5] = ar;
+    q[d][0] = bl; q[d][1] = b.x; q[d][2] = b.y; q[d][3] = b.z; q[d][4] = b.w; q[d][5] = br;
+  }
+  if (EDGE && (g >= L.groups() || jA >= Ny)) return;
+  float bet[QFR + 2];
+#pragma unroll
+  for (int d = 0; d < QFR + 2; ++d) {
+    int jj = jA - 1 + d;
+    if (EDGE) jj = jj < 0 ? 0 : (jj > Ny - 1 ? Ny - 1 : jj);
+    bet[d] = A.beta[jj];
+  }
+  const size_t po = (size_t)plane * L.plane();
+  const int i0 = g * 4 - OFF;
+#pragma unroll
+  for (int rr = 0; rr < QFR; ++rr) {
+    const int j = jA + rr;
+    if (EDGE && j >= Ny) break;
+    float wind = 0.f;
+    if (k == 0) wind = (A.tau0 * A.wind[j]) * A.iH0;
+    float out[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = i0 + e, c = e + 1;
+      const int d0 = rr, d1 = rr + 1, d2 = rr + 2;      // window rows j-1, j, j+1
+      float dq = 0.f;
+      const bool inside = !EDGE || (i >= 0 && i < Nx);
+      const bool interior = !EDGE || (j >= 1 && j <= Ny - 2 && i >= 1 && i <= Nx - 2);
+      if (inside) {
+        if (interior) {
+          const float fE = f[d1][c + 1], fW = f[d1][c - 1], fN = f[d2][c], fS = f[d0][c];
+          const float fNE = f[d2][c + 1], fNW = f[d2][c - 1], fSE = f[d0][c + 1], fSW = f[d0][c - 1];
+          const float gE = q[d1][c + 1] + bet[d1], gW = q[d1][c - 1] + bet[d1];
+          const float gN = q[d2][c] + bet[d2], gS = q[d0][c] + bet[d0];
+          const float gNE = q[d2][c + 1] + bet[d2], gNW = q[d2][c - 1] + bet[d2];
+          const float gSE = q[d0][c + 1] + bet[d0], gSW = q[d0][c - 1] + bet[d0];
+          const float jpp = (fE - fW) * (gN - gS) - (fN - fS) * (gE - gW);
+          const float jpx = fE * (gNE - gSE) - fW * (gNW - gSW) - fN * (gNE - gNW) + fS * (gSE - gSW);
+          const float jxp = gN * (fNE - fNW) - gS * (fSE - fSW) - gE * (fNE - fSE) + gW * (fNW - fSW);
+          dq = -(((jpp + jpx) + jxp) * A.ijden);
+        }
+        if (k == 0) dq = dq + wind;
+        if (interior) {
+          if (k == L.nl - 1) {
+            const float pc = f[d1][c];
+            const float lap = (f[d1][c + 1] - 2.f * pc + f[d1][c - 1]) * A.idx2 +
+                              (f[d2][c] - 2.f * pc + f[d0][c]) * A.idy2;
+            dq = dq + (-A.kappa * lap);
+          }
+          const float qc = q[d1][c];
+          const float lapq = (q[d1][c + 1] - 2.f * qc + q[d1][c - 1]) * A.idx2 +
+                             (q[d2][c] - 2.f * qc + q[d0][c]) * A.idy2;
+          dq = dq + A.nu * lapq;
+        }
+      }
+      out[e] = dq;
+    }
+    const size_t idx = po + (size_t)j * L.pitch + (size_t)g * 4;
+    const Vec4<float> F{out[0], out[1], out[2], out[3]};
+    if (st.Fout[0]) st4(st.Fout[0] + idx, F);
+    if (st.Yout[0]) {
+      const int er = QFR * ty + rr;
+      Vec4<float> acc = ld4(&s_epi[MAX_PREV][er][4 * tx]);
+#pragma unroll
+      for (int jj = 0; jj < MAX_PREV; ++jj) {
+        if (jj < st.nprev) {
+          const Vec4<float> kk = ld4(&s_epi[jj][er][4 * tx]);
+          acc.x = fmaf(st.adt[jj], kk.x, acc.x); acc.y = fmaf(st.adt[jj], kk.y, acc.y);
+          acc.z = fmaf(st.adt[jj], kk.z, acc.z); acc.w = fmaf(st.adt[jj], kk.w, acc.w);
+        }
+      }
+      acc.x = fmaf(st.adt_new, F.x, acc.x); acc.y = fmaf(st.adt_new, F.y, acc.y);
+      acc.z = fmaf(st.adt_new, F.z, acc.z); acc.w = fmaf(st.adt_new, F.w, acc.w);
+      st4(st.Yout[0] + idx, acc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(QTXG* QTY)
+qg_rhs_kernel_tma(const __grid_constant__ QgTmaps M, const QgArgs<float> A, const Stage<float> st) {
+  extern __shared__ __align__(128) unsigned char qsm[];
+  float (*s_q)[QHW] = reinterpret_cast<float (*)[QHW]>(qsm);
+  float (*s_p)[QHW] = reinterpret_cast<float (*)[QHW]>(qsm + QG_TMA_HALO_B);
+  float (*s_epi)[QFY][QTXG * 4] = reinterpret_cast<float (*)[QFY][QTXG * 4]>(qsm + 2 * QG_TMA_HALO_B);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(qsm + 2 * QG_TMA_HALO_B + (MAX_PREV + 1) * QG_TMA_EPI_B);
+  const Layout& L = A.L;
+  const int tid = threadIdx.y * QTXG + threadIdx.x;
+  const int g0 = blockIdx.x * QTXG, j0 = blockIdx.y * QFY;
+  const int plane = blockIdx.z;
+  const int k = L.nl == 1 ? 0 : plane - (int)__umulhi((unsigned)plane, A.nl_magic) * L.nl;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    const bool epi = st.Yout[0] != nullptr;
+    const unsigned bytes = 2u * QHR * QHW * 4u + (epi ? (unsigned)(1 + st.nprev) * (unsigned)QG_TMA_EPI_B : 0u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                 ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+    tma_load_3d(&s_q[0][0], &M.q, 4 * g0 - 4, j0 - 1, plane, bar);
+    tma_load_3d(&s_p[0][0], &M.psi, 4 * g0 - 4, j0 - 1, plane, bar);
+    if (epi) {
+      tma_load_3d(&s_epi[MAX_PREV][0][0], &M.base, 4 * g0, j0, plane, bar);
+#pragma unroll
+      for (int jj = 0; jj < MAX_PREV; ++jj)
+        if (jj < st.nprev) tma_load_3d(&s_epi[jj][0][0], &M.f[jj], 4 * g0, j0, plane, bar);
+    }
+  }
+  __syncthreads();                      // barrier initialised before anyone waits on it
+  {
+    unsigned ok = 0;
+    const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\t"
+                   "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                   "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(ba) : "memory");
+    }
+  }
+  // CTAs whose halo tile touches the domain ring (row 0 / Ny-1, column 0 / Nx-1) or overhangs
+  const int gR = (L.Nx - 1 + OFF) >> 2;
+  const bool edge = blockIdx.x == 0 || g0 + QTXG >= gR || blockIdx.y == 0 || j0 + QFY >= L.Ny - 1;
+  if (edge) {
+    if (A.apply_bc) {
+      for (int e = tid; e < QHR * QHW; e += QTXG * QTY) {
+        const int r = e / QHW, cidx = e - r * QHW;
+        const int jj = j0 - 1 + r, i = 4 * (g0 - 1) + cidx - OFF;
+        if (jj == 0 || jj == L.Ny - 1 || i == 0 || i == L.Nx - 1) s_q[r][cidx] = 0.f;
+      }
+      __syncthreads();
+    }
+    qg_tma_compute<true>(A, st, s_q, s_p, s_epi, g0, j0, plane, k);
+  } else {
+    qg_tma_compute<false>(A, st, s_q, s_p, s_epi, g0, j0, plane, k);
+  }
+}
+
 // ring := 0 in place on padded planes
 template <typename T>
 __global__ void qg_bc_kernel(T* __restrict__ q, Layout L) {
@@ -315,6 +498,10 @@ struct somax_b200_qg_s {
   bool beta1d = false, wind1d = false;
   void* y = nullptr; void* Ya = nullptr; void* Yb = nullptr; void* psi = nullptr;
   void* F[5] = {0, 0, 0, 0, 0};
+  // tensor maps of the 9 internal arrays for the TMA stencil (fp32): halo box and epilogue box
+  struct TmEntry { const void* ptr; CUtensorMap halo, epi; };
+  TmEntry tm[9];
+  int ntm = 0;
   StepGraph graph;
   size_t bytes = 0;
 };
@@ -332,6 +519,7 @@ QgArgs<T> make_qargs(somax_b200_qg_t h, const somax_b200_params* p, int apply_bc
   A.wind = (const T*)h->wind; A.w_cp = h->wind1d ? 1 : h->L.Nx; A.w_xs = h->wind1d ? 0 : 1;
   A.H0 = (T)p->H0; A.nu = (T)p->lateral_viscosity; A.kappa = (T)p->bottom_drag;
   A.tau0 = (T)p->wind_amplitude;
+  A.nl_magic = h->L.nl > 1 ? (unsigned)(((1ull << 32) + h->L.nl - 1) / h->L.nl) : 0u;
   return A;
 }
 
@@ -348,6 +536,80 @@ Stage<T> qstage() {
   return st;
 }
 
+// Tensor maps over a padded (plane, Ny, pitch) fp32 array; OOB elements read as zero.
+int qg_build_tmaps(somax_b200_qg_t h) {
+  h->ntm = 0;
+  if (h->dtype != SOMAX_B200_F32 || !(h->beta1d && h->wind1d) || getenv("SOMAX_B200_NO_TMA")) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !fn) {
+    cudaGetLastError();
+    return 0;                       // fall back to the cp.async kernel
+  }
+  auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  const Layout& L = h->L;
+  const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.Ny, (cuuint64_t)L.batch * L.nl};
+  const cuuint64_t strides[2] = {(cuuint64_t)L.pitch * 4, (cuuint64_t)L.plane() * 4};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const cuuint32_t box_halo[3] = {(cuuint32_t)QHW, (cuuint32_t)QHR, 1};
+  const cuuint32_t box_epi[3] = {(cuuint32_t)(QTXG * 4), (cuuint32_t)QFY, 1};
+  void* bufs[9] = {h->y, h->Ya, h->Yb, h->psi, h->F[0], h->F[1], h->F[2], h->F[3], h->F[4]};
+  for (int i = 0; i < 9; ++i) {
+    somax_b200_qg_s::TmEntry& e = h->tm[i];
+    e.ptr = bufs[i];
+    CUresult r1 = encode(&e.halo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, bufs[i], dims, strides, box_halo, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode(&e.epi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, bufs[i], dims, strides, box_epi, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) { h->ntm = 0; return 0; }
+  }
+  h->ntm = 9;
+  return 0;
+}
+
+const somax_b200_qg_s::TmEntry* qg_find_tm(somax_b200_qg_t h, const void* p) {
+  for (int i = 0; i < h->ntm; ++i)
+    if (h->tm[i].ptr == p) return &h->tm[i];
+  return nullptr;
+}
+
+// fp32 fast path through the TMA kernel; returns false when some operand is not an internal array
+bool qg_launch_tma(somax_b200_qg_t h, const QgArgs<float>& A, const Stage<float>& st, cudaStream_t s) {
+  if (h->ntm == 0) return false;
+  QgTmaps M;
+  const auto* eq = qg_find_tm(h, st.Yin[0]);
+  const auto* ep = qg_find_tm(h, h->psi);
+  if (!eq || !ep) return false;
+  M.q = eq->halo; M.psi = ep->halo;
+  M.base = eq->epi;
+  for (int jj = 0; jj < MAX_PREV; ++jj) M.f[jj] = eq->epi;
+  if (st.Yout[0]) {
+    const auto* eb = qg_find_tm(h, st.y[0] ? st.y[0] : st.Yin[0]);
+    if (!eb) return false;
+    M.base = eb->epi;
+    for (int jj = 0; jj < st.nprev; ++jj) {
+      const auto* ef = qg_find_tm(h, st.Fprev[jj][0]);
+      if (!ef) return false;
+      M.f[jj] = ef->epi;
+    }
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(qg_rhs_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)QG_TMA_SMEM) != cudaSuccess) { cudaGetLastError(); return false; }
+    attr_done = true;
+  }
+  const Layout& L = h->L;
+  dim3 block(QTXG, QTY);
+  dim3 grid((L.groups() + QTXG - 1) / QTXG, (L.Ny + QFY - 1) / QFY, L.batch * L.nl);
+  prof_begin("qg_rhs_kernel", s);
+  qg_rhs_kernel_tma<<<grid, block, QG_TMA_SMEM, s>>>(M, A, st);
+  return true;
+}
+
 // one RHS evaluation: psi = invert(Yin), then the fused stencil + RK epilogue
 template <typename T>
 int eval_rhs(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st_in, double dt, cudaStream_t s) {
@@ -357,6 +619,9 @@ int eval_rhs(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st_in, doubl
   const Layout& L = h->L;
   dim3 block(QTXG, QTY);
   dim3 grid((L.groups() + QTXG - 1) / QTXG, (L.Ny + QTY - 1) / QTY, L.batch * L.nl);
+  if constexpr (sizeof(T) == 4) {
+    if (qg_launch_tma(h, A, st, s)) { SB_LAUNCH_CHECK(); return 0; }
+  }
   prof_begin("qg_rhs_kernel", s);
   if (h->beta1d && h->wind1d) qg_rhs_kernel_fast<T><<<grid, block, 0, s>>>(A, (const T*)h->psi, st);
   else qg_rhs_kernel<T><<<grid, block, 0, s>>>(A, (const T*)h->psi, st);
@@ -547,6 +812,7 @@ int somax_b200_qg_create(somax_b200_qg_t* out, int dtype, int batch, int nl, int
     cudaMemset(*bp, 0, fb);
     h->bytes += fb;
   }
+  if (!rc) rc = qg_build_tmaps(h);
   if (rc) { somax_b200_qg_destroy(h); return rc; }
   h->bytes += qg_solver_bytes(h->solver);
   *out = h;
