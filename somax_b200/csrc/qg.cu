@@ -368,7 +368,7 @@ __device__ __forceinline__ void qg_tma_compute(const QgArgs<float>& A, const Sta
   }
 }
 
-__global__ void __launch_bounds__(QTXG* QTY)
+__global__ void __launch_bounds__(QTXG* QTY, 3)
 qg_rhs_kernel_tma(const __grid_constant__ QgTmaps M, const QgArgs<float> A, const Stage<float> st) {
   extern __shared__ __align__(128) unsigned char qsm[];
   float (*s_q)[QHW] = reinterpret_cast<float (*)[QHW]>(qsm);
