@@ -15,6 +15,8 @@
 namespace sb {
 
 template <typename T> struct C2 { T x, y; };
+template <> struct __align__(8) C2<float> { float x, y; };      // one 64-bit / 128-bit access
+template <> struct __align__(16) C2<double> { double x, y; };
 
 template <typename T>
 __host__ __device__ __forceinline__ C2<T> cadd(C2<T> a, C2<T> b) { return {a.x + b.x, a.y + b.y}; }

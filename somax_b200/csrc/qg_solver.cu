@@ -43,7 +43,7 @@ struct QgSolver {
   void* S = nullptr; void* W = nullptr;
   double* ctab = nullptr; long long* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
   int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0, KBs = 2; double* dbad = nullptr;
-  double* bsig = nullptr; double* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
+  double* bsig = nullptr; void* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
   double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; float* gvecf = nullptr; double* meet = nullptr; double* meetc = nullptr;
   void* tw = nullptr; void* twc = nullptr; void* twb = nullptr; void* dstmat = nullptr;
   FftPlan plan;
@@ -58,6 +58,8 @@ struct QgSolver {
 // (rows x 64 columns) tile with a single bulk copy: within a plane, element (row j, column k)
 // lives at ((k / 64) * ny + j) * 64 + (k % 64); the plane stride is ny * np, np = roundup(nx, 64).
 constexpr int SP_W = 64;
+constexpr int BD_ROWS = 8;     // rows per CTA of border_dot
+constexpr int GS_ROWS = 8;     // outputs (warps) per CTA of border_gsolve
 __host__ __device__ __forceinline__ size_t sp_off(int ny, int j, int k) {
   return ((size_t)(k >> 6) * ny + j) * SP_W + (k & (SP_W - 1));
 }
@@ -684,8 +686,14 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   const double bs = (COMBINE && act) ? bsig[c] : 0.0;
   const float cfix_f = (float)cfix, kfix_f = (float)(cfix * tb.dy2), dy2_f = (float)tb.dy2, bs_f = (float)bs;
   float carry_f = 0.f;
-  const double* gv = gvec + (FROM_VEC ? (size_t)plane * ny : 0);
-  const float* gvf = gvecf + (FROM_VEC ? (size_t)plane * ny : 0);
+  // FROM_VEC: the shared right-hand side g[j] of the tile after next is fetched (one element per
+  // thread, coalesced) while the current tile runs, and read back as a shared-memory broadcast
+  using GT = typename std::conditional<PLAIN, float, double>::type;
+  __shared__ GT gbuf[2][FROM_VEC ? RT : 1];
+  const GT* gsrc = nullptr;
+  if (FROM_VEC) {
+    if constexpr (PLAIN) gsrc = gvecf + (size_t)plane * ny; else gsrc = gvec + (size_t)plane * ny;
+  }
   const int m1 = ny / 2;
   const int cnt = half == 0 ? m1 : ny - m1;
   int j0, dj;
@@ -744,6 +752,10 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     carry = half == 0 ? xb : xa;     // the neighbour's value across the meeting point
     carry_f = (float)carry;
   }
+  if (FROM_VEC && ntile > 0) {
+    if (tid < tile_nr(0)) gbuf[0][tid] = gsrc[tile_jlo(0) + tid];
+    __syncthreads();
+  }
   unsigned phase_bits = 0;            // per-stage phase parity (stages may be skipped by FROM_VEC tiles)
 #ifdef SB_TH_DEBUG
   long long tdbg0 = clock64(), twait = 0, tsync = 0, tmode[3] = {0, 0, 0};
@@ -754,6 +766,9 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     const int st = t % NS;
     const int nrt = tile_nr(t);
     const int ilot = tile_ilo(t);
+    GT gnext = 0;
+    if (FROM_VEC && t + 1 < ntile && tid < tile_nr(t + 1)) gnext = gsrc[tile_jlo(t + 1) + tid];
+    const GT* gvt = gbuf[t & 1] - tile_jlo(t);      // indexed by the memory row
     if (tile_has_load(t)) {
 #ifdef SB_TH_DEBUG
       long long w0 = clock64();
@@ -783,7 +798,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
         const float (*Ct)[TH_COLS] = reinterpret_cast<const float (*)[TH_COLS]>(tabS) + ilo;
 #define SB_TILE(UPV, MODEV)                                                                        \
         thomas_tile_f32<SUBST, FROM_VEC, COMBINE, UPV, MODEV>(                                     \
-            reinterpret_cast<float (*)[TH_COLS]>(A), reinterpret_cast<const float (*)[TH_COLS]>(Vt), Ct, gvf, \
+            reinterpret_cast<float (*)[TH_COLS]>(A), reinterpret_cast<const float (*)[TH_COLS]>(Vt), Ct, (const float*)gvt, \
             tid, nr, s0, ilo, Js, cnt, jb, act, cfix_f, kfix_f, dy2_f, bs_f, carry_f)
         if (dj > 0) {
           if (mode == 0) SB_TILE(true, 0); else if (mode == 1) SB_TILE(true, 1); else SB_TILE(true, 2);
@@ -797,7 +812,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
                                           : (const double (*)[TH_COLS])(tabS + (size_t)ilo * TH_COLS);
         double* Dt = tileD + ((size_t)st * RT + row0) * tb.KB + (bad ? c : 0);
 #define SB_TILE(UPV, MODEV)                                                                        \
-        thomas_tile<T, SUBST, FROM_VEC, COMBINE, UPV, MODEV>(A, Vt, Ct, gv, Dt, tb.KB, tid, nr, s0, ilo, Js, \
+        thomas_tile<T, SUBST, FROM_VEC, COMBINE, UPV, MODEV>(A, Vt, Ct, (const double*)gvt, Dt, tb.KB, tid, nr, s0, ilo, Js, \
                                                              cnt, jb, act, bad, cfix, tb.dy2, bs, carry)
         if (dj > 0) {
           if (mode == 0) SB_TILE(true, 0); else if (mode == 1) SB_TILE(true, 1); else SB_TILE(true, 2);
@@ -810,6 +825,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
       tmode[mode] += clock64() - b0clk; nmode[mode]++;
 #endif
     }
+    if (FROM_VEC && t + 1 < ntile && tid < tile_nr(t + 1)) gbuf[(t + 1) & 1][tid] = gnext;
     if (!SUBST && t == ntile - 1)
       tb.meet[((size_t)plane * 2 + half) * tb.np + c] = PLAIN ? (double)carry_f : carry;
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
@@ -845,27 +861,36 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
 // One CTA per (row, plane); 128-bit loads over the 64-column strips of the blocked layout.
 template <typename T>
 __global__ void __launch_bounds__(256)
-border_dot(const T* __restrict__ V, const double* __restrict__ sig2n, int ny,
+border_dot(const T* __restrict__ V, const T* __restrict__ sig2n, int ny,
            int np, int ncols, double b, double* __restrict__ r) {
-  const int j = blockIdx.x, plane = blockIdx.y;
-  const T* pl = V + (size_t)plane * ny * np;
+  // one warp per row, BD_ROWS consecutive rows per CTA: per strip the CTA reads one contiguous
+  // BD_ROWS x 256-byte block.  sig2n is padded with zeros to np (the border slot drops out).
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * BD_ROWS + warp, plane = blockIdx.y;
+  if (j >= ny) return;
+  const T* pl = V + (size_t)plane * ny * np + (size_t)j * SP_W + 2 * lane;
+  const T* sg = sig2n + 2 * lane;
+  const int nstrip = np / SP_W;
+  const size_t sstride = (size_t)ny * SP_W;
   double acc = 0;
-  for (int c4 = threadIdx.x * 4; c4 < np; c4 += blockDim.x * 4) {
-    const Vec4<T> v = ld4(pl + sp_off(ny, j, c4));
-    if (c4 + 0 < ncols) acc += sig2n[c4 + 0] * (double)v.x;
-    if (c4 + 1 < ncols) acc += sig2n[c4 + 1] * (double)v.y;
-    if (c4 + 2 < ncols) acc += sig2n[c4 + 2] * (double)v.z;
-    if (c4 + 3 < ncols) acc += sig2n[c4 + 3] * (double)v.w;
+  int s0 = 0;
+  for (; s0 + 4 <= nstrip; s0 += 4) {
+    C2<T> x[4], w[4];     // (pairs of adjacent columns; 2-element vector loads)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      x[u] = *reinterpret_cast<const C2<T>*>(pl + (s0 + u) * sstride);
+      w[u] = *reinterpret_cast<const C2<T>*>(sg + (s0 + u) * SP_W);
+    }
+    T part = 0;       // 8 terms in working precision, then one add in fp64
+#pragma unroll
+    for (int u = 0; u < 4; ++u) part = fma(w[u].x, x[u].x, fma(w[u].y, x[u].y, part));
+    acc += (double)part;
   }
-  __shared__ double red[32];
-  for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    r[(size_t)plane * ny + j] = (double)pl[sp_off(ny, j, ncols)] - b * t;
-  }
+  for (; s0 < nstrip; ++s0)
+    acc += (double)(sg[s0 * SP_W] * pl[s0 * sstride] + sg[s0 * SP_W + 1] * pl[s0 * sstride + 1]);
+  for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, sh);
+  if (lane == 0)
+    r[(size_t)plane * ny + j] = (double)V[(size_t)plane * ny * np + sp_off(ny, j, ncols)] - b * acc;
 }
 
 // Border Schur solve = dense DST-I in y of one column per plane (length ny, N = ny + 1), brute
@@ -875,39 +900,36 @@ border_dot(const T* __restrict__ V, const double* __restrict__ sig2n, int ny,
 // step values come exactly from the table.  STAGE_A divides by the Schur diagonal; stage B
 // scales by 2/N and also writes the result where the sweeps / inverse transform read it.
 template <typename T, bool STAGE_A>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * GS_ROWS)
 border_gsolve(const double* __restrict__ in, const double* __restrict__ sintab,
               const double* __restrict__ sdiag, int ny, int np, int n, int nl,
               double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
               T* __restrict__ S) {
-  const int a = blockIdx.x + 1, plane = blockIdx.y, m = plane % nl;
-  const int N = ny + 1, N2 = 2 * N, B = blockDim.x;
-  auto sn = [&](long long k) { return sintab[(int)(k % N2)]; };          // sin(pi k / N)
-  const int t0 = threadIdx.x + 1;
-  // cos(pi k / N) = sin(pi (k + N/2) / N) needs N even; use the identity through the table of
-  // size 2N only when N is even, otherwise evaluate with cospi (N odd <=> ny even)
-  double s = sn((long long)a * t0), c, ds = sn((long long)a * B), dc;
-  if ((N & 1) == 0) {
-    c = sintab[(int)(((long long)a * t0 + N / 2) % N2)];
-    dc = sintab[(int)(((long long)a * B + N / 2) % N2)];
-  } else {
-    c = cospi((double)(((long long)a * t0) % N2) / (double)N);
-    dc = cospi((double)(((long long)a * B) % N2) / (double)N);
-  }
+  // one warp per output index a; sintab holds sin(pi k / N) for k < 2N followed by cos(pi k / N)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a = blockIdx.x * GS_ROWS + warp + 1, plane = blockIdx.y, m = plane % nl;
+  if (a > ny) return;
+  const unsigned N = ny + 1, N2 = 2 * N;
+  const double* costab = sintab + N2;
+  const unsigned t0 = lane + 1;
+  const unsigned k0 = ((unsigned)a * t0) % N2, kd = ((unsigned)a * 32u) % N2;
+  double s = sintab[k0], c = costab[k0];
+  const double ds = sintab[kd], dc = costab[kd];
   double acc = 0;
   const double* x = in + (size_t)plane * ny;
-  for (int t = t0; t <= ny; t += B) {
-    acc = fma(s, x[t - 1], acc);
-    const double s2 = fma(s, dc, c * ds), c2 = fma(c, dc, -(s * ds));   // rotate by pi a B / N
+  // sin(pi a (N - t) / N) = -(-1)^a sin(pi a t / N): fold the input, half the terms
+  const int half = (N - 1) / 2;
+  const double sgn = (a & 1) ? 1.0 : -1.0;
+  for (int t = t0; t <= half; t += 32) {
+    acc = fma(s, fma(sgn, x[N - t - 1], x[t - 1]), acc);
+    const double s2 = fma(s, dc, c * ds), c2 = fma(c, dc, -(s * ds));   // rotate by 32 pi a / N
     s = s2; c = c2;
   }
-  __shared__ double red[32];
+  if ((N & 1) == 0 && lane == 0)
+    acc = fma(sintab[(unsigned)(((unsigned long long)a * (N / 2)) % N2)], x[N / 2 - 1], acc);
   for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, sh);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  if (lane == 0) {
+    double t = acc;
     if (STAGE_A) {
       out[(size_t)plane * ny + (a - 1)] = t / sdiag[(size_t)m * ny + (a - 1)];
     } else {
@@ -1096,10 +1118,19 @@ static int build_fft_tables(QgSolver* s, const double* lambdas) {
       for (int c = 0; c < nc; ++c) acc += sig[c] * sig[c] / (lamx[c] + mu);
       sdiag[(size_t)m * ny + (l - 1)] = mu - 2.0 * b - b * b * (2.0 / n) * acc;
     }
-  std::vector<double> sintab(2 * (size_t)(ny + 1));
-  for (size_t t = 0; t < sintab.size(); ++t) sintab[t] = sin(M_PI * (double)t / (ny + 1));
+  // sin(pi t / N), t < 2N, followed by cos(pi t / N)
+  const size_t N2 = 2 * (size_t)(ny + 1);
+  std::vector<double> sintab(2 * N2);
+  for (size_t t = 0; t < N2; ++t) {
+    sintab[t] = sin(M_PI * (double)t / (ny + 1));
+    sintab[N2 + t] = cos(M_PI * (double)t / (ny + 1));
+  }
   if (int rc = dev_upload(bsig.data(), nc * 8, (void**)&s->bsig, &s->bytes)) return rc;
-  if (int rc = dev_upload(sig2n.data(), nc * 8, (void**)&s->sig2n, &s->bytes)) return rc;
+  {
+    std::vector<T> sg((size_t)s->np, (T)0);      // working precision, zero-padded to np
+    for (int c = 0; c < nc; ++c) sg[c] = (T)sig2n[c];
+    if (int rc = dev_upload(sg.data(), sg.size() * sizeof(T), &s->sig2n, &s->bytes)) return rc;
+  }
   if (int rc = dev_upload(sdiag.data(), sdiag.size() * 8, (void**)&s->sdiag, &s->bytes)) return rc;
   if (int rc = dev_upload(sintab.data(), sintab.size() * 8, (void**)&s->sintab, &s->bytes)) return rc;
   size_t vb = (size_t)s->planes * ny * 8;
@@ -1158,7 +1189,11 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
       }
   s->plan = make_fft_plan(nx);
   int rc = 0;
-  if (cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking) != cudaSuccess ||
+  // the low-k class is a handful of long serial CTAs: give its stream the highest priority so
+  // they are placed as soon as an SM frees up instead of queueing behind the wide launches
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&s->aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     delete s;
@@ -1277,13 +1312,13 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     if (int rc = launch_solve<T, false>(s, tb, S, nullptr, st)) return rc;
     const double b = 1.0 / (s->dx * s->dx);
     prof_begin("border_dot", st);
-    border_dot<T><<<dim3(ny, s->planes), 256, 0, st>>>(S, s->sig2n, ny, np, s->ncols, b, s->rvec);
+    border_dot<T><<<dim3((ny + BD_ROWS - 1) / BD_ROWS, s->planes), 32 * BD_ROWS, 0, st>>>(S, (const T*)s->sig2n, ny, np, s->ncols, b, s->rvec);
     SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_a", st);
-    border_gsolve<T, true><<<dim3(ny, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
+    border_gsolve<T, true><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
     SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_b", st);
-    border_gsolve<T, false><<<dim3(ny, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
+    border_gsolve<T, false><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
     SB_LAUNCH_CHECK();
     if (int rc = launch_solve<T, true>(s, tb, S, W, st)) return rc;
     if (int rc = launch_rowdst<T, true>(s->plan.lgn, Ai, S, psi, st)) return rc;
