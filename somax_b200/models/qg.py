@@ -145,14 +145,14 @@ class _QGBase(SomaxModel):
     _H0: float
 
     def _call_q(self, state, fn):
-        io = DeviceIO(self._engine.dtype)
+        io = DeviceIO(self._engine.dtype, self.__dict__.setdefault("_io_cache", {}))
         q = io.to_device(state.q)
         batch = self._engine.shape4(q, self._base_ndim)
         out = fn(self._engine.handle(batch), q, io)
         return out, io
 
     def _invert_pv(self, q):
-        io = DeviceIO(self._engine.dtype)
+        io = DeviceIO(self._engine.dtype, self.__dict__.setdefault("_io_cache", {}))
         qd = io.to_device(q)
         batch = self._engine.shape4(qd, self._base_ndim)
         psi = torch.empty_like(qd)

@@ -132,7 +132,7 @@ class _SWMBase(SomaxModel):
         raise ValueError(f"state shape {shp} does not match the model grid {core}")
 
     def _dev(self, state):
-        io = DeviceIO(self.dtype)
+        io = DeviceIO(self.dtype, self.__dict__.setdefault("_io_cache", {}))
         h, u, v = io.to_device(state.h), io.to_device(state.u), io.to_device(state.v)
         return io, h, u, v, self._handle(self._batch(h))
 
