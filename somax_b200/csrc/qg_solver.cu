@@ -528,6 +528,10 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+#ifdef SB_TH_DEBUG
+__device__ unsigned long long g_dbg[4096 * 4];
+__device__ unsigned g_dbg_n;
+#endif
 constexpr int TH_RT = 16;   // rows per register block of the recurrence
 // Launch classes of a sweep.  LOWK (TAB = true): the few strips of near-singular low x-wavenumbers
 // (and late-converging coefficient recurrences): fp64 carried recurrence for both pipelines,
@@ -758,8 +762,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   }
   unsigned phase_bits = 0;            // per-stage phase parity (stages may be skipped by FROM_VEC tiles)
 #ifdef SB_TH_DEBUG
-  long long tdbg0 = clock64(), twait = 0, tsync = 0, tmode[3] = {0, 0, 0};
-  int nmode[3] = {0, 0, 0};
+  unsigned long long tg0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tg0));
 #endif
 #pragma unroll 1
   for (int t = 0; t < ntile; ++t) {
@@ -770,13 +773,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     if (FROM_VEC && t + 1 < ntile && tid < tile_nr(t + 1)) gnext = gsrc[tile_jlo(t + 1) + tid];
     const GT* gvt = gbuf[t & 1] - tile_jlo(t);      // indexed by the memory row
     if (tile_has_load(t)) {
-#ifdef SB_TH_DEBUG
-      long long w0 = clock64();
-#endif
       mbar_wait(&full[st], (phase_bits >> st) & 1u);
-#ifdef SB_TH_DEBUG
-      twait += clock64() - w0;
-#endif
       phase_bits ^= 1u << st;
     }
 #pragma unroll 1
@@ -790,9 +787,6 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
       const int jb = j0 + dj * s0;
       // mode: 0 = constant coefficient, 1 = fully tabulated, 2 = generic
       const int mode = (nr < TH_RT || (ilo < Js && ilo + nr > Js)) ? 2 : (ilo >= Js ? 0 : 1);
-#ifdef SB_TH_DEBUG
-      long long b0clk = clock64();
-#endif
       if constexpr (PLAIN) {
         // float coefficient rows, read straight from L2 (only the first Js rows of a half)
         const float (*Ct)[TH_COLS] = reinterpret_cast<const float (*)[TH_COLS]>(tabS) + ilo;
@@ -821,22 +815,13 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
         }
 #undef SB_TILE
       }
-#ifdef SB_TH_DEBUG
-      tmode[mode] += clock64() - b0clk; nmode[mode]++;
-#endif
     }
     if (FROM_VEC && t + 1 < ntile && tid < tile_nr(t + 1)) gbuf[(t + 1) & 1][tid] = gnext;
     if (!SUBST && t == ntile - 1)
       tb.meet[((size_t)plane * 2 + half) * tb.np + c] = PLAIN ? (double)carry_f : carry;
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
-#ifdef SB_TH_DEBUG
-    long long y0 = clock64();
-#endif
     fence_async_smem();
     __syncthreads();
-#ifdef SB_TH_DEBUG
-    tsync += clock64() - y0;
-#endif
     if (tid == 0) {
       bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &tileA[st][0][0], (unsigned)(nrt * TH_COLS * sizeof(T)));
       if (TAB && !SUBST && strip_bad)
@@ -850,9 +835,15 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   }
   if (tid == 0) bulk_wait_read<0>();
 #ifdef SB_TH_DEBUG
-  if (TAB && (tid == 0 || tid == 32) && plane < tb.nl)
-    printf("TH %d%d%d strip %d plane %d half %d tid %d Js %d total %lld wait %lld sync %lld m0 %d %lld m1 %d %lld m2 %d %lld\n", (int)SUBST, (int)FROM_VEC,
-           (int)COMBINE, strip, plane, half, tid, Js, clock64() - tdbg0, twait, tsync, nmode[0], tmode[0], nmode[1], tmode[1], nmode[2], tmode[2]);
+  if (tid == 0 && (TAB || (blockIdx.x % 41 == 0)) && plane < tb.nl) {
+    unsigned long long tg1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tg1));
+    const unsigned slot = atomicAdd(&g_dbg_n, 1u);
+    if (slot < 4096) {
+      g_dbg[slot * 4 + 0] = (SUBST ? 1000 : 0) + (FROM_VEC ? 100 : 0) + (COMBINE ? 10 : 0) + (TAB ? 1 : 0);
+      g_dbg[slot * 4 + 1] = strip * 100 + plane * 10 + half;
+      g_dbg[slot * 4 + 2] = tg0; g_dbg[slot * 4 + 3] = tg1;
+    }
+  }
 #endif
 }
 
@@ -1189,11 +1180,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
       }
   s->plan = make_fft_plan(nx);
   int rc = 0;
-  // the low-k class is a handful of long serial CTAs: give its stream the highest priority so
-  // they are placed as soon as an SM frees up instead of queueing behind the wide launches
-  int prio_lo = 0, prio_hi = 0;
-  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  if (cudaStreamCreateWithPriority(&s->aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     delete s;
@@ -1275,17 +1262,21 @@ static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream
   T* fout = SECOND ? W : S;                 // eliminated right-hand side
   const T* Vv = SECOND ? S : nullptr;
   const double* bs = SECOND ? s->bsig : nullptr;
+  // The LOWK launches go first, on the caller's stream, so that their few long CTAs are resident
+  // before the wide PLAIN launches (auxiliary stream, released by an event a few microseconds
+  // later) fill every SM's shared memory; measured the other way round, the LOWK CTAs could not be
+  // placed until the PLAIN kernel drained and the two chains ran back to back.
   const bool two = nh > 0 && nh < nstrip;
-  cudaStream_t lo = two ? s->aux : st;
+  cudaStream_t pl = two ? s->aux : st;
   if (two) {
     SB_CUDA(cudaEventRecord(s->ev_fork, st));
     SB_CUDA(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
   }
-  if (int rc = launch_thomas_one<T, false, SECOND, false, true>(tfl, tb, 0, nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, lo)) return rc;
-  if (int rc = launch_thomas_one<T, true, false, SECOND, true>(tbl, tb, 0, nh, s->planes, fout, Vv, nullptr, nullptr, bs, S, lo)) return rc;
+  if (int rc = launch_thomas_one<T, false, SECOND, false, true>(tfl, tb, 0, nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, st)) return rc;
+  if (int rc = launch_thomas_one<T, false, SECOND, false, false>(tf, tb, nh, nstrip - nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, pl)) return rc;
+  if (int rc = launch_thomas_one<T, true, false, SECOND, true>(tbl, tb, 0, nh, s->planes, fout, Vv, nullptr, nullptr, bs, S, st)) return rc;
+  if (int rc = launch_thomas_one<T, true, false, SECOND, false>(tbk, tb, nh, nstrip - nh, s->planes, fout, Vv, nullptr, nullptr, bs, S, pl)) return rc;
   if (two) SB_CUDA(cudaEventRecord(s->ev_join, s->aux));
-  if (int rc = launch_thomas_one<T, false, SECOND, false, false>(tf, tb, nh, nstrip - nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, st)) return rc;
-  if (int rc = launch_thomas_one<T, true, false, SECOND, false>(tbk, tb, nh, nstrip - nh, s->planes, fout, Vv, nullptr, nullptr, bs, S, st)) return rc;
   if (two) SB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
   return 0;
 }
@@ -1339,6 +1330,17 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
   }
   return 0;
 }
+
+#ifdef SB_TH_DEBUG
+extern "C" int somax_b200_debug_dump(unsigned long long* out, unsigned* n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(n, g_dbg_n, sizeof(unsigned));
+  cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 4096 * 4);
+  unsigned zero = 0;
+  cudaMemcpyToSymbol(g_dbg_n, &zero, sizeof(unsigned));
+  return 0;
+}
+#endif
 
 template int qg_solver_run<float>(QgSolver*, const float*, float*, cudaStream_t);
 template int qg_solver_run<double>(QgSolver*, const double*, double*, cudaStream_t);
