@@ -51,8 +51,8 @@ SWM_PARAMS = dict(Lx=1e6, Ly=1e6, f0=1e-4, beta=1.6e-11, H=(500.0, 4500.0), g_pr
 TRANSFERS = {"qg": 79, "swm": 111}
 # algorithmic transfers of one launch of each kernel (DESIGN.md "kernels"): arrays it must read+write
 KERNEL_TRANSFERS = {
-    "rowdst_fwd_fft": 2.0, "rowdst_inv_fft": 2.0, "thomas_fwd_0": 2.0, "thomas_bwd_0": 2.0,
-    "thomas_fwd_1": 1.0, "thomas_bwd_1": 3.0, "border_dot": 1.0,
+    "rowdst_fwd_fft": 2.0, "rowdst_inv_fft": 2.0, "thomas_fwd_0": 2.0, "thomas_bwd_0": 1.0,
+    "thomas_fwd_1": 1.0, "thomas_bwd_1": 3.0,
     "qg_rhs_kernel": (37.0 + 6.0) / 6.0, "swm_rhs_kernel": 111.0 / 6.0 / 3.0 * 3.0,
 }
 

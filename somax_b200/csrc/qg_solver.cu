@@ -42,7 +42,7 @@ struct QgSolver {
   int np, ncols, planes;
   void* S = nullptr; void* W = nullptr;
   double* ctab = nullptr; long long* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
-  int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0, KBs = 2; double* dbad = nullptr;
+  int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0, KBs = 2; double* dbad = nullptr; double* dbad1 = nullptr; double* meet1 = nullptr; void* part = nullptr;
   double* bsig = nullptr; void* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
   double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; float* gvecf = nullptr; double* meet = nullptr; double* meetc = nullptr;
   void* tw = nullptr; void* twc = nullptr; void* twb = nullptr; void* dstmat = nullptr;
@@ -58,7 +58,6 @@ struct QgSolver {
 // (rows x 64 columns) tile with a single bulk copy: within a plane, element (row j, column k)
 // lives at ((k / 64) * ny + j) * 64 + (k % 64); the plane stride is ny * np, np = roundup(nx, 64).
 constexpr int SP_W = 64;
-constexpr int BD_ROWS = 8;     // rows per CTA of border_dot
 constexpr int GS_ROWS = 8;     // outputs (warps) per CTA of border_gsolve
 __host__ __device__ __forceinline__ size_t sp_off(int ny, int j, int k) {
   return ((size_t)(k >> 6) * ny + j) * SP_W + (k & (SP_W - 1));
@@ -482,8 +481,11 @@ struct ThomasTab {
   const double* ctabB; const long long* tabOff; const int* Jstrip;
   const double* cinf;        // [m][np] fixed point per column
   const double* meetc;       // [m][2][np]: c[m1-1] and c[ny-1-m1] per column (meeting-point solve)
-  int kbad[QG_MAX_NL]; int KB; double* dbad;
-  double* meet;              // [plane][2][np]: last eliminated value of each half (fp64)
+  int kbad[QG_MAX_NL]; int KB;
+  double* dbad; double* dbad1;   // fp64 side buffers [plane][j][KB] of the indefinite columns (solve 1 / 2)
+  double* meet; double* meet1;   // [plane][2][np]: last eliminated value of each half (solve 1 / 2)
+  void* part;                    // [plane][2 nstrip][ny]: per-warp partial border sums (KIND 1)
+  const void* sig2n;             // [np] border weights in working precision, zero-padded
   int ny, np, ncols, nl, nstrip;
   double dy2;
 };
@@ -497,7 +499,12 @@ struct ThomasTab {
 //   SUBST = false: elimination  d_s = (dy^2 f_s - d_{s-1}) c_s           (s counts from the end)
 //   SUBST = true : substitution x_s = d_s - c_s x_{s'}  outwards from the meeting point
 // FROM_VEC (elimination only): right-hand side is gvec[plane][j] for every column (border solve).
-// COMBINE (substitution only): out = V - bsig[c] * x (second solve applied to the first one's V).
+// KIND (substitution only): 0 = plain solve, x is stored.  The bordered solver never stores the
+// first solve's x: KIND 1 substitutes the eliminated first right-hand side D only to emit the
+// weighted row sums sum_c sig2n[c] x[j][c] the border system needs (per-warp partials, reduced by
+// border_reduce); KIND 2 substitutes D - bsig[c] * E (E = eliminated border right-hand side of
+// the second solve, linearity of the elimination) and stores the final x.  7 instead of 8
+// array transfers per inversion and no separate dot pass.
 // ---- bulk-async (TMA engine) helpers: 1-D cp.async.bulk + mbarrier, no tensor map needed ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -538,25 +545,25 @@ constexpr int TH_RT = 16;   // rows per register block of the recurrence
 // coefficient tiles staged through shared memory, big staged tiles because only a handful of
 // CTAs exist and each is a serial chain over ny/2 rows.  PLAIN (TAB = false): everything else, in
 // the pipeline's own precision, coefficients (needed for the first rows only) read from L2.
-template <typename T, bool TAB> struct ThRows {      // rows per staged tile
-  static constexpr int v = TAB ? (sizeof(T) == 4 ? 64 : 32) : TH_RT;
+template <typename T, int KIND, bool TAB> struct ThRows {      // rows per staged tile
+  static constexpr int v = TAB ? ((sizeof(T) == 4 && KIND != 2) ? 64 : 32) : TH_RT;
 };
-template <typename T, bool COMBINE, bool TAB> struct ThStages {   // ring depth
-  static constexpr int v = TAB ? 3 : (sizeof(T) == 4 ? (COMBINE ? 6 : 8) : (COMBINE ? 3 : 6));
+template <typename T, int KIND, bool TAB> struct ThStages {   // ring depth
+  static constexpr int v = TAB ? 3 : (sizeof(T) == 4 ? (KIND == 2 ? 6 : 8) : (KIND == 2 ? 3 : 6));
 };
 
 // Plain fp32 recurrence over one register block, for the well-conditioned strips of the fp32
 // pipeline: for x-wavenumbers k >~ n/32 the fp32 recurrence error stays at the rounding level
 // (~1e-7 per column; the error of a column grows like (n / k pi) eps with exact coefficients),
 // only the low-k strips need the fp64 carry.  Coefficient rows are plain floats.
-template <bool SUBST, bool FROM_VEC, bool COMBINE, bool UP, int MODE>
+template <bool SUBST, bool FROM_VEC, int KIND, bool UP, int MODE>
 __device__ __forceinline__ void thomas_tile_f32(float (*A)[TH_COLS], const float (*Vt)[TH_COLS],
                                                 const float (*Ct)[TH_COLS], const float* __restrict__ gv,
                                                 int tid, int nr, int s0, int ilo, int Js, int cnt, int jb,
                                                 bool act, float cfix, float kfix, float dy2, float bs,
                                                 float& carry) {
   constexpr int dj = UP ? 1 : -1;
-  float f[TH_RT], cj[TH_RT], vv[TH_RT];
+  float f[TH_RT], cj[TH_RT];
 #pragma unroll
   for (int r = 0; r < TH_RT; ++r) {
     const bool ok = MODE != 2 || r < nr;
@@ -567,7 +574,7 @@ __device__ __forceinline__ void thomas_tile_f32(float (*A)[TH_COLS], const float
     else cj[r] = (ok && i < Js) ? Ct[i - ilo][tid] : cfix;
     if (FROM_VEC) f[r] = ok ? gv[jb + dj * r] : 0.f;
     else f[r] = ok ? A[ok ? rm : 0][tid] : 0.f;
-    if (COMBINE) vv[r] = ok ? Vt[ok ? rm : 0][tid] : 0.f;
+    if (KIND == 2) f[r] = fmaf(-bs, ok ? Vt[ok ? rm : 0][tid] : 0.f, f[r]);
   }
   if (!SUBST) {
 #pragma unroll
@@ -580,8 +587,7 @@ __device__ __forceinline__ void thomas_tile_f32(float (*A)[TH_COLS], const float
   for (int r = 0; r < TH_RT; ++r) {
     if (MODE != 2 || r < nr) {
       const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);
-      if (COMBINE) A[rm][tid] = act ? fmaf(-bs, f[r], vv[r]) : vv[r];
-      else if (act) A[rm][tid] = f[r];
+      if (act) A[rm][tid] = f[r];
       else if (FROM_VEC) A[rm][tid] = 0.f;
     }
   }
@@ -592,15 +598,15 @@ __device__ __forceinline__ void thomas_tile_f32(float (*A)[TH_COLS], const float
 // tabulated (coefficients in Ct); MODE 2: generic (ragged end, block straddling the convergence
 // row, indefinite columns with their fp64 side buffer).  Phases are explicit (all loads, the
 // carried chain, all stores) so the shared-memory accesses pipeline.
-template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE, bool UP, int MODE>
+template <typename T, bool SUBST, bool FROM_VEC, int KIND, bool UP, int MODE>
 __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_COLS],
                                             const double (*Ct)[TH_COLS], const double* __restrict__ gv,
-                                            double* __restrict__ Dt, int KB, int tid, int nr, int s0,
+                                            double* __restrict__ Dt, const double* __restrict__ Dt1,
+                                            int KB, int tid, int nr, int s0,
                                             int ilo, int Js, int cnt, int jb, bool act, bool bad,
                                             double cfix, double dy2, double bs, double& carry) {
   constexpr int dj = UP ? 1 : -1;
   double f[TH_RT], cj[TH_RT];
-  T vv[TH_RT];
 #pragma unroll
   for (int r = 0; r < TH_RT; ++r) {
     const bool ok = MODE != 2 || r < nr;
@@ -611,14 +617,14 @@ __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_CO
     else cj[r] = (ok && i < Js) ? Ct[i - ilo][tid] : cfix;
     if (FROM_VEC) f[r] = ok ? gv[jb + dj * r] : 0.0;
     else f[r] = ok ? (double)A[ok ? rm : 0][tid] : 0.0;
-    if (COMBINE) vv[r] = ok ? Vt[ok ? rm : 0][tid] : T(0);
+    if (KIND == 2) f[r] = fma(-bs, ok ? (double)Vt[ok ? rm : 0][tid] : 0.0, f[r]);
   }
   if (MODE != 0 && SUBST && bad) {
     // indefinite column: the eliminated right-hand side comes from the staged fp64 side tile
 #pragma unroll
     for (int r = 0; r < TH_RT; ++r) {
       const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);
-      if (MODE != 2 || r < nr) f[r] = Dt[rm * KB];
+      if (MODE != 2 || r < nr) f[r] = KIND == 2 ? fma(-bs, Dt1[rm * KB], Dt[rm * KB]) : Dt[rm * KB];
     }
   }
   if (!SUBST) {
@@ -638,8 +644,7 @@ __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_CO
   for (int r = 0; r < TH_RT; ++r) {
     if (MODE != 2 || r < nr) {
       const int rm = UP ? r : (MODE != 2 ? TH_RT - 1 - r : nr - 1 - r);
-      if (COMBINE) A[rm][tid] = act ? (T)((double)vv[r] - bs * f[r]) : vv[r];
-      else if (act) A[rm][tid] = (T)f[r];
+      if (act) A[rm][tid] = (T)f[r];
       else if (FROM_VEC) A[rm][tid] = T(0);
       if (MODE != 0 && !SUBST && bad) Dt[rm * KB] = f[r];
     }
@@ -651,13 +656,15 @@ __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_CO
 // shared-memory ring: ONE cp.async.bulk per tile (TMA engine, completes on an mbarrier), the
 // recurrence runs on shared memory only (register blocks of TH_RT rows), and the finished tile
 // leaves with one bulk store.
-template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE, bool TAB>
+template <typename T, bool SUBST, bool FROM_VEC, int KIND, bool TAB>
 __global__ void __launch_bounds__(TH_COLS)
 thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* __restrict__ V,
              const double* __restrict__ gvec, const float* __restrict__ gvecf,
              const double* __restrict__ bsig, T* __restrict__ out) {
-  constexpr int NS = ThStages<T, COMBINE, TAB>::v;
-  constexpr int RT = ThRows<T, TAB>::v;
+  constexpr int NS = ThStages<T, KIND, TAB>::v;
+  constexpr int RT = ThRows<T, KIND, TAB>::v;
+  constexpr bool COMBINE = KIND == 2;      // a second operand tile (E) travels with the first
+  static_assert(SUBST || KIND == 0, "KIND applies to substitution sweeps");
   constexpr bool LOAD = !FROM_VEC;
   constexpr bool PLAIN = sizeof(T) == 4 && !TAB;     // fp32 arithmetic, float coefficient rows
   static_assert(TH_COLS == SP_W, "one CTA per 64-column strip");
@@ -671,8 +678,9 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   // fp64 side tiles [RT][KB] for the indefinite columns (low-k class only; KB even)
   double* tileD = reinterpret_cast<double*>(th_smem + NS * CT_B + NS * TILE_B * (COMBINE ? 2 : 1));
   const size_t SIDE_B = TAB ? (size_t)RT * tb.KB * sizeof(double) : 0;
+  double* tileD1 = tileD + (COMBINE ? NS * SIDE_B / sizeof(double) : 0);      // side tiles of E (KIND 2)
   unsigned long long* full = reinterpret_cast<unsigned long long*>(
-      th_smem + NS * CT_B + NS * TILE_B * (COMBINE ? 2 : 1) + NS * SIDE_B);
+      th_smem + NS * CT_B + NS * TILE_B * (COMBINE ? 2 : 1) + NS * SIDE_B * (COMBINE ? 2 : 1));
   const int tid = threadIdx.x;
   const int strip = strip_first + blockIdx.x;
   const int c = strip * TH_COLS + tid;
@@ -686,7 +694,10 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   const double* tabS = tb.ctabB + tb.tabOff[m * tb.nstrip + strip];
   const bool bad = TAB && act && c < tb.kbad[m];
   const bool strip_bad = TAB && strip * TH_COLS < tb.kbad[m];     // this strip holds indefinite columns
-  double* sideG = tb.dbad + ((size_t)plane * ny) * tb.KB;         // [j][KB] of this plane
+  // side buffer / meeting values written by this elimination, or read by this substitution
+  double* sideG = (FROM_VEC ? tb.dbad1 : tb.dbad) + ((size_t)plane * ny) * tb.KB;   // [j][KB] of this plane
+  const double* sideG1 = tb.dbad1 + ((size_t)plane * ny) * tb.KB;
+  double* meetW = FROM_VEC ? tb.meet1 : tb.meet;
   const double bs = (COMBINE && act) ? bsig[c] : 0.0;
   const float cfix_f = (float)cfix, kfix_f = (float)(cfix * tb.dy2), dy2_f = (float)tb.dy2, bs_f = (float)bs;
   float carry_f = 0.f;
@@ -730,11 +741,13 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     const unsigned bytes = (unsigned)(nr * TH_COLS * sizeof(T));
     const unsigned cbytes = (unsigned)(ncoef * TH_COLS * sizeof(double));
     const unsigned dbytes = (TAB && SUBST && strip_bad) ? (unsigned)(nr * tb.KB * sizeof(double)) : 0u;
-    const unsigned total = (LOAD ? bytes * (COMBINE ? 2u : 1u) : 0u) + cbytes + dbytes;
+    const unsigned total = (LOAD ? bytes * (COMBINE ? 2u : 1u) : 0u) + cbytes + dbytes * (COMBINE ? 2u : 1u);
     if (total == 0) return;
     const size_t off = strip0 + (size_t)tile_jlo(t) * SP_W;
     mbar_arrive_expect_tx(&full[st], total);
     if (dbytes) bulk_g2s(tileD + (size_t)st * RT * tb.KB, sideG + (size_t)tile_jlo(t) * tb.KB, dbytes, &full[st]);
+    if (dbytes && COMBINE)
+      bulk_g2s(tileD1 + (size_t)st * RT * tb.KB, sideG1 + (size_t)tile_jlo(t) * tb.KB, dbytes, &full[st]);
     if (LOAD) bulk_g2s(&tileA[st][0][0], in + off, bytes, &full[st]);
     if (COMBINE) bulk_g2s(&tileV[st][0][0], V + off, bytes, &full[st]);
     if (cbytes) bulk_g2s(&tileC[st][0][0], tabS + (size_t)ilo * TH_COLS, cbytes, &full[st]);
@@ -749,8 +762,12 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   if (SUBST && cnt > 0 && m1 > 0) {
     // meeting point: x_{m1-1} + ca x_{m1} = d_{m1-1};  x_{m1} + cb x_{m1-1} = e_{m1}
     const double ca = tb.meetc[((size_t)m * 2 + 0) * tb.np + c], cb = tb.meetc[((size_t)m * 2 + 1) * tb.np + c];
-    const double dm = tb.meet[((size_t)plane * 2 + 0) * tb.np + c];
-    const double em = tb.meet[((size_t)plane * 2 + 1) * tb.np + c];
+    double dm = tb.meet[((size_t)plane * 2 + 0) * tb.np + c];
+    double em = tb.meet[((size_t)plane * 2 + 1) * tb.np + c];
+    if (COMBINE) {      // eliminated D - bs E at the meeting rows
+      dm = fma(-bs, tb.meet1[((size_t)plane * 2 + 0) * tb.np + c], dm);
+      em = fma(-bs, tb.meet1[((size_t)plane * 2 + 1) * tb.np + c], em);
+    }
     const double den = 1.0 / (1.0 - ca * cb);
     const double xa = (dm - ca * em) * den, xb = (em - cb * dm) * den;
     carry = half == 0 ? xb : xa;     // the neighbour's value across the meeting point
@@ -759,6 +776,12 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   if (FROM_VEC && ntile > 0) {
     if (tid < tile_nr(0)) gbuf[0][tid] = gsrc[tile_jlo(0) + tid];
     __syncthreads();
+  }
+  T wdot[KIND == 1 ? 16 : 1];
+  if (KIND == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      wdot[i] = reinterpret_cast<const T*>(tb.sig2n)[strip * TH_COLS + (tid >> 4) * 16 + ((i + (tid & 15)) & 15)];
   }
   unsigned phase_bits = 0;            // per-stage phase parity (stages may be skipped by FROM_VEC tiles)
 #ifdef SB_TH_DEBUG
@@ -791,7 +814,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
         // float coefficient rows, read straight from L2 (only the first Js rows of a half)
         const float (*Ct)[TH_COLS] = reinterpret_cast<const float (*)[TH_COLS]>(tabS) + ilo;
 #define SB_TILE(UPV, MODEV)                                                                        \
-        thomas_tile_f32<SUBST, FROM_VEC, COMBINE, UPV, MODEV>(                                     \
+        thomas_tile_f32<SUBST, FROM_VEC, KIND, UPV, MODEV>(                                        \
             reinterpret_cast<float (*)[TH_COLS]>(A), reinterpret_cast<const float (*)[TH_COLS]>(Vt), Ct, (const float*)gvt, \
             tid, nr, s0, ilo, Js, cnt, jb, act, cfix_f, kfix_f, dy2_f, bs_f, carry_f)
         if (dj > 0) {
@@ -805,8 +828,9 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
         const double (*Ct)[TH_COLS] = TAB ? (const double (*)[TH_COLS])(tileC[st] + (ilo - ilot))
                                           : (const double (*)[TH_COLS])(tabS + (size_t)ilo * TH_COLS);
         double* Dt = tileD + ((size_t)st * RT + row0) * tb.KB + (bad ? c : 0);
+        const double* Dt1 = tileD1 + ((size_t)st * RT + row0) * tb.KB + (bad ? c : 0);
 #define SB_TILE(UPV, MODEV)                                                                        \
-        thomas_tile<T, SUBST, FROM_VEC, COMBINE, UPV, MODEV>(A, Vt, Ct, (const double*)gvt, Dt, tb.KB, tid, nr, s0, ilo, Js, \
+        thomas_tile<T, SUBST, FROM_VEC, KIND, UPV, MODEV>(A, Vt, Ct, (const double*)gvt, Dt, Dt1, tb.KB, tid, nr, s0, ilo, Js, \
                                                              cnt, jb, act, bad, cfix, tb.dy2, bs, carry)
         if (dj > 0) {
           if (mode == 0) SB_TILE(true, 0); else if (mode == 1) SB_TILE(true, 1); else SB_TILE(true, 2);
@@ -818,12 +842,31 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     }
     if (FROM_VEC && t + 1 < ntile && tid < tile_nr(t + 1)) gbuf[(t + 1) & 1][tid] = gnext;
     if (!SUBST && t == ntile - 1)
-      tb.meet[((size_t)plane * 2 + half) * tb.np + c] = PLAIN ? (double)carry_f : carry;
+      meetW[((size_t)plane * 2 + half) * tb.np + c] = PLAIN ? (double)carry_f : carry;
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
     fence_async_smem();
     __syncthreads();
+    if (KIND == 1) {
+      // border sums of the finished tile: thread (rr, qd) adds 16 columns of row rr with a rotated
+      // column order (conflict-free), the two quarters of a warp combine by shuffle
+      const int rr = tid & 15, qd = tid >> 4;
+      T* part = reinterpret_cast<T*>(tb.part) +
+                ((size_t)(plane * 2 * tb.nstrip + strip * 2 + (tid >> 5))) * ny + tile_jlo(t);
+#pragma unroll 1
+      for (int rb = 0; rb < nrt; rb += 16) {
+        const int row = rb + rr;
+        T acc = 0;
+        if (row < nrt) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc = fma(wdot[i], tileA[st][row][qd * 16 + ((i + rr) & 15)], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if ((tid & 16) == 0 && row < nrt) part[row] = acc;
+      }
+    }
     if (tid == 0) {
-      bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &tileA[st][0][0], (unsigned)(nrt * TH_COLS * sizeof(T)));
+      if (KIND != 1)
+        bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &tileA[st][0][0], (unsigned)(nrt * TH_COLS * sizeof(T)));
       if (TAB && !SUBST && strip_bad)
         bulk_s2g(sideG + (size_t)tile_jlo(t) * tb.KB, tileD + (size_t)st * RT * tb.KB,
                  (unsigned)(nrt * tb.KB * sizeof(double)));
@@ -839,7 +882,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     unsigned long long tg1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tg1));
     const unsigned slot = atomicAdd(&g_dbg_n, 1u);
     if (slot < 4096) {
-      g_dbg[slot * 4 + 0] = (SUBST ? 1000 : 0) + (FROM_VEC ? 100 : 0) + (COMBINE ? 10 : 0) + (TAB ? 1 : 0);
+      g_dbg[slot * 4 + 0] = (SUBST ? 1000 : 0) + (FROM_VEC ? 100 : 0) + KIND * 10 + (TAB ? 1 : 0);
       g_dbg[slot * 4 + 1] = strip * 100 + plane * 10 + half;
       g_dbg[slot * 4 + 2] = tg0; g_dbg[slot * 4 + 3] = tg1;
     }
@@ -847,41 +890,20 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
 #endif
 }
 
-// r[plane][j] = f_n[j] - b * sum_c sig2n[c] * V[plane][j][c]: right-hand side of the border
-// (Schur) system; the sum is the first solve evaluated at column n-1, f_n sits in slot n-1.
-// One CTA per (row, plane); 128-bit loads over the 64-column strips of the blocked layout.
+// r[plane][j] = f_n[j] - b * sum_c sig2n[c] * x[plane][j][c]: right-hand side of the border
+// (Schur) system.  The column sum arrives as 2 * nstrip per-warp partials from the KIND 1
+// substitution sweeps (fixed order: deterministic); f_n sits in the border slot of S.
 template <typename T>
 __global__ void __launch_bounds__(256)
-border_dot(const T* __restrict__ V, const T* __restrict__ sig2n, int ny,
-           int np, int ncols, double b, double* __restrict__ r) {
-  // one warp per row, BD_ROWS consecutive rows per CTA: per strip the CTA reads one contiguous
-  // BD_ROWS x 256-byte block.  sig2n is padded with zeros to np (the border slot drops out).
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * BD_ROWS + warp, plane = blockIdx.y;
+border_reduce(const T* __restrict__ S, const T* __restrict__ part, int ny, int np, int ncols,
+              int npart, double b, double* __restrict__ r) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, plane = blockIdx.y;
   if (j >= ny) return;
-  const T* pl = V + (size_t)plane * ny * np + (size_t)j * SP_W + 2 * lane;
-  const T* sg = sig2n + 2 * lane;
-  const int nstrip = np / SP_W;
-  const size_t sstride = (size_t)ny * SP_W;
+  const T* pp = part + (size_t)plane * npart * ny + j;
   double acc = 0;
-  int s0 = 0;
-  for (; s0 + 4 <= nstrip; s0 += 4) {
-    C2<T> x[4], w[4];     // (pairs of adjacent columns; 2-element vector loads)
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      x[u] = *reinterpret_cast<const C2<T>*>(pl + (s0 + u) * sstride);
-      w[u] = *reinterpret_cast<const C2<T>*>(sg + (s0 + u) * SP_W);
-    }
-    T part = 0;       // 8 terms in working precision, then one add in fp64
-#pragma unroll
-    for (int u = 0; u < 4; ++u) part = fma(w[u].x, x[u].x, fma(w[u].y, x[u].y, part));
-    acc += (double)part;
-  }
-  for (; s0 < nstrip; ++s0)
-    acc += (double)(sg[s0 * SP_W] * pl[s0 * sstride] + sg[s0 * SP_W + 1] * pl[s0 * sstride + 1]);
-  for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, sh);
-  if (lane == 0)
-    r[(size_t)plane * ny + j] = (double)V[(size_t)plane * ny * np + sp_off(ny, j, ncols)] - b * acc;
+#pragma unroll 8
+  for (int p = 0; p < npart; ++p) acc += (double)pp[(size_t)p * ny];
+  r[(size_t)plane * ny + j] = (double)S[(size_t)plane * ny * np + sp_off(ny, j, ncols)] - b * acc;
 }
 
 // Border Schur solve = dense DST-I in y of one column per plane (length ny, N = ny + 1), brute
@@ -1037,14 +1059,22 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
     size_t mb = (size_t)s->planes * 2 * np * 8;
     SB_CUDA(cudaMalloc((void**)&s->meet, mb));
     SB_CUDA(cudaMemset(s->meet, 0, mb));
-    s->bytes += mb;
+    SB_CUDA(cudaMalloc((void**)&s->meet1, mb));
+    SB_CUDA(cudaMemset(s->meet1, 0, mb));
+    s->bytes += 2 * mb;
+    const size_t pb = (size_t)s->planes * 2 * nstrip * ny * (s->dtype == SOMAX_B200_F32 ? 4 : 8);
+    SB_CUDA(cudaMalloc(&s->part, pb));
+    SB_CUDA(cudaMemset(s->part, 0, pb));
+    s->bytes += pb;
   }
   {
     s->KBs = std::max(2, (s->KB + 1) & ~1);      // side-buffer row length: even (16-byte bulk copies)
     size_t nb = (size_t)s->planes * ny * s->KBs * 8;
     SB_CUDA(cudaMalloc((void**)&s->dbad, nb));
     SB_CUDA(cudaMemset(s->dbad, 0, nb));
-    s->bytes += nb;
+    SB_CUDA(cudaMalloc((void**)&s->dbad1, nb));
+    SB_CUDA(cudaMemset(s->dbad1, 0, nb));
+    s->bytes += 2 * nb;
   }
   return 0;
 }
@@ -1210,7 +1240,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
 
 void qg_solver_destroy(QgSolver* s) {
   if (!s) return;
-  void* ptrs[] = {s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->bsig, s->sig2n,
+  void* ptrs[] = {s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->dbad1, s->meet1, s->part, s->bsig, s->sig2n,
                   s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->gvecf, s->tw, s->twc, s->twb, s->dstmat, s->meet, s->meetc};
   for (void* p : ptrs) cudaFree(p);
   if (s->aux) cudaStreamDestroy(s->aux);
@@ -1222,45 +1252,50 @@ void qg_solver_destroy(QgSolver* s) {
 size_t qg_solver_bytes(const QgSolver* s) { return s ? s->bytes : 0; }
 int qg_solver_kind(const QgSolver* s) { return s->kind; }
 
-template <typename T, bool SUBST, bool FROM_VEC, bool COMBINE, bool TAB>
+template <typename T, bool SUBST, bool FROM_VEC, int KIND, bool TAB>
 static int launch_thomas_one(const char* tag, const ThomasTab& tb, int strip_first, int nstrips, int planes,
                              const T* in, const T* V, const double* gvec, const float* gvecf,
                              const double* bsig, T* out, cudaStream_t st) {
   if (nstrips <= 0) return 0;
-  constexpr int NS = ThStages<T, COMBINE, TAB>::v;
-  constexpr int RT = ThRows<T, TAB>::v;
-  constexpr size_t smem0 = (size_t)NS * RT * TH_COLS * ((TAB ? sizeof(double) : 0) + sizeof(T) * (COMBINE ? 2 : 1)) + NS * 8;
+  constexpr int NS = ThStages<T, KIND, TAB>::v;
+  constexpr int RT = ThRows<T, KIND, TAB>::v;
+  constexpr int NOP = KIND == 2 ? 2 : 1;      // operand tiles (and side tiles) per stage
+  constexpr size_t smem0 = (size_t)NS * RT * TH_COLS * ((TAB ? sizeof(double) : 0) + sizeof(T) * NOP) + NS * 8;
   static_assert(smem0 <= 227 * 1024, "sweep ring exceeds shared memory");
-  const size_t smem = smem0 + (TAB ? (size_t)NS * RT * tb.KB * sizeof(double) : 0);
+  const size_t smem = smem0 + (TAB ? (size_t)NS * RT * tb.KB * sizeof(double) * NOP : 0);
   if (smem > 227 * 1024)
     return fail(SOMAX_B200_ERR_UNSUPPORTED, "too many indefinite Helmholtz columns for the staged side buffer");
   static size_t attr_done = 0;
   if (smem > 48 * 1024 && attr_done < smem) {
-    SB_CUDA(cudaFuncSetAttribute(thomas_sweep<T, SUBST, FROM_VEC, COMBINE, TAB>,
+    SB_CUDA(cudaFuncSetAttribute(thomas_sweep<T, SUBST, FROM_VEC, KIND, TAB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = smem;
   }
   prof_begin(tag, st);
-  thomas_sweep<T, SUBST, FROM_VEC, COMBINE, TAB><<<dim3(nstrips, planes, 2), TH_COLS, smem, st>>>(
+  thomas_sweep<T, SUBST, FROM_VEC, KIND, TAB><<<dim3(nstrips, planes, 2), TH_COLS, smem, st>>>(
       tb, strip_first, in, V, gvec, gvecf, bsig, out);
   SB_LAUNCH_CHECK();
   return 0;
 }
 
 // One solve = elimination + substitution sweeps.  Strips are independent of each other, so the
-// low-k launch class runs its two sweeps back to back on the auxiliary stream while the plain
-// class runs its two on the caller's stream; the streams join after the pair.
-//   SECOND = false: S <- A^-1 S.   SECOND = true: S <- S - bsig * A^-1 (gvec x 1), W scratch.
-template <typename T, bool SECOND>
+// two launch classes run as two chains on two streams and join after the pair.
+//   PHASE 0: S <- A^-1 S (plain solve; dense-x path).
+//   PHASE 1: S <- eliminated S (D), border row sums of A^-1 S into tb.part (x itself is not stored).
+//   PHASE 2: W <- eliminated (gvec x 1) (E), then S <- back-substitution of D - bsig * E.
+template <typename T, int PHASE>
 static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream_t st) {
   const int nstrip = s->np / SP_W, nh = std::min(s->nheavy, nstrip);
+  constexpr bool SECOND = PHASE == 2;
+  constexpr int KIND = PHASE;
   const char* tf = SECOND ? "thomas_fwd_1" : "thomas_fwd_0";
   const char* tbk = SECOND ? "thomas_bwd_1" : "thomas_bwd_0";
   const char* tfl = SECOND ? "thomas_fwd_1_lowk" : "thomas_fwd_0_lowk";
   const char* tbl = SECOND ? "thomas_bwd_1_lowk" : "thomas_bwd_0_lowk";
   const T* fin = SECOND ? nullptr : S;      // elimination input
   T* fout = SECOND ? W : S;                 // eliminated right-hand side
-  const T* Vv = SECOND ? S : nullptr;
+  const T* bin = S;                         // substitution input (D)
+  const T* Vv = SECOND ? W : nullptr;       // second operand (E)
   const double* bs = SECOND ? s->bsig : nullptr;
   // The LOWK launches go first, on the caller's stream, so that their few long CTAs are resident
   // before the wide PLAIN launches (auxiliary stream, released by an event a few microseconds
@@ -1272,12 +1307,14 @@ static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream
     SB_CUDA(cudaEventRecord(s->ev_fork, st));
     SB_CUDA(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
   }
-  if (int rc = launch_thomas_one<T, false, SECOND, false, true>(tfl, tb, 0, nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, st)) return rc;
-  if (int rc = launch_thomas_one<T, false, SECOND, false, false>(tf, tb, nh, nstrip - nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, pl)) return rc;
-  if (int rc = launch_thomas_one<T, true, false, SECOND, true>(tbl, tb, 0, nh, s->planes, fout, Vv, nullptr, nullptr, bs, S, st)) return rc;
-  if (int rc = launch_thomas_one<T, true, false, SECOND, false>(tbk, tb, nh, nstrip - nh, s->planes, fout, Vv, nullptr, nullptr, bs, S, pl)) return rc;
-  if (two) SB_CUDA(cudaEventRecord(s->ev_join, s->aux));
-  if (two) SB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+  if (int rc = launch_thomas_one<T, false, SECOND, 0, true>(tfl, tb, 0, nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, st)) return rc;
+  if (int rc = launch_thomas_one<T, false, SECOND, 0, false>(tf, tb, nh, nstrip - nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, pl)) return rc;
+  if (int rc = launch_thomas_one<T, true, false, KIND, true>(tbl, tb, 0, nh, s->planes, bin, Vv, nullptr, nullptr, bs, S, st)) return rc;
+  if (int rc = launch_thomas_one<T, true, false, KIND, false>(tbk, tb, nh, nstrip - nh, s->planes, bin, Vv, nullptr, nullptr, bs, S, pl)) return rc;
+  if (two) {
+    SB_CUDA(cudaEventRecord(s->ev_join, s->aux));
+    SB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+  }
   return 0;
 }
 
@@ -1288,7 +1325,8 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
   tb.ctabB = s->ctab; tb.tabOff = s->coff; tb.Jstrip = s->krow; tb.cinf = s->cinf; tb.meetc = s->meetc;
   tb.nstrip = s->np / SP_W;
   for (int m = 0; m < QG_MAX_NL; ++m) tb.kbad[m] = s->kbad[m];
-  tb.KB = s->KBs; tb.dbad = s->dbad; tb.meet = s->meet; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
+  tb.KB = s->KBs; tb.dbad = s->dbad; tb.dbad1 = s->dbad1; tb.meet = s->meet; tb.meet1 = s->meet1;
+  tb.part = s->part; tb.sig2n = s->sig2n; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
   tb.dy2 = s->dy * s->dy;
   T* S = (T*)s->S;
   if (s->kind == SOMAX_B200_SOLVER_FFT) {
@@ -1300,10 +1338,10 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     for (int a = 0; a < QG_MAX_NL; ++a)
       for (int c = 0; c < QG_MAX_NL; ++c) { Af.mix[a][c] = (T)s->l2m.c[a][c]; Ai.mix[a][c] = (T)s->m2l.c[a][c]; }
     if (int rc = launch_rowdst<T, false>(s->plan.lgn, Af, q, S, st)) return rc;
-    if (int rc = launch_solve<T, false>(s, tb, S, nullptr, st)) return rc;
+    if (int rc = launch_solve<T, 1>(s, tb, S, nullptr, st)) return rc;
     const double b = 1.0 / (s->dx * s->dx);
-    prof_begin("border_dot", st);
-    border_dot<T><<<dim3((ny + BD_ROWS - 1) / BD_ROWS, s->planes), 32 * BD_ROWS, 0, st>>>(S, (const T*)s->sig2n, ny, np, s->ncols, b, s->rvec);
+    prof_begin("border_reduce", st);
+    border_reduce<T><<<dim3((ny + 255) / 256, s->planes), 256, 0, st>>>(S, (const T*)s->part, ny, np, s->ncols, 2 * (np / SP_W), b, s->rvec);
     SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_a", st);
     border_gsolve<T, true><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
@@ -1311,7 +1349,7 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     prof_begin("border_gsolve_b", st);
     border_gsolve<T, false><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
     SB_LAUNCH_CHECK();
-    if (int rc = launch_solve<T, true>(s, tb, S, W, st)) return rc;
+    if (int rc = launch_solve<T, 2>(s, tb, S, W, st)) return rc;
     if (int rc = launch_rowdst<T, true>(s->plan.lgn, Ai, S, psi, st)) return rc;
   } else {
     const size_t smem = (size_t)nl * n * sizeof(T);
@@ -1323,7 +1361,7 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     prof_begin("rowdst_dense_0", st);
     rowdst_dense<T, false><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->l2m, (const T*)s->dstmat, q, S, 1.0);
     SB_LAUNCH_CHECK();
-    if (int rc = launch_solve<T, false>(s, tb, S, nullptr, st)) return rc;
+    if (int rc = launch_solve<T, 0>(s, tb, S, nullptr, st)) return rc;
     prof_begin("rowdst_dense_1", st);
     rowdst_dense<T, true><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->m2l, (const T*)s->dstmat, S, psi, 2.0 / (n + 1));
     SB_LAUNCH_CHECK();
