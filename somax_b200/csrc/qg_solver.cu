@@ -549,7 +549,10 @@ template <typename T, int KIND, bool TAB> struct ThRows {      // rows per stage
   static constexpr int v = TAB ? ((sizeof(T) == 4 && KIND != 2) ? 64 : 32) : TH_RT;
 };
 template <typename T, int KIND, bool TAB> struct ThStages {   // ring depth
-  static constexpr int v = TAB ? 3 : (sizeof(T) == 4 ? (KIND == 2 ? 6 : 8) : (KIND == 2 ? 3 : 6));
+  // PLAIN rings are kept small enough that a whole sweep (123 strips x 3 planes x 2 halves at
+  // 8192^2) is resident in ONE wave next to the LOWK CTAs: every CTA runs for the whole sweep, so
+  // a second wave of a few CTAs would double the kernel time
+  static constexpr int v = TAB ? 3 : (sizeof(T) == 4 ? (KIND == 2 ? 4 : 6) : (KIND == 2 ? 2 : 3));
 };
 
 // Plain fp32 recurrence over one register block, for the well-conditioned strips of the fp32
