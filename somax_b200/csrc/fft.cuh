@@ -30,6 +30,26 @@ __host__ __device__ __forceinline__ C2<T> cmul(C2<T> a, C2<T> b) {
 template <typename T>
 __host__ __device__ __forceinline__ C2<T> mul_mi(C2<T> a) { return {a.y, -a.x}; }
 
+// fp32 on the device: a C2<float> is one 64-bit register pair, so complex add / sub are single
+// packed instructions (add.rn.f32x2 -> FADD2).  Same rounding as the scalar form; FADD2 takes one
+// issue slot for both lanes, and the transform kernels are issue bound (tools/micro/ffma2_rate.cu).
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned long long c2_pack(C2<float> a) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r;
+}
+__device__ __forceinline__ C2<float> c2_unpack(unsigned long long r) {
+  C2<float> a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r)); return a;
+}
+__device__ __forceinline__ C2<float> cadd(C2<float> a, C2<float> b) {
+  unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c2_pack(a)), "l"(c2_pack(b)));
+  return c2_unpack(r);
+}
+__device__ __forceinline__ C2<float> csub(C2<float> a, C2<float> b) {
+  unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c2_pack(a)), "l"(c2_pack(b)));
+  return c2_unpack(r);
+}
+#endif
+
 // complex index -> padded complex index.  Three-level padding (one slot per 16, per 128 and per
 // 1024 elements) keeps both the natural-stride butterfly accesses and the digit-reversed reads
 // of the real-odd split spread over the shared-memory banks (simulated: 16 -> 5 wavefronts per
