@@ -380,3 +380,73 @@ def test_qg_two_dimensional_coefficient_fields(dtype):
     assert rel(dq, om.rhs(om.bc(q0.astype(np.float64)))) <= (2e-5 if dtype == np.float32 else 1e-11)
     q1 = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, 6000.0, 600.0).ys.q[0]
     assert rel(q1, om.integrate(q0.astype(np.float64), 0.0, 6000.0, 600.0)) <= TOL[dtype]
+
+
+def test_qg_energy_enstrophy_series():
+    """SURVEY 8(d) parity protocol: KE / enstrophy every 10 steps over a run within 1e-4."""
+    import somax_b200 as sb
+    om, gm = qg_pair(64, 64, np.float32)
+    q0 = qstate(3, 64, 64, np.float32, ring=True)
+    dt = 600.0
+    ts = [10 * dt * (i + 1) for i in range(10)]
+    sol = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, ts[-1], dt, saveat=sb.SaveAt(ts=ts), max_steps=None)
+    assert sol.ys.q.shape[0] == 10
+    ref = q0.astype(np.float64)
+    for i in range(10):
+        ref = om.integrate(ref, 0.0, 10 * dt, dt)       # BC of the restart is idempotent
+        d, dref = gm.diagnose(sb.BaroclinicQGState(q=sol.ys.q[i])), om.diagnose(ref)
+        assert np.allclose(d.kinetic_energy, dref["kinetic_energy"], rtol=1e-4), i
+        assert np.allclose(d.enstrophy, dref["enstrophy"], rtol=1e-4), i
+
+
+def test_qg_graph_replay_matches_eager_stepping():
+    """>= 9 steps in one call replay a captured two-step CUDA graph; one-step calls run the eager
+    path.  Both must give the same bits (same kernels, same order)."""
+    import somax_b200 as sb
+    import torch
+    _, gm = qg_pair(32, 32, np.float32)
+    q0 = torch.as_tensor(qstate(3, 32, 32, np.float32, ring=True)).cuda()
+    dt = 600.0
+    a = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, 21 * dt, dt, max_steps=None).ys.q[0]
+    b = q0
+    for _ in range(21):
+        b = gm.integrate(sb.BaroclinicQGState(q=b), 0.0, dt, dt).ys.q[0]
+    # a restart re-applies the ring BC to the state it is handed, which the long run does not do
+    # to its intermediate states: compare the interior, where both are the same recurrence
+    assert torch.equal(a[:, 1:-1, 1:-1], b[:, 1:-1, 1:-1])
+
+
+def test_swm_graph_replay_matches_eager_stepping():
+    """One 20-step call (CUDA-graph replay) against four 5-step calls (eager launches)."""
+    import somax_b200 as sb
+    import torch
+    gm, st0 = sb.gfd_testcases.baroclinic_instability_swm(nx=32, ny=32)
+    dt = 10.0
+    dev = type(st0)(**{f: torch.as_tensor(np.asarray(getattr(st0, f), np.float32)).cuda() for f in ("h", "u", "v")})
+    a = gm.integrate(dev, 0.0, 20 * dt, dt, max_steps=None).ys
+    b = dev
+    for _ in range(4):
+        s = gm.integrate(b, 0.0, 5 * dt, dt, max_steps=None).ys
+        b = type(st0)(h=s.h[0], u=s.u[0], v=s.v[0])
+    for f in ("h", "u", "v"):
+        x, y = getattr(a, f)[0][:, 1:-1, 1:-1], getattr(b, f)[:, 1:-1, 1:-1]
+        assert torch.isfinite(x).all()
+        assert rel(x.cpu().numpy(), y.cpu().numpy()) <= 1e-6, f
+
+
+def test_pinned_host_tensor_io_path():
+    """Pinned CPU tensors go H2D / D2H without a staging copy and give the numpy path's bits."""
+    import somax_b200 as sb
+    import torch
+    _, gm = qg_pair(32, 32, np.float32)
+    q0 = qstate(3, 32, 32, np.float32, ring=True)
+    ref = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, 3000.0, 600.0).ys.q[0]
+    pin = torch.as_tensor(q0).pin_memory()
+    out = gm.integrate(sb.BaroclinicQGState(q=pin), 0.0, 3000.0, 600.0).ys.q[0]
+    assert isinstance(out, torch.Tensor) and not out.is_cuda and out.is_pinned()
+    assert np.array_equal(out.numpy(), ref)
+    assert gm.last_io.h2d_bytes == q0.nbytes and gm.last_io.d2h_bytes == q0.nbytes
+    # the numpy path hands out an owned copy: a second call must not change the first result
+    ref2 = gm.integrate(sb.BaroclinicQGState(q=q0 * 0.5), 0.0, 3000.0, 600.0).ys.q[0]
+    assert not np.array_equal(ref, ref2) and np.array_equal(
+        ref, gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, 3000.0, 600.0).ys.q[0])
