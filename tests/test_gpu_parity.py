@@ -450,3 +450,69 @@ def test_pinned_host_tensor_io_path():
     ref2 = gm.integrate(sb.BaroclinicQGState(q=q0 * 0.5), 0.0, 3000.0, 600.0).ys.q[0]
     assert not np.array_equal(ref, ref2) and np.array_equal(
         ref, gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, 3000.0, 600.0).ys.q[0])
+
+
+def test_full_size_8192_properties():
+    """BASELINE's target size (3 x 8192^2).  The oracle is too slow here, so the solver is pinned by
+    size-independent properties: (i) the fp64 pipeline's psi satisfies the discrete Helmholtz system
+    in mode space (residual against the right-hand side), (ii) the fp32 pipeline agrees with the
+    residual-checked fp64 pipeline, on the inversion and after two Tsit5 steps, within the fp32
+    tolerances, (iii) zero PV gives zero tendency."""
+    import somax_b200 as sb
+    import torch
+    nx = ny = 8192
+    args = dict(Lx=4e6, Ly=4e6, f0=9.375e-5, beta=1.754e-11, n_layers=3, H=(400.0, 1100.0, 2600.0),
+                g_prime=(9.81, 0.025, 0.0125), lateral_viscosity=15.0, bottom_drag=1e-7,
+                wind_amplitude=1.3e-10)
+    m64 = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype="float64", **args)
+    m32 = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype="float32", **args)
+    # smooth synthetic state (SURVEY 8(d)) + a little white noise so every wavenumber is excited
+    g = torch.Generator(device="cuda").manual_seed(5)
+    jj = torch.arange(1, ny + 1, device="cuda", dtype=torch.float64)[:, None]
+    mm = torch.arange(1, 9, device="cuda", dtype=torch.float64)[None, :]
+    Sy = torch.sin(np.pi * jj * mm / (ny + 1))                      # (ny, 8)
+    Sx = torch.sin(np.pi * jj * mm / (nx + 1))                      # (nx, 8)  (nx == ny)
+    q = torch.zeros((3, ny + 2, nx + 2), dtype=torch.float64, device="cuda")
+    for k, amp in enumerate((4e-6, 2e-6, 1e-6)):
+        a = torch.randn((8, 8), generator=g, device="cuda", dtype=torch.float64)
+        a = a / torch.sqrt(mm.T ** 2 + mm ** 2)
+        q[k, 1:-1, 1:-1] = amp * (Sy @ a @ Sx.T)
+        q[k, 1:-1, 1:-1] += 1e-2 * amp * torch.randn((ny, nx), generator=g, device="cuda", dtype=torch.float64)
+    q32 = q.to(torch.float32)
+    qd = q32.to(torch.float64)                  # both pipelines see the same (fp32-representable) data
+
+    def trel(x, y):
+        return float(torch.linalg.vector_norm((x.double() - y.double()).flatten()) /
+                     torch.linalg.vector_norm(y.double().flatten()))
+
+    psi64 = m64._invert_pv(qd)
+    psi32 = m32._invert_pv(q32)
+    assert float(psi64[:, 0].abs().max()) == 0.0 and float(psi64[:, :, -1].abs().max()) == 0.0
+    # (i) residual in mode space: (dxx + dyy - lambda_m) psi_m = q_m on the interior
+    Cl2m = torch.as_tensor(m64.modal.Cl2m, device="cuda", dtype=torch.float64)
+    lam = torch.as_tensor(m64.helmholtz_lambdas, device="cuda", dtype=torch.float64)
+    dx, dy = m64.grid.dx, m64.grid.dy
+    for mode in range(3):
+        pm = torch.einsum("l,lyx->yx", Cl2m[mode], psi64)
+        qm = torch.einsum("l,lyx->yx", Cl2m[mode], qd)[1:-1, 1:-1]
+        lap = (pm[1:-1, 2:] - 2 * pm[1:-1, 1:-1] + pm[1:-1, :-2]) / dx ** 2 + \
+              (pm[2:, 1:-1] - 2 * pm[1:-1, 1:-1] + pm[:-2, 1:-1]) / dy ** 2 - lam[mode] * pm[1:-1, 1:-1]
+        res = float(torch.linalg.vector_norm(lap - qm) / torch.linalg.vector_norm(qm))
+        assert res <= 1e-7, (mode, res)         # cond ~ (n/pi)^2 ~ 7e6 times fp64 rounding
+        del pm, qm, lap
+    # (ii) fp32 pipeline against the fp64 pipeline
+    assert trel(psi32, psi64) <= 2e-6
+    del psi32, psi64
+    dt = 600.0 * 128 / nx
+    s64 = m64.integrate(sb.BaroclinicQGState(q=qd), 0.0, 2 * dt, dt).ys.q[0]
+    s32 = m32.integrate(sb.BaroclinicQGState(q=q32), 0.0, 2 * dt, dt).ys.q[0]
+    assert bool(torch.isfinite(s32).all())
+    assert trel(s32, s64) <= 1e-5
+    d32 = m32.diagnose(sb.BaroclinicQGState(q=s32))
+    d64 = m64.diagnose(sb.BaroclinicQGState(q=s64))
+    assert np.allclose(np.asarray(d32.kinetic_energy, np.float64), np.asarray(d64.kinetic_energy, np.float64), rtol=1e-4)
+    assert np.allclose(np.asarray(d32.enstrophy, np.float64), np.asarray(d64.enstrophy, np.float64), rtol=1e-4)
+    # (iii) zero PV => zero tendency (tests/models/test_qg_baroclinic.py:79-94), wind off
+    m0 = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype="float32", **{**args, "wind_amplitude": 0.0})
+    dq = m0.vector_field(0.0, sb.BaroclinicQGState(q=torch.zeros_like(q32))).q
+    assert float(dq.abs().max()) < 1e-12

@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "large_grids or integrate_parity" 2>&1 | tail -3
-bash tools/_run2.sh
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "full_size" 2>&1 | tail -15
+timeout 600 python tools/thomas_probe.py 0
