@@ -516,3 +516,29 @@ def test_full_size_8192_properties():
     m0 = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype="float32", **{**args, "wind_amplitude": 0.0})
     dq = m0.vector_field(0.0, sb.BaroclinicQGState(q=torch.zeros_like(q32))).q
     assert float(dq.abs().max()) < 1e-12
+
+
+def test_full_size_swm_4096_properties():
+    """BASELINE config 3 at its largest size (2 x 4096^2, periodic jet): fp32 pipeline against the
+    fp64 pipeline after 10 steps, and layer-mass conservation of the flux-form continuity equation
+    (periodic domain: sum of h over the interior is constant up to rounding)."""
+    import somax_b200 as sb
+    import torch
+    n = 4096
+    dt = 20.0 * 64 / n
+    out = {}
+    for dtype in ("float64", "float32"):
+        gm, st0 = sb.gfd_testcases.baroclinic_instability_swm(nx=n, ny=n, dtype=dtype)
+        dev = type(st0)(**{f: torch.as_tensor(getattr(st0, f)).cuda() for f in ("h", "u", "v")})
+        ys = gm.integrate(dev, 0.0, 10 * dt, dt, max_steps=None).ys
+        out[dtype] = {f: getattr(ys, f)[0] for f in ("h", "u", "v")}
+        if dtype == "float64":
+            m0 = dev.h[:, 1:-1, 1:-1].sum(dim=(1, 2))
+            m1 = out[dtype]["h"][:, 1:-1, 1:-1].sum(dim=(1, 2))
+            assert float(((m1 - m0) / m0).abs().max()) <= 1e-12
+        del gm, dev, ys
+    for f, tol in (("h", 1e-6), ("u", 2e-4), ("v", 2e-3)):      # u, v: the fp32 formulation floor (see assert_swm_parity)
+        a, b = out["float32"][f].double(), out["float64"][f]
+        assert bool(torch.isfinite(a).all())
+        err = float(torch.linalg.vector_norm((a - b).flatten()) / torch.linalg.vector_norm(b.flatten()))
+        assert err <= tol, (f, err)
