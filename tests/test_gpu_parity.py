@@ -542,3 +542,22 @@ def test_full_size_swm_4096_properties():
         assert bool(torch.isfinite(a).all())
         err = float(torch.linalg.vector_norm((a - b).flatten()) / torch.linalg.vector_norm(b.flatten()))
         assert err <= tol, (f, err)
+
+
+def test_fp32_fallback_kernels_agree(monkeypatch):
+    """The fp32 defaults (TMA stencil, three-pass row transform) against the kernels they replaced
+    (cp.async stencil, radix-8 transform), which stay as fallbacks behind environment switches."""
+    import somax_b200 as sb
+    nx, ny = 4096, 48
+    q0 = qstate(3, nx, ny, np.float32, ring=True)
+    dt = 600.0 * 128 / nx
+    res = {}
+    for name, env in (("default", {}), ("fallback", {"SOMAX_B200_NO_TMA": "1", "SOMAX_B200_FFT_RADIX8": "1"})):
+        for k in ("SOMAX_B200_NO_TMA", "SOMAX_B200_FFT_RADIX8"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _, gm = qg_pair(nx, ny, np.float32)
+        res[name] = (gm._invert_pv(q0), gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, 3 * dt, dt).ys.q[0])
+    assert rel(res["default"][0], res["fallback"][0]) <= 1e-6
+    assert rel(res["default"][1], res["fallback"][1]) <= 1e-6
