@@ -59,6 +59,7 @@ struct QgSolver {
 // lives at ((k / 64) * ny + j) * 64 + (k % 64); the plane stride is ny * np, np = roundup(nx, 64).
 constexpr int SP_W = 64;
 constexpr int GS_ROWS = 8;     // outputs (warps) per CTA of border_gsolve
+constexpr int GS_SMALL_NY = 1024;   // up to here: one thread per output (border_gsolve_small)
 __host__ __device__ __forceinline__ size_t sp_off(int ny, int j, int k) {
   return ((size_t)(k >> 6) * ny + j) * SP_W + (k & (SP_W - 1));
 }
@@ -957,6 +958,41 @@ border_gsolve(const double* __restrict__ in, const double* __restrict__ sintab,
   }
 }
 
+// Same transform for short columns (ny <= GS_SMALL_NY, ensembles of small grids): one THREAD per
+// output index, so there is no per-warp set-up or reduction; the input is a warp-uniform
+// (broadcast) load and the rotation advances by pi a / N per term.
+template <typename T, bool STAGE_A>
+__global__ void __launch_bounds__(128)
+border_gsolve_small(const double* __restrict__ in, const double* __restrict__ sintab,
+                    const double* __restrict__ sdiag, int ny, int np, int n, int nl,
+                    double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
+                    T* __restrict__ S) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x + 1, plane = blockIdx.y, m = plane % nl;
+  if (a > ny) return;
+  const unsigned N = ny + 1, N2 = 2 * N;
+  const double* costab = sintab + N2;
+  const double ds = sintab[a], dc = costab[a];        // a < N2
+  double s = ds, c = dc, acc = 0;
+  const double* x = in + (size_t)plane * ny;
+  const int half = (N - 1) / 2;
+  const double sgn = (a & 1) ? 1.0 : -1.0;
+  for (int t = 1; t <= half; ++t) {
+    acc = fma(s, fma(sgn, x[N - t - 1], x[t - 1]), acc);
+    const double s2 = fma(s, dc, c * ds), c2 = fma(c, dc, -(s * ds));
+    s = s2; c = c2;
+  }
+  if ((N & 1) == 0) acc = fma(sintab[(unsigned)(((unsigned long long)a * (N / 2)) % N2)], x[N / 2 - 1], acc);
+  double t = acc;
+  if (STAGE_A) {
+    out[(size_t)plane * ny + (a - 1)] = t / sdiag[(size_t)m * ny + (a - 1)];
+  } else {
+    t *= 2.0 / N;
+    gvec[(size_t)plane * ny + (a - 1)] = t;
+    if (sizeof(T) == 4) gvecf[(size_t)plane * ny + (a - 1)] = (float)t;
+    S[(size_t)plane * ny * np + sp_off(ny, a - 1, n - 1)] = (T)t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side: tables
 // ------------------------------------------------------------------------------------------
@@ -1347,10 +1383,16 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     border_reduce<T><<<dim3((ny + 255) / 256, s->planes), 256, 0, st>>>(S, (const T*)s->part, ny, np, s->ncols, 2 * (np / SP_W), b, s->rvec);
     SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_a", st);
-    border_gsolve<T, true><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
+    if (ny <= GS_SMALL_NY)
+      border_gsolve_small<T, true><<<dim3((ny + 127) / 128, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
+    else
+      border_gsolve<T, true><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
     SB_LAUNCH_CHECK();
     prof_begin("border_gsolve_b", st);
-    border_gsolve<T, false><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
+    if (ny <= GS_SMALL_NY)
+      border_gsolve_small<T, false><<<dim3((ny + 127) / 128, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
+    else
+      border_gsolve<T, false><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
     SB_LAUNCH_CHECK();
     if (int rc = launch_solve<T, 2>(s, tb, S, W, st)) return rc;
     if (int rc = launch_rowdst<T, true>(s->plan.lgn, Ai, S, psi, st)) return rc;
