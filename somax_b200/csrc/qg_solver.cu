@@ -75,7 +75,9 @@ template <int LGN> struct RowCfg {
   static constexpr int n = 1 << LGN;
   static constexpr int EPT = LGN >= 12 ? 16 : (LGN >= 8 ? 8 : (LGN >= 7 ? 4 : 2));
   static constexpr int G = n / EPT;                       // threads per row
-  static constexpr int RPB = G >= 128 ? 1 : 128 / G;      // rows per block
+  static constexpr int RPB = G >= 128 ? 1 : (G == 32 ? 8 : 128 / G);      // rows per block
+  // G == 32: a row belongs to one warp, so the passes synchronise with __syncwarp only
+  static constexpr bool WARP_ROWS = G == 32;
   static constexpr int threads = G * RPB;
   static constexpr int minblocks = threads >= 512 ? 2 : (threads >= 256 ? 3 : 4);
 };
@@ -97,7 +99,7 @@ __device__ __forceinline__ void fft_passes_ct(C2<T>* s, int lt, const C2<T>* __r
     constexpr int lr = FftCT<LGN>::lgr(PASS);
     constexpr int LGLC = LGN - 3 * PASS;      // every earlier pass is radix 8
     if (valid) fft_dif_pass_ct<T, LGN, LGLC, (1 << lr), G>(s, lt, tw);
-    __syncthreads();
+    if (RowCfg<LGN>::WARP_ROWS) __syncwarp(); else __syncthreads();
     fft_passes_ct<T, LGN, G, PASS + 1>(s, lt, tw, valid);
   }
 }
@@ -169,7 +171,7 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
       }
       if (lt == 0) { z[zi(0)] = 0; z[zi(n)] = 0; }
     }
-    __syncthreads();
+    if (Cfg::WARP_ROWS) __syncwarp(); else __syncthreads();
     fft_passes_ct<T, LGN, G, 0>(s, lt, A.twc, valid);
     if (valid) {
 #pragma unroll
@@ -183,7 +185,7 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
         }
       }
     }
-    __syncthreads();
+    if (Cfg::WARP_ROWS) __syncwarp(); else __syncthreads();
   }
 }
 
