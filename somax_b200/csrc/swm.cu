@@ -270,11 +270,38 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
   const int jc = j < Ny ? j : Ny - 1;
   const T windx = (A.tau0 * A.wx[jc]) * A.iH0, windy = (A.tau0 * A.wy[jc]) * A.iH0;
 
+  // fp32: the Tsit5 epilogue operands of this layer (step-start state and previous stage
+  // derivatives of h, u, v: up to 18 vectors per thread) are prefetched with 16-byte cp.async into
+  // per-thread shared slots before the tile load, so their HBM latency hides behind the tile
+  // load, the barriers and the stencil arithmetic instead of sitting in front of the final FMAs.
+  constexpr bool STAGE_EPI = sizeof(T) == 4;
+  extern __shared__ __align__(16) unsigned char swm_dyn[];
+  T (*s_epi)[TXG * TY][4] = reinterpret_cast<T (*)[TXG * TY][4]>(swm_dyn);     // [3 * (MAX_PREV + 1)]
+  const bool epi_valid = j < Ny && g < ngroups && st.Yout[FH] != nullptr;
+
   for (int k = 0; k < L.nl; ++k) {
     const size_t plane_off = ((size_t)b * L.nl + k) * L.plane();
     const T* ph = st.Yin[FH] + plane_off;
     const T* pu = st.Yin[FU] + plane_off;
     const T* pv = st.Yin[FV] + plane_off;
+    if (STAGE_EPI) {
+      if (epi_valid) {
+        const size_t eidx = plane_off + (size_t)j * pitch + (size_t)g * 4;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+          const T* base = (st.y[f] ? st.y[f] : st.Yin[f]) + eidx;
+          unsigned sa = (unsigned)__cvta_generic_to_shared(&s_epi[f * (MAX_PREV + 1) + MAX_PREV][tid][0]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(base) : "memory");
+#pragma unroll
+          for (int jj = 0; jj < MAX_PREV; ++jj)
+            if (jj < st.nprev) {
+              sa = (unsigned)__cvta_generic_to_shared(&s_epi[f * (MAX_PREV + 1) + jj][tid][0]);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(st.Fprev[jj][f] + eidx) : "memory");
+            }
+        }
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
     __syncthreads();
     for (int e = tid; e < (TY + 2) * (TXG + 2); e += TXG * TY) {
       const int rr = e / (TXG + 2), gs = e - rr * (TXG + 2);
@@ -444,9 +471,34 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
       out_h[e] = dh; out_u[e] = du; out_v[e] = dv;
     }
     const size_t idx = plane_off + (size_t)j * pitch + (size_t)g * 4;
-    rk_epilogue4_fast(st, FH, idx, Vec4<T>{out_h[0], out_h[1], out_h[2], out_h[3]});
-    rk_epilogue4_fast(st, FU, idx, Vec4<T>{out_u[0], out_u[1], out_u[2], out_u[3]});
-    rk_epilogue4_fast(st, FV, idx, Vec4<T>{out_v[0], out_v[1], out_v[2], out_v[3]});
+    if (!STAGE_EPI) {
+      rk_epilogue4_fast(st, FH, idx, Vec4<T>{out_h[0], out_h[1], out_h[2], out_h[3]});
+      rk_epilogue4_fast(st, FU, idx, Vec4<T>{out_u[0], out_u[1], out_u[2], out_u[3]});
+      rk_epilogue4_fast(st, FV, idx, Vec4<T>{out_v[0], out_v[1], out_v[2], out_v[3]});
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      const Vec4<T> Fv[3] = {Vec4<T>{out_h[0], out_h[1], out_h[2], out_h[3]},
+                             Vec4<T>{out_u[0], out_u[1], out_u[2], out_u[3]},
+                             Vec4<T>{out_v[0], out_v[1], out_v[2], out_v[3]}};
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        const Vec4<T> F = Fv[f];
+        if (st.Fout[f]) st4(st.Fout[f] + idx, F);
+        if (!st.Yout[f]) continue;
+        Vec4<T> acc = ld4(&s_epi[f * (MAX_PREV + 1) + MAX_PREV][tid][0]);
+#pragma unroll
+        for (int jj = 0; jj < MAX_PREV; ++jj) {
+          if (jj < st.nprev) {
+            const Vec4<T> kk = ld4(&s_epi[f * (MAX_PREV + 1) + jj][tid][0]);
+            acc.x = fma(st.adt[jj], kk.x, acc.x); acc.y = fma(st.adt[jj], kk.y, acc.y);
+            acc.z = fma(st.adt[jj], kk.z, acc.z); acc.w = fma(st.adt[jj], kk.w, acc.w);
+          }
+        }
+        acc.x = fma(st.adt_new, F.x, acc.x); acc.y = fma(st.adt_new, F.y, acc.y);
+        acc.z = fma(st.adt_new, F.z, acc.z); acc.w = fma(st.adt_new, F.w, acc.w);
+        st4(st.Yout[f] + idx, acc);
+      }
+    }
   }
 }
 
@@ -571,7 +623,16 @@ int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A, const Stage<T>& st_in, c
   dim3 block(TXG, TY);
   dim3 grid((L.groups() + TXG - 1) / TXG, (L.Ny + TY - 1) / TY, L.batch);
   prof_begin("swm_rhs_kernel", s);
-  if (h->f1d && h->wx1d && h->wy1d) swm_rhs_kernel_fast<T><<<grid, block, 0, s>>>(A, st);
+  if (h->f1d && h->wx1d && h->wy1d) {
+    // fp32: per-thread shared slots for the prefetched epilogue operands
+    const size_t dyn = sizeof(T) == 4 ? (size_t)3 * (MAX_PREV + 1) * TXG * TY * 4 * sizeof(T) : 0;
+    static bool attr_done = false;
+    if (dyn > 0 && !attr_done) {
+      SB_CUDA(cudaFuncSetAttribute(swm_rhs_kernel_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      attr_done = true;
+    }
+    swm_rhs_kernel_fast<T><<<grid, block, dyn, s>>>(A, st);
+  }
   else swm_rhs_kernel<T><<<grid, block, 0, s>>>(A, st);
   SB_LAUNCH_CHECK();
   return 0;
