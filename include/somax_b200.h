@@ -124,6 +124,43 @@ int somax_b200_qg_steps(somax_b200_qg_t h, void* q, long n_steps, double dt, dou
 int somax_b200_qg_diag(somax_b200_qg_t h, const void* q, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Slab-distributed QG: ONE grid partitioned in y-slabs over `nranks` GPUs (one process per GPU).
+ * Same model as somax_b200_qg_* with batch = 1 and the FFT solver; replaces the same reference
+ * functions (qg/baroclinic.py:135-195 under core/model.py:47-88).  Rank r owns rows
+ * [r*ny/nranks, (r+1)*ny/nranks) and works on the window (nl, ny/nranks + 2, Nx) of the global
+ * (nl, Ny, Nx) array that starts at global row r*ny/nranks (its first / last row is the physical
+ * ring on the edge ranks, the neighbour's row elsewhere).  Exchanges (distributed-DST transposes,
+ * border partials, halo rows) are device kernels that store into the peers' memory, mapped with
+ * CUDA IPC over NVLink; ranks are ordered by flag barriers in peer memory.  Needs nx = 2^p,
+ * (nx / 64) % nranks == 0, ny % nranks == 0.
+ *
+ * nlocal == 1: this process holds slab `rank_first`; call export() on every rank, all-gather
+ * the blobs by any means (they are plain bytes), then attach().  nlocal == nranks: every slab
+ * lives in this process on the current device (validation of the decomposition on one GPU).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct somax_b200_qgs_s* somax_b200_qgs_t;
+
+/* beta_y, wind: the GLOBAL (Ny, Nx) host arrays (as for somax_b200_qg_create). */
+int somax_b200_qgs_create(somax_b200_qgs_t* out, int dtype, int nl, int ny, int nx, double dx,
+                          double dy, const double* Cl2m, const double* Cm2l, const double* lambdas,
+                          const double* beta_y, const double* wind, int nranks, int rank_first,
+                          int nlocal, unsigned spec_flags);
+int somax_b200_qgs_destroy(somax_b200_qgs_t g);
+size_t somax_b200_qgs_device_bytes(somax_b200_qgs_t g);
+/* Size of one rank's export blob (CUDA IPC handles of the buffers its peers store into). */
+size_t somax_b200_qgs_export_bytes(void);
+int somax_b200_qgs_export(somax_b200_qgs_t g, void* blob);
+/* blobs: nranks * export_bytes, in rank order (this rank's own entry is ignored). */
+int somax_b200_qgs_attach(somax_b200_qgs_t g, const void* blobs);
+/* SomaxModel.integrate on the slabs, in place: q_slabs[v] (DEVICE) is local slab v's window
+ * (nl, ny/nranks + 2, Nx), halo rows valid on entry and on return.  Collective: every rank of
+ * the group must make the same call. */
+int somax_b200_qgs_steps(somax_b200_qgs_t g, void* const* q_slabs, long n_steps, double dt,
+                         double dt_last, const somax_b200_params* p, void* stream);
+/* After synchronising the stream: number of barriers that gave up waiting for a peer (0 = ok). */
+int somax_b200_qgs_status(somax_b200_qgs_t g, int* barrier_timeouts);
+
+/* ------------------------------------------------------------------------------------------
  * Shallow-water model (NonlinearShallowWater2D = nl 1 with g_prime = [g], H0 = 1).
  * ------------------------------------------------------------------------------------------ */
 

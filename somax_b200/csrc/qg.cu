@@ -11,6 +11,8 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstring>
+#include <string>
 #include <vector>
 
 namespace sb {
@@ -24,6 +26,7 @@ template <typename T>
 struct QgArgs {
   Layout L;
   int apply_bc;
+  int bc_ylo, bc_yhi;   // row 0 / row Ny-1 is the physical ring (0 on a slab whose neighbour owns it: halo row)
   T dx2, dy2, jden;   // dx^2, dy^2, 12 dx dy
   T idx2, idy2, ijden, iH0;   // reciprocals (fast kernel)
   const T* beta; int b_cp, b_xs;
@@ -52,7 +55,7 @@ qg_rhs_kernel(QgArgs<T> A, const T* __restrict__ psi, Stage<T> st) {
     int jj = j0 - 1 + r, ii = c0 - 1 + c;
     T q = 0, t = 0, p = 0;
     if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
-      const bool ring = (jj == 0 || jj == Ny - 1 || ii == 0 || ii == Nx - 1);
+      const bool ring = ((jj == 0 && A.bc_ylo) || (jj == Ny - 1 && A.bc_yhi) || ii == 0 || ii == Nx - 1);
       size_t o = (size_t)jj * pitch + OFF + ii;
       q = (A.apply_bc && ring) ? T(0) : pq[o];
       t = q + A.beta[(size_t)jj * A.b_cp + (size_t)ii * A.b_xs];
@@ -153,7 +156,7 @@ qg_rhs_kernel_fast(QgArgs<T> A, const T* __restrict__ psi, Stage<T> st) {
       p = ld4(pp + o);
       if (A.apply_bc) {
         const int i0 = gg * 4 - OFF;     // column of .x
-        if (jj == 0 || jj == Ny - 1) q = Vec4<T>{0, 0, 0, 0};
+        if ((jj == 0 && A.bc_ylo) || (jj == Ny - 1 && A.bc_yhi)) q = Vec4<T>{0, 0, 0, 0};
         if (i0 == 0 || i0 == Nx - 1) q.x = 0;
         if (i0 + 1 == 0 || i0 + 1 == Nx - 1) q.y = 0;
         if (i0 + 2 == 0 || i0 + 2 == Nx - 1) q.z = 0;
@@ -414,7 +417,7 @@ qg_rhs_kernel_tma(const __grid_constant__ QgTmaps M, const QgArgs<float> A, cons
       for (int e = tid; e < QHR * QHW; e += QTXG * QTY) {
         const int r = e / QHW, cidx = e - r * QHW;
         const int jj = j0 - 1 + r, i = 4 * (g0 - 1) + cidx - OFF;
-        if (jj == 0 || jj == L.Ny - 1 || i == 0 || i == L.Nx - 1) s_q[r][cidx] = 0.f;
+        if ((jj == 0 && A.bc_ylo) || (jj == L.Ny - 1 && A.bc_yhi) || i == 0 || i == L.Nx - 1) s_q[r][cidx] = 0.f;
       }
       __syncthreads();
     }
@@ -426,11 +429,11 @@ qg_rhs_kernel_tma(const __grid_constant__ QgTmaps M, const QgArgs<float> A, cons
 
 // ring := 0 in place on padded planes
 template <typename T>
-__global__ void qg_bc_kernel(T* __restrict__ q, Layout L) {
+__global__ void qg_bc_kernel(T* __restrict__ q, Layout L, int bc_ylo, int bc_yhi) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int j = blockIdx.y, p = blockIdx.z;
   if (i >= L.Nx) return;
-  if (j == 0 || j == L.Ny - 1 || i == 0 || i == L.Nx - 1)
+  if ((j == 0 && bc_ylo) || (j == L.Ny - 1 && bc_yhi) || i == 0 || i == L.Nx - 1)
     q[(size_t)p * L.plane() + (size_t)j * L.pitch + OFF + i] = T(0);
 }
 
@@ -494,6 +497,7 @@ struct somax_b200_qg_s {
   double dx, dy;
   unsigned spec;
   QgSolver* solver = nullptr;
+  int bc_ylo = 1, bc_yhi = 1;   // physical ring rows (a slab of the distributed model clears them)
   void* beta = nullptr; void* wind = nullptr;
   bool beta1d = false, wind1d = false;
   void* y = nullptr; void* Ya = nullptr; void* Yb = nullptr; void* psi = nullptr;
@@ -511,7 +515,7 @@ namespace {
 template <typename T>
 QgArgs<T> make_qargs(somax_b200_qg_t h, const somax_b200_params* p, int apply_bc) {
   QgArgs<T> A;
-  A.L = h->L; A.apply_bc = apply_bc;
+  A.L = h->L; A.apply_bc = apply_bc; A.bc_ylo = h->bc_ylo; A.bc_yhi = h->bc_yhi;
   A.dx2 = (T)(h->dx * h->dx); A.dy2 = (T)(h->dy * h->dy); A.jden = (T)(12.0 * h->dx * h->dy);
   A.idx2 = (T)(1.0 / (h->dx * h->dx)); A.idy2 = (T)(1.0 / (h->dy * h->dy));
   A.ijden = (T)(1.0 / (12.0 * h->dx * h->dy)); A.iH0 = (T)(1.0 / p->H0);
@@ -610,12 +614,21 @@ bool qg_launch_tma(somax_b200_qg_t h, const QgArgs<float>& A, const Stage<float>
   return true;
 }
 
+template <typename T>
+int launch_stencil(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st_in, double dt, cudaStream_t s);
+
 // one RHS evaluation: psi = invert(Yin), then the fused stencil + RK epilogue
 template <typename T>
 int eval_rhs(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st_in, double dt, cudaStream_t s) {
+  if (int rc = qg_solver_run<T>(h->solver, st_in.Yin[0], (T*)h->psi, s)) return rc;
+  return launch_stencil<T>(h, A, st_in, dt, s);
+}
+
+// the fused stencil + RK epilogue alone (psi already in h->psi)
+template <typename T>
+int launch_stencil(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st_in, double dt, cudaStream_t s) {
   Stage<T> st = st_in;
   stage_finalize(st, dt);
-  if (int rc = qg_solver_run<T>(h->solver, st.Yin[0], (T*)h->psi, s)) return rc;
   const Layout& L = h->L;
   dim3 block(QTXG, QTY);
   dim3 grid((L.groups() + QTXG - 1) / QTXG, (L.Ny + QTY - 1) / QTY, L.batch * L.nl);
@@ -634,7 +647,7 @@ int qg_bc_inplace(somax_b200_qg_t h, void* q, cudaStream_t s) {
   const Layout& L = h->L;
   dim3 b(256), g((L.Nx + 255) / 256, L.Ny, L.batch * L.nl);
   prof_begin("qg_bc_kernel", s);
-  qg_bc_kernel<T><<<g, b, 0, s>>>((T*)q, L);
+  qg_bc_kernel<T><<<g, b, 0, s>>>((T*)q, L, h->bc_ylo, h->bc_yhi);
   SB_LAUNCH_CHECK();
   return 0;
 }
@@ -861,3 +874,5 @@ int somax_b200_qg_diag(somax_b200_qg_t h, const void* q, double* out, void* stre
 }
 
 }  // extern "C"
+
+#include "qg_slab.cuh"

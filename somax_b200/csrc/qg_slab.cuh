@@ -1,0 +1,502 @@
+// Slab-distributed quasi-geostrophic model: ONE grid partitioned in y-slabs over several B200s
+// (BASELINE config "3-layer QG double-gyre 8192^2 slab-decomposed over 2/4/8 B200").
+//
+// Included at the end of qg.cu (it drives the same stencil / solver stages).  Rank r of P owns
+// rows [r*ny/P, (r+1)*ny/P) of every layer, stored as a window (ny/P + 2 rows) of the global
+// padded array: its first / last row is the physical ring on the edge ranks and a halo row of
+// the neighbour's data elsewhere.  One right-hand-side evaluation:
+//
+//   rows_fwd   layer->mode mix + DST-I in x of the slab's rows            (local, R)
+//   X1         transpose: strips of R -> the owning rank's column array S  (peer stores, NVLink)
+//   cols(1)    first Thomas solve in y on the rank's x-wavenumber strips
+//   X2         border row-sum partials -> every rank                       (peer stores)
+//   border     fixed-order reduction + Schur solve, replicated (bitwise the single-GPU result)
+//   cols(2)    second Thomas solve on the rank's strips
+//   X3         transpose back: row blocks of S -> the owning rank's R      (peer stores)
+//   rows_inv   inverse transform + mode->layer mix -> psi slab
+//   X4         psi halo rows -> neighbours                                 (peer stores)
+//   stencil    fused Arakawa / viscosity / wind / drag + Tsit5 epilogue on the slab
+//   X5         new stage state halo rows -> neighbours' inbox              (peer stores)
+//
+// All exchanges are device kernels storing straight into the peer's memory (CUDA IPC mappings
+// over NVLink / NVSwitch); ordering between ranks is a flag barrier in peer memory (one small
+// kernel, release/acquire at system scope), four per evaluation.  There is no host
+// synchronisation and no staging buffer.  With every slab in one process (nlocal == nranks, used
+// to validate the decomposition on one device) the same kernels run on one stream and the
+// barriers are not needed.
+//
+// Replaces, for this configuration, the same reference functions as qg.cu
+// (qg/baroclinic.py:135-195, core/model.py:47-88).
+
+namespace sb {
+
+constexpr int QGS_MAX_RANKS = 16;
+constexpr int QGS_NBUF = 6;    // exported buffers: cols.S, cols.part, R, psi, inbox, flags
+
+struct Seg {
+  const char* src; char* dst;
+  unsigned rows, row_bytes;
+  size_t spitch, dpitch;
+};
+
+template <typename V>
+__global__ void __launch_bounds__(256) seg_copy_kernel(const Seg* __restrict__ segs) {
+  const Seg sg = segs[blockIdx.y];
+  const unsigned vpr = sg.row_bytes / (unsigned)sizeof(V);
+  const size_t total = (size_t)sg.rows * vpr;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const unsigned r = (unsigned)(e / vpr), c = (unsigned)(e - (size_t)r * vpr);
+    *reinterpret_cast<V*>(sg.dst + (size_t)r * sg.dpitch + (size_t)c * sizeof(V)) =
+        *reinterpret_cast<const V*>(sg.src + (size_t)r * sg.spitch + (size_t)c * sizeof(V));
+  }
+}
+
+struct SegTable {
+  Seg* dev = nullptr;
+  int n = 0, vec = 16, gx = 1;
+};
+
+struct FlagPtrs { unsigned* p[QGS_MAX_RANKS]; };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Barrier across the ranks of one slab group: thread t publishes `epoch` in rank t's slot for
+// this rank and waits for rank t's epoch in its own slot.  Everything this rank stored to peer
+// memory earlier in the stream is complete (stream order) and fenced before the flag is released.
+__global__ void slab_barrier_kernel(FlagPtrs F, int me, int nranks, unsigned epoch, unsigned* err) {
+  const int t = threadIdx.x;
+  if (t >= nranks || t == me) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(F.p[t] + me), "r"(epoch) : "memory");
+  if (*reinterpret_cast<volatile unsigned*>(err)) return;      // a peer went missing before: do not wait again
+  const unsigned long long t0 = gtimer();
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(F.p[me] + t) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    if (gtimer() - t0 > 20000000000ull) { *err = 1u; break; }   // 20 s: report instead of hanging the GPU
+  }
+}
+
+struct SlabRank {
+  somax_b200_qg_t core = nullptr;   // stencil buffers + row-transform solver of the slab (ny_loc rows)
+  QgSolver* cols = nullptr;         // column solver of the whole grid (ny rows); only strips [s0, s1) are used
+  int rank = 0, s0 = 0, s1 = 0;
+  void* inbox = nullptr;            // [2][planes][pitch]: halo rows of the newest stage state from below / above
+  unsigned* flags = nullptr;        // [QGS_MAX_RANKS] barrier slots + [QGS_MAX_RANKS] error word
+  SegTable x1, xb, x2, x3, xpsi, xstate[3], xin[3];
+};
+
+struct SlabPeer { void* buf[QGS_NBUF]; };
+
+}  // namespace sb
+
+struct somax_b200_qgs_s {
+  int dtype = 0, nl = 0, ny = 0, nx = 0, nranks = 0, rank_first = 0, nlocal = 0, ny_loc = 0, spr = 0;
+  double dx = 0, dy = 0;
+  std::vector<sb::SlabRank> local;
+  sb::SlabPeer peers[sb::QGS_MAX_RANKS];
+  bool attached = false;
+  std::vector<void*> ipc_opened;
+  unsigned epoch = 0;
+  size_t bytes = 0;
+};
+
+namespace {
+
+struct IpcBlob {
+  cudaIpcMemHandle_t handle[QGS_NBUF];
+  unsigned long long offset[QGS_NBUF];
+};
+
+inline size_t qgs_es(const somax_b200_qgs_s* g) { return g->dtype == SOMAX_B200_F32 ? 4 : 8; }
+
+int seg_upload(SegTable& t, const std::vector<Seg>& v, size_t* bytes) {
+  t.n = (int)v.size();
+  if (t.n == 0) return 0;
+  t.vec = 16;
+  size_t maxb = 0;
+  for (const Seg& s : v) {
+    const size_t m = (size_t)s.src | (size_t)s.dst | s.row_bytes | s.spitch | s.dpitch;
+    if (m & 15) t.vec = std::min(t.vec, (m & 7) ? 4 : 8);
+    maxb = std::max(maxb, (size_t)s.rows * s.row_bytes);
+  }
+  t.gx = (int)std::min<size_t>(64, std::max<size_t>(1, maxb / t.vec / (256 * 8)));
+  SB_CUDA(cudaMalloc((void**)&t.dev, v.size() * sizeof(Seg)));
+  SB_CUDA(cudaMemcpy(t.dev, v.data(), v.size() * sizeof(Seg), cudaMemcpyHostToDevice));
+  *bytes += v.size() * sizeof(Seg);
+  return 0;
+}
+
+int seg_launch(const char* tag, const SegTable& t, cudaStream_t s) {
+  if (t.n == 0) return 0;
+  prof_begin(tag, s);
+  const dim3 grid(t.gx, t.n);
+  if (t.vec == 16) seg_copy_kernel<int4><<<grid, 256, 0, s>>>(t.dev);
+  else if (t.vec == 8) seg_copy_kernel<unsigned long long><<<grid, 256, 0, s>>>(t.dev);
+  else seg_copy_kernel<unsigned><<<grid, 256, 0, s>>>(t.dev);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+// Exchange tables of local rank R against the peer pointer table (all pointers valid in this process).
+int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
+  const size_t es = qgs_es(g);
+  const int P = g->nranks, p = R.rank, nyl = g->ny_loc, ny = g->ny, spr = g->spr;
+  const QgSolverView vr = qg_solver_view(R.core->solver), vc = qg_solver_view(R.cols);
+  const int planes = vc.planes, np = vc.np, nstrip = vc.nstrip;
+  const Layout& L = R.core->L;
+  char* Rl = (char*)vr.S;
+  char* Sl = (char*)vc.S;
+  const size_t blk = (size_t)nyl * SP_W * es;          // one strip of the slab's rows
+  const size_t col = (size_t)ny * SP_W * es;           // one strip of the whole grid
+  std::vector<Seg> x1, xb, x2, x3, xpsi;
+  const int last_owner = (nstrip - 1) / spr;
+  for (int r = 0; r < P; ++r) {
+    char* Sr = (char*)g->peers[r].buf[0];
+    char* partr = (char*)g->peers[r].buf[1];
+    char* Rr = (char*)g->peers[r].buf[2];
+    for (int pl = 0; pl < planes; ++pl) {
+      // X1: my rows of rank r's strips -> its column array
+      x1.push_back(Seg{Rl + ((size_t)pl * nstrip + (size_t)r * spr) * blk,
+                       Sr + ((size_t)pl * nstrip + (size_t)r * spr) * col + (size_t)p * nyl * SP_W * es,
+                       (unsigned)spr, (unsigned)blk, blk, col});
+      // raw border column (x index ncols) of my rows -> every rank that does not own its strip
+      if (r != last_owner)
+        xb.push_back(Seg{Rl + ((size_t)pl * nyl * np + sp_off(nyl, 0, vc.ncols)) * es,
+                         Sr + ((size_t)pl * ny * np + sp_off(ny, p * nyl, vc.ncols)) * es,
+                         (unsigned)nyl, (unsigned)es, SP_W * es, SP_W * es});
+      // X2: border partial sums of my strips -> every other rank
+      if (r != p) {
+        const size_t o = ((size_t)pl * 2 * nstrip + 2 * (size_t)R.s0) * ny * es;
+        x2.push_back(Seg{(char*)vc.part + o, partr + o, 1u, (unsigned)(2 * (size_t)spr * ny * es), 0, 0});
+      }
+      // X3: rank r's rows of my strips -> its row array
+      x3.push_back(Seg{Sl + ((size_t)pl * nstrip + (size_t)R.s0) * col + (size_t)r * nyl * SP_W * es,
+                       Rr + ((size_t)pl * nstrip + (size_t)R.s0) * blk,
+                       (unsigned)spr, (unsigned)blk, col, blk});
+    }
+  }
+  // halo rows: my first owned row (1) -> rank p-1's top halo row; my last owned row -> rank p+1's row 0
+  const size_t rowb = (size_t)L.pitch * es, planeb = L.plane() * es;
+  const size_t inbox_slot = (size_t)planes * rowb;
+  auto halo = [&](const char* mine, int buf, bool to_inbox, std::vector<Seg>& out) {
+    if (p > 0) {
+      char* d = (char*)g->peers[p - 1].buf[buf];
+      out.push_back(to_inbox ? Seg{mine + 1 * rowb, d + inbox_slot, (unsigned)planes, (unsigned)rowb, planeb, rowb}
+                             : Seg{mine + 1 * rowb, d + (size_t)(L.Ny - 1) * rowb, (unsigned)planes, (unsigned)rowb, planeb, planeb});
+    }
+    if (p < P - 1) {
+      char* d = (char*)g->peers[p + 1].buf[buf];
+      out.push_back(to_inbox ? Seg{mine + (size_t)nyl * rowb, d, (unsigned)planes, (unsigned)rowb, planeb, rowb}
+                             : Seg{mine + (size_t)nyl * rowb, d, (unsigned)planes, (unsigned)rowb, planeb, planeb});
+    }
+  };
+  halo((const char*)R.core->psi, 3, false, xpsi);
+  void* st[3] = {R.core->y, R.core->Ya, R.core->Yb};
+  if (int rc = seg_upload(R.x1, x1, &g->bytes)) return rc;
+  if (int rc = seg_upload(R.xb, xb, &g->bytes)) return rc;
+  if (int rc = seg_upload(R.x2, x2, &g->bytes)) return rc;
+  if (int rc = seg_upload(R.x3, x3, &g->bytes)) return rc;
+  if (int rc = seg_upload(R.xpsi, xpsi, &g->bytes)) return rc;
+  for (int b = 0; b < 3; ++b) {
+    std::vector<Seg> xs, xi;
+    halo((const char*)st[b], 4, true, xs);
+    // inbox -> ghost rows of my own buffer b (slot 0: from below -> row 0; slot 1: from above -> row Ny-1)
+    if (p > 0) xi.push_back(Seg{(const char*)R.inbox, (char*)st[b], (unsigned)planes, (unsigned)rowb, rowb, planeb});
+    if (p < P - 1)
+      xi.push_back(Seg{(const char*)R.inbox + inbox_slot, (char*)st[b] + (size_t)(L.Ny - 1) * rowb,
+                       (unsigned)planes, (unsigned)rowb, rowb, planeb});
+    if (int rc = seg_upload(R.xstate[b], xs, &g->bytes)) return rc;
+    if (int rc = seg_upload(R.xin[b], xi, &g->bytes)) return rc;
+  }
+  return 0;
+}
+
+void qgs_local_ptrs(const SlabRank& R, void** out) {
+  const QgSolverView vr = qg_solver_view(R.core->solver), vc = qg_solver_view(R.cols);
+  out[0] = vc.S; out[1] = vc.part; out[2] = vr.S; out[3] = R.core->psi; out[4] = R.inbox; out[5] = R.flags;
+}
+
+int qgs_barrier(somax_b200_qgs_s* g, cudaStream_t s) {
+  if (g->nlocal == g->nranks) return 0;      // one process, one stream: stream order is the barrier
+  SlabRank& R = g->local[0];
+  FlagPtrs F;
+  for (int r = 0; r < QGS_MAX_RANKS; ++r) F.p[r] = r < g->nranks ? (unsigned*)g->peers[r].buf[5] : nullptr;
+  ++g->epoch;
+  prof_begin("slab_barrier", s);
+  slab_barrier_kernel<<<1, 32, 0, s>>>(F, R.rank, g->nranks, g->epoch, R.flags + QGS_MAX_RANKS);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+int buf_index(const SlabRank& R, const void* p) {
+  return p == R.core->y ? 0 : (p == R.core->Ya ? 1 : 2);
+}
+
+// One evaluation on every local slab.  role[]: indices (0 = y, 1 = Ya, 2 = Yb) of the buffers
+// holding Yin / the step start state / Yout for this stage, identical on all ranks.
+template <typename T>
+int qgs_eval(somax_b200_qgs_s* g, const somax_b200_params* p, int in_b, int y_b, int out_b, int e,
+             double hd, bool store_f, int f_slot, cudaStream_t s) {
+  auto bufp = [](SlabRank& R, int b) -> void* { return b == 0 ? R.core->y : (b == 1 ? R.core->Ya : R.core->Yb); };
+  for (SlabRank& R : g->local)
+    if (int rc = qg_solver_rows_fwd<T>(R.core->solver, (const T*)bufp(R, in_b), s)) return rc;
+  for (SlabRank& R : g->local) {
+    if (int rc = seg_launch("slab_x1_transpose", R.x1, s)) return rc;
+    if (int rc = seg_launch("slab_x1_border", R.xb, s)) return rc;
+  }
+  if (int rc = qgs_barrier(g, s)) return rc;
+  for (SlabRank& R : g->local) {
+    // halo rows of Yin pushed by the neighbours after the previous evaluation
+    if (int rc = seg_launch("slab_halo_in", R.xin[in_b], s)) return rc;
+    if (int rc = qg_solver_cols<T>(R.cols, 1, R.s0, R.s1, s)) return rc;
+  }
+  for (SlabRank& R : g->local)
+    if (int rc = seg_launch("slab_x2_partials", R.x2, s)) return rc;
+  if (int rc = qgs_barrier(g, s)) return rc;
+  for (SlabRank& R : g->local) {
+    if (int rc = qg_solver_border<T>(R.cols, s)) return rc;
+    if (int rc = qg_solver_cols<T>(R.cols, 2, R.s0, R.s1, s)) return rc;
+  }
+  for (SlabRank& R : g->local)
+    if (int rc = seg_launch("slab_x3_transpose", R.x3, s)) return rc;
+  if (int rc = qgs_barrier(g, s)) return rc;
+  for (SlabRank& R : g->local)
+    if (int rc = qg_solver_rows_inv<T>(R.core->solver, (T*)R.core->psi, s)) return rc;
+  for (SlabRank& R : g->local)
+    if (int rc = seg_launch("slab_halo_psi", R.xpsi, s)) return rc;
+  if (int rc = qgs_barrier(g, s)) return rc;
+  for (SlabRank& R : g->local) {
+    QgArgs<T> A = make_qargs<T>(R.core, p, 1);
+    Stage<T> st = qstage<T>();
+    st.Yin[0] = (const T*)bufp(R, in_b);
+    st.Yout[0] = (T*)bufp(R, out_b);
+    st.dt = (T)hd; st.a_new = (T)TSIT5_A[e][e];
+    if (e > 0) {
+      st.nprev = e; st.y[0] = (const T*)bufp(R, y_b);
+      for (int jj = 0; jj < e; ++jj) { st.a[jj] = (T)TSIT5_A[e][jj]; st.Fprev[jj][0] = (const T*)R.core->F[jj]; }
+    }
+    st.Fout[0] = store_f ? (T*)R.core->F[f_slot] : nullptr;
+    if (int rc = launch_stencil<T>(R.core, A, st, hd, s)) return rc;
+  }
+  for (SlabRank& R : g->local)
+    if (int rc = seg_launch("slab_halo_state", R.xstate[out_b], s)) return rc;
+  return 0;
+}
+
+template <typename T>
+int qgs_steps_impl(somax_b200_qgs_s* g, void* const* q, long n_steps, double dt, double dt_last,
+                   const somax_b200_params* p, cudaStream_t s) {
+  const long total = n_steps + (dt_last > 0 ? 1 : 0);
+  int y = 0, Yc = 1, Yn = 2;
+  auto bufp = [](SlabRank& R, int b) -> void* { return b == 0 ? R.core->y : (b == 1 ? R.core->Ya : R.core->Yb); };
+  for (size_t v = 0; v < g->local.size(); ++v) {
+    SlabRank& R = g->local[v];
+    if (int rc = pack_field<T>((const T*)q[v], (T*)R.core->y, R.core->L, s)) return rc;
+    if (int rc = qg_bc_inplace<T>(R.core, R.core->y, s)) return rc;     // x ring everywhere, y ring on the edge ranks
+  }
+  int newest = 0;      // buffer whose halo rows are still in the neighbours' inboxes (0: the caller's are valid)
+  bool pending = false;
+  if (total > 0) {
+    auto step_dt = [&](long i) { return (i < n_steps) ? dt : dt_last; };
+    // the very first evaluation reads the caller's halo rows: make the inbox agree with them
+    for (SlabRank& R : g->local) {
+      // inbox <- own ghost rows of y (so that the generic "inbox -> ghost rows" copy is a no-op)
+      const Layout& L = R.core->L;
+      const size_t es = sizeof(T), rowb = (size_t)L.pitch * es, planeb = L.plane() * es;
+      const int planes = L.batch * L.nl;
+      SB_CUDA(cudaMemcpy2DAsync(R.inbox, rowb, R.core->y, planeb, rowb, planes, cudaMemcpyDeviceToDevice, s));
+      SB_CUDA(cudaMemcpy2DAsync((char*)R.inbox + (size_t)planes * rowb, rowb,
+                                (char*)R.core->y + (size_t)(L.Ny - 1) * rowb, planeb, rowb, planes,
+                                cudaMemcpyDeviceToDevice, s));
+    }
+    if (int rc = qgs_barrier(g, s)) return rc;      // nobody pushes into an inbox before it is primed
+    if (int rc = qgs_eval<T>(g, p, y, y, Yc, 0, step_dt(0), true, 0, s)) return rc;
+    auto stages = [&](double hd) -> int {
+      for (int e = 1; e <= 5; ++e) {
+        if (int rc = qgs_eval<T>(g, p, Yc, y, Yn, e, hd, e <= 4, e, s)) return rc;
+        std::swap(Yc, Yn);
+      }
+      return 0;
+    };
+    auto full_step = [&](double hd, double hnext) -> int {
+      if (int rc = stages(hd)) return rc;
+      if (int rc = qgs_eval<T>(g, p, Yc, Yc, Yn, 0, hnext, true, 0, s)) return rc;
+      const int oy = y; y = Yc; Yc = Yn; Yn = oy;
+      return 0;
+    };
+    for (long i = 0; i + 1 < total; ++i)
+      if (int rc = full_step(step_dt(i), step_dt(i + 1))) return rc;
+    if (int rc = stages(step_dt(total - 1))) return rc;
+    std::swap(y, Yc);
+    newest = y; pending = true;
+  }
+  if (pending) {
+    // halo rows of the final state: pushed after its stencil; land them before handing the slab back
+    if (int rc = qgs_barrier(g, s)) return rc;
+    for (SlabRank& R : g->local)
+      if (int rc = seg_launch("slab_halo_in", R.xin[newest], s)) return rc;
+    if (int rc = qgs_barrier(g, s)) return rc;      // the inboxes may be primed again by the next call
+  }
+  for (size_t v = 0; v < g->local.size(); ++v) {
+    SlabRank& R = g->local[v];
+    if (int rc = unpack_field<T>((const T*)bufp(R, y), (T*)q[v], R.core->L, s)) return rc;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int somax_b200_qgs_create(somax_b200_qgs_t* out, int dtype, int nl, int ny, int nx, double dx,
+                          double dy, const double* Cl2m, const double* Cm2l, const double* lambdas,
+                          const double* beta_y, const double* wind, int nranks, int rank_first,
+                          int nlocal, unsigned spec_flags) {
+  if (!out) return fail(SOMAX_B200_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (nranks < 1 || nranks > QGS_MAX_RANKS || rank_first < 0 || nlocal < 1 || rank_first + nlocal > nranks)
+    return fail(SOMAX_B200_ERR_INVALID, "need 1 <= nranks <= 16 and local ranks inside [0, nranks)");
+  if (nlocal != nranks && nlocal != 1)
+    return fail(SOMAX_B200_ERR_UNSUPPORTED, "a process holds either one slab or all of them");
+  const bool pow2 = nx >= 64 && (nx & (nx - 1)) == 0;
+  if (!pow2 || (nx / 64) % nranks != 0 || ny % nranks != 0 || ny / nranks < 3)
+    return fail(SOMAX_B200_ERR_UNSUPPORTED,
+                "slab decomposition needs nx = 2^p with nx/64 divisible by nranks, and ny divisible by nranks (>= 3 rows each)");
+  if (!Cl2m || !Cm2l || !lambdas || !beta_y || !wind) return fail(SOMAX_B200_ERR_INVALID, "null coefficient pointer");
+  if (int rc = require_device()) return rc;
+  auto* g = new somax_b200_qgs_s();
+  g->dtype = dtype; g->nl = nl; g->ny = ny; g->nx = nx; g->dx = dx; g->dy = dy;
+  g->nranks = nranks; g->rank_first = rank_first; g->nlocal = nlocal;
+  g->ny_loc = ny / nranks; g->spr = (nx / 64) / nranks;
+  const int Nx = nx + 2, nyl = g->ny_loc;
+  const size_t es = qgs_es(g);
+  int rc = 0;
+  g->local.resize(nlocal);
+  for (int v = 0; v < nlocal && !rc; ++v) {
+    SlabRank& R = g->local[v];
+    R.rank = rank_first + v; R.s0 = R.rank * g->spr; R.s1 = R.s0 + g->spr;
+    const size_t row0 = (size_t)R.rank * nyl;      // the slab's window starts at global row row0
+    rc = somax_b200_qg_create(&R.core, dtype, 1, nl, nyl, nx, dx, dy, Cl2m, Cm2l, lambdas,
+                              beta_y + row0 * Nx, wind + row0 * Nx, SOMAX_B200_SOLVER_FFT, spec_flags);
+    if (rc) break;
+    R.core->bc_ylo = R.rank == 0; R.core->bc_yhi = R.rank == nranks - 1;
+    rc = qg_solver_create(&R.cols, dtype, 1, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, SOMAX_B200_SOLVER_FFT);
+    if (rc) break;
+    const size_t ib = 2 * (size_t)nl * R.core->L.pitch * es;
+    if (cudaMalloc(&R.inbox, ib) != cudaSuccess || cudaMemset(R.inbox, 0, ib) != cudaSuccess ||
+        cudaMalloc((void**)&R.flags, 2 * QGS_MAX_RANKS * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(R.flags, 0, 2 * QGS_MAX_RANKS * sizeof(unsigned)) != cudaSuccess) {
+      rc = fail(SOMAX_B200_ERR_CUDA, "cudaMalloc (slab inbox / flags) failed");
+      break;
+    }
+    g->bytes += somax_b200_qg_device_bytes(R.core) + qg_solver_bytes(R.cols) + ib;
+  }
+  if (!rc && nlocal == nranks) {
+    for (int v = 0; v < nlocal; ++v) qgs_local_ptrs(g->local[v], g->peers[v].buf);
+    for (int v = 0; v < nlocal && !rc; ++v) rc = qgs_build_tables(g, g->local[v]);
+    g->attached = !rc;
+  }
+  if (!rc) rc = (cudaDeviceSynchronize() == cudaSuccess) ? 0 : fail(SOMAX_B200_ERR_CUDA, "slab create: device error");
+  if (rc) { somax_b200_qgs_destroy(g); return rc; }
+  *out = g;
+  return 0;
+}
+
+int somax_b200_qgs_destroy(somax_b200_qgs_t g) {
+  if (!g) return 0;
+  cudaDeviceSynchronize();
+  for (void* p : g->ipc_opened) cudaIpcCloseMemHandle(p);
+  for (SlabRank& R : g->local) {
+    SegTable* ts[] = {&R.x1, &R.xb, &R.x2, &R.x3, &R.xpsi, &R.xstate[0], &R.xstate[1], &R.xstate[2],
+                      &R.xin[0], &R.xin[1], &R.xin[2]};
+    for (SegTable* t : ts) cudaFree(t->dev);
+    cudaFree(R.inbox); cudaFree(R.flags);
+    qg_solver_destroy(R.cols);
+    somax_b200_qg_destroy(R.core);
+  }
+  delete g;
+  return 0;
+}
+
+size_t somax_b200_qgs_device_bytes(somax_b200_qgs_t g) { return g ? g->bytes : 0; }
+size_t somax_b200_qgs_export_bytes(void) { return sizeof(IpcBlob); }
+
+int somax_b200_qgs_export(somax_b200_qgs_t g, void* blob) {
+  if (!g || !blob) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  if (g->nlocal != 1) return fail(SOMAX_B200_ERR_INVALID, "export is for one-slab-per-process groups");
+  void* ptrs[QGS_NBUF];
+  qgs_local_ptrs(g->local[0], ptrs);
+  IpcBlob b;
+  memset(&b, 0, sizeof(b));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  typedef CUresult (*range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  range_fn get_range = nullptr;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess && fn)
+    get_range = reinterpret_cast<range_fn>(fn);
+  else
+    cudaGetLastError();
+  for (int i = 0; i < QGS_NBUF; ++i) {
+    cudaError_t e = cudaIpcGetMemHandle(&b.handle[i], ptrs[i]);
+    if (e != cudaSuccess) return fail(SOMAX_B200_ERR_COMM, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    CUdeviceptr base = 0; size_t sz = 0;
+    if (get_range && get_range(&base, &sz, (CUdeviceptr)ptrs[i]) == CUDA_SUCCESS)
+      b.offset[i] = (unsigned long long)((CUdeviceptr)ptrs[i] - base);
+  }
+  memcpy(blob, &b, sizeof(b));
+  return 0;
+}
+
+int somax_b200_qgs_attach(somax_b200_qgs_t g, const void* blobs) {
+  if (!g || !blobs) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  if (g->nlocal != 1) return fail(SOMAX_B200_ERR_INVALID, "attach is for one-slab-per-process groups");
+  if (g->attached) return fail(SOMAX_B200_ERR_INVALID, "already attached");
+  const IpcBlob* B = reinterpret_cast<const IpcBlob*>(blobs);
+  const int me = g->local[0].rank;
+  for (int r = 0; r < g->nranks; ++r) {
+    if (r == me) { qgs_local_ptrs(g->local[0], g->peers[r].buf); continue; }
+    for (int i = 0; i < QGS_NBUF; ++i) {
+      void* p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, B[r].handle[i], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return fail(SOMAX_B200_ERR_COMM, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+      g->ipc_opened.push_back(p);
+      g->peers[r].buf[i] = (char*)p + B[r].offset[i];
+    }
+  }
+  if (int rc = qgs_build_tables(g, g->local[0])) return rc;
+  g->attached = true;
+  return 0;
+}
+
+int somax_b200_qgs_steps(somax_b200_qgs_t g, void* const* q_slabs, long n_steps, double dt,
+                         double dt_last, const somax_b200_params* p, void* stream) {
+  if (!g || !q_slabs || !p) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  if (!g->attached) return fail(SOMAX_B200_ERR_INVALID, "slab group not attached to its peers");
+  if (n_steps < 0 || !(dt > 0) || dt_last < 0) return fail(SOMAX_B200_ERR_INVALID, "need n_steps>=0, dt>0, dt_last>=0");
+  for (int v = 0; v < g->nlocal; ++v)
+    if (!q_slabs[v]) return fail(SOMAX_B200_ERR_INVALID, "null slab pointer");
+  return g->dtype == SOMAX_B200_F32
+             ? qgs_steps_impl<float>(g, q_slabs, n_steps, dt, dt_last, p, (cudaStream_t)stream)
+             : qgs_steps_impl<double>(g, q_slabs, n_steps, dt, dt_last, p, (cudaStream_t)stream);
+}
+
+int somax_b200_qgs_status(somax_b200_qgs_t g, int* barrier_timeouts) {
+  if (!g || !barrier_timeouts) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  *barrier_timeouts = 0;
+  for (SlabRank& R : g->local) {
+    unsigned e = 0;
+    SB_CUDA(cudaMemcpy(&e, R.flags + QGS_MAX_RANKS, sizeof(e), cudaMemcpyDeviceToHost));
+    *barrier_timeouts += (int)e;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -57,12 +57,8 @@ struct QgSolver {
 // Spectral arrays (S, W) are stored BLOCKED in 64-column strips so that the y-sweeps can move a
 // (rows x 64 columns) tile with a single bulk copy: within a plane, element (row j, column k)
 // lives at ((k / 64) * ny + j) * 64 + (k % 64); the plane stride is ny * np, np = roundup(nx, 64).
-constexpr int SP_W = 64;
 constexpr int GS_ROWS = 8;     // outputs (warps) per CTA of border_gsolve
 constexpr int GS_SMALL_NY = 1024;   // up to here: one thread per output (border_gsolve_small)
-__host__ __device__ __forceinline__ size_t sp_off(int ny, int j, int k) {
-  return ((size_t)(k >> 6) * ny + j) * SP_W + (k & (SP_W - 1));
-}
 
 // ------------------------------------------------------------------------------------------
 // row kernels, FFT path, compile-time sized (the ones actually launched for nx = 2^LGN)
@@ -1325,8 +1321,13 @@ static int launch_thomas_one(const char* tag, const ThomasTab& tb, int strip_fir
 //   PHASE 1: S <- eliminated S (D), border row sums of A^-1 S into tb.part (x itself is not stored).
 //   PHASE 2: W <- eliminated (gvec x 1) (E), then S <- back-substitution of D - bsig * E.
 template <typename T, int PHASE>
-static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream_t st) {
-  const int nstrip = s->np / SP_W, nh = std::min(s->nheavy, nstrip);
+static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream_t st, int sa = 0, int sb = -1) {
+  // strips [sa, sb) only (slab-distributed solve: every rank owns a range of x-wavenumber strips)
+  const int nstrip_all = s->np / SP_W;
+  if (sb < 0) sb = nstrip_all;
+  const int hA = std::min(sa, s->nheavy), hB = std::min(sb, s->nheavy);   // LOWK strips [hA, hB)
+  const int pA = std::max(sa, s->nheavy), pB = std::max(sb, s->nheavy);   // PLAIN strips [pA, pB)
+  const int nh = hB - hA, npl = pB - pA;
   constexpr bool SECOND = PHASE == 2;
   constexpr int KIND = PHASE;
   const char* tf = SECOND ? "thomas_fwd_1" : "thomas_fwd_0";
@@ -1342,16 +1343,16 @@ static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream
   // before the wide PLAIN launches (auxiliary stream, released by an event a few microseconds
   // later) fill every SM's shared memory; measured the other way round, the LOWK CTAs could not be
   // placed until the PLAIN kernel drained and the two chains ran back to back.
-  const bool two = nh > 0 && nh < nstrip;
+  const bool two = nh > 0 && npl > 0;
   cudaStream_t pl = two ? s->aux : st;
   if (two) {
     SB_CUDA(cudaEventRecord(s->ev_fork, st));
     SB_CUDA(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
   }
-  if (int rc = launch_thomas_one<T, false, SECOND, 0, true>(tfl, tb, 0, nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, st)) return rc;
-  if (int rc = launch_thomas_one<T, false, SECOND, 0, false>(tf, tb, nh, nstrip - nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, pl)) return rc;
-  if (int rc = launch_thomas_one<T, true, false, KIND, true>(tbl, tb, 0, nh, s->planes, bin, Vv, nullptr, nullptr, bs, S, st)) return rc;
-  if (int rc = launch_thomas_one<T, true, false, KIND, false>(tbk, tb, nh, nstrip - nh, s->planes, bin, Vv, nullptr, nullptr, bs, S, pl)) return rc;
+  if (int rc = launch_thomas_one<T, false, SECOND, 0, true>(tfl, tb, hA, nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, st)) return rc;
+  if (int rc = launch_thomas_one<T, false, SECOND, 0, false>(tf, tb, pA, npl, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, pl)) return rc;
+  if (int rc = launch_thomas_one<T, true, false, KIND, true>(tbl, tb, hA, nh, s->planes, bin, Vv, nullptr, nullptr, bs, S, st)) return rc;
+  if (int rc = launch_thomas_one<T, true, false, KIND, false>(tbk, tb, pA, npl, s->planes, bin, Vv, nullptr, nullptr, bs, S, pl)) return rc;
   if (two) {
     SB_CUDA(cudaEventRecord(s->ev_join, s->aux));
     SB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
@@ -1359,46 +1360,85 @@ static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream
   return 0;
 }
 
-template <typename T>
-int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
-  const int ny = s->ny, n = s->nx, np = s->np, nl = s->nl;
+static ThomasTab make_tab(const QgSolver* s) {
   ThomasTab tb;
   tb.ctabB = s->ctab; tb.tabOff = s->coff; tb.Jstrip = s->krow; tb.cinf = s->cinf; tb.meetc = s->meetc;
   tb.nstrip = s->np / SP_W;
   for (int m = 0; m < QG_MAX_NL; ++m) tb.kbad[m] = s->kbad[m];
   tb.KB = s->KBs; tb.dbad = s->dbad; tb.dbad1 = s->dbad1; tb.meet = s->meet; tb.meet1 = s->meet1;
-  tb.part = s->part; tb.sig2n = s->sig2n; tb.ny = ny; tb.np = np; tb.ncols = s->ncols; tb.nl = nl;
+  tb.part = s->part; tb.sig2n = s->sig2n; tb.ny = s->ny; tb.np = s->np; tb.ncols = s->ncols; tb.nl = s->nl;
   tb.dy2 = s->dy * s->dy;
+  return tb;
+}
+
+template <typename T>
+static void make_row_args(const QgSolver* s, RowArgsCT<T>& Af, RowArgsCT<T>& Ai) {
+  Af.L = s->L; Af.ny = s->ny; Af.np = s->np; Af.nl = s->nl; Af.nrows = s->batch * s->ny;
+  Af.tw = (const C2<T>*)s->tw; Af.twc = (const C2<T>*)s->twc; Af.twb = (const C2<T>*)s->twb; Af.scale = (T)1;
+  Ai = Af; Ai.scale = (T)(2.0 / s->nx);
+  for (int a = 0; a < QG_MAX_NL; ++a)
+    for (int c = 0; c < QG_MAX_NL; ++c) { Af.mix[a][c] = (T)s->l2m.c[a][c]; Ai.mix[a][c] = (T)s->m2l.c[a][c]; }
+}
+
+// The FFT-path inversion in its four stages.  qg_solver_run chains them on one device; the
+// slab-distributed model (qg_slab.cuh) runs the row stages on a y-slab and the column stages on
+// a range of x-wavenumber strips, with peer-memory exchanges in between.
+template <typename T>
+int qg_solver_rows_fwd(QgSolver* s, const T* q, cudaStream_t st) {
+  RowArgsCT<T> Af, Ai;
+  make_row_args<T>(s, Af, Ai);
+  return launch_rowdst<T, false>(s->plan.lgn, Af, q, (T*)s->S, st);
+}
+
+template <typename T>
+int qg_solver_rows_inv(QgSolver* s, T* psi, cudaStream_t st) {
+  RowArgsCT<T> Af, Ai;
+  make_row_args<T>(s, Af, Ai);
+  return launch_rowdst<T, true>(s->plan.lgn, Ai, (const T*)s->S, psi, st);
+}
+
+template <typename T>
+int qg_solver_cols(QgSolver* s, int phase, int sa, int sb, cudaStream_t st) {
+  const ThomasTab tb = make_tab(s);
+  if (phase == 1) return launch_solve<T, 1>(s, tb, (T*)s->S, nullptr, st, sa, sb);
+  return launch_solve<T, 2>(s, tb, (T*)s->S, (T*)s->W, st, sa, sb);
+}
+
+template <typename T>
+int qg_solver_border(QgSolver* s, cudaStream_t st) {
+  const int ny = s->ny, n = s->nx, np = s->np, nl = s->nl;
   T* S = (T*)s->S;
+  const double b = 1.0 / (s->dx * s->dx);
+  prof_begin("border_reduce", st);
+  border_reduce<T><<<dim3((ny + 255) / 256, s->planes), 256, 0, st>>>(S, (const T*)s->part, ny, np, s->ncols, 2 * (np / SP_W), b, s->rvec);
+  SB_LAUNCH_CHECK();
+  prof_begin("border_gsolve_a", st);
+  if (ny <= GS_SMALL_NY)
+    border_gsolve_small<T, true><<<dim3((ny + 127) / 128, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
+  else
+    border_gsolve<T, true><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
+  SB_LAUNCH_CHECK();
+  prof_begin("border_gsolve_b", st);
+  if (ny <= GS_SMALL_NY)
+    border_gsolve_small<T, false><<<dim3((ny + 127) / 128, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
+  else
+    border_gsolve<T, false><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
+  const int ny = s->ny, n = s->nx, np = s->np, nl = s->nl;
   if (s->kind == SOMAX_B200_SOLVER_FFT) {
-    T* W = (T*)s->W;
-    RowArgsCT<T> Af, Ai;
-    Af.L = s->L; Af.ny = ny; Af.np = np; Af.nl = nl; Af.nrows = s->batch * ny;
-    Af.tw = (const C2<T>*)s->tw; Af.twc = (const C2<T>*)s->twc; Af.twb = (const C2<T>*)s->twb; Af.scale = (T)1;
-    Ai = Af; Ai.scale = (T)(2.0 / n);
-    for (int a = 0; a < QG_MAX_NL; ++a)
-      for (int c = 0; c < QG_MAX_NL; ++c) { Af.mix[a][c] = (T)s->l2m.c[a][c]; Ai.mix[a][c] = (T)s->m2l.c[a][c]; }
-    if (int rc = launch_rowdst<T, false>(s->plan.lgn, Af, q, S, st)) return rc;
-    if (int rc = launch_solve<T, 1>(s, tb, S, nullptr, st)) return rc;
-    const double b = 1.0 / (s->dx * s->dx);
-    prof_begin("border_reduce", st);
-    border_reduce<T><<<dim3((ny + 255) / 256, s->planes), 256, 0, st>>>(S, (const T*)s->part, ny, np, s->ncols, 2 * (np / SP_W), b, s->rvec);
-    SB_LAUNCH_CHECK();
-    prof_begin("border_gsolve_a", st);
-    if (ny <= GS_SMALL_NY)
-      border_gsolve_small<T, true><<<dim3((ny + 127) / 128, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
-    else
-      border_gsolve<T, true><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
-    SB_LAUNCH_CHECK();
-    prof_begin("border_gsolve_b", st);
-    if (ny <= GS_SMALL_NY)
-      border_gsolve_small<T, false><<<dim3((ny + 127) / 128, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
-    else
-      border_gsolve<T, false><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
-    SB_LAUNCH_CHECK();
-    if (int rc = launch_solve<T, 2>(s, tb, S, W, st)) return rc;
-    if (int rc = launch_rowdst<T, true>(s->plan.lgn, Ai, S, psi, st)) return rc;
+    if (int rc = qg_solver_rows_fwd<T>(s, q, st)) return rc;
+    if (int rc = qg_solver_cols<T>(s, 1, 0, -1, st)) return rc;
+    if (int rc = qg_solver_border<T>(s, st)) return rc;
+    if (int rc = qg_solver_cols<T>(s, 2, 0, -1, st)) return rc;
+    if (int rc = qg_solver_rows_inv<T>(s, psi, st)) return rc;
   } else {
+    const ThomasTab tb = make_tab(s);
+    T* S = (T*)s->S;
     const size_t smem = (size_t)nl * n * sizeof(T);
     if (smem > 48 * 1024) {
       SB_CUDA(cudaFuncSetAttribute(rowdst_dense<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1416,6 +1456,13 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
   return 0;
 }
 
+QgSolverView qg_solver_view(const QgSolver* s) {
+  QgSolverView v;
+  v.S = s->S; v.part = s->part; v.ny = s->ny; v.nx = s->nx; v.np = s->np; v.planes = s->planes;
+  v.nstrip = s->np / SP_W; v.ncols = s->ncols; v.kind = s->kind; v.nheavy = s->nheavy;
+  return v;
+}
+
 #ifdef SB_TH_DEBUG
 extern "C" int somax_b200_debug_dump(unsigned long long* out, unsigned* n) {
   cudaDeviceSynchronize();
@@ -1429,6 +1476,13 @@ extern "C" int somax_b200_debug_dump(unsigned long long* out, unsigned* n) {
 
 template int qg_solver_run<float>(QgSolver*, const float*, float*, cudaStream_t);
 template int qg_solver_run<double>(QgSolver*, const double*, double*, cudaStream_t);
+#define SB_INST_STAGES(T)                                                  \
+  template int qg_solver_rows_fwd<T>(QgSolver*, const T*, cudaStream_t);   \
+  template int qg_solver_rows_inv<T>(QgSolver*, T*, cudaStream_t);         \
+  template int qg_solver_cols<T>(QgSolver*, int, int, int, cudaStream_t);  \
+  template int qg_solver_border<T>(QgSolver*, cudaStream_t);
+SB_INST_STAGES(float)
+SB_INST_STAGES(double)
 
 }  // namespace sb
 

@@ -1,0 +1,155 @@
+"""GPU: the y-slab decomposition of ONE QG grid (BASELINE config 4) against the single-GPU path
+and the CPU oracle.
+
+* all slabs in one process on one device (`local=True`): same kernels, same exchange tables, the
+  peer stores land in the same device - validates the decomposition itself on a 1-GPU box;
+* one process per GPU over CUDA IPC + flag barriers (needs >= 2 GPUs: `gpurun --gpus 2`).
+
+The slab path evaluates exactly the single-GPU arithmetic (row transforms per row, Thomas solves
+per strip, the border partials reduced in the same fixed order, the stencil per cell), so the
+comparison with the single-GPU result is bit-exact; against the fp64 oracle the BASELINE
+tolerances apply (rel-L2 <= 1e-5 fp32 / 1e-12 fp64).
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ARGS = dict(lateral_viscosity=15.0, bottom_drag=1e-7, wind_amplitude=1.3e-10)
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def state(nl, nx, ny, dtype):
+    from oracle.testcases import synthetic_qg_state
+    q = synthetic_qg_state(nl, nx, ny, dtype=np.float64)
+    rng = np.random.default_rng(11)          # a non-zero ring: the BC of state0 must be applied per slab
+    q[:, 0, :] = 1e-6 * rng.standard_normal(q[:, 0, :].shape)
+    q[:, -1, :] = 1e-6 * rng.standard_normal(q[:, -1, :].shape)
+    q[:, :, 0] = 1e-6 * rng.standard_normal(q[:, :, 0].shape)
+    q[:, :, -1] = 1e-6 * rng.standard_normal(q[:, :, -1].shape)
+    return q.astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nx,ny,world,steps", [(128, 64, 2, 3), (256, 96, 4, 3), (256, 256, 2, 12),
+                                               (512, 64, 8, 2)])
+def test_local_slabs_match_single_gpu_and_oracle(nx, ny, world, steps, dtype):
+    import somax_b200 as sb
+    from oracle import qg as oqg
+    from somax_b200.parallel import SlabQG
+    gm = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype=np.dtype(dtype).name, solver=1, **ARGS)
+    q0 = state(3, nx, ny, dtype)
+    dt = 600.0 * 128.0 / nx
+    t1 = steps * dt + 0.37 * dt               # a clipped last step as well
+    one = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, t1, dt).ys.q[0]
+    sl = SlabQG(gm, world, local=True)
+    got = sl.integrate(q0, 0.0, t1, dt)
+    sl.close()
+    assert got.shape == one.shape and got.dtype == one.dtype
+    assert np.array_equal(got, one), rel(got, one)
+    ref = oqg.create_baroclinic(nx=nx, ny=ny, **ARGS).integrate(q0.astype(np.float64), 0.0, t1, dt)
+    assert rel(got, ref) <= (1e-5 if dtype == np.float32 else 1e-12)
+
+
+def test_local_slabs_barotropic_and_halo_rows():
+    """nl = 1; the windows come back with valid halo rows (a second call continues from them)."""
+    import torch
+    import somax_b200 as sb
+    from somax_b200.parallel import SlabQG, merge_slabs, split_slabs
+    nx = ny = 128
+    gm = sb.BarotropicQG.create(nx=nx, ny=ny, lateral_viscosity=15.0, bottom_drag=1e-7, wind_amplitude=1.3e-10)
+    q0 = state(1, nx, ny, np.float32)[0]
+    one = gm.integrate(sb.BarotropicQGState(q=q0), 0.0, 6 * 600.0, 600.0).ys.q[0]
+    sl = SlabQG(gm, 2, local=True)
+    slabs = [s.contiguous().clone() for s in split_slabs(torch.as_tensor(q0[None]).cuda(), 2)]
+    sl._steps(slabs, 3, 600.0, 0.0)
+    sl.check_peers()
+    # halo rows agree with the neighbour's owned rows
+    assert torch.equal(slabs[0][:, -1], slabs[1][:, 1]) and torch.equal(slabs[1][:, 0], slabs[0][:, -2])
+    sl._steps(slabs, 3, 600.0, 0.0)
+    sl.check_peers()
+    got = merge_slabs(slabs)[0].cpu().numpy()
+    sl.close()
+    # two calls of 3 steps = the single-GPU model called twice (BC of state0 is re-applied per call)
+    mid = gm.integrate(sb.BarotropicQGState(q=q0), 0.0, 3 * 600.0, 600.0).ys.q[0]
+    two = gm.integrate(sb.BarotropicQGState(q=mid), 0.0, 3 * 600.0, 600.0).ys.q[0]
+    assert np.array_equal(got, two)
+    assert rel(one, two) < 1e-3
+
+
+def test_slab_create_rejects_bad_shapes():
+    import somax_b200 as sb
+    from somax_b200._lib import SomaxB200Error
+    from somax_b200.parallel import SlabQG
+    gm = sb.BaroclinicQG.create(nx=64, ny=64, **ARGS)
+    with pytest.raises(SomaxB200Error):
+        SlabQG(gm, 2, local=True)             # 1 strip of 64 wavenumbers cannot be split in 2
+    gm = sb.BaroclinicQG.create(nx=128, ny=63, solver=1, **ARGS)
+    with pytest.raises((SomaxB200Error, ValueError)):
+        SlabQG(gm, 2, local=True)
+
+
+def _mp_worker(rank, world, port, nx, ny, steps, dtype_name, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import somax_b200 as sb
+    from somax_b200.parallel import SlabQG, slab_owned, slab_window
+    dtype = np.dtype(dtype_name)
+    gm = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype=dtype_name, solver=1, **ARGS)
+    q0 = state(3, nx, ny, dtype.type)
+    dt = 600.0 * 128.0 / nx
+    sl = SlabQG(gm, world)
+    w = slab_window(ny, rank, world)
+    slab = torch.as_tensor(q0[:, w, :]).cuda().contiguous()
+    sl.integrate_slab(slab, 0.0, steps * dt, dt)
+    own = slab_owned(ny, rank, world)
+    q.put((rank, own.start, own.stop, slab[:, own.start - w.start:own.stop - w.start].cpu().numpy()))
+    dist.barrier()
+    sl.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_multi_process_slabs_match_single_gpu(dtype):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = 4 if world >= 4 else 2
+    import somax_b200 as sb
+    nx, ny, steps = 256, 192, 5
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_mp_worker, args=(r, world, port, nx, ny, steps, np.dtype(dtype).name, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = sorted((out.get(timeout=300) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    gm = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype=np.dtype(dtype).name, solver=1, **ARGS)
+    q0 = state(3, nx, ny, dtype)
+    dt = 600.0 * 128.0 / nx
+    one = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, steps * dt, dt).ys.q[0]
+    got = np.empty_like(one)
+    for _, lo, hi, a in parts:
+        got[:, lo:hi] = a
+    assert np.array_equal(got, one), rel(got, one)
