@@ -7,8 +7,11 @@ and the CPU oracle.
 
 The slab path evaluates exactly the single-GPU arithmetic (row transforms per row, Thomas solves
 per strip, the border partials reduced in the same fixed order, the stencil per cell), so the
-comparison with the single-GPU result is bit-exact; against the fp64 oracle the BASELINE
-tolerances apply (rel-L2 <= 1e-5 fp32 / 1e-12 fp64).
+comparison with the single-GPU result is bit-exact in fp64.  In fp32 the TMA stencil has two
+instantiations (predicated CTAs that touch a window edge / predicate-free interior CTAs) whose
+FMA contraction differs in the last bit, and a slab has a different set of edge CTAs than the
+whole grid: there the agreement is a few ulp (rel-L2 <= 1e-6).  Against the fp64 oracle the
+BASELINE tolerances apply (rel-L2 <= 1e-5 fp32 / 1e-12 fp64).
 """
 import os
 import socket
@@ -25,6 +28,13 @@ def rel(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def assert_same(got, one, dtype):
+    if np.dtype(dtype) == np.float64:
+        assert np.array_equal(got, one), rel(got, one)
+    else:
+        assert rel(got, one) <= 1e-6, rel(got, one)
 
 
 def state(nl, nx, ny, dtype):
@@ -54,7 +64,7 @@ def test_local_slabs_match_single_gpu_and_oracle(nx, ny, world, steps, dtype):
     got = sl.integrate(q0, 0.0, t1, dt)
     sl.close()
     assert got.shape == one.shape and got.dtype == one.dtype
-    assert np.array_equal(got, one), rel(got, one)
+    assert_same(got, one, dtype)
     ref = oqg.create_baroclinic(nx=nx, ny=ny, **ARGS).integrate(q0.astype(np.float64), 0.0, t1, dt)
     assert rel(got, ref) <= (1e-5 if dtype == np.float32 else 1e-12)
 
@@ -81,7 +91,7 @@ def test_local_slabs_barotropic_and_halo_rows():
     # two calls of 3 steps = the single-GPU model called twice (BC of state0 is re-applied per call)
     mid = gm.integrate(sb.BarotropicQGState(q=q0), 0.0, 3 * 600.0, 600.0).ys.q[0]
     two = gm.integrate(sb.BarotropicQGState(q=mid), 0.0, 3 * 600.0, 600.0).ys.q[0]
-    assert np.array_equal(got, two)
+    assert_same(got, two, np.float32)
     assert rel(one, two) < 1e-3
 
 
@@ -152,4 +162,4 @@ def test_multi_process_slabs_match_single_gpu(dtype):
     got = np.empty_like(one)
     for _, lo, hi, a in parts:
         got[:, lo:hi] = a
-    assert np.array_equal(got, one), rel(got, one)
+    assert_same(got, one, dtype)
