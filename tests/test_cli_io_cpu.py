@@ -1,0 +1,214 @@
+"""CPU: RunSpec, the test-case registry, the save-time grid and the zarr v3 dataset IO.
+
+Ports of the reference's host-side tests for the "next" rows of the hot-path table
+(tests/test_io_xarray.py, tests/test_cli_spec.py, tests/test_cli_run.py:341-381); nothing here
+computes model physics.
+"""
+import json
+from dataclasses import dataclass
+
+import numpy as np
+import pytest
+
+from somax_b200 import io
+from somax_b200.cli import spec as S
+from somax_b200.cli._run import (_build_diagnostic_grid, _build_save_times, _flatten_diagnostics,
+                                 format_field_stats, format_time_seconds, format_wallclock)
+from somax_b200.core import State
+from somax_b200.models.qg import BaroclinicQGState, BarotropicQGState
+from somax_b200.models.swm import MultilayerSW2DState
+
+
+def make_spec(**ts):
+    t = dict(t0=0.0, t1=86400.0, dt=600.0, save_interval=21600.0)
+    t.update(ts)
+    return S.RunSpec(testcase=S.TestCaseSpec("doublegyre_qg", grid={"nx": 64, "ny": 64, "Lx": 1e6, "Ly": 1e6},
+                                             consts={"f0": 1e-4, "beta": 1.6e-11},
+                                             params={"lateral_viscosity": 500.0, "bottom_drag": 1e-7,
+                                                     "wind_amplitude": 1e-12}),
+                     timestepping=S.TimesteppingSpec(**t))
+
+
+# ------------------------------------------------------------------ spec
+def test_spec_validate_and_errors():
+    make_spec().validate()
+    for bad, msg in ((dict(t1=0.0), "must be >"), (dict(dt=0.0), "dt"), (dict(save_interval=0.0), "save_interval"),
+                     (dict(save_interval=1e9), "cannot exceed")):
+        with pytest.raises(ValueError, match=msg):
+            make_spec(**bad).validate()
+    sp = make_spec()
+    sp.testcase.name = ""
+    with pytest.raises(ValueError, match="non-empty"):
+        sp.validate()
+
+
+def test_spec_debug_merge_is_deep_and_consumed():
+    sp = make_spec()
+    assert sp.with_debug_applied() is sp
+    sp.debug = S.DebugSpec(testcase={"grid": {"nx": 32}}, timestepping={"t1": 3600.0})
+    out = sp.with_debug_applied()
+    assert out.testcase.grid == {"nx": 32, "ny": 64, "Lx": 1e6, "Ly": 1e6}
+    assert sp.testcase.grid["nx"] == 64                       # original untouched
+    assert out.timestepping.t1 == 3600.0 and out.timestepping.dt == 600.0
+    assert out.debug == S.DebugSpec()
+    sp.debug = S.DebugSpec(testcase={"nope": {}})
+    with pytest.raises(ValueError, match="does not match"):
+        sp.with_debug_applied()
+    sp.debug = S.DebugSpec(testcase={"grid": 3})
+    with pytest.raises(ValueError, match="both sides"):
+        sp.with_debug_applied()
+
+
+def test_spec_yaml_round_trip(tmp_path):
+    sp = make_spec()
+    sp.assertions = {"cfl": {"max": 0.5}}
+    p = tmp_path / "c.yaml"
+    S.dump_yaml(sp, str(p))
+    back = S.load_yaml(str(p))
+    assert back.to_dict() == sp.to_dict()
+    with pytest.raises(ValueError, match="missing required block"):
+        S.RunSpec.from_dict({"testcase": {"name": "x"}})
+    (tmp_path / "l.yaml").write_text("- 1\n- 2\n")
+    with pytest.raises(ValueError, match="top-level mapping"):
+        S.load_yaml(str(tmp_path / "l.yaml"))
+
+
+def test_registry_names():
+    from somax_b200.cli import get_adapter, list_test_cases
+    assert list_test_cases() == ["baroclinic_instability_swm", "barotropic_jet_instability",
+                                 "doublegyre_baroclinic_qg", "doublegyre_qg"]
+    with pytest.raises(KeyError, match="unknown test case"):
+        get_adapter("nope")
+
+
+# ------------------------------------------------------------------ save grid (tests/test_cli_run.py:341-381)
+def test_save_times_exact_multiple_and_remainder():
+    ts = _build_save_times(make_spec(t1=86400.0, save_interval=21600.0))
+    assert ts.dtype == np.float64 and np.allclose(ts, [0, 21600, 43200, 64800, 86400])
+    ts = _build_save_times(make_spec(t1=100.0, dt=1.0, save_interval=30.0))
+    assert np.allclose(ts, [0, 30, 60, 90, 100])               # last interval shorter, t1 appended
+    assert np.allclose(_build_save_times(make_spec(), only_final=True), [0, 86400.0])
+    ts = _build_save_times(make_spec(t0=10.0, t1=20.0, dt=1.0, save_interval=10.0))
+    assert np.allclose(ts, [10.0, 20.0])
+
+
+def test_diagnostic_grid_subdivides():
+    save = np.asarray([0.0, 10.0, 20.0])
+    g, idx = _build_diagnostic_grid(save, 1)
+    assert g is save and idx == {0, 1, 2}
+    g, idx = _build_diagnostic_grid(save, 4)
+    assert np.allclose(g, np.linspace(0, 20, 9)) and idx == {0, 4, 8}
+    assert np.allclose(g[sorted(idx)], save)
+
+
+def test_formatters():
+    assert format_time_seconds(42) == "42 s"
+    assert format_time_seconds(600) == "600 s (10.00 min)"
+    assert format_time_seconds(86400) == "8.64e+04 s (1.00 day)"
+    assert format_wallclock(0.5) == "500 ms" and format_wallclock(2.0) == "2.00 s"
+    assert format_wallclock(125.0) == "2m5s" and format_wallclock(3725.0) == "1h2m5s"
+    assert format_field_stats("h", min_val=1, mean_val=2, max_val=3, nan_count=0) == "h[m]=[1,2,3]"
+    assert format_field_stats("zz", min_val=1, mean_val=2, max_val=3, nan_count=2) == "zz=[1,2,3] NaN=2"
+
+
+def test_flatten_diagnostics():
+    @dataclass
+    class D:
+        a: object
+        b: object
+        c: object
+        d: object = None
+    flat = _flatten_diagnostics(D(a=np.float32(2.0), b=np.array([1.0, 3.0]), c=np.arange(40.0).reshape(5, 8)))
+    assert flat == {"a": 2.0, "b_layer_0": 1.0, "b_layer_1": 3.0, "c_mean": 19.5, "c_max": 39.0, "c_min": 0.0}
+    assert _flatten_diagnostics(None) == {} and _flatten_diagnostics(3) == {}
+
+
+# ------------------------------------------------------------------ datasets (tests/test_io_xarray.py)
+def test_dims_by_rank_and_time_axis():
+    q = np.arange(3 * 6 * 5, dtype=np.float32).reshape(3, 6, 5)
+    ds = io.state_to_dataset(BaroclinicQGState(q=q))
+    assert ds["q"].dims == ("layer", "y", "x") and "time" not in ds.coords
+    ds = io.state_to_dataset(BarotropicQGState(q=q[0]), time=12.5)
+    assert ds["q"].dims == ("time", "y", "x") and ds["q"].shape == (1, 6, 5)
+    assert ds["time"].values.dtype == np.float64 and ds["time"].values.tolist() == [12.5]
+    assert ds.attrs["state_class"] == "BarotropicQGState" and ds.attrs["state_module"] == "somax_b200.models.qg"
+
+    @dataclass
+    class Odd(State):
+        x: object
+        w: object
+    ds = io.state_to_dataset(Odd(x=np.zeros(4), w=np.zeros((2, 2, 2, 2))))
+    assert ds["x"].dims == ("x",) and ds["w"].dims == ("dim0", "dim1", "dim2", "dim3")
+
+
+def test_snapshots_errors_and_round_trip():
+    h = np.random.default_rng(0).standard_normal((5, 2, 4, 3)).astype(np.float32)
+    snaps = MultilayerSW2DState(h=h, u=h + 1, v=h + 2)
+    with pytest.raises(ValueError, match="leading dim 5 but ts has length 3"):
+        io.snapshots_to_dataset(snaps, np.arange(3.0))
+    with pytest.raises(ValueError, match="ts must be 1-D"):
+        io.snapshots_to_dataset(snaps, np.zeros((5, 1)))
+    ds = io.snapshots_to_dataset(snaps, np.arange(5.0), attrs={"dt": 2.0})
+    assert ds["u"].dims == ("time", "layer", "y", "x") and ds.attrs["dt"] == 2.0
+    last = io.dataset_to_state(ds)                               # default: time_index = -1
+    assert isinstance(last, MultilayerSW2DState) and np.array_equal(last.v, h[-1] + 2)
+    assert np.array_equal(io.dataset_to_state(ds, time_index=1).h, h[1])
+
+
+def test_dataset_to_state_errors():
+    ds = io.state_to_dataset(BarotropicQGState(q=np.zeros((4, 4), np.float32)))
+    only_h = io.Dataset({"h": (("layer", "y", "x"), np.zeros((2, 4, 4), np.float32))})
+    with pytest.raises(ValueError, match="missing variable 'u'"):
+        io.dataset_to_state(only_h, MultilayerSW2DState)
+    ds.attrs.pop("state_class")
+    with pytest.raises(ValueError, match="state_class"):
+        io.dataset_to_state(ds)
+    ds.attrs.update(state_class="Popen", state_module="subprocess")
+    with pytest.raises(ValueError, match="refusing to auto-import"):
+        io.dataset_to_state(ds)
+    # a store written by the reference itself names its own module tree: mapped to this package
+    ds.attrs.update(state_class="BarotropicQGState", state_module="somax._src.models.qg.barotropic")
+    assert isinstance(io.dataset_to_state(ds), BarotropicQGState)
+
+
+def test_zarr_v3_store_layout_round_trip_and_append(tmp_path):
+    rng = np.random.default_rng(1)
+    q = rng.standard_normal((3, 3, 6, 5)).astype(np.float32)
+    ds = io.snapshots_to_dataset(BaroclinicQGState(q=q), np.asarray([0.0, 10.0, 20.0]),
+                                 attrs={"testcase_name": "t", "dt": np.float64(0.5)})
+    store = tmp_path / "snapshots.zarr"
+    io.save_dataset(ds, store, mode="w")
+    root = json.loads((store / "zarr.json").read_text())
+    assert root["zarr_format"] == 3 and root["node_type"] == "group"
+    assert root["attributes"]["state_class"] == "BaroclinicQGState" and root["attributes"]["dt"] == 0.5
+    meta = json.loads((store / "q" / "zarr.json").read_text())
+    assert meta["shape"] == [3, 3, 6, 5] and meta["data_type"] == "float32"
+    assert meta["dimension_names"] == ["time", "layer", "y", "x"]
+    assert meta["chunk_grid"]["configuration"]["chunk_shape"] == [1, 3, 6, 5]
+    assert [c["name"] for c in meta["codecs"]] == ["bytes"]
+    assert (store / "q" / "c" / "2" / "0" / "0" / "0").stat().st_size == 3 * 6 * 5 * 4
+    back = io.load_dataset(store)
+    assert np.array_equal(back["q"].values, q) and back["time"].values.tolist() == [0.0, 10.0, 20.0]
+    assert back.attrs["state_module"] == "somax_b200.models.qg"       # attrs survive the round trip
+    assert np.array_equal(io.dataset_to_state(back).q, q[-1])
+    with pytest.raises(FileExistsError):
+        io.save_dataset(ds, store, mode="w-")
+    more = io.snapshots_to_dataset(BaroclinicQGState(q=q[:2] + 7), np.asarray([30.0, 40.0]))
+    io.append_to_dataset(more, store)
+    back = io.load_dataset(store)
+    assert back["q"].shape == (5, 3, 6, 5) and np.array_equal(back["q"].values[3:], q[:2] + 7)
+    assert back["time"].values.tolist() == [0.0, 10.0, 20.0, 30.0, 40.0]
+    with pytest.raises(ValueError, match="differ"):
+        io.append_to_dataset(io.snapshots_to_dataset(BaroclinicQGState(q=q[:1, :, :3]), np.asarray([50.0])), store)
+    io.save_dataset(io.state_to_dataset(BaroclinicQGState(q=q[0]), time=1.0), store, mode="w")   # overwrite
+    assert io.load_dataset(store)["q"].shape == (1, 3, 6, 5)
+
+
+def test_async_snapshot_writer_host_states(tmp_path):
+    w = io.AsyncSnapshotWriter(tmp_path / "s.zarr", BarotropicQGState, attrs={"k": 1})
+    for t in range(4):
+        w.put(float(t), BarotropicQGState(q=np.full((4, 3), t, np.float64)))
+    w.close()
+    ds = io.load_dataset(tmp_path / "s.zarr")
+    assert ds["q"].shape == (4, 4, 3) and ds["q"].values[3].max() == 3.0 and ds.attrs["k"] == 1
+    assert ds["time"].values.tolist() == [0.0, 1.0, 2.0, 3.0]
