@@ -9,3 +9,4 @@ from .spec import (DebugSpec, OutputSpec, RunSpec, TestCaseSpec, TimesteppingSpe
                    load_yaml)
 from ._factories import TEST_CASES, get_adapter, list_test_cases  # noqa: F401
 from ._run import (IntegrationDivergedError, SimulationResult, restart, simulate, spinup)  # noqa: F401
+from ._assertions import AssertionFailedError  # noqa: F401,E402

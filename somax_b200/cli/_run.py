@@ -26,6 +26,7 @@ from typing import Any
 import numpy as np
 
 from .. import io
+from . import _assertions
 from ._factories import get_adapter
 from .spec import RunSpec, dump_yaml
 
@@ -304,6 +305,7 @@ def _integrate_and_write(spec: RunSpec, output_dir: Path, *, mode: str, initial_
     model, factory_state0 = adapter(grid=spec.testcase.grid, consts=spec.testcase.consts,
                                     stratification=spec.testcase.stratification, params=spec.testcase.params)
     state0 = initial_state if initial_state is not None else factory_state0
+    _assertions.run_preflight(spec, model)      # CFL etc. before any compute is spent
     state0 = _to_device_state(state0, model.dtype)
     only_final = mode == "spinup"
     save_ts = _build_save_times(spec, only_final=only_final)
@@ -349,6 +351,7 @@ def _integrate_and_write(spec: RunSpec, output_dir: Path, *, mode: str, initial_
                 logger.warning("model.diagnose failed: %s", exc)
             metrics.update(wallclock_seconds=wallclock, n_steps=n_steps, t0=ts.t0, t1=ts.t1,
                            save_interval=ts.save_interval, mode=mode)
+        _assertions.run_postflight(spec, metrics)   # before any artifact is moved into place
         snapshots_path = None
         if write_snaps:
             snapshots_path = output_dir / "snapshots.zarr"

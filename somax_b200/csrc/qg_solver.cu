@@ -539,6 +539,7 @@ __device__ unsigned long long g_dbg[4096 * 4];
 __device__ unsigned g_dbg_n;
 #endif
 constexpr int TH_RT = 16;   // rows per register block of the recurrence
+
 // Launch classes of a sweep.  LOWK (TAB = true): the few strips of near-singular low x-wavenumbers
 // (and late-converging coefficient recurrences): fp64 carried recurrence for both pipelines,
 // coefficient tiles staged through shared memory, big staged tiles because only a handful of

@@ -212,3 +212,51 @@ def test_async_snapshot_writer_host_states(tmp_path):
     ds = io.load_dataset(tmp_path / "s.zarr")
     assert ds["q"].shape == (4, 4, 3) and ds["q"].values[3].max() == 3.0 and ds.attrs["k"] == 1
     assert ds["time"].values.tolist() == [0.0, 1.0, 2.0, 3.0]
+
+
+# ------------------------------------------------------------------ assertions + CLI (host only)
+def test_assertions_cfl_and_bounded_metric():
+    from types import SimpleNamespace
+    from somax_b200.cli._assertions import (AssertionFailedError, check_bounded_metric, check_cfl, run_postflight,
+                                            run_preflight)
+    sp = make_spec()                                              # dt = 600
+    model = SimpleNamespace(grid=SimpleNamespace(dx=15625.0, dy=15625.0))
+    check_cfl(sp, model, wave_speed_m_per_s=1.0)
+    with pytest.raises(AssertionFailedError, match="CFL = 8.506 > max_cfl = 0.5"):
+        check_cfl(sp, model, wave_speed_m_per_s=221.5)
+    with pytest.raises(AssertionFailedError, match="no .grid"):
+        check_cfl(sp, SimpleNamespace(), wave_speed_m_per_s=1.0)
+    check_bounded_metric(sp, {"e": 2.0}, name="e", min=1.0, max=3.0)
+    for metrics, kw, msg in (({}, {}, "not present"), ({"e": float("nan")}, {}, "non-finite"),
+                             ({"e": 0.5}, {"min": 1.0}, "below min"), ({"e": 5.0}, {"max": 3.0}, "above max"),
+                             ({"e": "x"}, {}, "not a numeric")):
+        with pytest.raises(AssertionFailedError, match=msg):
+            check_bounded_metric(sp, metrics, name="e", **kw)
+    sp.assertions = {"cfl": {"wave_speed_m_per_s": 1.0}, "bounded_metric": {"name": "e", "max": 1.0}}
+    run_preflight(sp, model)                                      # postflight names are skipped
+    with pytest.raises(AssertionFailedError, match="above max"):
+        run_postflight(sp, {"e": 2.0})
+    sp.assertions = {"typo": {}}
+    with pytest.raises(AssertionFailedError, match="unknown assertion 'typo'"):
+        run_preflight(sp, model)
+
+
+def test_cli_discovery_and_shipped_configs(capsys):
+    import glob
+    import os
+    from somax_b200.cli import app
+    assert app.main(["list-testcases"]) == 0
+    assert "  - doublegyre_baroclinic_qg" in capsys.readouterr().out
+    assert app.main(["list-models"]) == 0
+    out = capsys.readouterr().out
+    assert "  - BaroclinicQG" in out and "  - MultilayerShallowWater2D" in out
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfgs = sorted(glob.glob(os.path.join(root, "configs", "*.yaml")))
+    assert len(cfgs) >= 3
+    for c in cfgs:
+        sp = S.load_yaml(c)
+        dbg = sp.with_debug_applied()
+        dbg.validate()
+        assert dbg.testcase.grid["nx"] < sp.testcase.grid["nx"]
+        assert app.main(["show-config", c]) == 0
+    assert "# Resolved RunSpec from" in capsys.readouterr().out

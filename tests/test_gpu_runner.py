@@ -100,3 +100,28 @@ def test_swm_finite_run_and_divergence_guard(tmp_path):
     assert not (out / "metrics.json").exists()
     log = (out / "run.log").read_text()
     assert "ABORT at chunk" in log and "FAILED during integrate: IntegrationDivergedError" in log
+
+
+def test_cli_run_debug_config_and_assertions(tmp_path):
+    """`somax-sim run --config configs/swm_jet.yaml --debug` end to end; a violated CFL assertion
+    stops the run before any stepping."""
+    import os
+    from somax_b200 import io
+    from somax_b200.cli import AssertionFailedError, app, load_yaml, simulate
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = os.path.join(root, "configs", "swm_jet.yaml")
+    assert app.main(["run", "--config", cfg, "--output-dir", str(tmp_path / "o"), "--debug",
+                     "--diagnostics-per-save", "2"]) == 0
+    snaps = io.load_dataset(tmp_path / "o" / "snapshots.zarr")
+    assert snaps["h"].shape == (3, 2, 34, 34) and snaps["time"].values.tolist() == [0.0, 1800.0, 3600.0]
+    assert np.isfinite(snaps["u"].values).all()
+    spec = load_yaml(cfg).with_debug_applied()
+    spec.timestepping.dt = 300.0                                  # gravity-wave CFL ~ 2
+    with pytest.raises(AssertionFailedError, match="cfl check FAILED"):
+        simulate(spec, tmp_path / "cfl")
+    assert not (tmp_path / "cfl" / "run.log").exists()
+    spec = load_yaml(cfg).with_debug_applied()
+    spec.assertions = {"bounded_metric": {"name": "total_energy", "max": 1.0}}
+    with pytest.raises(AssertionFailedError, match="above max"):
+        simulate(spec, tmp_path / "post")
+    assert not (tmp_path / "post" / "final_state.zarr").exists()
