@@ -227,6 +227,7 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    quiet_stdout()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kind, nl, nx, ny, members = WORKLOADS[args.workload]
@@ -380,7 +381,7 @@ def run_gpu(args):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -400,6 +401,7 @@ def run_gpu_slab(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    quiet_stdout()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kind, nl, nx, ny, members = WORKLOADS[args.workload]
@@ -504,10 +506,31 @@ def run_gpu_slab(args):
                                       "share": round(r["total_ms"] / total_prof, 4)} for r in prof]},
             "cpu_baseline": None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     slab_model.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr while libraries initialise (NCCL prints its version banner on stdout);
+    `emit` writes the one JSON line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
 
 
 def main():
