@@ -10,7 +10,10 @@
 //   X1         transpose: strips of R -> the owning rank's column array S  (peer stores, NVLink)
 //   cols(1)    first Thomas solve in y on the rank's x-wavenumber strips
 //   X2         border row-sum partials -> every rank                       (peer stores)
-//   border     fixed-order reduction + Schur solve, replicated (bitwise the single-GPU result)
+//   border     fixed-order reduction of all partials (replicated, cheap), then the Schur solve
+//              (two dense fp64 DSTs in y) with the OUTPUT rows split over the ranks: slices of
+//              ghat, then of gvec / the border column, are pushed to the peers (XG1, XG2);
+//              bitwise the single-GPU result
 //   cols(2)    second Thomas solve on the rank's strips
 //   X3         transpose back: row blocks of S -> the owning rank's R      (peer stores)
 //   rows_inv   inverse transform + mode->layer mix -> psi slab
@@ -20,7 +23,7 @@
 //
 // All exchanges are device kernels storing straight into the peer's memory (CUDA IPC mappings
 // over NVLink / NVSwitch); ordering between ranks is a flag barrier in peer memory (one small
-// kernel, release/acquire at system scope), four per evaluation.  There is no host
+// kernel, release/acquire at system scope), six per evaluation.  There is no host
 // synchronisation and no staging buffer.  With every slab in one process (nlocal == nranks, used
 // to validate the decomposition on one device) the same kernels run on one stream and the
 // barriers are not needed.
@@ -31,7 +34,7 @@
 namespace sb {
 
 constexpr int QGS_MAX_RANKS = 16;
-constexpr int QGS_NBUF = 6;    // exported buffers: cols.S, cols.part, R, psi, inbox, flags
+constexpr int QGS_NBUF = 9;    // exported buffers: cols.S, cols.part, R, psi, inbox, flags, ghat, gvec, gvecf
 
 struct Seg {
   const char* src; char* dst;
@@ -88,7 +91,7 @@ struct SlabRank {
   int rank = 0, s0 = 0, s1 = 0;
   void* inbox = nullptr;            // [2][planes][pitch]: halo rows of the newest stage state from below / above
   unsigned* flags = nullptr;        // [QGS_MAX_RANKS] barrier slots + [QGS_MAX_RANKS] error word
-  SegTable x1, xb, x2, x3, xpsi, xstate[3], xin[3];
+  SegTable x1, xb, x2, x3, xpsi, xstate[3], xin[3], xg1, xg2, xg2f;
 };
 
 struct SlabPeer { void* buf[QGS_NBUF]; };
@@ -154,8 +157,9 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
   char* Sl = (char*)vc.S;
   const size_t blk = (size_t)nyl * SP_W * es;          // one strip of the slab's rows
   const size_t col = (size_t)ny * SP_W * es;           // one strip of the whole grid
-  std::vector<Seg> x1, xb, x2, x3, xpsi;
+  std::vector<Seg> x1, xb, x2, x3, xpsi, xg1, xg2, xg2f;
   const int last_owner = (nstrip - 1) / spr;
+  const int a0 = p * nyl;                                // my slice of the border-system outputs
   for (int r = 0; r < P; ++r) {
     char* Sr = (char*)g->peers[r].buf[0];
     char* partr = (char*)g->peers[r].buf[1];
@@ -174,6 +178,21 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
       if (r != p) {
         const size_t o = ((size_t)pl * 2 * nstrip + 2 * (size_t)R.s0) * ny * es;
         x2.push_back(Seg{(char*)vc.part + o, partr + o, 1u, (unsigned)(2 * (size_t)spr * ny * es), 0, 0});
+      }
+      // XG1 / XG2: my slice of ghat, then of gvec (+ float copy, + border column of S for the
+      // rank that owns the last strip) -> every other rank
+      if (r != p) {
+        const size_t go = ((size_t)pl * ny + a0) * sizeof(double);
+        xg1.push_back(Seg{(const char*)vc.ghat + go, (char*)g->peers[r].buf[6] + go, 1u, (unsigned)(nyl * sizeof(double)), 0, 0});
+        xg2.push_back(Seg{(const char*)vc.gvec + go, (char*)g->peers[r].buf[7] + go, 1u, (unsigned)(nyl * sizeof(double)), 0, 0});
+        if (es == 4) {
+          const size_t fo = ((size_t)pl * ny + a0) * sizeof(float);
+          xg2f.push_back(Seg{(const char*)vc.gvecf + fo, (char*)g->peers[r].buf[8] + fo, 1u, (unsigned)(nyl * sizeof(float)), 0, 0});
+        }
+        if (r == last_owner) {
+          const size_t so = ((size_t)pl * ny * np + sp_off(ny, a0, vc.nx - 1)) * es;
+          xg2f.push_back(Seg{Sl + so, Sr + so, (unsigned)nyl, (unsigned)es, SP_W * es, SP_W * es});
+        }
       }
       // X3: rank r's rows of my strips -> its row array
       x3.push_back(Seg{Sl + ((size_t)pl * nstrip + (size_t)R.s0) * col + (size_t)r * nyl * SP_W * es,
@@ -203,6 +222,9 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
   if (int rc = seg_upload(R.x2, x2, &g->bytes)) return rc;
   if (int rc = seg_upload(R.x3, x3, &g->bytes)) return rc;
   if (int rc = seg_upload(R.xpsi, xpsi, &g->bytes)) return rc;
+  if (int rc = seg_upload(R.xg1, xg1, &g->bytes)) return rc;
+  if (int rc = seg_upload(R.xg2, xg2, &g->bytes)) return rc;
+  if (int rc = seg_upload(R.xg2f, xg2f, &g->bytes)) return rc;
   for (int b = 0; b < 3; ++b) {
     std::vector<Seg> xs, xi;
     halo((const char*)st[b], 4, true, xs);
@@ -220,6 +242,7 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
 void qgs_local_ptrs(const SlabRank& R, void** out) {
   const QgSolverView vr = qg_solver_view(R.core->solver), vc = qg_solver_view(R.cols);
   out[0] = vc.S; out[1] = vc.part; out[2] = vr.S; out[3] = R.core->psi; out[4] = R.inbox; out[5] = R.flags;
+  out[6] = vc.ghat; out[7] = vc.gvec; out[8] = vc.gvecf ? (void*)vc.gvecf : (void*)vc.gvec;
 }
 
 int qgs_barrier(somax_b200_qgs_s* g, cudaStream_t s) {
@@ -259,10 +282,23 @@ int qgs_eval(somax_b200_qgs_s* g, const somax_b200_params* p, int in_b, int y_b,
   for (SlabRank& R : g->local)
     if (int rc = seg_launch("slab_x2_partials", R.x2, s)) return rc;
   if (int rc = qgs_barrier(g, s)) return rc;
+  const int nyl = g->ny_loc;
   for (SlabRank& R : g->local) {
-    if (int rc = qg_solver_border<T>(R.cols, s)) return rc;
-    if (int rc = qg_solver_cols<T>(R.cols, 2, R.s0, R.s1, s)) return rc;
+    if (int rc = qg_solver_border_stage<T>(R.cols, 0, 0, -1, s)) return rc;
+    if (int rc = qg_solver_border_stage<T>(R.cols, 1, R.rank * nyl, (R.rank + 1) * nyl, s)) return rc;
   }
+  for (SlabRank& R : g->local)
+    if (int rc = seg_launch("slab_xg_border", R.xg1, s)) return rc;
+  if (int rc = qgs_barrier(g, s)) return rc;
+  for (SlabRank& R : g->local)
+    if (int rc = qg_solver_border_stage<T>(R.cols, 2, R.rank * nyl, (R.rank + 1) * nyl, s)) return rc;
+  for (SlabRank& R : g->local) {
+    if (int rc = seg_launch("slab_xg_border", R.xg2, s)) return rc;
+    if (int rc = seg_launch("slab_xg_border", R.xg2f, s)) return rc;
+  }
+  if (int rc = qgs_barrier(g, s)) return rc;
+  for (SlabRank& R : g->local)
+    if (int rc = qg_solver_cols<T>(R.cols, 2, R.s0, R.s1, s)) return rc;
   for (SlabRank& R : g->local)
     if (int rc = seg_launch("slab_x3_transpose", R.x3, s)) return rc;
   if (int rc = qgs_barrier(g, s)) return rc;
@@ -414,7 +450,7 @@ int somax_b200_qgs_destroy(somax_b200_qgs_t g) {
   for (void* p : g->ipc_opened) cudaIpcCloseMemHandle(p);
   for (SlabRank& R : g->local) {
     SegTable* ts[] = {&R.x1, &R.xb, &R.x2, &R.x3, &R.xpsi, &R.xstate[0], &R.xstate[1], &R.xstate[2],
-                      &R.xin[0], &R.xin[1], &R.xin[2]};
+                      &R.xin[0], &R.xin[1], &R.xin[2], &R.xg1, &R.xg2, &R.xg2f};
     for (SegTable* t : ts) cudaFree(t->dev);
     cudaFree(R.inbox); cudaFree(R.flags);
     qg_solver_destroy(R.cols);

@@ -920,11 +920,11 @@ __global__ void __launch_bounds__(32 * GS_ROWS)
 border_gsolve(const double* __restrict__ in, const double* __restrict__ sintab,
               const double* __restrict__ sdiag, int ny, int np, int n, int nl,
               double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
-              T* __restrict__ S) {
+              T* __restrict__ S, int a_first, int a_count) {
   // one warp per output index a; sintab holds sin(pi k / N) for k < 2N followed by cos(pi k / N)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a = blockIdx.x * GS_ROWS + warp + 1, plane = blockIdx.y, m = plane % nl;
-  if (a > ny) return;
+  const int a = a_first + blockIdx.x * GS_ROWS + warp + 1, plane = blockIdx.y, m = plane % nl;
+  if (a > a_first + a_count) return;
   const unsigned N = ny + 1, N2 = 2 * N;
   const double* costab = sintab + N2;
   const unsigned t0 = lane + 1;
@@ -965,9 +965,9 @@ __global__ void __launch_bounds__(128)
 border_gsolve_small(const double* __restrict__ in, const double* __restrict__ sintab,
                     const double* __restrict__ sdiag, int ny, int np, int n, int nl,
                     double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
-                    T* __restrict__ S) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x + 1, plane = blockIdx.y, m = plane % nl;
-  if (a > ny) return;
+                    T* __restrict__ S, int a_first, int a_count) {
+  const int a = a_first + blockIdx.x * blockDim.x + threadIdx.x + 1, plane = blockIdx.y, m = plane % nl;
+  if (a > a_first + a_count) return;
   const unsigned N = ny + 1, N2 = 2 * N;
   const double* costab = sintab + N2;
   const double ds = sintab[a], dc = costab[a];        // a < N2
@@ -1405,26 +1405,44 @@ int qg_solver_cols(QgSolver* s, int phase, int sa, int sb, cudaStream_t st) {
   return launch_solve<T, 2>(s, tb, (T*)s->S, (T*)s->W, st, sa, sb);
 }
 
+// stage 0: reduction of the border partials (rvec); stage 1: DST + Schur diagonal (ghat) for the
+// outputs [a0, a1); stage 2: second DST (gvec, gvecf, border column of S) for the outputs [a0, a1).
+// The slab-distributed model gives every rank a slice of the outputs and exchanges the slices.
 template <typename T>
-int qg_solver_border(QgSolver* s, cudaStream_t st) {
+int qg_solver_border_stage(QgSolver* s, int stage, int a0, int a1, cudaStream_t st) {
   const int ny = s->ny, n = s->nx, np = s->np, nl = s->nl;
   T* S = (T*)s->S;
-  const double b = 1.0 / (s->dx * s->dx);
-  prof_begin("border_reduce", st);
-  border_reduce<T><<<dim3((ny + 255) / 256, s->planes), 256, 0, st>>>(S, (const T*)s->part, ny, np, s->ncols, 2 * (np / SP_W), b, s->rvec);
+  if (a1 < 0) a1 = ny;
+  const int cnt = a1 - a0;
+  if (stage == 0) {
+    const double b = 1.0 / (s->dx * s->dx);
+    prof_begin("border_reduce", st);
+    border_reduce<T><<<dim3((ny + 255) / 256, s->planes), 256, 0, st>>>(S, (const T*)s->part, ny, np, s->ncols, 2 * (np / SP_W), b, s->rvec);
+    SB_LAUNCH_CHECK();
+    return 0;
+  }
+  if (cnt <= 0) return 0;
+  if (stage == 1) {
+    prof_begin("border_gsolve_a", st);
+    if (ny <= GS_SMALL_NY)
+      border_gsolve_small<T, true><<<dim3((cnt + 127) / 128, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, a0, cnt);
+    else
+      border_gsolve<T, true><<<dim3((cnt + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, a0, cnt);
+  } else {
+    prof_begin("border_gsolve_b", st);
+    if (ny <= GS_SMALL_NY)
+      border_gsolve_small<T, false><<<dim3((cnt + 127) / 128, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, a0, cnt);
+    else
+      border_gsolve<T, false><<<dim3((cnt + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, a0, cnt);
+  }
   SB_LAUNCH_CHECK();
-  prof_begin("border_gsolve_a", st);
-  if (ny <= GS_SMALL_NY)
-    border_gsolve_small<T, true><<<dim3((ny + 127) / 128, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
-  else
-    border_gsolve<T, true><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr);
-  SB_LAUNCH_CHECK();
-  prof_begin("border_gsolve_b", st);
-  if (ny <= GS_SMALL_NY)
-    border_gsolve_small<T, false><<<dim3((ny + 127) / 128, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
-  else
-    border_gsolve<T, false><<<dim3((ny + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S);
-  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int qg_solver_border(QgSolver* s, cudaStream_t st) {
+  for (int stage = 0; stage < 3; ++stage)
+    if (int rc = qg_solver_border_stage<T>(s, stage, 0, -1, st)) return rc;
   return 0;
 }
 
@@ -1459,7 +1477,7 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
 
 QgSolverView qg_solver_view(const QgSolver* s) {
   QgSolverView v;
-  v.S = s->S; v.part = s->part; v.ny = s->ny; v.nx = s->nx; v.np = s->np; v.planes = s->planes;
+  v.S = s->S; v.part = s->part; v.ghat = s->ghat; v.gvec = s->gvec; v.gvecf = s->gvecf; v.ny = s->ny; v.nx = s->nx; v.np = s->np; v.planes = s->planes;
   v.nstrip = s->np / SP_W; v.ncols = s->ncols; v.kind = s->kind; v.nheavy = s->nheavy;
   return v;
 }
@@ -1481,7 +1499,8 @@ template int qg_solver_run<double>(QgSolver*, const double*, double*, cudaStream
   template int qg_solver_rows_fwd<T>(QgSolver*, const T*, cudaStream_t);   \
   template int qg_solver_rows_inv<T>(QgSolver*, T*, cudaStream_t);         \
   template int qg_solver_cols<T>(QgSolver*, int, int, int, cudaStream_t);  \
-  template int qg_solver_border<T>(QgSolver*, cudaStream_t);
+  template int qg_solver_border<T>(QgSolver*, cudaStream_t);                \
+  template int qg_solver_border_stage<T>(QgSolver*, int, int, int, cudaStream_t);
 SB_INST_STAGES(float)
 SB_INST_STAGES(double)
 

@@ -37,11 +37,15 @@ template <typename T> int qg_solver_rows_fwd(QgSolver* s, const T* q, cudaStream
 template <typename T> int qg_solver_rows_inv(QgSolver* s, T* psi, cudaStream_t stream);
 template <typename T> int qg_solver_cols(QgSolver* s, int phase, int sa, int sb, cudaStream_t stream);
 template <typename T> int qg_solver_border(QgSolver* s, cudaStream_t stream);
+// border in three stages (0 reduce; 1 first DST -> ghat[a0, a1); 2 second DST -> gvec / gvecf /
+// border column of S for rows [a0, a1)); a1 < 0 = all rows
+template <typename T> int qg_solver_border_stage(QgSolver* s, int stage, int a0, int a1, cudaStream_t stream);
 
 // Raw view of the spectral storage: S is [plane][strip][ny][64] (strip = 64 x-wavenumbers),
 // part is [plane][2 * nstrip][ny]; ncols is the x index of the border column.
 struct QgSolverView {
   void* S; void* part;
+  double* ghat; double* gvec; float* gvecf;   // border system: [plane][ny]
   int ny, nx, np, planes, nstrip, ncols, kind, nheavy;
 };
 QgSolverView qg_solver_view(const QgSolver* s);
