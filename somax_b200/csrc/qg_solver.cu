@@ -534,7 +534,7 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-#ifdef SB_TH_DEBUG
+#if defined(SB_TH_DEBUG) || defined(SB_TH_PHASES)
 __device__ unsigned long long g_dbg[4096 * 4];
 __device__ unsigned g_dbg_n;
 #endif
@@ -659,8 +659,18 @@ __device__ __forceinline__ void thomas_tile(T (*A)[TH_COLS], const T (*Vt)[TH_CO
 // shared-memory ring: ONE cp.async.bulk per tile (TMA engine, completes on an mbarrier), the
 // recurrence runs on shared memory only (register blocks of TH_RT rows), and the finished tile
 // leaves with one bulk store.
+// Threads 0..63 own one column each (two warps); a third warp's lane 0 is the PRODUCER: it
+// issues every bulk load / store and waits for the stores' shared-memory reads, so those waits are
+// off the recurrence warps' critical path (a sweep CTA is a serial chain over ny/2 rows: with the
+// issue work in warp 0, a rank of the slab-distributed model that owns a few strips - one CTA per
+// SM - spent most of each tile period in it).
+#ifndef SB_TH_PRODUCER
+#define SB_TH_PRODUCER 1
+#endif
+constexpr int TH_THREADS = TH_COLS + (SB_TH_PRODUCER ? 32 : 0);
+constexpr int TH_ISSUER = SB_TH_PRODUCER ? TH_COLS : 0;      // thread that issues the bulk copies
 template <typename T, bool SUBST, bool FROM_VEC, int KIND, bool TAB>
-__global__ void __launch_bounds__(TH_COLS)
+__global__ void __launch_bounds__(TH_THREADS)
 thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* __restrict__ V,
              const double* __restrict__ gvec, const float* __restrict__ gvecf,
              const double* __restrict__ bsig, T* __restrict__ out) {
@@ -684,12 +694,14 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   double* tileD1 = tileD + (COMBINE ? NS * SIDE_B / sizeof(double) : 0);      // side tiles of E (KIND 2)
   unsigned long long* full = reinterpret_cast<unsigned long long*>(
       th_smem + NS * CT_B + NS * TILE_B * (COMBINE ? 2 : 1) + NS * SIDE_B * (COMBINE ? 2 : 1));
-  const int tid = threadIdx.x;
+  const bool worker = threadIdx.x < TH_COLS;            // owns a column (the producer warp does not)
+  const bool issuer = threadIdx.x == TH_ISSUER;
+  const int tid = worker ? threadIdx.x : 0;             // column of the thread inside the strip
   const int strip = strip_first + blockIdx.x;
   const int c = strip * TH_COLS + tid;
   const int plane = blockIdx.y, m = plane % tb.nl;
   const int half = blockIdx.z;
-  const bool act = c < tb.ncols;
+  const bool act = worker && c < tb.ncols;
   const int ny = tb.ny;
   const size_t strip0 = (size_t)plane * ny * tb.np + (size_t)strip * ny * SP_W;   // strip base
   const double cfix = tb.cinf[(size_t)m * tb.np + c];
@@ -730,7 +742,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     return SUBST ? cnt - 1 - (s0 + nr - 1) : s0;
   };
 
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -758,7 +770,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   auto tile_has_load = [&](int t) {
     return LOAD || (TAB && tile_ilo(t) < Js) || (TAB && SUBST && strip_bad);
   };
-  if (tid == 0)
+  if (issuer)
     for (int t = 0; t < NS - 1; ++t) load_tile(t);
 
   double carry = 0.0;
@@ -777,7 +789,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     carry_f = (float)carry;
   }
   if (FROM_VEC && ntile > 0) {
-    if (tid < tile_nr(0)) gbuf[0][tid] = gsrc[tile_jlo(0) + tid];
+    if (worker && tid < tile_nr(0)) gbuf[0][tid] = gsrc[tile_jlo(0) + tid];
     __syncthreads();
   }
   T wdot[KIND == 1 ? 16 : 1];
@@ -787,6 +799,10 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
       wdot[i] = reinterpret_cast<const T*>(tb.sig2n)[strip * TH_COLS + (tid >> 4) * 16 + ((i + (tid & 15)) & 15)];
   }
   unsigned phase_bits = 0;            // per-stage phase parity (stages may be skipped by FROM_VEC tiles)
+#ifdef SB_TH_PHASES
+  long long ph_wait = 0, ph_comp = 0, ph_sync = 0;
+  const long long ph_begin = clock64();
+#endif
 #ifdef SB_TH_DEBUG
   unsigned long long tg0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tg0));
 #endif
@@ -796,14 +812,21 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     const int nrt = tile_nr(t);
     const int ilot = tile_ilo(t);
     GT gnext = 0;
-    if (FROM_VEC && t + 1 < ntile && tid < tile_nr(t + 1)) gnext = gsrc[tile_jlo(t + 1) + tid];
+    if (FROM_VEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) gnext = gsrc[tile_jlo(t + 1) + tid];
     const GT* gvt = gbuf[t & 1] - tile_jlo(t);      // indexed by the memory row
-    if (tile_has_load(t)) {
+#ifdef SB_TH_PHASES
+    long long ph0 = clock64();
+#endif
+    if (worker && tile_has_load(t)) {
       mbar_wait(&full[st], (phase_bits >> st) & 1u);
       phase_bits ^= 1u << st;
     }
+#ifdef SB_TH_PHASES
+    long long ph1 = clock64();
+    ph_wait += ph1 - ph0;
+#endif
 #pragma unroll 1
-    for (int b0 = 0; b0 < nrt; b0 += TH_RT) {       // register blocks, in sequence order
+    for (int b0 = 0; worker && b0 < nrt; b0 += TH_RT) {       // register blocks, in sequence order
       const int nr = min(TH_RT, nrt - b0);
       const int s0 = t * RT + b0;
       const int ilo = SUBST ? cnt - 1 - (s0 + nr - 1) : s0;
@@ -843,13 +866,17 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
 #undef SB_TILE
       }
     }
-    if (FROM_VEC && t + 1 < ntile && tid < tile_nr(t + 1)) gbuf[(t + 1) & 1][tid] = gnext;
-    if (!SUBST && t == ntile - 1)
+#ifdef SB_TH_PHASES
+    long long ph2 = clock64();
+    ph_comp += ph2 - ph1;
+#endif
+    if (FROM_VEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) gbuf[(t + 1) & 1][tid] = gnext;
+    if (worker && !SUBST && t == ntile - 1)
       meetW[((size_t)plane * 2 + half) * tb.np + c] = PLAIN ? (double)carry_f : carry;
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
     fence_async_smem();
     __syncthreads();
-    if (KIND == 1) {
+    if (KIND == 1 && worker) {
       // border sums of the finished tile: thread (rr, qd) adds 16 columns of row rr with a rotated
       // column order (conflict-free), the two quarters of a warp combine by shuffle
       const int rr = tid & 15, qd = tid >> 4;
@@ -867,7 +894,10 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
         if ((tid & 16) == 0 && row < nrt) part[row] = acc;
       }
     }
-    if (tid == 0) {
+#ifdef SB_TH_PHASES
+    ph_sync += clock64() - ph2;
+#endif
+    if (issuer) {
       if (KIND != 1)
         bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &tileA[st][0][0], (unsigned)(nrt * TH_COLS * sizeof(T)));
       if (TAB && !SUBST && strip_bad)
@@ -879,9 +909,19 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
       load_tile(t + NS - 1);
     }
   }
-  if (tid == 0) bulk_wait_read<0>();
+  if (issuer) bulk_wait_read<0>();
+#ifdef SB_TH_PHASES
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    const unsigned slot = atomicAdd(&g_dbg_n, 1u);
+    if (slot < 4096) {
+      g_dbg[slot * 4 + 0] = ((SUBST ? 1000 : 0) + (FROM_VEC ? 100 : 0) + KIND * 10 + (TAB ? 1 : 0)) * 10 + half +
+                            ((unsigned long long)(clock64() - ph_begin) << 32);
+      g_dbg[slot * 4 + 1] = ph_wait; g_dbg[slot * 4 + 2] = ph_comp; g_dbg[slot * 4 + 3] = ph_sync;
+    }
+  }
+#endif
 #ifdef SB_TH_DEBUG
-  if (tid == 0 && (TAB || (blockIdx.x % 41 == 0)) && plane < tb.nl) {
+  if (threadIdx.x == 0 && (TAB || (blockIdx.x % 41 == 0)) && plane < tb.nl) {
     unsigned long long tg1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tg1));
     const unsigned slot = atomicAdd(&g_dbg_n, 1u);
     if (slot < 4096) {
@@ -1310,7 +1350,7 @@ static int launch_thomas_one(const char* tag, const ThomasTab& tb, int strip_fir
     attr_done = smem;
   }
   prof_begin(tag, st);
-  thomas_sweep<T, SUBST, FROM_VEC, KIND, TAB><<<dim3(nstrips, planes, 2), TH_COLS, smem, st>>>(
+  thomas_sweep<T, SUBST, FROM_VEC, KIND, TAB><<<dim3(nstrips, planes, 2), TH_THREADS, smem, st>>>(
       tb, strip_first, in, V, gvec, gvecf, bsig, out);
   SB_LAUNCH_CHECK();
   return 0;
@@ -1482,7 +1522,7 @@ QgSolverView qg_solver_view(const QgSolver* s) {
   return v;
 }
 
-#ifdef SB_TH_DEBUG
+#if defined(SB_TH_DEBUG) || defined(SB_TH_PHASES)
 extern "C" int somax_b200_debug_dump(unsigned long long* out, unsigned* n) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(n, g_dbg_n, sizeof(unsigned));
