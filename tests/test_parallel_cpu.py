@@ -52,3 +52,68 @@ def test_gloo_world_size_2():
     for rank, t, g in res:
         assert t == 15.0
         assert g == [[float(m), float(m) ** 2] for m in range(5)]
+
+
+def test_slab_geometry_helpers():
+    """Windows / owned rows of the y-slab decomposition (host logic of parallel.SlabQG)."""
+    import numpy as np
+    from somax_b200.parallel import merge_slabs, slab_owned, slab_rows, slab_window, split_slabs
+    ny = 24
+    for world in (1, 2, 3, 4, 8):
+        rows = [slab_rows(ny, r, world) for r in range(world)]
+        assert [j for r in rows for j in r] == list(range(ny))
+        owned = [slab_owned(ny, r, world) for r in range(world)]
+        assert owned[0].start == 0 and owned[-1].stop == ny + 2           # ring rows belong to the edge ranks
+        assert all(a.stop == b.start for a, b in zip(owned, owned[1:]))    # a partition of the Ny rows
+        for r in range(world):
+            w = slab_window(ny, r, world)
+            assert w.stop - w.start == ny // world + 2
+            assert w.start <= owned[r].start and owned[r].stop <= w.stop
+        q = np.random.default_rng(world).standard_normal((3, ny + 2, 7))
+        slabs = [s.copy() for s in split_slabs(q, world)]
+        for r in range(world - 1):                                         # neighbours share two rows
+            assert np.array_equal(slabs[r][:, -2:], slabs[r + 1][:, :2])
+        # halo rows are not authoritative: garbage there must not reach the merged array
+        for r, s in enumerate(slabs):
+            if r > 0:
+                s[:, 0] = np.nan
+            if r < world - 1:
+                s[:, -1] = np.nan
+        assert np.array_equal(merge_slabs(slabs), q)
+    with pytest.raises(ValueError):
+        slab_rows(25, 0, 2)
+    with pytest.raises(ValueError):
+        slab_rows(24, 2, 2)
+
+
+def _blob_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the set-up exchange of SlabQG._attach: every rank contributes an opaque byte blob, all ranks
+    # end up with the blobs in rank order
+    nb = 216
+    mine = torch.full((nb,), rank + 1, dtype=torch.uint8)
+    parts = [torch.empty(nb, dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    q.put((rank, bytes(torch.cat(parts).numpy().tobytes())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_blob_all_gather_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_blob_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = bytes([1] * 216 + [2] * 216)
+    assert all(blob == want for _, blob in res)
