@@ -99,7 +99,7 @@ struct SlabPeer { void* buf[QGS_NBUF]; };
 }  // namespace sb
 
 struct somax_b200_qgs_s {
-  int dtype = 0, nl = 0, ny = 0, nx = 0, nranks = 0, rank_first = 0, nlocal = 0, ny_loc = 0, spr = 0;
+  int dtype = 0, nl = 0, ny = 0, nx = 0, nranks = 0, rank_first = 0, nlocal = 0, ny_loc = 0, spr = 0, nseg = 1;
   double dx = 0, dy = 0;
   std::vector<sb::SlabRank> local;
   sb::SlabPeer peers[sb::QGS_MAX_RANKS];
@@ -410,6 +410,10 @@ int somax_b200_qgs_create(somax_b200_qgs_t* out, int dtype, int nl, int ny, int 
   g->dtype = dtype; g->nl = nl; g->ny = ny; g->nx = nx; g->dx = dx; g->dy = dy;
   g->nranks = nranks; g->rank_first = rank_first; g->nlocal = nlocal;
   g->ny_loc = ny / nranks; g->spr = (nx / 64) / nranks;
+  // y-sweeps: with few strips per rank a sweep CTA is a bare serial chain over ny/2 rows, so the
+  // chains are cut into segments (two-pass, see ThomasTab) once the strips no longer fill the GPU
+  g->nseg = nranks >= 4 ? std::min(nranks, 8) : 1;
+  if (const char* e = getenv("SOMAX_B200_SLAB_NSEG")) g->nseg = std::max(1, std::min(atoi(e), 16));
   const int Nx = nx + 2, nyl = g->ny_loc;
   const size_t es = qgs_es(g);
   int rc = 0;
@@ -422,7 +426,7 @@ int somax_b200_qgs_create(somax_b200_qgs_t* out, int dtype, int nl, int ny, int 
                               beta_y + row0 * Nx, wind + row0 * Nx, SOMAX_B200_SOLVER_FFT, spec_flags);
     if (rc) break;
     R.core->bc_ylo = R.rank == 0; R.core->bc_yhi = R.rank == nranks - 1;
-    rc = qg_solver_create(&R.cols, dtype, 1, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, SOMAX_B200_SOLVER_FFT);
+    rc = qg_solver_create(&R.cols, dtype, 1, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, SOMAX_B200_SOLVER_FFT, g->nseg);
     if (rc) break;
     const size_t ib = 2 * (size_t)nl * R.core->L.pitch * es;
     if (cudaMalloc(&R.inbox, ib) != cudaSuccess || cudaMemset(R.inbox, 0, ib) != cudaSuccess ||

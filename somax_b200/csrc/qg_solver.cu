@@ -49,6 +49,8 @@ struct QgSolver {
   FftPlan plan;
   Mix l2m, m2l;
   int nheavy = 0;
+  int nseg = 1, seg_len = 0;                        // segmented sweeps (ThomasTab)
+  double* segbuf = nullptr; double* segprod = nullptr;
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t bytes = 0;
@@ -487,6 +489,15 @@ struct ThomasTab {
   const void* sig2n;             // [np] border weights in working precision, zero-padded
   int ny, np, ncols, nl, nstrip;
   double dy2;
+  // Segmented sweeps (slab-distributed model, where a rank owns few strips and a sweep CTA is a
+  // bare serial chain): each half-column is cut into nseg segments of seg_len rows handled by
+  // different CTAs.  The recurrence y_s = g_s - c_s y_{s-1} is linear, so pass 1 (probe) runs every
+  // segment from a zero carry without storing and records its end value e; pass 2 (apply) starts
+  // segment k from cin_k = e_{k-1} + p_{k-1} cin_{k-1} (p = product of -c_s over a segment,
+  // tabulated on the host) and does the real work.  pass 0 = unsegmented (nseg = 1).
+  int nseg, seg_len, pass;
+  double* segbuf;            // [plane][half][seg][np] end values of pass 1
+  const double* segprod;     // [kind: 0 elimination, 1 substitution][half][mode][seg][np]
 };
 
 
@@ -700,7 +711,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   const int strip = strip_first + blockIdx.x;
   const int c = strip * TH_COLS + tid;
   const int plane = blockIdx.y, m = plane % tb.nl;
-  const int half = blockIdx.z;
+  const int half = blockIdx.z & 1, seg = blockIdx.z >> 1;
   const bool act = worker && c < tb.ncols;
   const int ny = tb.ny;
   const size_t strip0 = (size_t)plane * ny * tb.np + (size_t)strip * ny * SP_W;   // strip base
@@ -729,16 +740,19 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   int j0, dj;
   if (!SUBST) { j0 = half == 0 ? 0 : ny - 1; dj = half == 0 ? 1 : -1; }
   else        { j0 = half == 0 ? m1 - 1 : m1; dj = half == 0 ? -1 : 1; }
-  const int ntile = (cnt + RT - 1) / RT;
+  // this CTA's segment [sa, sb) of the half's sequence (the whole half when nseg = 1)
+  const int sa = min(cnt, seg * tb.seg_len), sb = tb.nseg > 1 ? min(cnt, sa + tb.seg_len) : cnt;
+  const bool probe = tb.pass == 1;
+  const int ntile = (sb - sa + RT - 1) / RT;
   // tile t covers sequence numbers s0..s0+nr-1, i.e. memory rows jlo..jlo+nr-1 (ascending), and
   // table indices ilo..ilo+nr-1 (i = s for elimination, cnt-1-s for substitution)
-  auto tile_nr = [&](int t) { return min(RT, cnt - t * RT); };
+  auto tile_nr = [&](int t) { return min(RT, sb - (sa + t * RT)); };
   auto tile_jlo = [&](int t) {
-    const int s0 = t * RT, nr = min(RT, cnt - s0);
+    const int s0 = sa + t * RT, nr = min(RT, sb - s0);
     return dj > 0 ? j0 + s0 : j0 - (s0 + nr - 1);
   };
   auto tile_ilo = [&](int t) {
-    const int s0 = t * RT, nr = min(RT, cnt - s0);
+    const int s0 = sa + t * RT, nr = min(RT, sb - s0);
     return SUBST ? cnt - 1 - (s0 + nr - 1) : s0;
   };
 
@@ -788,6 +802,16 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     carry = half == 0 ? xb : xa;     // the neighbour's value across the meeting point
     carry_f = (float)carry;
   }
+  if (tb.nseg > 1) {
+    if (probe) {
+      carry = 0.0;                    // pass 1: every segment from a zero carry
+    } else {
+      const double* eb = tb.segbuf + ((size_t)(plane * 2 + half) * tb.nseg) * tb.np + c;
+      const double* pb = tb.segprod + ((size_t)(((SUBST ? 2 : 0) + half) * tb.nl + m) * tb.nseg) * tb.np + c;
+      for (int k = 0; k < seg; ++k) carry = fma(pb[(size_t)k * tb.np], carry, eb[(size_t)k * tb.np]);
+    }
+    carry_f = (float)carry;
+  }
   if (FROM_VEC && ntile > 0) {
     if (worker && tid < tile_nr(0)) gbuf[0][tid] = gsrc[tile_jlo(0) + tid];
     __syncthreads();
@@ -828,7 +852,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
 #pragma unroll 1
     for (int b0 = 0; worker && b0 < nrt; b0 += TH_RT) {       // register blocks, in sequence order
       const int nr = min(TH_RT, nrt - b0);
-      const int s0 = t * RT + b0;
+      const int s0 = sa + t * RT + b0;
       const int ilo = SUBST ? cnt - 1 - (s0 + nr - 1) : s0;
       const int row0 = dj > 0 ? b0 : nrt - b0 - nr;   // first memory row of the block inside the tile
       T (*A)[TH_COLS] = tileA[st] + row0;
@@ -871,12 +895,12 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     ph_comp += ph2 - ph1;
 #endif
     if (FROM_VEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) gbuf[(t + 1) & 1][tid] = gnext;
-    if (worker && !SUBST && t == ntile - 1)
+    if (worker && !SUBST && !probe && t == ntile - 1 && sb == cnt)
       meetW[((size_t)plane * 2 + half) * tb.np + c] = PLAIN ? (double)carry_f : carry;
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
     fence_async_smem();
     __syncthreads();
-    if (KIND == 1 && worker) {
+    if (KIND == 1 && worker && !probe) {
       // border sums of the finished tile: thread (rr, qd) adds 16 columns of row rr with a rotated
       // column order (conflict-free), the two quarters of a warp combine by shuffle
       const int rr = tid & 15, qd = tid >> 4;
@@ -898,9 +922,9 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     ph_sync += clock64() - ph2;
 #endif
     if (issuer) {
-      if (KIND != 1)
+      if (KIND != 1 && !probe)
         bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &tileA[st][0][0], (unsigned)(nrt * TH_COLS * sizeof(T)));
-      if (TAB && !SUBST && strip_bad)
+      if (TAB && !SUBST && strip_bad && !probe)
         bulk_s2g(sideG + (size_t)tile_jlo(t) * tb.KB, tileD + (size_t)st * RT * tb.KB,
                  (unsigned)(nrt * tb.KB * sizeof(double)));
       bulk_commit();
@@ -910,6 +934,8 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     }
   }
   if (issuer) bulk_wait_read<0>();
+  if (probe && worker)
+    tb.segbuf[((size_t)(plane * 2 + half) * tb.nseg + seg) * tb.np + c] = PLAIN ? (double)carry_f : carry;
 #ifdef SB_TH_PHASES
   if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
     const unsigned slot = atomicAdd(&g_dbg_n, 1u);
@@ -1047,6 +1073,9 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
   const int hcap = ny - ny / 2;                 // longest run of one half (table indices 0..hcap-1)
   const int m1 = ny / 2;
   std::vector<double> cinf((size_t)nl * np, 0.0), meetc((size_t)nl * 2 * np, 0.0), ctab;
+  const int nseg = s->nseg;
+  s->seg_len = nseg > 1 ? (((hcap + nseg - 1) / nseg + 63) / 64) * 64 : hcap;
+  std::vector<double> segprod(nseg > 1 ? (size_t)4 * nl * nseg * np : 0, 1.0), crow(nseg > 1 ? hcap : 0);
   std::vector<int> Jstrip((size_t)nl * nstrip, 0);
   std::vector<long long> tabOff((size_t)nl * nstrip, 0);
   const double dy2 = s->dy * s->dy;
@@ -1085,6 +1114,22 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
       if (ib >= jconv) cb = cinf[(size_t)m * np + c];
       meetc[((size_t)m * 2 + 0) * np + c] = ca;
       meetc[((size_t)m * 2 + 1) * np + c] = cb;
+      if (nseg > 1) {
+        // products of -c_i over the segments of both halves, for the elimination (i = s) and the
+        // substitution (i = cnt - 1 - s) sequences
+        double ci = 0.0;
+        for (int i = 0; i < hcap; ++i) { ci = (i < jconv) ? 1.0 / (delta[c] - ci) : cinf[(size_t)m * np + c]; crow[i] = ci; }
+        for (int h = 0; h < 2; ++h) {
+          const int cnt = h == 0 ? m1 : ny - m1;
+          for (int k = 0; k < nseg; ++k) {
+            const int sa = std::min(cnt, k * s->seg_len), sb = std::min(cnt, sa + s->seg_len);
+            double pe = 1.0, ps = 1.0;
+            for (int q = sa; q < sb; ++q) { pe *= -crow[q]; ps *= -crow[cnt - 1 - q]; }
+            segprod[((size_t)((0 + h) * nl + m) * nseg + k) * np + c] = pe;
+            segprod[((size_t)((2 + h) * nl + m) * nseg + k) * np + c] = ps;
+          }
+        }
+      }
     }
     s->KB = std::max(s->KB, s->kbad[m]);
     for (int st = 0; st < nstrip; ++st) {
@@ -1133,6 +1178,13 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
   if (int rc = dev_upload(tabOff.data(), tabOff.size() * 8, (void**)&s->coff, &s->bytes)) return rc;
   if (int rc = dev_upload(cinf.data(), cinf.size() * 8, (void**)&s->cinf, &s->bytes)) return rc;
   if (int rc = dev_upload(meetc.data(), meetc.size() * 8, (void**)&s->meetc, &s->bytes)) return rc;
+  if (nseg > 1) {
+    if (int rc = dev_upload(segprod.data(), segprod.size() * 8, (void**)&s->segprod, &s->bytes)) return rc;
+    const size_t sbytes = (size_t)s->planes * 2 * nseg * np * 8;
+    SB_CUDA(cudaMalloc((void**)&s->segbuf, sbytes));
+    SB_CUDA(cudaMemset(s->segbuf, 0, sbytes));
+    s->bytes += sbytes;
+  }
   {
     size_t mb = (size_t)s->planes * 2 * np * 8;
     SB_CUDA(cudaMalloc((void**)&s->meet, mb));
@@ -1253,7 +1305,7 @@ static int build_dense_tables(QgSolver* s) {
 
 int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int nx, double dx,
                      double dy, const double* Cl2m, const double* Cm2l, const double* lambdas,
-                     int solver_kind) {
+                     int solver_kind, int nseg) {
   *out = nullptr;
   if (nl < 1 || nl > QG_MAX_NL) return fail(SOMAX_B200_ERR_UNSUPPORTED, "QG supports 1 <= nl <= 4");
   const bool pow2 = nx >= 8 && (nx & (nx - 1)) == 0;
@@ -1272,6 +1324,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
   auto* s = new QgSolver();
   s->dtype = dtype; s->batch = batch; s->nl = nl; s->ny = ny; s->nx = nx; s->kind = kind;
   s->dx = dx; s->dy = dy; s->L = make_layout(batch, nl, ny, nx);
+  s->nseg = std::max(1, std::min(nseg, 16));
   s->np = ((nx + SP_W - 1) / SP_W) * SP_W; s->planes = batch * nl;
   s->ncols = (kind == SOMAX_B200_SOLVER_FFT) ? nx - 1 : nx;
   for (int a = 0; a < QG_MAX_NL; ++a)
@@ -1318,7 +1371,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
 
 void qg_solver_destroy(QgSolver* s) {
   if (!s) return;
-  void* ptrs[] = {s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->dbad1, s->meet1, s->part, s->bsig, s->sig2n,
+  void* ptrs[] = {s->segbuf, s->segprod, s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->dbad1, s->meet1, s->part, s->bsig, s->sig2n,
                   s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->gvecf, s->tw, s->twc, s->twb, s->dstmat, s->meet, s->meetc};
   for (void* p : ptrs) cudaFree(p);
   if (s->aux) cudaStreamDestroy(s->aux);
@@ -1348,6 +1401,20 @@ static int launch_thomas_one(const char* tag, const ThomasTab& tb, int strip_fir
     SB_CUDA(cudaFuncSetAttribute(thomas_sweep<T, SUBST, FROM_VEC, KIND, TAB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = smem;
+  }
+  if (tb.nseg > 1) {
+    ThomasTab t1 = tb;
+    t1.pass = 1;
+    prof_begin(TAB ? "thomas_probe_lowk" : "thomas_probe", st);
+    thomas_sweep<T, SUBST, FROM_VEC, KIND, TAB><<<dim3(nstrips, planes, 2 * tb.nseg), TH_THREADS, smem, st>>>(
+        t1, strip_first, in, V, gvec, gvecf, bsig, out);
+    SB_LAUNCH_CHECK();
+    t1.pass = 2;
+    prof_begin(tag, st);
+    thomas_sweep<T, SUBST, FROM_VEC, KIND, TAB><<<dim3(nstrips, planes, 2 * tb.nseg), TH_THREADS, smem, st>>>(
+        t1, strip_first, in, V, gvec, gvecf, bsig, out);
+    SB_LAUNCH_CHECK();
+    return 0;
   }
   prof_begin(tag, st);
   thomas_sweep<T, SUBST, FROM_VEC, KIND, TAB><<<dim3(nstrips, planes, 2), TH_THREADS, smem, st>>>(
@@ -1409,6 +1476,7 @@ static ThomasTab make_tab(const QgSolver* s) {
   tb.KB = s->KBs; tb.dbad = s->dbad; tb.dbad1 = s->dbad1; tb.meet = s->meet; tb.meet1 = s->meet1;
   tb.part = s->part; tb.sig2n = s->sig2n; tb.ny = s->ny; tb.np = s->np; tb.ncols = s->ncols; tb.nl = s->nl;
   tb.dy2 = s->dy * s->dy;
+  tb.nseg = s->nseg; tb.seg_len = s->seg_len; tb.pass = 0; tb.segbuf = s->segbuf; tb.segprod = s->segprod;
   return tb;
 }
 

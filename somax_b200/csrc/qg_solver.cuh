@@ -15,7 +15,7 @@ __host__ __device__ __forceinline__ size_t sp_off(int ny, int j, int k) {
 
 int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int nx, double dx,
                      double dy, const double* Cl2m, const double* Cm2l, const double* lambdas,
-                     int solver_kind);
+                     int solver_kind, int nseg = 1);   // nseg > 1: segmented y-sweeps (see ThomasTab)
 void qg_solver_destroy(QgSolver* s);
 size_t qg_solver_bytes(const QgSolver* s);
 int qg_solver_kind(const QgSolver* s);

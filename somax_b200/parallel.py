@@ -106,6 +106,22 @@ def merge_slabs(slabs, out=None):
     return out
 
 
+def gather_blobs(blob: bytes, world: int) -> bytes:
+    """All-gather one opaque byte blob per rank (the CUDA-IPC handles of a slab); returns the
+    blobs concatenated in rank order.  NCCL groups stage through device memory, gloo on the host."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return bytes(blob)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() != world:
+        raise RuntimeError(f"torch.distributed must be initialised with world size {world}")
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    parts = [torch.empty(len(blob), dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+
+
 class SlabQG:
     """A `BaroclinicQG` / `BarotropicQG` model stepped on y-slabs over several GPUs
     (`libsomax_b200`'s `somax_b200_qgs_*`; reference path: core/model.py:53-88 over
@@ -148,23 +164,12 @@ class SlabQG:
     def _attach(self):
         import ctypes as C
 
-        import torch
-        import torch.distributed as dist
-
         from . import _lib
         L = _lib.lib()
         nb = int(L.somax_b200_qgs_export_bytes())
         mine = (C.c_ubyte * nb)()
         _lib.check(L.somax_b200_qgs_export(self._h, mine))
-        blob = torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8).clone()
-        if self.world > 1:
-            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-            parts = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(self.world)]
-            dist.all_gather(parts, blob.to(dev))
-            allb = torch.cat([p.cpu() for p in parts])
-        else:
-            allb = blob
-        raw = bytes(allb.numpy().tobytes())
+        raw = gather_blobs(bytes(mine), self.world)
         buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
         _lib.check(L.somax_b200_qgs_attach(self._h, buf))
 

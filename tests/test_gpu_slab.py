@@ -30,9 +30,12 @@ def rel(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
-def assert_same(got, one, dtype):
+def assert_same(got, one, dtype, exact=True):
     if np.dtype(dtype) == np.float64:
-        assert np.array_equal(got, one), rel(got, one)
+        if exact:
+            assert np.array_equal(got, one), rel(got, one)
+        else:
+            assert rel(got, one) <= 1e-12, rel(got, one)
     else:
         assert rel(got, one) <= 1e-6, rel(got, one)
 
@@ -49,12 +52,16 @@ def state(nl, nx, ny, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("nx,ny,world,steps", [(128, 64, 2, 3), (256, 96, 4, 3), (256, 256, 2, 12),
-                                               (512, 64, 8, 2)])
-def test_local_slabs_match_single_gpu_and_oracle(nx, ny, world, steps, dtype):
+@pytest.mark.parametrize("nx,ny,world,steps,nseg", [(128, 64, 2, 3, 1), (256, 96, 4, 3, 1), (256, 256, 2, 12, 1),
+                                                    (512, 64, 8, 2, 1), (256, 512, 4, 3, 4), (128, 1024, 2, 2, 8),
+                                                    (256, 384, 2, 3, 3)])
+def test_local_slabs_match_single_gpu_and_oracle(nx, ny, world, steps, nseg, dtype, monkeypatch):
+    """nseg > 1: the y-sweeps of the slab model run segmented (probe + apply passes); the result is
+    then the single-GPU one up to rounding instead of bit for bit."""
     import somax_b200 as sb
     from oracle import qg as oqg
     from somax_b200.parallel import SlabQG
+    monkeypatch.setenv("SOMAX_B200_SLAB_NSEG", str(nseg))
     gm = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype=np.dtype(dtype).name, solver=1, **ARGS)
     q0 = state(3, nx, ny, dtype)
     dt = 600.0 * 128.0 / nx
@@ -64,14 +71,15 @@ def test_local_slabs_match_single_gpu_and_oracle(nx, ny, world, steps, dtype):
     got = sl.integrate(q0, 0.0, t1, dt)
     sl.close()
     assert got.shape == one.shape and got.dtype == one.dtype
-    assert_same(got, one, dtype)
+    assert_same(got, one, dtype, exact=nseg == 1)
     ref = oqg.create_baroclinic(nx=nx, ny=ny, **ARGS).integrate(q0.astype(np.float64), 0.0, t1, dt)
     assert rel(got, ref) <= (1e-5 if dtype == np.float32 else 1e-12)
 
 
-def test_local_slabs_barotropic_and_halo_rows():
+def test_local_slabs_barotropic_and_halo_rows(monkeypatch):
     """nl = 1; the windows come back with valid halo rows (a second call continues from them)."""
     import torch
+    monkeypatch.setenv("SOMAX_B200_SLAB_NSEG", "1")
     import somax_b200 as sb
     from somax_b200.parallel import SlabQG, merge_slabs, split_slabs
     nx = ny = 128
@@ -160,7 +168,7 @@ def test_multi_process_slabs_match_single_gpu(dtype):
     got = np.empty_like(one)
     for _, lo, hi, a in parts:
         got[:, lo:hi] = a
-    assert_same(got, one, dtype)
+    assert_same(got, one, dtype, exact=world < 4)      # 4 ranks and more run segmented sweeps
 
 
 def test_full_size_slabs_match_single_gpu():

@@ -92,11 +92,8 @@ def _blob_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     # the set-up exchange of SlabQG._attach: every rank contributes an opaque byte blob, all ranks
     # end up with the blobs in rank order
-    nb = 216
-    mine = torch.full((nb,), rank + 1, dtype=torch.uint8)
-    parts = [torch.empty(nb, dtype=torch.uint8) for _ in range(world)]
-    dist.all_gather(parts, mine)
-    q.put((rank, bytes(torch.cat(parts).numpy().tobytes())))
+    from somax_b200.parallel import gather_blobs
+    q.put((rank, gather_blobs(bytes([rank + 1] * 216), world)))
     dist.barrier()
     dist.destroy_process_group()
 
