@@ -260,3 +260,73 @@ def test_cli_discovery_and_shipped_configs(capsys):
         assert dbg.testcase.grid["nx"] < sp.testcase.grid["nx"]
         assert app.main(["show-config", c]) == 0
     assert "# Resolved RunSpec from" in capsys.readouterr().out
+
+
+# ------------------------------------------------------------------ chunk loop with a stand-in model (host logic only)
+class _DecayModel:
+    """dq/dt = -k q integrated exactly: a stand-in with the three methods the chunk loop calls."""
+
+    def __init__(self, blow_up_after=None):
+        self.k, self.calls, self.blow_up_after = 1e-3, [], blow_up_after
+
+    def integrate(self, state, t0, t1, dt, max_steps=None):
+        from types import SimpleNamespace
+        self.calls.append((t0, t1, dt, max_steps))
+        q = np.asarray(state.q) * np.exp(-self.k * (t1 - t0))
+        if self.blow_up_after is not None and len(self.calls) > self.blow_up_after:
+            q = q.copy()
+            q[0, 0] = np.nan
+        return SimpleNamespace(ys=BarotropicQGState(q=q[None]), stats={"num_steps": int(np.ceil((t1 - t0) / dt))})
+
+    def diag_scalars(self, state):
+        q = np.nan_to_num(np.asarray(state.q))
+        return np.array([float((q ** 2).sum())]), np.array([float(np.abs(q).sum())]), 0.0
+
+
+def test_chunk_loop_logs_snapshots_and_aborts(tmp_path):
+    from somax_b200.cli._run import IntegrationDivergedError, RunLog, _chunked_integrate_with_diagnostics
+    save_ts = np.asarray([0.0, 100.0, 200.0, 250.0])
+    state0 = BarotropicQGState(q=np.ones((4, 5)))
+    model, snaps = _DecayModel(), []
+    log = RunLog(tmp_path, label="somax-sim/run")
+    final, n_steps = _chunked_integrate_with_diagnostics(
+        model, state0, save_ts, 10.0, diagnostics_per_save=2, max_steps_per_chunk=77, run_log=log, mode="run",
+        on_snapshot=lambda i, t, st: snaps.append((i, t, float(np.asarray(st.q)[0, 0]))))
+    log.stop("finished cleanly")
+    # 3 save intervals x 2 sub-chunks, each integrated with the per-chunk step cap
+    assert [(a, b) for a, b, _, _ in model.calls] == [(0, 50), (50, 100), (100, 150), (150, 200), (200, 225), (225, 250)]
+    assert all(c[3] == 77 for c in model.calls) and n_steps == 26
+    assert [s[:2] for s in snaps] == [(0, 0.0), (1, 100.0), (2, 200.0), (3, 250.0)]     # snapshots only at save times
+    assert np.isclose(snaps[-1][2], np.exp(-0.25)) and np.isclose(np.asarray(final.q)[0, 0], np.exp(-0.25))
+    lines = (tmp_path / "run.log").read_text().splitlines()
+    chunk = [ln for ln in lines if "| chunk " in ln]
+    assert len(chunk) == 7 and "chunk 0/6 sim_t=0 s | q[1/s]=[1,1,1] | physics: kinetic_energy=20 enstrophy=20 | initial state" in chunk[0]
+    assert "chunk 6/6 sim_t=250 s (4.17 min) | q[1/s]=[0.779,0.779,0.779]" in chunk[-1] and "| wall=" in chunk[-1]
+    assert any("all 6 chunks completed in" in ln for ln in lines) and lines[-1].endswith("finished cleanly")
+
+    model, snaps = _DecayModel(blow_up_after=2), []
+    (tmp_path / "b").mkdir()
+    log = RunLog(tmp_path / "b", label="somax-sim/run")
+    with pytest.raises(IntegrationDivergedError, match=r"during chunk 3/6 \(sim_t=150 s \(2.50 min\)\)"):
+        _chunked_integrate_with_diagnostics(model, state0, save_ts, 10.0, diagnostics_per_save=2,
+                                            max_steps_per_chunk=77, run_log=log, mode="run",
+                                            on_snapshot=lambda i, t, st: snaps.append(i))
+    log.stop("FAILED")
+    assert len(model.calls) == 3 and snaps == [0, 1]            # stops at the first non-finite chunk
+    text = (tmp_path / "b" / "run.log").read_text()
+    assert "NaN=1" in text and "ABORT at chunk 3/6: non-finite state" in text
+
+
+def test_energy_growth_warning(tmp_path):
+    from types import SimpleNamespace
+    from somax_b200.cli._run import RunLog, _chunked_integrate_with_diagnostics
+
+    class Growing(_DecayModel):
+        def integrate(self, state, t0, t1, dt, max_steps=None):
+            return SimpleNamespace(ys=BarotropicQGState(q=(np.asarray(state.q) * 5.0)[None]), stats={"num_steps": 1})
+
+    log = RunLog(tmp_path, label="somax-sim/run")
+    _chunked_integrate_with_diagnostics(Growing(), BarotropicQGState(q=np.ones((3, 3))), np.asarray([0.0, 1.0, 2.0]), 1.0,
+                                        diagnostics_per_save=1, max_steps_per_chunk=10, run_log=log, mode="run")
+    log.stop()
+    assert "!! energy grew 25.0x from previous chunk" in (tmp_path / "run.log").read_text()
