@@ -1530,15 +1530,19 @@ int qg_solver_border_stage(QgSolver* s, int stage, int a0, int a1, cudaStream_t 
     return 0;
   }
   if (cnt <= 0) return 0;
+  // one thread per output pays off only when there are enough outputs to fill the GPU with
+  // threads (ensembles of small grids); a single grid keeps one warp per output (ny = 1024,
+  // 3 planes: 10 us against 38 us)
+  const bool small = ny <= GS_SMALL_NY && (long)s->planes * ny >= 65536;
   if (stage == 1) {
     prof_begin("border_gsolve_a", st);
-    if (ny <= GS_SMALL_NY)
+    if (small)
       border_gsolve_small<T, true><<<dim3((cnt + 127) / 128, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, a0, cnt);
     else
       border_gsolve<T, true><<<dim3((cnt + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, a0, cnt);
   } else {
     prof_begin("border_gsolve_b", st);
-    if (ny <= GS_SMALL_NY)
+    if (small)
       border_gsolve_small<T, false><<<dim3((cnt + 127) / 128, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, a0, cnt);
     else
       border_gsolve<T, false><<<dim3((cnt + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, a0, cnt);

@@ -51,6 +51,8 @@ def test_spec_debug_merge_is_deep_and_consumed():
     assert sp.testcase.grid["nx"] == 64                       # original untouched
     assert out.timestepping.t1 == 3600.0 and out.timestepping.dt == 600.0
     assert out.debug == S.DebugSpec()
+    sp.assertions = {"cfl": {"wave_speed_m_per_s": 1.0}}
+    assert sp.with_debug_applied().assertions == {}           # reference behaviour (spec.py:225-230): not carried over
     sp.debug = S.DebugSpec(testcase={"nope": {}})
     with pytest.raises(ValueError, match="does not match"):
         sp.with_debug_applied()

@@ -115,7 +115,8 @@ def test_cli_run_debug_config_and_assertions(tmp_path):
     snaps = io.load_dataset(tmp_path / "o" / "snapshots.zarr")
     assert snaps["h"].shape == (3, 2, 34, 34) and snaps["time"].values.tolist() == [0.0, 1800.0, 3600.0]
     assert np.isfinite(snaps["u"].values).all()
-    spec = load_yaml(cfg).with_debug_applied()
+    spec = load_yaml(cfg).with_debug_applied()                    # (drops `assertions`, as the reference's does)
+    spec.assertions = {"cfl": {"wave_speed_m_per_s": 221.5, "max_cfl": 0.5}}
     spec.timestepping.dt = 300.0                                  # gravity-wave CFL ~ 2
     with pytest.raises(AssertionFailedError, match="cfl check FAILED"):
         simulate(spec, tmp_path / "cfl")
