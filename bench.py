@@ -543,11 +543,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="qg3_8192", choices=sorted(WORKLOADS))
     ap.add_argument("--decomp", default="members", choices=["members", "slab"],
-                    help="N > 1: 'members' = one grid per GPU (weak); 'slab' = ONE grid in y-slabs (strong)")
+                    help="N > 1: 'members' = one grid per GPU (weak); 'slab' = ONE grid in y-slabs (strong); "
+                         "with one GPU both are the single-GPU path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.decomp == "slab":
+    elif args.decomp == "slab" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_gpu_slab(args)
     else:
         run_gpu(args)
