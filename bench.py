@@ -6,10 +6,11 @@
 A "step" is one full Tsit5 step (6 fresh RHS evaluations: PV inversion + fused stencil/RK
 epilogue each) of the whole grid.  One cell-update = one interior cell of one layer advanced by
 one step.  N = 1 runs BASELINE.json's target configuration, the 3-layer QG double gyre at 8192^2
-in fp32 (it fits one B200).  For N > 1 the ensemble shards by member (one 8192^2 member per
-rank, no data-path collective; "weak" scaling); `--decomp slab` instead partitions ONE 8192^2
-grid in N y-slabs (BASELINE config 4, "strong" scaling; distributed DST by peer-memory
-transposes over NVLink) - see DESIGN.md section "multi-GPU".
+in fp32 (it fits one B200).  For N > 1 the same ONE 8192^2 grid is partitioned in N y-slabs
+(BASELINE config 4, "strong" scaling; halo rows and the transposes of the distributed DST are
+peer-memory stores over NVLink); `--decomp members` instead gives every rank its own grid / shards
+an ensemble by member (no data-path collective; the default for the ensemble and shallow-water
+workloads) - see DESIGN.md section "multi-GPU".
 
 Rank 0 prints ONE JSON line (keys: see the graft bench contract; `roofline` is for the kernel
 with the largest share of the step, `cpu_baseline` times the numpy/scipy oracle port on the
@@ -193,7 +194,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "cell_updates_per_s", "value": v, "unit": "Gcell-steps/s",
         "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": el / K * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "strong" if (args.gpus > 1 and args.decomp == "slab") else "weak",
+        "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": args.workload, "sample_grid": sn},
         "cpu_baseline": {"value": v, "unit": "Gcell-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Gcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -542,10 +544,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="qg3_8192", choices=sorted(WORKLOADS))
-    ap.add_argument("--decomp", default="members", choices=["members", "slab"],
-                    help="N > 1: 'members' = one grid per GPU (weak); 'slab' = ONE grid in y-slabs (strong); "
-                         "with one GPU both are the single-GPU path")
+    ap.add_argument("--decomp", default=None, choices=["members", "slab"],
+                    help="N > 1: 'slab' = ONE grid in y-slabs (strong scaling; the default for single-grid QG "
+                         "workloads: BASELINE config 4); 'members' = one grid per GPU / members sharded by rank "
+                         "(the default for ensembles and shallow water); with one GPU both are the single-GPU path")
     args = ap.parse_args()
+    if args.decomp is None:
+        kind, _nl, _nx, _ny, members = WORKLOADS[args.workload]
+        args.decomp = "slab" if (kind == "qg" and members == 1) else "members"
     if args.impl == "reference":
         run_reference(args)
     elif args.decomp == "slab" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
