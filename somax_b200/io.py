@@ -274,7 +274,7 @@ def load_dataset(path) -> Dataset:
         nchunks = [(-(-n // c)) for n, c in zip(shape, cshape)]
         for idx in np.ndindex(*nchunks) if shape else [()]:
             key = sep.join(["c"] + [str(i) for i in idx]) if shape else "c"
-            p = adir / key if sep == "/" else adir / key
+            p = adir / key
             if not p.exists():
                 continue
             block = np.fromfile(p, dtype=dt).reshape(cshape)
@@ -317,13 +317,18 @@ class AsyncSnapshotWriter:
     """Snapshot sink for the runner: device -> pinned host copies are issued on a side stream and
     the zarr chunks are written by a worker thread, so stepping continues while a snapshot leaves
     the device.  `put` is called with the state at a save time; `close`
-    drains."""
+    drains.  The pinned staging buffers form a ring of `depth + 1` sets that is allocated once
+    (`cudaHostAlloc` of a state-sized buffer costs more than the copy it serves): `put` blocks only
+    when every set is still waiting to be written."""
 
     def __init__(self, path, state_class, attrs=None, depth: int = 2):
         import queue
         import threading
         self.path, self.state_class, self.attrs = Path(path), state_class, dict(attrs or {})
-        self._q = queue.Queue(maxsize=depth)
+        self._q = queue.Queue()
+        self._free = queue.Queue()
+        for _ in range(depth + 1):
+            self._free.put({})                  # one set of pinned leaves per slot, filled on first use
         self._err = None
         self._first = True
         self._th = threading.Thread(target=self._run, daemon=True)
@@ -335,8 +340,8 @@ class AsyncSnapshotWriter:
             item = self._q.get()
             if item is None:
                 return
+            t, leaves, ev, slot = item
             try:
-                t, leaves, ev = item
                 if ev is not None:
                     ev.synchronize()
                 st = self.state_class(**{k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in leaves.items()})
@@ -348,6 +353,8 @@ class AsyncSnapshotWriter:
                     append_to_dataset(ds, self.path)
             except Exception as exc:      # surfaced by close()
                 self._err = exc
+            finally:
+                self._free.put(slot)
 
     def put(self, t, state):
         leaves, ev = {}, None
@@ -355,6 +362,7 @@ class AsyncSnapshotWriter:
             import torch
         except Exception:   # pragma: no cover
             torch = None
+        slot = self._free.get()
         cuda_leaves = torch is not None and any(
             isinstance(getattr(state, f.name), torch.Tensor) and getattr(state, f.name).is_cuda
             for f in dataclasses.fields(state))
@@ -365,7 +373,9 @@ class AsyncSnapshotWriter:
             with torch.cuda.stream(self._side):
                 for f in dataclasses.fields(state):
                     x = getattr(state, f.name)
-                    host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+                    host = slot.get(f.name)
+                    if host is None or host.shape != x.shape or host.dtype != x.dtype:
+                        host = slot[f.name] = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
                     host.copy_(x, non_blocking=True)
                     x.record_stream(self._side)
                     leaves[f.name] = host
@@ -374,7 +384,7 @@ class AsyncSnapshotWriter:
         else:
             for f in dataclasses.fields(state):
                 leaves[f.name] = np.array(_host(getattr(state, f.name)))
-        self._q.put((t, leaves, ev))
+        self._q.put((t, leaves, ev, slot))
 
     def close(self):
         self._q.put(None)
