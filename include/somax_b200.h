@@ -38,7 +38,7 @@ typedef enum {
   SOMAX_B200_ERR_UNSUPPORTED = -2, /* valid request the CUDA path does not implement */
   SOMAX_B200_ERR_CUDA = -3,        /* CUDA runtime error (message has the cudaError string) */
   SOMAX_B200_ERR_NO_DEVICE = -4,   /* no sm_100 device: there is NO CPU fallback */
-  SOMAX_B200_ERR_COMM = -5         /* NCCL / communicator error */
+  SOMAX_B200_ERR_COMM = -5         /* peer mapping (CUDA IPC) / slab-group error */
 } somax_b200_status;
 
 typedef enum { SOMAX_B200_F32 = 0, SOMAX_B200_F64 = 1 } somax_b200_dtype;

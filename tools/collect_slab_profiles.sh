@@ -9,5 +9,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 600 ncu --set full --clock-control none -k regex:seg_copy -c 14 -o gpurun_out/${R}_slab_full -f \
   python tools/prof_slab_local.py 4096 4 1 > /dev/null 2>&1
 python tools/ncu_summary.py gpurun_out/${R}_slab_full.ncu-rep gpurun_out/${R}_qg3_4096_slab4local_ncu_full.csv
+# the segmented y-sweeps (probe / apply passes) of the same run
+SOMAX_B200_SLAB_NSEG=8 timeout 600 ncu --set full --clock-control none -k regex:thomas_sweep -c 16 \
+  -o gpurun_out/${R}_slab_sweeps -f python tools/prof_slab_local.py 4096 4 1 > /dev/null 2>&1
+python tools/ncu_summary.py gpurun_out/${R}_slab_sweeps.ncu-rep gpurun_out/${R}_qg3_4096_slab4local_sweeps_ncu_full.csv
 rm -f gpurun_out/*.ncu-rep
 ls -la gpurun_out | tail -5
