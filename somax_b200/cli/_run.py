@@ -86,17 +86,28 @@ def format_field_stats(name, *, min_val, mean_val, max_val, nan_count) -> str:
 # run.log (cli/_progress.py): "<time> | <level> | <label> | <message>", truncated per run, plus a
 # daemon thread that writes an "alive" line every 10 s
 # ----------------------------------------------------------------------------------------
+RUN_LOG_FORMAT = "{time:YYYY-MM-DD HH:mm:ss} | {level: <7} | {label: <16} | {message}"
+
+
 class RunLog:
-    def __init__(self, output_dir: Path, label: str, alive_interval: float = 10.0):
-        self.path = Path(output_dir) / "run.log"
+    """`<output_dir>/run.log` (truncated per run) + the periodic "alive" tick (cli/_progress.py:78-201)."""
+
+    def __init__(self, output_dir, label: str, alive_interval: float = 10.0, enable_alive_thread: bool = True):
+        if alive_interval <= 0:
+            raise ValueError(f"alive_interval must be > 0 (got {alive_interval})")
+        out = Path(output_dir)
+        out.mkdir(parents=True, exist_ok=True)
+        self.path = out / "run.log"
         self.label = label
         self._f = open(self.path, "w")
         self._lock = threading.Lock()
         self._t0 = time.perf_counter()
         self._halt = threading.Event()
         self.debug("started")
-        self._th = threading.Thread(target=self._alive, args=(alive_interval,), daemon=True)
-        self._th.start()
+        self._th = None
+        if enable_alive_thread:
+            self._th = threading.Thread(target=self._alive, args=(alive_interval,), daemon=True)
+            self._th.start()
 
     def debug(self, msg: str):
         line = f"{time.strftime('%Y-%m-%d %H:%M:%S')} | {'DEBUG': <7} | {self.label: <16} | {msg}"
@@ -111,11 +122,20 @@ class RunLog:
             self.debug(f"alive ({format_wallclock(time.perf_counter() - self._t0)} elapsed)")
 
     def stop(self, final_message: str | None = None):
+        """Idempotent: a second call neither raises nor writes."""
         self._halt.set()
         if final_message is not None:
             self.debug(final_message)
         with self._lock:
             self._f.close()
+
+
+def start_run_log(output_dir, *, label: str, alive_interval: float = 10.0, enable_alive_thread: bool = True) -> RunLog:
+    return RunLog(output_dir, label, alive_interval, enable_alive_thread)
+
+
+def stop_run_log(ctx: RunLog, *, final_message: str | None = None) -> None:
+    ctx.stop(final_message)
 
 
 # ----------------------------------------------------------------------------------------
@@ -297,6 +317,40 @@ def _chunked_integrate_with_diagnostics(model, state0, save_ts, dt, *, diagnosti
     return state, n_steps
 
 
+def _assert_finite_state(stacked, *, mode: str) -> None:
+    """Unconditional safety net on a time-stacked state (cli/_run.py:703-757): raise
+    `IntegrationDivergedError` naming the fields with non-finite values, and say whether the first
+    saved slice was already bad (CFL violation at t0 / bad initial state) or the run blew up later."""
+    bad, first_bad = [], []
+    for f in dataclasses.fields(stacked):
+        leaf = getattr(stacked, f.name)
+        if hasattr(leaf, "is_cuda"):
+            import torch
+            nonfin = ~torch.isfinite(leaf)
+            n_bad, size = int(nonfin.sum()), leaf.numel()
+            n_first, size_first = (int(nonfin[0].sum()), leaf[0].numel()) if leaf.shape[0] >= 1 else (0, 0)
+        else:
+            a = np.asarray(leaf)
+            nonfin = ~np.isfinite(a)
+            n_bad, size = int(nonfin.sum()), a.size
+            n_first, size_first = (int(nonfin[0].sum()), a[0].size) if a.shape[0] >= 1 else (0, 0)
+        if n_bad:
+            bad.append(f"{f.name} ({n_bad}/{size} non-finite)")
+            if n_first:
+                first_bad.append(f"{f.name} ({n_first}/{size_first} at t0)")
+    if not bad:
+        return
+    lines = [f"somax-sim {mode} integration produced non-finite values:", "  " + "; ".join(bad)]
+    if first_bad:
+        lines += ["  → already non-finite at the first saved step:", "    " + "; ".join(first_bad),
+                  "  This usually means CFL violation at t0 or bad initial conditions."]
+    else:
+        lines.append("  Mid-integration blow-up. Most common cause: CFL violation "
+                     "(time step too large for the grid spacing and the fastest wave).")
+    lines.append("  Refusing to write artifacts. Check the timestepping (dt vs dx, wave speeds) and try a smaller dt.")
+    raise IntegrationDivergedError("\n".join(lines))
+
+
 def _integrate_and_write(spec: RunSpec, output_dir: Path, *, mode: str, initial_state,
                          diagnostics_per_save: int = 1) -> SimulationResult:
     output_dir = Path(output_dir)
@@ -343,6 +397,8 @@ def _integrate_and_write(spec: RunSpec, output_dir: Path, *, mode: str, initial_
     try:
         if writer:
             writer.close()
+        _assert_finite_state(type(final_state)(**{f.name: getattr(final_state, f.name)[None]
+                                                  for f in dataclasses.fields(final_state)}), mode=mode)
         metrics: dict[str, Any] = {}
         if spec.output.write_metrics and not only_final:
             try:

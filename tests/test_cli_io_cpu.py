@@ -332,3 +332,90 @@ def test_energy_growth_warning(tmp_path):
                                         diagnostics_per_save=1, max_steps_per_chunk=10, run_log=log, mode="run")
     log.stop()
     assert "!! energy grew 25.0x from previous chunk" in (tmp_path / "run.log").read_text()
+
+
+# ------------------------------------------------------------------ more ports of the reference's host-side tests
+def test_allowlist_prefix_and_explicit_class(tmp_path):
+    """tests/test_io_xarray.py:286-306: 'somaxxx' is not under 'somax.'; an explicit state_class
+    skips the allowlist and fails later on the missing variables."""
+    from somax_b200.models.swm import NonlinearSW2DState
+    for mod in ("os", "somaxxx.evil", "somax_b200x.evil"):
+        ds = io.Dataset({"h": (("y", "x"), np.ones((4, 4), np.float32))}, attrs={"state_class": "Whatever", "state_module": mod})
+        io.save_dataset(ds, tmp_path / "t.zarr")
+        loaded = io.load_dataset(tmp_path / "t.zarr")
+        with pytest.raises(ValueError, match="refusing to auto-import"):
+            io.dataset_to_state(loaded)
+        with pytest.raises(ValueError, match="missing variable"):
+            io.dataset_to_state(loaded, state_class=NonlinearSW2DState)
+
+
+def test_assert_finite_state_messages():
+    """tests/test_cli_run.py:51-111."""
+    from somax_b200.cli._run import IntegrationDivergedError, _assert_finite_state
+    from somax_b200.models.swm import NonlinearSW2DState
+    z = np.zeros((3, 4, 4))
+    _assert_finite_state(NonlinearSW2DState(h=np.ones((3, 4, 4)), u=z, v=z), mode="run")
+    h = np.ones((3, 4, 4))
+    h[1, 0, 0] = np.nan
+    with pytest.raises(IntegrationDivergedError) as ei:
+        _assert_finite_state(NonlinearSW2DState(h=h, u=z, v=z), mode="run")
+    assert "h (1/48 non-finite)" in str(ei.value) and "Mid-integration blow-up" in str(ei.value)
+    with pytest.raises(IntegrationDivergedError, match="non-finite"):
+        _assert_finite_state(NonlinearSW2DState(h=np.full((2, 3, 3), np.inf), u=np.zeros((2, 3, 3)), v=np.zeros((2, 3, 3))), mode="run")
+    h = np.ones((3, 4, 4))
+    h[0] = np.nan
+    with pytest.raises(IntegrationDivergedError) as ei:
+        _assert_finite_state(NonlinearSW2DState(h=h, u=z, v=z), mode="run")
+    assert "already non-finite at the first saved step" in str(ei.value) and "CFL" in str(ei.value)
+    with pytest.raises(IntegrationDivergedError, match="spinup integration"):
+        _assert_finite_state(NonlinearSW2DState(h=np.full((2, 3, 3), np.nan), u=np.zeros((2, 3, 3)), v=np.zeros((2, 3, 3))), mode="spinup")
+
+
+def test_run_log_lifecycle(tmp_path):
+    """tests/test_cli_progress.py:32-165."""
+    import time as _time
+    from somax_b200.cli._run import RUN_LOG_FORMAT, start_run_log, stop_run_log
+    ctx = start_run_log(tmp_path / "deep" / "nested", label="test/run", alive_interval=10.0, enable_alive_thread=False)
+    log = tmp_path / "deep" / "nested" / "run.log"
+    assert log.exists() and "started" in log.read_text() and "test/run" in log.read_text()
+    ctx.debug("chunk 1/3 | physics: x")
+    stop_run_log(ctx, final_message="finished cleanly")
+    stop_run_log(ctx)                                    # idempotent
+    lines = log.read_text().splitlines()
+    assert lines[-1].endswith("finished cleanly") and all("| test/run" in ln and "| DEBUG   |" in ln for ln in lines)
+    assert len(lines) == 3 and "{message}" in RUN_LOG_FORMAT
+    for bad in (0.0, -1.0):
+        with pytest.raises(ValueError, match="alive_interval must be > 0"):
+            start_run_log(tmp_path, label="x", alive_interval=bad)
+    ctx = start_run_log(tmp_path / "alive", label="x", alive_interval=0.05)
+    _time.sleep(0.3)
+    stop_run_log(ctx)
+    assert (tmp_path / "alive" / "run.log").read_text().count("alive (") >= 2
+    ctx = start_run_log(tmp_path / "quiet", label="x", alive_interval=0.05, enable_alive_thread=False)
+    _time.sleep(0.2)
+    stop_run_log(ctx)
+    assert "alive (" not in (tmp_path / "quiet" / "run.log").read_text()
+
+
+def test_save_times_monthly_over_a_year_and_attrs():
+    """tests/test_cli_run.py:362-412."""
+    from somax_b200.cli._run import _attrs_for
+    month, year = 2_592_000.0, 31_557_600.0
+    sp = make_spec(t1=year, dt=600.0, save_interval=month)
+    ts = _build_save_times(sp)
+    assert len(ts) == 14 and np.allclose(np.diff(ts)[:12], month) and ts[-1] == year and ts[-1] - ts[-2] < month
+    attrs = _attrs_for(sp, mode="run")
+    assert attrs["somax_sim_mode"] == "run" and attrs["testcase_name"] == "doublegyre_qg"
+    assert all(type(attrs[k]) is float for k in ("t0", "t1", "dt", "save_interval"))
+
+
+def test_spinup_config_disables_outputs_and_production_enables():
+    """tests/test_configs.py:74-90."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spin = S.load_yaml(os.path.join(root, "configs", "doublegyre_bc_qg_spinup.yaml"))
+    assert spin.output.write_snapshots is False and spin.output.write_metrics is False
+    for name in ("doublegyre_bt_qg", "doublegyre_bc_qg", "swm_jet"):
+        sp = S.load_yaml(os.path.join(root, "configs", name + ".yaml"))
+        assert sp.output.write_snapshots and sp.output.write_metrics
+        assert S.RunSpec.from_dict(sp.to_dict()).to_dict() == sp.to_dict()
