@@ -1,6 +1,8 @@
 """Arakawa C-grid operators: numpy restatement of the finitevolx calls somax makes.
 
-Test infrastructure only (see ``oracle/__init__.py``).  PARITY UNPINNED.
+Test infrastructure only (see ``oracle/__init__.py``).  The conventions that used to be open
+(App. E) are PINNED by numbers the reference itself printed in its executed tutorials
+(tests/golden/reference_notebook_outputs.json, tests/test_oracle_reference_pins.py).
 
 Arrays are ``[..., j, i] = [..., y, x]`` with shape ``(..., Ny, Nx)``, one ghost
 ring (``Ny = ny + 2``).  Co-located indexing: ``T[j,i]`` cell centre, ``U[j,i]``
@@ -19,24 +21,34 @@ import numpy as np
 
 @dataclass(frozen=True)
 class OperatorSpec:
-    """The unverified finitevolx/spectraldiffx choices.
+    """The finitevolx/spectraldiffx conventions SURVEY.md App. E left open.  The DEFAULTS are the
+    ones that reproduce the reference's own printed tutorial outputs (module docstring); the
+    other settings are kept so that the tests can show they do NOT.
 
     One switch flips oracle and CUDA kernels together (the same bits travel
     through the C ABI as ``spec_flags``).
     """
 
-    #: Advection2D writes [2:-2,2:-2] (True) or [1:-1,1:-1] (False).  App. E-3.
+    #: Advection2D writes [2:-2,2:-2] (True) or [1:-1,1:-1] (False).  Pinned True by
+    #: step17_shallow_water_2d.ipynb cells 9 and 18 (False: max|u| 0.909 vs 0.8879 printed).
     advection_region2: bool = True
-    #: Diffusion2D = nu * 5-point laplacian on [1:-1,1:-1] (False) or flux form
-    #: with interior-only (zero-ghost) face fluxes (True).  App. E-3.
-    diffusion_flux_form: bool = False
-    #: DST Helmholtz eigenvalues: 5-point finite-difference (True) or continuous.
-    #: Only the FD flavour is implemented on the GPU (it is what makes the
-    #: transform-in-x / tridiagonal-in-y factorisation exact).  App. E-1.
+    #: Diffusion2D = flux form with interior-only (zero-ghost) face fluxes (True) or
+    #: nu * 5-point laplacian on [1:-1,1:-1] (False).  Pinned True by step17 cell 18:
+    #: d(sum u^2)/d(nu) = -3.126971e-04 printed; flux form -3.1268e-04, laplacian -3.0798e-04.
+    diffusion_flux_form: bool = True
+    #: DST Helmholtz eigenvalues: 5-point finite-difference (True) or continuous.  Pinned True
+    #: by step09 cell 7 (5.585729e-02 printed; FD 5.585726e-02, continuous 5.5778e-02).  Only
+    #: the FD flavour exists on the GPU (it is what makes the transform-in-x /
+    #: tridiagonal-in-y factorisation exact): the C ABI refuses the other one.
     dst_fd_eigenvalues: bool = True
+    #: The DST solve takes every point of the array it is given as an unknown (True) or the
+    #: interior only with a zero ring (False).  Pinned True by the same cells; the C ABI
+    #: refuses False.
+    dst_full_array: bool = True
 
     def flags(self) -> int:
-        return (1 if self.advection_region2 else 0) | (2 if self.diffusion_flux_form else 0)
+        return ((1 if self.advection_region2 else 0) | (2 if self.diffusion_flux_form else 0)
+                | (0 if self.dst_fd_eigenvalues else 4) | (0 if self.dst_full_array else 8))
 
 
 DEFAULT_SPEC = OperatorSpec()

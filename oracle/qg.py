@@ -1,6 +1,7 @@
 """Barotropic / baroclinic QG: numpy restatement of the reference models.
 
-Test infrastructure only.  PARITY UNPINNED (see oracle/__init__.py).
+Test infrastructure only.  Elliptic conventions pinned by the reference's executed tutorials
+(oracle/elliptic.py); see oracle/__init__.py for what is and is not pinned.
 ref: somax/_src/models/qg/baroclinic.py:135-228,277-332; qg/barotropic.py:113-248.
 """
 from __future__ import annotations
@@ -21,7 +22,10 @@ class QGModel:
     """State is ``q`` with shape (nl, Ny, Nx) (barotropic: nl = 1).
 
     The barotropic model (qg/barotropic.py:123-152) is the nl=1 case with
-    Cl2m=Cm2l=[[1]], lambda=[0] and H0=1 (wind not divided by H; drag on the only layer).
+    Cl2m=Cm2l=[[1]], lambda=[0] and H0=1 (wind not divided by H; drag on the only layer) and
+    ``zero_psi_ring=False``: BarotropicQG._invert_pv (qg/barotropic.py:113-121) returns the
+    solver's output as it is, while BaroclinicQG._invert_pv zeroes the ring of psi
+    (qg/baroclinic.py:157-158).  With the full-array DST solve the ring of psi is not zero.
     """
 
     nx: int
@@ -40,6 +44,7 @@ class QGModel:
     rossby_radii: np.ndarray | None = None
     spec: OperatorSpec = field(default_factory=lambda: DEFAULT_SPEC)
     workers: int | None = None
+    zero_psi_ring: bool = True
 
     @property
     def nl(self):
@@ -55,7 +60,7 @@ class QGModel:
         qm = np.einsum("lm,m...->l...", self.Cl2m.astype(dt), q)
         pm = helmholtz_dst(qm, self.dx, self.dy, self.lambdas, self.spec, self.workers)
         psi = np.einsum("lm,m...->l...", self.Cm2l.astype(dt), pm)
-        return op.zero_boundaries(psi)
+        return op.zero_boundaries(psi) if self.zero_psi_ring else psi
 
     # ref: qg/baroclinic.py:161-190
     def rhs(self, q):
@@ -134,4 +139,4 @@ def create_barotropic(nx=64, ny=64, Lx=1e6, Ly=1e6, f0=1e-4, beta=1.6e-11,
     return QGModel(nx=nx, ny=ny, dx=Lx / nx, dy=Ly / ny, Cl2m=one, Cm2l=one.copy(),
                    lambdas=np.zeros(1), beta_y=beta * (Y - Ly / 2.0),
                    wind=_wind(Y, Ly, wind_profile), H0=1.0, nu=lateral_viscosity,
-                   kappa=bottom_drag, tau0=wind_amplitude, spec=spec)
+                   kappa=bottom_drag, tau0=wind_amplitude, spec=spec, zero_psi_ring=False)

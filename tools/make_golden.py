@@ -1,8 +1,10 @@
 """Generate tests/golden/*.npz from the CPU oracle (fp64).
 
-The reference cannot run in this image (no JAX), so these vectors freeze the ORACLE, not the
-reference: parity stays "unpinned" until tools/capture_reference.py is run on a machine with
-somax + JAX installed and its output is compared with these files.
+The reference cannot run in this image (no JAX), so these vectors freeze the ORACLE; the oracle's
+conventions are pinned by the reference's own printed tutorial outputs
+(tests/golden/reference_notebook_outputs.json, tests/test_oracle_reference_pins.py).
+tools/capture_reference.py regenerates the same vectors from the real reference on a machine
+with somax + JAX.
 Run: PYTHONPATH=. python tools/make_golden.py
 """
 from pathlib import Path
