@@ -49,13 +49,21 @@ typedef enum { SOMAX_B200_BC_PERIODIC = 0, SOMAX_B200_BC_WALL = 1 } somax_b200_s
 /* Elliptic-solver selection for the PV inversion (qg/baroclinic.py:146-152, bc="dst"). */
 typedef enum {
   SOMAX_B200_SOLVER_AUTO = 0,   /* FFT path when nx is a power of two >= 8, else dense */
-  SOMAX_B200_SOLVER_FFT = 1,    /* radix FFT DST-I(nx-1) in x + bordered last column + Thomas in y */
-  SOMAX_B200_SOLVER_DENSE = 2   /* dense DST-I(nx) matrix in x + Thomas in y (any nx <= 2048) */
+  SOMAX_B200_SOLVER_FFT = 1,    /* radix FFT DST-I(nx-1) in x + three border columns (Schur) + Thomas in y */
+  SOMAX_B200_SOLVER_DENSE = 2   /* dense DST-I(nx+2) matrix in x + Thomas in y (any nx <= 2046) */
 } somax_b200_solver;
 
-/* Unverified finitevolx conventions; same bits as oracle.OperatorSpec.flags(). */
+/* finitevolx / spectraldiffx conventions; same bits as
+ * oracle.OperatorSpec.flags().  The reference's behaviour, pinned by the outputs it printed in its
+ * executed tutorials (tests/golden/reference_notebook_outputs.json), is
+ * ADVECTION_REGION2 | DIFFUSION_FLUX with the DST bits clear. */
 #define SOMAX_B200_SPEC_ADVECTION_REGION2 1u /* Advection2D writes [2:-2,2:-2] */
 #define SOMAX_B200_SPEC_DIFFUSION_FLUX 2u    /* Diffusion2D in flux form with zero ghost fluxes */
+#define SOMAX_B200_SPEC_DST_CONTINUOUS 4u    /* continuous DST eigenvalues: NOT the reference, ERR_UNSUPPORTED */
+#define SOMAX_B200_SPEC_DST_INTERIOR 8u      /* DST on the interior with a zero ring: NOT the reference, ERR_UNSUPPORTED */
+/* BarotropicQG._invert_pv keeps the ring of psi the solver returns (qg/barotropic.py:113-121);
+ * without this bit the ring of psi is zero, as BaroclinicQG._invert_pv leaves it (qg/baroclinic.py:157-158). */
+#define SOMAX_B200_SPEC_KEEP_PSI_RING 16u
 
 typedef struct somax_b200_qg_s* somax_b200_qg_t;
 typedef struct somax_b200_swm_s* somax_b200_swm_t;
@@ -102,7 +110,9 @@ size_t somax_b200_qg_device_bytes(somax_b200_qg_t h);
 /* BaroclinicQG.apply_boundary_conditions (qg/baroclinic.py:192-195): ring := 0.  out may alias q. */
 int somax_b200_qg_apply_bc(somax_b200_qg_t h, const void* q, void* out, void* stream);
 
-/* BaroclinicQG._invert_pv (qg/baroclinic.py:135-159): psi = ring0(Cm2l . Helm^-1 . Cl2m . q). */
+/* BaroclinicQG._invert_pv (qg/baroclinic.py:135-159): psi = ring0(Cm2l . Helm^-1 . Cl2m . q); the
+ * Helmholtz solve takes every point of the (Ny, Nx) array, ring included, as an unknown, exactly as
+ * finitevolx.pv_inversion(bc="dst") does.  With SPEC_KEEP_PSI_RING: BarotropicQG._invert_pv. */
 int somax_b200_qg_invert(somax_b200_qg_t h, const void* q, void* psi, void* stream);
 
 /* BaroclinicQG.vector_field (qg/baroclinic.py:161-190).  apply_bc != 0 evaluates

@@ -512,6 +512,10 @@ struct somax_b200_qg_s {
 
 namespace {
 
+// BarotropicQG._invert_pv returns the solver's output as it is (qg/barotropic.py:113-121);
+// BaroclinicQG._invert_pv zeroes the ring of psi (qg/baroclinic.py:157-158).
+inline int keep_psi_ring(const somax_b200_qg_s* h) { return (h->spec & SOMAX_B200_SPEC_KEEP_PSI_RING) ? 1 : 0; }
+
 template <typename T>
 QgArgs<T> make_qargs(somax_b200_qg_t h, const somax_b200_params* p, int apply_bc) {
   QgArgs<T> A;
@@ -620,7 +624,7 @@ int launch_stencil(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st_in,
 // one RHS evaluation: psi = invert(Yin), then the fused stencil + RK epilogue
 template <typename T>
 int eval_rhs(somax_b200_qg_t h, const QgArgs<T>& A, const Stage<T>& st_in, double dt, cudaStream_t s) {
-  if (int rc = qg_solver_run<T>(h->solver, st_in.Yin[0], (T*)h->psi, s)) return rc;
+  if (int rc = qg_solver_run<T>(h->solver, st_in.Yin[0], (T*)h->psi, A.apply_bc, keep_psi_ring(h), s)) return rc;
   return launch_stencil<T>(h, A, st_in, dt, s);
 }
 
@@ -760,7 +764,7 @@ template <typename T>
 int qg_invert_impl(somax_b200_qg_t h, const void* q, void* psi, cudaStream_t s) {
   const Layout& L = h->L;
   if (int rc = pack_field<T>((const T*)q, (T*)h->Ya, L, s)) return rc;
-  if (int rc = qg_solver_run<T>(h->solver, (const T*)h->Ya, (T*)h->psi, s)) return rc;
+  if (int rc = qg_solver_run<T>(h->solver, (const T*)h->Ya, (T*)h->psi, 0, keep_psi_ring(h), s)) return rc;
   return unpack_field<T>((const T*)h->psi, (T*)psi, L, s);
 }
 
@@ -776,7 +780,7 @@ template <typename T>
 int qg_diag_impl(somax_b200_qg_t h, const void* q, double* out, cudaStream_t s) {
   const Layout& L = h->L;
   if (int rc = pack_field<T>((const T*)q, (T*)h->Ya, L, s)) return rc;
-  if (int rc = qg_solver_run<T>(h->solver, (const T*)h->Ya, (T*)h->psi, s)) return rc;
+  if (int rc = qg_solver_run<T>(h->solver, (const T*)h->Ya, (T*)h->psi, 0, keep_psi_ring(h), s)) return rc;
   SB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * L.batch * (2 * L.nl + 1), s));
   dim3 b(256), g(std::min((L.Nx + 255) / 256, 64), std::min(L.Ny, 128), L.batch * L.nl);
   prof_begin("qg_diag_kernel", s);
@@ -790,12 +794,12 @@ int qg_diag_impl(somax_b200_qg_t h, const void* q, double* out, cudaStream_t s) 
 #define SB_DISPATCH(h, fn, ...) \
   ((h)->dtype == SOMAX_B200_F32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
 
-extern "C" {
-
-int somax_b200_qg_create(somax_b200_qg_t* out, int dtype, int batch, int nl, int ny, int nx,
-                         double dx, double dy, const double* Cl2m, const double* Cm2l,
-                         const double* lambdas, const double* beta_y, const double* wind,
-                         int solver, unsigned spec_flags) {
+// rows > 0: the PV-inversion row stage covers window rows [jo, jo + rows) only (slab of the
+// distributed model, qg_slab.cuh); default: the whole array.
+static int qg_create_impl(somax_b200_qg_t* out, int dtype, int batch, int nl, int ny, int nx,
+                          double dx, double dy, const double* Cl2m, const double* Cm2l,
+                          const double* lambdas, const double* beta_y, const double* wind,
+                          int solver, unsigned spec_flags, int rows, int jo, int ylo, int yhi) {
   if (!out) return fail(SOMAX_B200_ERR_INVALID, "out is null");
   *out = nullptr;
   if (dtype != SOMAX_B200_F32 && dtype != SOMAX_B200_F64)
@@ -805,11 +809,14 @@ int somax_b200_qg_create(somax_b200_qg_t* out, int dtype, int batch, int nl, int
   if (!Cl2m || !Cm2l || !lambdas || !beta_y || !wind)
     return fail(SOMAX_B200_ERR_INVALID, "null coefficient pointer");
   if ((long)batch * nl > 65535) return fail(SOMAX_B200_ERR_UNSUPPORTED, "batch*nl > 65535");
+  if (spec_flags & (SOMAX_B200_SPEC_DST_CONTINUOUS | SOMAX_B200_SPEC_DST_INTERIOR))
+    return fail(SOMAX_B200_ERR_UNSUPPORTED,
+                "only the reference's DST convention is implemented: finite-difference eigenvalues on the whole array");
   if (int rc = require_device()) return rc;
   auto* h = new somax_b200_qg_s();
   h->dtype = dtype; h->L = make_layout(batch, nl, ny, nx); h->ny = ny; h->nx = nx;
   h->dx = dx; h->dy = dy; h->spec = spec_flags;
-  int rc = qg_solver_create(&h->solver, dtype, batch, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, solver);
+  int rc = qg_solver_create(&h->solver, dtype, batch, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, solver, 1, rows, jo, ylo, yhi);
   auto up = [&](const double* src, void** dst, bool* one) {
     return dtype == SOMAX_B200_F32 ? upload_coef<float>(src, (float**)dst, h->L.Ny, h->L.Nx, one)
                                    : upload_coef<double>(src, (double**)dst, h->L.Ny, h->L.Nx, one);
@@ -830,6 +837,16 @@ int somax_b200_qg_create(somax_b200_qg_t* out, int dtype, int batch, int nl, int
   h->bytes += qg_solver_bytes(h->solver);
   *out = h;
   return 0;
+}
+
+extern "C" {
+
+int somax_b200_qg_create(somax_b200_qg_t* out, int dtype, int batch, int nl, int ny, int nx,
+                         double dx, double dy, const double* Cl2m, const double* Cm2l,
+                         const double* lambdas, const double* beta_y, const double* wind,
+                         int solver, unsigned spec_flags) {
+  return qg_create_impl(out, dtype, batch, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, beta_y, wind,
+                        solver, spec_flags, -1, 0, 1, 1);
 }
 
 int somax_b200_qg_destroy(somax_b200_qg_t h) {

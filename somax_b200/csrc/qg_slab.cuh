@@ -4,7 +4,9 @@
 // Included at the end of qg.cu (it drives the same stencil / solver stages).  Rank r of P owns
 // rows [r*ny/P, (r+1)*ny/P) of every layer, stored as a window (ny/P + 2 rows) of the global
 // padded array: its first / last row is the physical ring on the edge ranks and a halo row of
-// the neighbour's data elsewhere.  One right-hand-side evaluation:
+// the neighbour's data elsewhere.  The PV inversion takes EVERY row of the global array as an
+// unknown (oracle/elliptic.py), so for the solve the edge ranks also own their ring row: rank r
+// holds the solver rows [slab_r0(r), slab_r1(r)) of the Ny = ny + 2.  One right-hand-side evaluation:
 //
 //   rows_fwd   layer->mode mix + DST-I in x of the slab's rows            (local, R)
 //   X1         transpose: strips of R -> the owning rank's column array S  (peer stores, NVLink)
@@ -34,7 +36,7 @@
 namespace sb {
 
 constexpr int QGS_MAX_RANKS = 16;
-constexpr int QGS_NBUF = 9;    // exported buffers: cols.S, cols.part, R, psi, inbox, flags, ghat, gvec, gvecf
+constexpr int QGS_NBUF = 10;   // exported buffers: cols.S, cols.part, R, psi, inbox, flags, ghat, gvec, gvecf, cols.bext
 
 struct Seg {
   const char* src; char* dst;
@@ -91,7 +93,7 @@ struct SlabRank {
   int rank = 0, s0 = 0, s1 = 0;
   void* inbox = nullptr;            // [2][planes][pitch]: halo rows of the newest stage state from below / above
   unsigned* flags = nullptr;        // [QGS_MAX_RANKS] barrier slots + [QGS_MAX_RANKS] error word
-  SegTable x1, xb, x2, x3, xpsi, xstate[3], xin[3], xg1, xg2, xg2f;
+  SegTable x1, xb, x2, x3, xpsi, xstate[3], xin[3], xg1, xg2, xg2f, xring;
 };
 
 struct SlabPeer { void* buf[QGS_NBUF]; };
@@ -117,6 +119,9 @@ struct IpcBlob {
 };
 
 inline size_t qgs_es(const somax_b200_qgs_s* g) { return g->dtype == SOMAX_B200_F32 ? 4 : 8; }
+// solver rows (= global field rows) owned by rank r: the edge ranks include their ring row
+inline int slab_r0(const somax_b200_qgs_s* g, int r) { return r == 0 ? 0 : r * g->ny_loc + 1; }
+inline int slab_r1(const somax_b200_qgs_s* g, int r) { return r == g->nranks - 1 ? g->ny + 2 : (r + 1) * g->ny_loc + 1; }
 
 int seg_upload(SegTable& t, const std::vector<Seg>& v, size_t* bytes) {
   t.n = (int)v.size();
@@ -149,55 +154,76 @@ int seg_launch(const char* tag, const SegTable& t, cudaStream_t s) {
 // Exchange tables of local rank R against the peer pointer table (all pointers valid in this process).
 int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
   const size_t es = qgs_es(g);
-  const int P = g->nranks, p = R.rank, nyl = g->ny_loc, ny = g->ny, spr = g->spr;
+  const int P = g->nranks, p = R.rank, nyl = g->ny_loc, spr = g->spr;
   const QgSolverView vr = qg_solver_view(R.core->solver), vc = qg_solver_view(R.cols);
   const int planes = vc.planes, np = vc.np, nstrip = vc.nstrip;
+  const int NyS = vc.ny;                                 // solver rows of the whole grid (ny + 2)
+  const int my0 = slab_r0(g, p), my1 = slab_r1(g, p), myrows = my1 - my0;      // == vr.ny
   const Layout& L = R.core->L;
   char* Rl = (char*)vr.S;
   char* Sl = (char*)vc.S;
-  const size_t blk = (size_t)nyl * SP_W * es;          // one strip of the slab's rows
-  const size_t col = (size_t)ny * SP_W * es;           // one strip of the whole grid
-  std::vector<Seg> x1, xb, x2, x3, xpsi, xg1, xg2, xg2f;
+  const size_t blk = (size_t)myrows * SP_W * es;       // one strip of my rows
+  const size_t col = (size_t)NyS * SP_W * es;          // one strip of the whole grid
+  std::vector<Seg> x1, xb, x2, x3, xpsi, xg1, xg2, xg2f, xring;
+  // BarotropicQG keeps the ring of psi: the solved border columns 0 and nx+1 of my rows (my slice of
+  // the border-system outputs) go from the column solver's bext to the row solver's (local copy)
+  for (int pl = 0; pl < planes; ++pl)
+    for (int w = 0; w < 2; ++w)
+      xring.push_back(Seg{(const char*)vc.bext + (((size_t)pl * 2 + w) * NyS + my0) * es,
+                          (char*)vr.bext + ((size_t)pl * 2 + w) * myrows * es, 1u, (unsigned)(myrows * es), 0, 0});
   const int last_owner = (nstrip - 1) / spr;
-  const int a0 = p * nyl;                                // my slice of the border-system outputs
+  const int a0 = my0, na = myrows;                       // my slice of the border-system outputs
   for (int r = 0; r < P; ++r) {
     char* Sr = (char*)g->peers[r].buf[0];
     char* partr = (char*)g->peers[r].buf[1];
     char* Rr = (char*)g->peers[r].buf[2];
+    char* bextr = (char*)g->peers[r].buf[9];
+    const int r0 = slab_r0(g, r), rrows = slab_r1(g, r) - r0;
+    const size_t blkr = (size_t)rrows * SP_W * es;
     for (int pl = 0; pl < planes; ++pl) {
       // X1: my rows of rank r's strips -> its column array
       x1.push_back(Seg{Rl + ((size_t)pl * nstrip + (size_t)r * spr) * blk,
-                       Sr + ((size_t)pl * nstrip + (size_t)r * spr) * col + (size_t)p * nyl * SP_W * es,
+                       Sr + ((size_t)pl * nstrip + (size_t)r * spr) * col + (size_t)my0 * SP_W * es,
                        (unsigned)spr, (unsigned)blk, blk, col});
-      // raw border column (x index ncols) of my rows -> every rank that does not own its strip
+      // raw border columns of my rows -> every rank (each one reduces the border system): column nx
+      // (slot ncols of S; its strip's owner gets it with X1), columns 0 and nx+1 (bext)
       if (r != last_owner)
-        xb.push_back(Seg{Rl + ((size_t)pl * nyl * np + sp_off(nyl, 0, vc.ncols)) * es,
-                         Sr + ((size_t)pl * ny * np + sp_off(ny, p * nyl, vc.ncols)) * es,
-                         (unsigned)nyl, (unsigned)es, SP_W * es, SP_W * es});
-      // X2: border partial sums of my strips -> every other rank
+        xb.push_back(Seg{Rl + ((size_t)pl * myrows * np + sp_off(myrows, 0, vc.ncols)) * es,
+                         Sr + ((size_t)pl * NyS * np + sp_off(NyS, my0, vc.ncols)) * es,
+                         (unsigned)myrows, (unsigned)es, SP_W * es, SP_W * es});
+      for (int w = 0; w < 2; ++w)
+        xb.push_back(Seg{(const char*)vr.bext + ((size_t)pl * 2 + w) * myrows * es,
+                         bextr + (((size_t)pl * 2 + w) * NyS + my0) * es, 1u, (unsigned)(myrows * es), 0, 0});
+      // X2: border partial sums (even / odd columns) of my strips -> every other rank
+      if (r != p)
+        for (int par = 0; par < 2; ++par) {
+          const size_t o = (((size_t)pl * 2 + par) * 2 * nstrip + 2 * (size_t)R.s0) * NyS * es;
+          x2.push_back(Seg{(char*)vc.part + o, partr + o, 1u, (unsigned)(2 * (size_t)spr * NyS * es), 0, 0});
+        }
+      // XG1 / XG2: my slice of ghat (3 columns), then of gvec (2 combinations; + float copy, + border
+      // column nx of S for the rank that owns the last strip) -> every other rank
       if (r != p) {
-        const size_t o = ((size_t)pl * 2 * nstrip + 2 * (size_t)R.s0) * ny * es;
-        x2.push_back(Seg{(char*)vc.part + o, partr + o, 1u, (unsigned)(2 * (size_t)spr * ny * es), 0, 0});
-      }
-      // XG1 / XG2: my slice of ghat, then of gvec (+ float copy, + border column of S for the
-      // rank that owns the last strip) -> every other rank
-      if (r != p) {
-        const size_t go = ((size_t)pl * ny + a0) * sizeof(double);
-        xg1.push_back(Seg{(const char*)vc.ghat + go, (char*)g->peers[r].buf[6] + go, 1u, (unsigned)(nyl * sizeof(double)), 0, 0});
-        xg2.push_back(Seg{(const char*)vc.gvec + go, (char*)g->peers[r].buf[7] + go, 1u, (unsigned)(nyl * sizeof(double)), 0, 0});
-        if (es == 4) {
-          const size_t fo = ((size_t)pl * ny + a0) * sizeof(float);
-          xg2f.push_back(Seg{(const char*)vc.gvecf + fo, (char*)g->peers[r].buf[8] + fo, 1u, (unsigned)(nyl * sizeof(float)), 0, 0});
+        for (int i = 0; i < 3; ++i) {
+          const size_t go = (((size_t)pl * 3 + i) * NyS + a0) * sizeof(double);
+          xg1.push_back(Seg{(const char*)vc.ghat + go, (char*)g->peers[r].buf[6] + go, 1u, (unsigned)(na * sizeof(double)), 0, 0});
+        }
+        for (int i = 0; i < 2; ++i) {
+          const size_t go = (((size_t)pl * 2 + i) * NyS + a0) * sizeof(double);
+          xg2.push_back(Seg{(const char*)vc.gvec + go, (char*)g->peers[r].buf[7] + go, 1u, (unsigned)(na * sizeof(double)), 0, 0});
+          if (es == 4) {
+            const size_t fo = (((size_t)pl * 2 + i) * NyS + a0) * sizeof(float);
+            xg2f.push_back(Seg{(const char*)vc.gvecf + fo, (char*)g->peers[r].buf[8] + fo, 1u, (unsigned)(na * sizeof(float)), 0, 0});
+          }
         }
         if (r == last_owner) {
-          const size_t so = ((size_t)pl * ny * np + sp_off(ny, a0, vc.nx - 1)) * es;
-          xg2f.push_back(Seg{Sl + so, Sr + so, (unsigned)nyl, (unsigned)es, SP_W * es, SP_W * es});
+          const size_t so = ((size_t)pl * NyS * np + sp_off(NyS, a0, vc.nx - 1)) * es;
+          xg2f.push_back(Seg{Sl + so, Sr + so, (unsigned)na, (unsigned)es, SP_W * es, SP_W * es});
         }
       }
       // X3: rank r's rows of my strips -> its row array
-      x3.push_back(Seg{Sl + ((size_t)pl * nstrip + (size_t)R.s0) * col + (size_t)r * nyl * SP_W * es,
-                       Rr + ((size_t)pl * nstrip + (size_t)R.s0) * blk,
-                       (unsigned)spr, (unsigned)blk, col, blk});
+      x3.push_back(Seg{Sl + ((size_t)pl * nstrip + (size_t)R.s0) * col + (size_t)r0 * SP_W * es,
+                       Rr + ((size_t)pl * nstrip + (size_t)R.s0) * blkr,
+                       (unsigned)spr, (unsigned)blkr, col, blkr});
     }
   }
   // halo rows: my first owned row (1) -> rank p-1's top halo row; my last owned row -> rank p+1's row 0
@@ -225,6 +251,7 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
   if (int rc = seg_upload(R.xg1, xg1, &g->bytes)) return rc;
   if (int rc = seg_upload(R.xg2, xg2, &g->bytes)) return rc;
   if (int rc = seg_upload(R.xg2f, xg2f, &g->bytes)) return rc;
+  if (int rc = seg_upload(R.xring, xring, &g->bytes)) return rc;
   for (int b = 0; b < 3; ++b) {
     std::vector<Seg> xs, xi;
     halo((const char*)st[b], 4, true, xs);
@@ -242,7 +269,7 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
 void qgs_local_ptrs(const SlabRank& R, void** out) {
   const QgSolverView vr = qg_solver_view(R.core->solver), vc = qg_solver_view(R.cols);
   out[0] = vc.S; out[1] = vc.part; out[2] = vr.S; out[3] = R.core->psi; out[4] = R.inbox; out[5] = R.flags;
-  out[6] = vc.ghat; out[7] = vc.gvec; out[8] = vc.gvecf ? (void*)vc.gvecf : (void*)vc.gvec;
+  out[6] = vc.ghat; out[7] = vc.gvec; out[8] = vc.gvecf ? (void*)vc.gvecf : (void*)vc.gvec; out[9] = vc.bext;
 }
 
 int qgs_barrier(somax_b200_qgs_s* g, cudaStream_t s) {
@@ -268,7 +295,7 @@ int qgs_eval(somax_b200_qgs_s* g, const somax_b200_params* p, int in_b, int y_b,
              double hd, bool store_f, int f_slot, cudaStream_t s) {
   auto bufp = [](SlabRank& R, int b) -> void* { return b == 0 ? R.core->y : (b == 1 ? R.core->Ya : R.core->Yb); };
   for (SlabRank& R : g->local)
-    if (int rc = qg_solver_rows_fwd<T>(R.core->solver, (const T*)bufp(R, in_b), s)) return rc;
+    if (int rc = qg_solver_rows_fwd<T>(R.core->solver, (const T*)bufp(R, in_b), 1, s)) return rc;
   for (SlabRank& R : g->local) {
     if (int rc = seg_launch("slab_x1_transpose", R.x1, s)) return rc;
     if (int rc = seg_launch("slab_x1_border", R.xb, s)) return rc;
@@ -282,16 +309,15 @@ int qgs_eval(somax_b200_qgs_s* g, const somax_b200_params* p, int in_b, int y_b,
   for (SlabRank& R : g->local)
     if (int rc = seg_launch("slab_x2_partials", R.x2, s)) return rc;
   if (int rc = qgs_barrier(g, s)) return rc;
-  const int nyl = g->ny_loc;
   for (SlabRank& R : g->local) {
     if (int rc = qg_solver_border_stage<T>(R.cols, 0, 0, -1, s)) return rc;
-    if (int rc = qg_solver_border_stage<T>(R.cols, 1, R.rank * nyl, (R.rank + 1) * nyl, s)) return rc;
+    if (int rc = qg_solver_border_stage<T>(R.cols, 1, slab_r0(g, R.rank), slab_r1(g, R.rank), s)) return rc;
   }
   for (SlabRank& R : g->local)
     if (int rc = seg_launch("slab_xg_border", R.xg1, s)) return rc;
   if (int rc = qgs_barrier(g, s)) return rc;
   for (SlabRank& R : g->local)
-    if (int rc = qg_solver_border_stage<T>(R.cols, 2, R.rank * nyl, (R.rank + 1) * nyl, s)) return rc;
+    if (int rc = qg_solver_border_stage<T>(R.cols, 2, slab_r0(g, R.rank), slab_r1(g, R.rank), s)) return rc;
   for (SlabRank& R : g->local) {
     if (int rc = seg_launch("slab_xg_border", R.xg2, s)) return rc;
     if (int rc = seg_launch("slab_xg_border", R.xg2f, s)) return rc;
@@ -302,8 +328,12 @@ int qgs_eval(somax_b200_qgs_s* g, const somax_b200_params* p, int in_b, int y_b,
   for (SlabRank& R : g->local)
     if (int rc = seg_launch("slab_x3_transpose", R.x3, s)) return rc;
   if (int rc = qgs_barrier(g, s)) return rc;
-  for (SlabRank& R : g->local)
-    if (int rc = qg_solver_rows_inv<T>(R.core->solver, (T*)R.core->psi, s)) return rc;
+  for (SlabRank& R : g->local) {
+    const int keep = keep_psi_ring(R.core);
+    if (keep)
+      if (int rc = seg_launch("slab_ring_cols", R.xring, s)) return rc;
+    if (int rc = qg_solver_rows_inv<T>(R.core->solver, (T*)R.core->psi, keep, s)) return rc;
+  }
   for (SlabRank& R : g->local)
     if (int rc = seg_launch("slab_halo_psi", R.xpsi, s)) return rc;
   if (int rc = qgs_barrier(g, s)) return rc;
@@ -422,8 +452,11 @@ int somax_b200_qgs_create(somax_b200_qgs_t* out, int dtype, int nl, int ny, int 
     SlabRank& R = g->local[v];
     R.rank = rank_first + v; R.s0 = R.rank * g->spr; R.s1 = R.s0 + g->spr;
     const size_t row0 = (size_t)R.rank * nyl;      // the slab's window starts at global row row0
-    rc = somax_b200_qg_create(&R.core, dtype, 1, nl, nyl, nx, dx, dy, Cl2m, Cm2l, lambdas,
-                              beta_y + row0 * Nx, wind + row0 * Nx, SOMAX_B200_SOLVER_FFT, spec_flags);
+    // the slab's row stage covers the solver rows it owns: window rows [jo, jo + rows)
+    const int jo = R.rank == 0 ? 0 : 1, rows = slab_r1(g, R.rank) - slab_r0(g, R.rank);
+    rc = qg_create_impl(&R.core, dtype, 1, nl, nyl, nx, dx, dy, Cl2m, Cm2l, lambdas,
+                        beta_y + row0 * Nx, wind + row0 * Nx, SOMAX_B200_SOLVER_FFT, spec_flags,
+                        rows, jo, R.rank == 0, R.rank == nranks - 1);
     if (rc) break;
     R.core->bc_ylo = R.rank == 0; R.core->bc_yhi = R.rank == nranks - 1;
     rc = qg_solver_create(&R.cols, dtype, 1, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, SOMAX_B200_SOLVER_FFT, g->nseg);
@@ -454,7 +487,7 @@ int somax_b200_qgs_destroy(somax_b200_qgs_t g) {
   for (void* p : g->ipc_opened) cudaIpcCloseMemHandle(p);
   for (SlabRank& R : g->local) {
     SegTable* ts[] = {&R.x1, &R.xb, &R.x2, &R.x3, &R.xpsi, &R.xstate[0], &R.xstate[1], &R.xstate[2],
-                      &R.xin[0], &R.xin[1], &R.xin[2], &R.xg1, &R.xg2, &R.xg2f};
+                      &R.xin[0], &R.xin[1], &R.xin[2], &R.xg1, &R.xg2, &R.xg2f, &R.xring};
     for (SegTable* t : ts) cudaFree(t->dev);
     cudaFree(R.inbox); cudaFree(R.flags);
     qg_solver_destroy(R.cols);

@@ -1,18 +1,22 @@
 // PV inversion for the QG models: psi = ring0(Cm2l . Helm^-1_lambda . Cl2m . q).
 //
 // Replaces BaroclinicQG._invert_pv / finitevolx.pv_inversion(bc="dst") (reference
-// qg/baroclinic.py:135-159; recipe SURVEY.md App. B.4).  The reference transforms with a
-// DST-I in both directions and divides by the 5-point eigenvalues, i.e. it solves the
-// discrete system (delta_xx + delta_yy - lambda) psi = q with psi = 0 on the ghost ring
-// EXACTLY.  Any exact direct solver of that system is therefore equivalent to rounding.
-// DST-I of length nx needs an FFT of length 2(nx+1), which for nx = 2^p has a large prime
-// factor (8193 = 3*2731), so this solver is B200-first instead:
+// qg/baroclinic.py:135-159; recipe SURVEY.md App. B.4).  The reference transforms the WHOLE
+// (Ny, Nx) array it is given - ghost ring included - with a DST-I in both directions and divides
+// by the 5-point eigenvalues (pinned by the reference's printed tutorial outputs, see
+// oracle/elliptic.py), i.e. it solves the discrete system (delta_xx + delta_yy - lambda) psi = q
+// on Ny x Nx unknowns with psi = 0 one cell outside the array EXACTLY.  Any exact direct solver
+// of that system is therefore equivalent to rounding.  DST-I of length Nx = nx + 2 needs an FFT
+// of length 2(nx+3), which for nx = 2^p is never a power of two (8195 = 5*11*149), so this
+// solver is B200-first instead:
 //
-//   FFT path (nx = 2^p): columns 1..nx-1 are transformed with a DST-I of size nx-1 (an
-//     in-shared-memory radix-8 complex FFT of length nx); the last column is a border
-//     handled by a Schur complement: solve 1 gives v, g = S^-1(f_n - b v(n-1)) via a dense
-//     DST in y on that single column, solve 2 adds the harmonic correction for g.
-//   dense path (any nx <= 2048): x transform as a dense DST-I matrix product.
+//   FFT path (nx = 2^p): array columns 1..nx-1 are transformed with a DST-I of size nx-1 (an
+//     in-shared-memory complex FFT of length nx); columns 0, nx and nx+1 are border unknowns
+//     g0, g1, g2 handled by a Schur complement (tools/proto_bordered3.py): solve 1 gives v, the
+//     border right-hand sides f_0 - b v(1), f_nx - b v(nx-1), f_nx+1 go through a dense DST in y
+//     and a host-inverted 3 x 3 matrix per y-mode, solve 2 adds the harmonic correction
+//     b sin(pi k / nx) (g0 +- g1) (sign by the parity of the x-wavenumber k).
+//   dense path (any nx <= 2046): x transform as a dense DST-I(nx+2) matrix product.
 //   Both: the y direction is solved per x-wavenumber by the Thomas algorithm, marching in y
 //     with one thread per wavenumber (coalesced), carried in fp64 even for fp32 data (the
 //     second-difference recurrences lose ~ (ny/pi)^2 eps otherwise), coefficients from a
@@ -36,14 +40,19 @@ constexpr int TH_COLS = 64;   // columns (threads) per Thomas CTA
 struct Mix { double c[QG_MAX_NL][QG_MAX_NL]; };
 
 struct QgSolver {
+  // ny = SOLVER rows (every row of the array is an unknown: L.Ny for a whole grid, the owned rows
+  // for the row stage of a slab); solver row j is field row jo + j; ylo / yhi: row 0 / ny-1 is a
+  // physical ring row.  nx = interior columns (array columns = nx + 2).
   int dtype, batch, nl, ny, nx, kind;
+  int jo = 0, ylo = 1, yhi = 1;
   double dx, dy;
   Layout L;
   int np, ncols, planes;
   void* S = nullptr; void* W = nullptr;
   double* ctab = nullptr; long long* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
   int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0, KBs = 2; double* dbad = nullptr; double* dbad1 = nullptr; double* meet1 = nullptr; void* part = nullptr;
-  double* bsig = nullptr; void* sig2n = nullptr; double* sdiag = nullptr; double* sintab = nullptr;
+  double* bsig = nullptr; void* sig2n = nullptr; double* minv = nullptr; double* sintab = nullptr;
+  void* bext = nullptr;                             // [plane][2][ny]: border columns 0 and nx+1
   double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; float* gvecf = nullptr; double* meet = nullptr; double* meetc = nullptr;
   void* tw = nullptr; void* twc = nullptr; void* twb = nullptr; void* dstmat = nullptr;
   FftPlan plan;
@@ -83,7 +92,13 @@ template <int LGN> struct RowCfg {
 template <typename T>
 struct RowArgsCT {
   Layout L;
-  int ny, np, nl, nrows;
+  // ny = solver rows (the whole array: L.Ny; a slab: the rows it owns); solver row j is field row
+  // jo + j.  ylo / yhi: solver row 0 / ny-1 is a physical ring row.  ringmode: FWD = the ring of the
+  // input is to be read as zero (boundary condition applied on load); INV = the ring of psi is not
+  // written (BaroclinicQG zeroes it, qg/baroclinic.py:157-158; it stays at its initial zero).
+  // bext: [plane][2][ny] border columns 0 and nx+1 (raw mixed right-hand side in, solution out).
+  int ny, np, nl, nrows, jo, ylo, yhi, ringmode;
+  T* bext;
   T mix[QG_MAX_NL][QG_MAX_NL];
   const C2<T>* tw;    // exp(-i pi t / n), t = 0..2n-1 (real-odd split)
   const C2<T>* twc;   // compact per-pass butterfly twiddles (fft.cuh: twc_offset)
@@ -102,6 +117,28 @@ __device__ __forceinline__ void fft_passes_ct(C2<T>* s, int lt, const C2<T>* __r
   }
 }
 
+// Border columns 0 (which = 0) and nx+1 (which = 1) of one row, handled by two threads of the row:
+// FWD mixes the layers' raw values into bext (zero when the input ring is read as zero); INV mixes
+// the solved modal values of bext into psi unless the ring of psi is left alone.
+template <typename T, bool INV>
+__device__ __forceinline__ void row_border_cols(const RowArgsCT<T>& A, const T* __restrict__ in,
+                                                T* __restrict__ out, int b, int a, int j, int fj,
+                                                int which, int n) {
+  if (A.ringmode) {
+    if (!INV) A.bext[(((size_t)b * A.nl + a) * 2 + which) * A.ny + j] = T(0);
+    return;
+  }
+  const int col = which ? n + 1 : 0;
+  T acc = 0;
+  for (int c = 0; c < A.nl; ++c) {
+    const T v = INV ? A.bext[(((size_t)b * A.nl + c) * 2 + which) * A.ny + j]
+                    : in[(((size_t)b * A.nl + c) * A.L.Ny + fj) * A.L.pitch + OFF + col];
+    acc += A.mix[a][c] * v;
+  }
+  if (INV) out[(((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + col] = acc;
+  else A.bext[(((size_t)b * A.nl + a) * 2 + which) * A.ny + j] = acc;
+}
+
 template <typename T, int LGN, bool INV>
 __global__ void __launch_bounds__(RowCfg<LGN>::threads, RowCfg<LGN>::minblocks)
 rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
@@ -115,21 +152,34 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
   const int row = blockIdx.x * Cfg::RPB + lrow;
   const bool valid = row < A.nrows;
   const int b = valid ? row / A.ny : 0, j = valid ? row - b * A.ny : 0;
+  const int fj = A.jo + j;
   auto zi = [&](int t) { return 2 * fft_pad(t >> 1) + (t & 1); };
   // source row of layer/mode c and destination row of mode/layer a
   // element p of the source row of layer/mode c, and of the destination row of mode/layer a
   // (field rows are contiguous; spectral rows are blocked in 64-column strips)
   auto src = [&](int c, int p) -> const T* {
     return INV ? in + ((size_t)b * A.nl + c) * A.ny * A.np + sp_off(A.ny, j, p)
-               : in + (((size_t)b * A.nl + c) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1 + p;
+               : in + (((size_t)b * A.nl + c) * A.L.Ny + fj) * A.L.pitch + OFF + 1 + p;
   };
   auto dst = [&](int a, int p) -> T* {
-    return INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1 + p
+    return INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + 1 + p
                : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, p);
   };
+  const bool ring_row = valid && A.ringmode && ((j == 0 && A.ylo) || (j == A.ny - 1 && A.yhi));
+  if (ring_row) {
+    // FWD: a ring row of the boundary-conditioned input is zero, so is its transform;
+    // INV: the ring of psi is left alone
+    if (!INV)
+      for (int a = 0; a < A.nl; ++a) {
+        for (int p = lt; p < n; p += G) *dst(a, p) = T(0);
+        if (lt < 2) A.bext[(((size_t)b * A.nl + a) * 2 + lt) * A.ny + j] = T(0);
+      }
+  }
+  const bool work = valid && !ring_row;    // (block-wide barriers below are reached by everyone)
 
   for (int a = 0; a < A.nl; ++a) {
-    if (valid) {
+    if (work && lt < 2) row_border_cols<T, INV>(A, in, out, b, a, j, fj, lt, n);
+    if (work) {
       if constexpr (EPT >= 4) {
         constexpr int NV = EPT / 4;
         Vec4<T> acc[NV];
@@ -170,8 +220,8 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
       if (lt == 0) { z[zi(0)] = 0; z[zi(n)] = 0; }
     }
     if (Cfg::WARP_ROWS) __syncwarp(); else __syncthreads();
-    fft_passes_ct<T, LGN, G, 0>(s, lt, A.twc, valid);
-    if (valid) {
+    fft_passes_ct<T, LGN, G, 0>(s, lt, A.twc, work);
+    if (work) {
 #pragma unroll
       for (int k0 = 1; k0 <= n / 2; k0 += G) {
         const int k = k0 + lt;
@@ -242,11 +292,23 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
   C* s = reinterpret_cast<C*>(smem_raw);
   const int lt = threadIdx.x, lane = lt & 31;
   const int row = blockIdx.x;
-  const int b = row / A.ny, j = row - b * A.ny;
+  const int b = row / A.ny, j = row - b * A.ny, fj = A.jo + j;
   const C* __restrict__ tw1 = A.twb;               // [LG1][G]: exp(-2 pi i lt 2^jj / n)
   const C* __restrict__ tw2 = A.twb + LG1 * G;     // [LG2][R3]: exp(-2 pi i pos 2^jj / G)
+  if (A.ringmode && ((j == 0 && A.ylo) || (j == A.ny - 1 && A.yhi))) {
+    // FWD: a ring row of the boundary-conditioned input is zero, so is its transform;
+    // INV: the ring of psi is left alone
+    if (!INV)
+      for (int a = 0; a < A.nl; ++a) {
+        float* orow = out + ((size_t)b * A.nl + a) * A.ny * A.np;
+        for (int p = lt; p < n; p += G) orow[sp_off(A.ny, j, p)] = 0.f;
+        if (lt < 2) A.bext[(((size_t)b * A.nl + a) * 2 + lt) * A.ny + j] = 0.f;
+      }
+    return;
+  }
 
   for (int a = 0; a < A.nl; ++a) {
+    if (lt < 2) row_border_cols<float, INV>(A, in, out, b, a, j, fj, lt, n);
     // ---- stage the mixed, odd-extended row: z_t at word t of the line (128-bit, conflict-free).
     // A thread's vector holds x_{4i+1..4i+4}; the lower half needs x_{4i..4i+3}: x_4i comes from
     // the lane below by shuffle, and across a warp boundary lane 31 stores it for its neighbour
@@ -262,7 +324,7 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
         const float mx = A.mix[a][c];
         // element p = 4 lt + 4 G e: field rows are contiguous, spectral rows advance 4G/64 strips
         const float* src = INV ? in + ((size_t)b * A.nl + c) * A.ny * A.np + sp_off(A.ny, j, 4 * lt)
-                               : in + (((size_t)b * A.nl + c) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + 1 + 4 * lt;
+                               : in + (((size_t)b * A.nl + c) * A.L.Ny + fj) * A.L.pitch + OFF + 1 + 4 * lt;
         const size_t estride = INV ? (size_t)(4 * G / SP_W) * A.ny * SP_W : (size_t)4 * G;
         Vec4<float> w[NV];
 #pragma unroll
@@ -280,7 +342,7 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
         float hi = -acc[e].w;
         if (i == n / 4 - 1) {
           // x_n is the border column, not part of the transform: z_n = 0
-          *(INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF + n
+          *(INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + n
                 : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, n - 1)) = acc[e].w;
           hi = 0.f;
         } else if (lane == 31) {
@@ -362,7 +424,7 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
     // ---- real-odd split, pairs (k, n-k), k = 1 + lt + G m.  X_k is element p = k-1 of the
     // destination row; both destinations move by a constant stride per m (G columns = G/64 strips)
     {
-      float* orow = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + (j + 1)) * A.L.pitch + OFF
+      float* orow = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF
                         : out + ((size_t)b * A.nl + a) * A.ny * A.np;
       const int k1 = 1 + lt;
       float* pk = INV ? orow + k1 : orow + sp_off(A.ny, j, k1 - 1);
@@ -430,24 +492,35 @@ static int launch_rowdst(int lgn, const RowArgsCT<T>& A, const T* in, T* out, cu
 }
 
 // ------------------------------------------------------------------------------------------
-// row kernels, dense path: out[k] = scale * sum_i Smat[i*n + k] * (mixed row)[i]
+// row kernels, dense path: out[k] = scale * sum_i Smat[i*n + k] * (mixed row)[i] over ALL n = Nx
+// columns of the array (no border columns); ringmode as in RowArgsCT.
 // ------------------------------------------------------------------------------------------
 template <typename T, bool INV>
-__global__ void rowdst_dense(Layout L, int ny, int n, int np, int nl, Mix mix,
+__global__ void rowdst_dense(Layout L, int ny, int n, int np, int nl, int ringmode, Mix mix,
                              const T* __restrict__ Smat, const T* __restrict__ in,
                              T* __restrict__ out, double scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* xs = reinterpret_cast<T*>(smem_raw);   // nl * n
   const int row = blockIdx.x;
   const int b = row / ny, j = row - b * ny;
+  const bool ring_row = ringmode && (j == 0 || j == ny - 1);
+  if (ring_row) {
+    if (!INV)
+      for (int e = threadIdx.x; e < nl * n; e += blockDim.x) {
+        const int a = e / n, k = e - a * n;
+        out[((size_t)b * nl + a) * ny * np + sp_off(ny, j, k)] = T(0);
+      }
+    return;
+  }
   for (int e = threadIdx.x; e < nl * n; e += blockDim.x) {
     int a = e / n, i = e - a * n;
     double val = 0;
-    for (int c = 0; c < nl; ++c) {
-      T src = INV ? in[((size_t)b * nl + c) * ny * np + sp_off(ny, j, i)]
-                  : in[(((size_t)b * nl + c) * L.Ny + (j + 1)) * L.pitch + OFF + 1 + i];
-      val += mix.c[a][c] * (double)src;
-    }
+    if (INV || !ringmode || (i > 0 && i < n - 1))
+      for (int c = 0; c < nl; ++c) {
+        T src = INV ? in[((size_t)b * nl + c) * ny * np + sp_off(ny, j, i)]
+                    : in[(((size_t)b * nl + c) * L.Ny + j) * L.pitch + OFF + i];
+        val += mix.c[a][c] * (double)src;
+      }
     xs[e] = (T)val;
   }
   __syncthreads();
@@ -460,8 +533,12 @@ __global__ void rowdst_dense(Layout L, int ny, int n, int np, int nl, Mix mix,
         if (a < nl) acc[a] += sv * (double)xs[a * n + i];
     }
     for (int a = 0; a < nl; ++a) {
-      if (INV) out[(((size_t)b * nl + a) * L.Ny + (j + 1)) * L.pitch + OFF + 1 + k] = (T)(scale * acc[a]);
-      else out[((size_t)b * nl + a) * ny * np + sp_off(ny, j, k)] = (T)(scale * acc[a]);
+      if (INV) {
+        if (!ringmode || (k > 0 && k < n - 1))
+          out[(((size_t)b * nl + a) * L.Ny + j) * L.pitch + OFF + k] = (T)(scale * acc[a]);
+      } else {
+        out[((size_t)b * nl + a) * ny * np + sp_off(ny, j, k)] = (T)(scale * acc[a]);
+      }
     }
   }
 }
@@ -485,8 +562,8 @@ struct ThomasTab {
   int kbad[QG_MAX_NL]; int KB;
   double* dbad; double* dbad1;   // fp64 side buffers [plane][j][KB] of the indefinite columns (solve 1 / 2)
   double* meet; double* meet1;   // [plane][2][np]: last eliminated value of each half (solve 1 / 2)
-  void* part;                    // [plane][2 nstrip][ny]: per-warp partial border sums (KIND 1)
-  const void* sig2n;             // [np] border weights in working precision, zero-padded
+  void* part;                    // [plane][2: even / odd column][2 nstrip][ny]: per-warp partial border sums (KIND 1)
+  const void* sig2n;             // [np] border weights (2/n) sin(pi k / n) in working precision, zero-padded
   int ny, np, ncols, nl, nstrip;
   double dy2;
   // Segmented sweeps (slab-distributed model, where a rank owns few strips and a sweep CTA is a
@@ -508,13 +585,15 @@ struct ThomasTab {
 // parallelism of the classic sweep for the same memory passes.
 //   SUBST = false: elimination  d_s = (dy^2 f_s - d_{s-1}) c_s           (s counts from the end)
 //   SUBST = true : substitution x_s = d_s - c_s x_{s'}  outwards from the meeting point
-// FROM_VEC (elimination only): right-hand side is gvec[plane][j] for every column (border solve).
+// FROM_VEC (elimination only): right-hand side is gvec[plane][c & 1][j] for column c (border
+// solve: (g0 + g1)(y) for the odd x-wavenumbers k = c + 1, (g0 - g1)(y) for the even ones).
 // KIND (substitution only): 0 = plain solve, x is stored.  The bordered solver never stores the
 // first solve's x: KIND 1 substitutes the eliminated first right-hand side D only to emit the
-// weighted row sums sum_c sig2n[c] x[j][c] the border system needs (per-warp partials, reduced by
-// border_reduce); KIND 2 substitutes D - bsig[c] * E (E = eliminated border right-hand side of
-// the second solve, linearity of the elimination) and stores the final x.  7 instead of 8
-// array transfers per inversion and no separate dot pass.
+// weighted row sums sum_c sig2n[c] x[j][c] the border system needs, separately over the even
+// and the odd columns (per-warp partials, reduced by border_reduce: their sum is v at block
+// column 1, their difference v at block column n-1); KIND 2 substitutes D - bsig[c] * E (E =
+// eliminated border right-hand side of the second solve, linearity of the elimination) and
+// stores the final x.  7 instead of 8 array transfers per inversion and no separate dot pass.
 // ---- bulk-async (TMA engine) helpers: 1-D cp.async.bulk + mbarrier, no tensor map needed ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -730,11 +809,12 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   // FROM_VEC: the shared right-hand side g[j] of the tile after next is fetched (one element per
   // thread, coalesced) while the current tile runs, and read back as a shared-memory broadcast
   using GT = typename std::conditional<PLAIN, float, double>::type;
-  __shared__ GT gbuf[2][FROM_VEC ? RT : 1];
+  __shared__ GT gbuf[2][FROM_VEC ? 2 * RT : 1];      // [buffer][column parity][row of the tile]
   const GT* gsrc = nullptr;
   if (FROM_VEC) {
-    if constexpr (PLAIN) gsrc = gvecf + (size_t)plane * ny; else gsrc = gvec + (size_t)plane * ny;
+    if constexpr (PLAIN) gsrc = gvecf + (size_t)plane * 2 * ny; else gsrc = gvec + (size_t)plane * 2 * ny;
   }
+  const int gpar = FROM_VEC ? (c & 1) * RT : 0;
   const int m1 = ny / 2;
   const int cnt = half == 0 ? m1 : ny - m1;
   int j0, dj;
@@ -813,7 +893,10 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     carry_f = (float)carry;
   }
   if (FROM_VEC && ntile > 0) {
-    if (worker && tid < tile_nr(0)) gbuf[0][tid] = gsrc[tile_jlo(0) + tid];
+    if (worker && tid < tile_nr(0)) {
+      gbuf[0][tid] = gsrc[tile_jlo(0) + tid];
+      gbuf[0][RT + tid] = gsrc[ny + tile_jlo(0) + tid];
+    }
     __syncthreads();
   }
   T wdot[KIND == 1 ? 16 : 1];
@@ -835,9 +918,12 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     const int st = t % NS;
     const int nrt = tile_nr(t);
     const int ilot = tile_ilo(t);
-    GT gnext = 0;
-    if (FROM_VEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) gnext = gsrc[tile_jlo(t + 1) + tid];
-    const GT* gvt = gbuf[t & 1] - tile_jlo(t);      // indexed by the memory row
+    GT gnext = 0, gnext1 = 0;
+    if (FROM_VEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) {
+      gnext = gsrc[tile_jlo(t + 1) + tid];
+      gnext1 = gsrc[ny + tile_jlo(t + 1) + tid];
+    }
+    const GT* gvt = gbuf[t & 1] + gpar - tile_jlo(t);      // indexed by the memory row
 #ifdef SB_TH_PHASES
     long long ph0 = clock64();
 #endif
@@ -894,7 +980,10 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     long long ph2 = clock64();
     ph_comp += ph2 - ph1;
 #endif
-    if (FROM_VEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) gbuf[(t + 1) & 1][tid] = gnext;
+    if (FROM_VEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) {
+      gbuf[(t + 1) & 1][tid] = gnext;
+      gbuf[(t + 1) & 1][RT + tid] = gnext1;
+    }
     if (worker && !SUBST && !probe && t == ntile - 1 && sb == cnt)
       meetW[((size_t)plane * 2 + half) * tb.np + c] = PLAIN ? (double)carry_f : carry;
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
@@ -904,18 +993,25 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
       // border sums of the finished tile: thread (rr, qd) adds 16 columns of row rr with a rotated
       // column order (conflict-free), the two quarters of a warp combine by shuffle
       const int rr = tid & 15, qd = tid >> 4;
+      const size_t pstride = (size_t)2 * tb.nstrip * ny;      // even-column block -> odd-column block
       T* part = reinterpret_cast<T*>(tb.part) +
-                ((size_t)(plane * 2 * tb.nstrip + strip * 2 + (tid >> 5))) * ny + tile_jlo(t);
+                ((size_t)plane * 4 * tb.nstrip + strip * 2 + (tid >> 5)) * ny + tile_jlo(t);
 #pragma unroll 1
       for (int rb = 0; rb < nrt; rb += 16) {
         const int row = rb + rr;
-        T acc = 0;
+        // column (i + rr) & 15 has the parity of i + rr: even i and odd i accumulate separately
+        T acc0 = 0, acc1 = 0;
         if (row < nrt) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc = fma(wdot[i], tileA[st][row][qd * 16 + ((i + rr) & 15)], acc);
+          for (int i = 0; i < 16; i += 2) {
+            acc0 = fma(wdot[i], tileA[st][row][qd * 16 + ((i + rr) & 15)], acc0);
+            acc1 = fma(wdot[i + 1], tileA[st][row][qd * 16 + ((i + 1 + rr) & 15)], acc1);
+          }
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        if ((tid & 16) == 0 && row < nrt) part[row] = acc;
+        T ev = (rr & 1) ? acc1 : acc0, od = (rr & 1) ? acc0 : acc1;
+        ev += __shfl_xor_sync(0xffffffffu, ev, 16);
+        od += __shfl_xor_sync(0xffffffffu, od, 16);
+        if ((tid & 16) == 0 && row < nrt) { part[row] = ev; part[pstride + row] = od; }
       }
     }
 #ifdef SB_TH_PHASES
@@ -959,34 +1055,70 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
 #endif
 }
 
-// r[plane][j] = f_n[j] - b * sum_c sig2n[c] * x[plane][j][c]: right-hand side of the border
-// (Schur) system.  The column sum arrives as 2 * nstrip per-warp partials from the KIND 1
-// substitution sweeps (fixed order: deterministic); f_n sits in the border slot of S.
+// Right-hand sides of the border (Schur) system, r[plane][3][ny]:
+//   r0 = f_0 - b v(1),  r1 = f_n - b v(n-1),  r2 = f_{n+1}
+// with v(1) = E + O and v(n-1) = E - O, E / O = sum over the even / odd columns c (odd / even
+// x-wavenumbers k = c + 1) of sig2n[c] x[j][c].  The sums arrive as 2 * nstrip per-warp partials per
+// parity from the KIND 1 substitution sweeps (fixed order: deterministic); f_n sits in the border
+// slot of S, f_0 and f_{n+1} in bext.
 template <typename T>
 __global__ void __launch_bounds__(256)
-border_reduce(const T* __restrict__ S, const T* __restrict__ part, int ny, int np, int ncols,
-              int npart, double b, double* __restrict__ r) {
+border_reduce(const T* __restrict__ S, const T* __restrict__ bext, const T* __restrict__ part,
+              int ny, int np, int ncols, int npart, double b, double* __restrict__ r) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, plane = blockIdx.y;
   if (j >= ny) return;
-  const T* pp = part + (size_t)plane * npart * ny + j;
-  double acc = 0;
+  const T* pe = part + (size_t)plane * 2 * npart * ny + j;
+  const T* po = pe + (size_t)npart * ny;
+  double ev = 0, od = 0;
 #pragma unroll 8
-  for (int p = 0; p < npart; ++p) acc += (double)pp[(size_t)p * ny];
-  r[(size_t)plane * ny + j] = (double)S[(size_t)plane * ny * np + sp_off(ny, j, ncols)] - b * acc;
+  for (int p = 0; p < npart; ++p) { ev += (double)pe[(size_t)p * ny]; od += (double)po[(size_t)p * ny]; }
+  double* rp = r + (size_t)plane * 3 * ny + j;
+  rp[0] = (double)bext[((size_t)plane * 2 + 0) * ny + j] - b * (ev + od);
+  rp[ny] = (double)S[(size_t)plane * ny * np + sp_off(ny, j, ncols)] - b * (ev - od);
+  rp[2 * ny] = (double)bext[((size_t)plane * 2 + 1) * ny + j];
 }
 
-// Border Schur solve = dense DST-I in y of one column per plane (length ny, N = ny + 1), brute
-// force in fp64: out[a] = scale(a) * sum_{t=1..ny} sin(pi a t / N) in[t].  Each thread owns the
+// Border Schur solve = dense DST-I in y of three columns per plane (length ny, N = ny + 1), brute
+// force in fp64: out_i[a] = sum_{t=1..ny} sin(pi a t / N) in_i[t].  Each thread owns the
 // terms t = t0, t0 + B, t0 + 2B, ... and advances sin/cos(pi a t / N) by the fixed angle
-// pi a B / N with a rotation (4 FMAs) instead of gathering from the sine table; the start and
-// step values come exactly from the table.  STAGE_A divides by the Schur diagonal; stage B
-// scales by 2/N and also writes the result where the sweeps / inverse transform read it.
+// pi a B / N with a rotation (4 FMAs, shared by the three columns) instead of gathering from the
+// sine table; the start and step values come exactly from the table.  STAGE_A multiplies by the
+// host-inverted 3 x 3 Schur block of y-mode a; stage B scales by 2/N and writes the results where
+// the sweeps / inverse transform read them: gvec = (g0 + g1, g0 - g1), g1 in the border slot of S,
+// g0 and g2 in bext.
+template <typename T, bool STAGE_A>
+__device__ __forceinline__ void border_store(double t0, double t1, double t2, int a, int plane, int m,
+                                             const double* __restrict__ minv, int ny, int np, int n,
+                                             double* __restrict__ out, double* __restrict__ gvec,
+                                             float* __restrict__ gvecf, T* __restrict__ S,
+                                             T* __restrict__ bext) {
+  if (STAGE_A) {
+    const double* M = minv + ((size_t)m * ny + (a - 1)) * 9;
+    double* o = out + (size_t)plane * 3 * ny + (a - 1);
+    o[0] = M[0] * t0 + M[1] * t1 + M[2] * t2;
+    o[ny] = M[3] * t0 + M[4] * t1 + M[5] * t2;
+    o[2 * ny] = M[6] * t0 + M[7] * t1 + M[8] * t2;
+  } else {
+    const double sc = 2.0 / (ny + 1);
+    t0 *= sc; t1 *= sc; t2 *= sc;
+    double* gv = gvec + (size_t)plane * 2 * ny + (a - 1);
+    gv[0] = t0 + t1; gv[ny] = t0 - t1;
+    if (sizeof(T) == 4) {
+      float* gf = gvecf + (size_t)plane * 2 * ny + (a - 1);
+      gf[0] = (float)(t0 + t1); gf[ny] = (float)(t0 - t1);
+    }
+    S[(size_t)plane * ny * np + sp_off(ny, a - 1, n - 1)] = (T)t1;
+    bext[((size_t)plane * 2 + 0) * ny + (a - 1)] = (T)t0;
+    bext[((size_t)plane * 2 + 1) * ny + (a - 1)] = (T)t2;
+  }
+}
+
 template <typename T, bool STAGE_A>
 __global__ void __launch_bounds__(32 * GS_ROWS)
 border_gsolve(const double* __restrict__ in, const double* __restrict__ sintab,
-              const double* __restrict__ sdiag, int ny, int np, int n, int nl,
+              const double* __restrict__ minv, int ny, int np, int n, int nl,
               double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
-              T* __restrict__ S, int a_first, int a_count) {
+              T* __restrict__ S, T* __restrict__ bext, int a_first, int a_count) {
   // one warp per output index a; sintab holds sin(pi k / N) for k < 2N followed by cos(pi k / N)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a = a_first + blockIdx.x * GS_ROWS + warp + 1, plane = blockIdx.y, m = plane % nl;
@@ -997,30 +1129,33 @@ border_gsolve(const double* __restrict__ in, const double* __restrict__ sintab,
   const unsigned k0 = ((unsigned)a * t0) % N2, kd = ((unsigned)a * 32u) % N2;
   double s = sintab[k0], c = costab[k0];
   const double ds = sintab[kd], dc = costab[kd];
-  double acc = 0;
-  const double* x = in + (size_t)plane * ny;
+  double acc0 = 0, acc1 = 0, acc2 = 0;
+  const double* x0 = in + (size_t)plane * 3 * ny;
+  const double* x1 = x0 + ny;
+  const double* x2 = x1 + ny;
   // sin(pi a (N - t) / N) = -(-1)^a sin(pi a t / N): fold the input, half the terms
   const int half = (N - 1) / 2;
   const double sgn = (a & 1) ? 1.0 : -1.0;
   for (int t = t0; t <= half; t += 32) {
-    acc = fma(s, fma(sgn, x[N - t - 1], x[t - 1]), acc);
+    acc0 = fma(s, fma(sgn, x0[N - t - 1], x0[t - 1]), acc0);
+    acc1 = fma(s, fma(sgn, x1[N - t - 1], x1[t - 1]), acc1);
+    acc2 = fma(s, fma(sgn, x2[N - t - 1], x2[t - 1]), acc2);
     const double s2 = fma(s, dc, c * ds), c2 = fma(c, dc, -(s * ds));   // rotate by 32 pi a / N
     s = s2; c = c2;
   }
-  if ((N & 1) == 0 && lane == 0)
-    acc = fma(sintab[(unsigned)(((unsigned long long)a * (N / 2)) % N2)], x[N / 2 - 1], acc);
-  for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, sh);
-  if (lane == 0) {
-    double t = acc;
-    if (STAGE_A) {
-      out[(size_t)plane * ny + (a - 1)] = t / sdiag[(size_t)m * ny + (a - 1)];
-    } else {
-      t *= 2.0 / N;
-      gvec[(size_t)plane * ny + (a - 1)] = t;
-      if (sizeof(T) == 4) gvecf[(size_t)plane * ny + (a - 1)] = (float)t;
-      S[(size_t)plane * ny * np + sp_off(ny, a - 1, n - 1)] = (T)t;
-    }
+  if ((N & 1) == 0 && lane == 0) {
+    const double sm = sintab[(unsigned)(((unsigned long long)a * (N / 2)) % N2)];
+    acc0 = fma(sm, x0[N / 2 - 1], acc0);
+    acc1 = fma(sm, x1[N / 2 - 1], acc1);
+    acc2 = fma(sm, x2[N / 2 - 1], acc2);
   }
+  for (int sh = 16; sh > 0; sh >>= 1) {
+    acc0 += __shfl_down_sync(0xffffffffu, acc0, sh);
+    acc1 += __shfl_down_sync(0xffffffffu, acc1, sh);
+    acc2 += __shfl_down_sync(0xffffffffu, acc2, sh);
+  }
+  if (lane == 0)
+    border_store<T, STAGE_A>(acc0, acc1, acc2, a, plane, m, minv, ny, np, n, out, gvec, gvecf, S, bext);
 }
 
 // Same transform for short columns (ny <= GS_SMALL_NY, ensembles of small grids): one THREAD per
@@ -1029,33 +1164,34 @@ border_gsolve(const double* __restrict__ in, const double* __restrict__ sintab,
 template <typename T, bool STAGE_A>
 __global__ void __launch_bounds__(128)
 border_gsolve_small(const double* __restrict__ in, const double* __restrict__ sintab,
-                    const double* __restrict__ sdiag, int ny, int np, int n, int nl,
+                    const double* __restrict__ minv, int ny, int np, int n, int nl,
                     double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
-                    T* __restrict__ S, int a_first, int a_count) {
+                    T* __restrict__ S, T* __restrict__ bext, int a_first, int a_count) {
   const int a = a_first + blockIdx.x * blockDim.x + threadIdx.x + 1, plane = blockIdx.y, m = plane % nl;
   if (a > a_first + a_count) return;
   const unsigned N = ny + 1, N2 = 2 * N;
   const double* costab = sintab + N2;
   const double ds = sintab[a], dc = costab[a];        // a < N2
-  double s = ds, c = dc, acc = 0;
-  const double* x = in + (size_t)plane * ny;
+  double s = ds, c = dc, acc0 = 0, acc1 = 0, acc2 = 0;
+  const double* x0 = in + (size_t)plane * 3 * ny;
+  const double* x1 = x0 + ny;
+  const double* x2 = x1 + ny;
   const int half = (N - 1) / 2;
   const double sgn = (a & 1) ? 1.0 : -1.0;
   for (int t = 1; t <= half; ++t) {
-    acc = fma(s, fma(sgn, x[N - t - 1], x[t - 1]), acc);
+    acc0 = fma(s, fma(sgn, x0[N - t - 1], x0[t - 1]), acc0);
+    acc1 = fma(s, fma(sgn, x1[N - t - 1], x1[t - 1]), acc1);
+    acc2 = fma(s, fma(sgn, x2[N - t - 1], x2[t - 1]), acc2);
     const double s2 = fma(s, dc, c * ds), c2 = fma(c, dc, -(s * ds));
     s = s2; c = c2;
   }
-  if ((N & 1) == 0) acc = fma(sintab[(unsigned)(((unsigned long long)a * (N / 2)) % N2)], x[N / 2 - 1], acc);
-  double t = acc;
-  if (STAGE_A) {
-    out[(size_t)plane * ny + (a - 1)] = t / sdiag[(size_t)m * ny + (a - 1)];
-  } else {
-    t *= 2.0 / N;
-    gvec[(size_t)plane * ny + (a - 1)] = t;
-    if (sizeof(T) == 4) gvecf[(size_t)plane * ny + (a - 1)] = (float)t;
-    S[(size_t)plane * ny * np + sp_off(ny, a - 1, n - 1)] = (T)t;
+  if ((N & 1) == 0) {
+    const double sm = sintab[(unsigned)(((unsigned long long)a * (N / 2)) % N2)];
+    acc0 = fma(sm, x0[N / 2 - 1], acc0);
+    acc1 = fma(sm, x1[N / 2 - 1], acc1);
+    acc2 = fma(sm, x2[N / 2 - 1], acc2);
   }
+  border_store<T, STAGE_A>(acc0, acc1, acc2, a, plane, m, minv, ny, np, n, out, gvec, gvecf, S, bext);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1192,7 +1328,7 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
     SB_CUDA(cudaMalloc((void**)&s->meet1, mb));
     SB_CUDA(cudaMemset(s->meet1, 0, mb));
     s->bytes += 2 * mb;
-    const size_t pb = (size_t)s->planes * 2 * nstrip * ny * (s->dtype == SOMAX_B200_F32 ? 4 : 8);
+    const size_t pb = (size_t)s->planes * 4 * nstrip * ny * (s->dtype == SOMAX_B200_F32 ? 4 : 8);
     SB_CUDA(cudaMalloc(&s->part, pb));
     SB_CUDA(cudaMemset(s->part, 0, pb));
     s->bytes += pb;
@@ -1251,23 +1387,43 @@ static int build_fft_tables(QgSolver* s, const double* lambdas) {
       if (int rc = dev_upload(twb.data(), twb.size() * sizeof(C2<T>), &s->twb, &s->bytes)) return rc;
     }
   }
+  // block column 1 weights sin(pi k / n); block column n-1 is the same times (-1)^(k+1)
   std::vector<double> sig(nc), lamx(nc), bsig(nc), sig2n(nc);
   for (int c = 0; c < nc; ++c) {
     const int k = c + 1;
-    sig[c] = ((k & 1) ? 1.0 : -1.0) * sin(M_PI * k / n);
+    sig[c] = sin(M_PI * k / n);
     const double sn = sin(M_PI * k / (2.0 * n));
     lamx[c] = -(4.0 * b) * sn * sn;
     bsig[c] = b * sig[c];
     sig2n[c] = (2.0 / n) * sig[c];
   }
-  std::vector<double> sdiag((size_t)nl * ny);
+  // Schur block of the border unknowns (g0, g1, g2) per (mode, y-mode), inverted here:
+  //   [ d - b^2 al   -b^2 be      0 ]        al = (2/n) sum_k sig_k^2 / (lamx_k + mu)
+  //   [ -b^2 be      d - b^2 al   b ]        be = (2/n) sum_k (-1)^(k+1) sig_k^2 / (lamx_k + mu)
+  //   [ 0            b            d ]        d  = mu - 2 b,  mu = lamy_l - lambda_m
+  std::vector<double> minv((size_t)nl * ny * 9);
   for (int m = 0; m < nl; ++m)
     for (int l = 1; l <= ny; ++l) {
       const double sn = sin(M_PI * l / (2.0 * (ny + 1)));
       const double mu = -(4.0 / (s->dy * s->dy)) * sn * sn - lambdas[m];
-      double acc = 0;
-      for (int c = 0; c < nc; ++c) acc += sig[c] * sig[c] / (lamx[c] + mu);
-      sdiag[(size_t)m * ny + (l - 1)] = mu - 2.0 * b - b * b * (2.0 / n) * acc;
+      double al = 0, be = 0;
+      for (int c = 0; c < nc; ++c) {
+        const double t = sig[c] * sig[c] / (lamx[c] + mu);
+        al += t; be += (c & 1) ? -t : t;
+      }
+      al *= 2.0 / n; be *= 2.0 / n;
+      const double d = mu - 2.0 * b, A = d - b * b * al, B = -b * b * be;
+      const double M[3][3] = {{A, B, 0.0}, {B, A, b}, {0.0, b, d}};
+      const double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) -
+                         M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                         M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+      double* o = minv.data() + ((size_t)m * ny + (l - 1)) * 9;
+      for (int i = 0; i < 3; ++i)
+        for (int jj = 0; jj < 3; ++jj) {
+          const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (jj + 1) % 3, j2 = (jj + 2) % 3;
+          // inverse = adjugate / det; cofactor (jj, i) by cyclic indices
+          o[i * 3 + jj] = (M[j1][i1] * M[j2][i2] - M[j1][i2] * M[j2][i1]) / det;
+        }
     }
   // sin(pi t / N), t < 2N, followed by cos(pi t / N)
   const size_t N2 = 2 * (size_t)(ny + 1);
@@ -1282,20 +1438,22 @@ static int build_fft_tables(QgSolver* s, const double* lambdas) {
     for (int c = 0; c < nc; ++c) sg[c] = (T)sig2n[c];
     if (int rc = dev_upload(sg.data(), sg.size() * sizeof(T), &s->sig2n, &s->bytes)) return rc;
   }
-  if (int rc = dev_upload(sdiag.data(), sdiag.size() * 8, (void**)&s->sdiag, &s->bytes)) return rc;
+  if (int rc = dev_upload(minv.data(), minv.size() * 8, (void**)&s->minv, &s->bytes)) return rc;
   if (int rc = dev_upload(sintab.data(), sintab.size() * 8, (void**)&s->sintab, &s->bytes)) return rc;
   size_t vb = (size_t)s->planes * ny * 8;
-  SB_CUDA(cudaMalloc((void**)&s->rvec, vb));
-  SB_CUDA(cudaMalloc((void**)&s->ghat, vb));
-  SB_CUDA(cudaMalloc((void**)&s->gvec, vb));
-  SB_CUDA(cudaMalloc((void**)&s->gvecf, vb / 2));
-  s->bytes += 3 * vb + vb / 2;
+  SB_CUDA(cudaMalloc((void**)&s->rvec, 3 * vb));
+  SB_CUDA(cudaMalloc((void**)&s->ghat, 3 * vb));
+  SB_CUDA(cudaMalloc((void**)&s->gvec, 2 * vb));
+  SB_CUDA(cudaMalloc((void**)&s->gvecf, vb));
+  SB_CUDA(cudaMalloc(&s->bext, 2 * (size_t)s->planes * ny * sizeof(T)));
+  SB_CUDA(cudaMemset(s->bext, 0, 2 * (size_t)s->planes * ny * sizeof(T)));
+  s->bytes += 9 * vb + 2 * (size_t)s->planes * ny * sizeof(T);
   return 0;
 }
 
 template <typename T>
 static int build_dense_tables(QgSolver* s) {
-  const int n = s->nx;
+  const int n = s->nx + 2;      // every column of the array is an unknown
   std::vector<T> mat((size_t)n * n);
   for (int i = 0; i < n; ++i)
     for (int k = 0; k < n; ++k)
@@ -1305,7 +1463,7 @@ static int build_dense_tables(QgSolver* s) {
 
 int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int nx, double dx,
                      double dy, const double* Cl2m, const double* Cm2l, const double* lambdas,
-                     int solver_kind, int nseg) {
+                     int solver_kind, int nseg, int rows, int jo, int ylo, int yhi) {
   *out = nullptr;
   if (nl < 1 || nl > QG_MAX_NL) return fail(SOMAX_B200_ERR_UNSUPPORTED, "QG supports 1 <= nl <= 4");
   const bool pow2 = nx >= 8 && (nx & (nx - 1)) == 0;
@@ -1317,16 +1475,19 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
     if ((size_t)fft_padded_len(nx) * 2 * es > 200 * 1024)
       return fail(SOMAX_B200_ERR_UNSUPPORTED, "FFT solver: one row must fit in shared memory (nx <= 8192 fp64 / 16384 fp32)");
   } else if (kind == SOMAX_B200_SOLVER_DENSE) {
-    if (nx > 2048) return fail(SOMAX_B200_ERR_UNSUPPORTED, "dense DST solver limited to nx <= 2048; use nx = 2^p for the FFT path");
+    if (nx > 2046) return fail(SOMAX_B200_ERR_UNSUPPORTED, "dense DST solver limited to nx <= 2046; use nx = 2^p for the FFT path");
   } else {
     return fail(SOMAX_B200_ERR_INVALID, "unknown solver kind");
   }
   auto* s = new QgSolver();
-  s->dtype = dtype; s->batch = batch; s->nl = nl; s->ny = ny; s->nx = nx; s->kind = kind;
+  s->dtype = dtype; s->batch = batch; s->nl = nl; s->nx = nx; s->kind = kind;
   s->dx = dx; s->dy = dy; s->L = make_layout(batch, nl, ny, nx);
+  s->ny = rows > 0 ? rows : ny + 2; s->jo = rows > 0 ? jo : 0;
+  s->ylo = rows > 0 ? ylo : 1; s->yhi = rows > 0 ? yhi : 1;
+  ny = s->ny;      // from here on: solver rows
   s->nseg = std::max(1, std::min(nseg, 16));
-  s->np = ((nx + SP_W - 1) / SP_W) * SP_W; s->planes = batch * nl;
-  s->ncols = (kind == SOMAX_B200_SOLVER_FFT) ? nx - 1 : nx;
+  s->ncols = (kind == SOMAX_B200_SOLVER_FFT) ? nx - 1 : nx + 2;
+  s->np = ((std::max(nx, s->ncols) + SP_W - 1) / SP_W) * SP_W; s->planes = batch * nl;
   for (int a = 0; a < QG_MAX_NL; ++a)
     for (int c = 0; c < QG_MAX_NL; ++c) {
       s->l2m.c[a][c] = (a < nl && c < nl) ? Cl2m[a * nl + c] : 0.0;
@@ -1357,7 +1518,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
   };
   rc = alloc0(&s->S);
   if (!rc && kind == SOMAX_B200_SOLVER_FFT) rc = alloc0(&s->W);
-  if (!rc) rc = build_thomas_tables(s, lambdas, kind == SOMAX_B200_SOLVER_FFT ? nx : nx + 1);
+  if (!rc) rc = build_thomas_tables(s, lambdas, kind == SOMAX_B200_SOLVER_FFT ? nx : nx + 3);
   if (!rc) {
     if (kind == SOMAX_B200_SOLVER_FFT)
       rc = dtype == SOMAX_B200_F32 ? build_fft_tables<float>(s, lambdas) : build_fft_tables<double>(s, lambdas);
@@ -1372,7 +1533,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
 void qg_solver_destroy(QgSolver* s) {
   if (!s) return;
   void* ptrs[] = {s->segbuf, s->segprod, s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->dbad1, s->meet1, s->part, s->bsig, s->sig2n,
-                  s->sdiag, s->sintab, s->rvec, s->ghat, s->gvec, s->gvecf, s->tw, s->twc, s->twb, s->dstmat, s->meet, s->meetc};
+                  s->minv, s->bext, s->sintab, s->rvec, s->ghat, s->gvec, s->gvecf, s->tw, s->twc, s->twb, s->dstmat, s->meet, s->meetc};
   for (void* p : ptrs) cudaFree(p);
   if (s->aux) cudaStreamDestroy(s->aux);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -1483,6 +1644,7 @@ static ThomasTab make_tab(const QgSolver* s) {
 template <typename T>
 static void make_row_args(const QgSolver* s, RowArgsCT<T>& Af, RowArgsCT<T>& Ai) {
   Af.L = s->L; Af.ny = s->ny; Af.np = s->np; Af.nl = s->nl; Af.nrows = s->batch * s->ny;
+  Af.jo = s->jo; Af.ylo = s->ylo; Af.yhi = s->yhi; Af.ringmode = 0; Af.bext = (T*)s->bext;
   Af.tw = (const C2<T>*)s->tw; Af.twc = (const C2<T>*)s->twc; Af.twb = (const C2<T>*)s->twb; Af.scale = (T)1;
   Ai = Af; Ai.scale = (T)(2.0 / s->nx);
   for (int a = 0; a < QG_MAX_NL; ++a)
@@ -1493,16 +1655,18 @@ static void make_row_args(const QgSolver* s, RowArgsCT<T>& Af, RowArgsCT<T>& Ai)
 // slab-distributed model (qg_slab.cuh) runs the row stages on a y-slab and the column stages on
 // a range of x-wavenumber strips, with peer-memory exchanges in between.
 template <typename T>
-int qg_solver_rows_fwd(QgSolver* s, const T* q, cudaStream_t st) {
+int qg_solver_rows_fwd(QgSolver* s, const T* q, int ring_zero, cudaStream_t st) {
   RowArgsCT<T> Af, Ai;
   make_row_args<T>(s, Af, Ai);
+  Af.ringmode = ring_zero;
   return launch_rowdst<T, false>(s->plan.lgn, Af, q, (T*)s->S, st);
 }
 
 template <typename T>
-int qg_solver_rows_inv(QgSolver* s, T* psi, cudaStream_t st) {
+int qg_solver_rows_inv(QgSolver* s, T* psi, int keep_ring, cudaStream_t st) {
   RowArgsCT<T> Af, Ai;
   make_row_args<T>(s, Af, Ai);
+  Ai.ringmode = !keep_ring;
   return launch_rowdst<T, true>(s->plan.lgn, Ai, (const T*)s->S, psi, st);
 }
 
@@ -1525,7 +1689,7 @@ int qg_solver_border_stage(QgSolver* s, int stage, int a0, int a1, cudaStream_t 
   if (stage == 0) {
     const double b = 1.0 / (s->dx * s->dx);
     prof_begin("border_reduce", st);
-    border_reduce<T><<<dim3((ny + 255) / 256, s->planes), 256, 0, st>>>(S, (const T*)s->part, ny, np, s->ncols, 2 * (np / SP_W), b, s->rvec);
+    border_reduce<T><<<dim3((ny + 255) / 256, s->planes), 256, 0, st>>>(S, (const T*)s->bext, (const T*)s->part, ny, np, s->ncols, 2 * (np / SP_W), b, s->rvec);
     SB_LAUNCH_CHECK();
     return 0;
   }
@@ -1537,15 +1701,15 @@ int qg_solver_border_stage(QgSolver* s, int stage, int a0, int a1, cudaStream_t 
   if (stage == 1) {
     prof_begin("border_gsolve_a", st);
     if (small)
-      border_gsolve_small<T, true><<<dim3((cnt + 127) / 128, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, a0, cnt);
+      border_gsolve_small<T, true><<<dim3((cnt + 127) / 128, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->minv, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, nullptr, a0, cnt);
     else
-      border_gsolve<T, true><<<dim3((cnt + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->sdiag, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, a0, cnt);
+      border_gsolve<T, true><<<dim3((cnt + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->minv, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, nullptr, a0, cnt);
   } else {
     prof_begin("border_gsolve_b", st);
     if (small)
-      border_gsolve_small<T, false><<<dim3((cnt + 127) / 128, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, a0, cnt);
+      border_gsolve_small<T, false><<<dim3((cnt + 127) / 128, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->minv, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, (T*)s->bext, a0, cnt);
     else
-      border_gsolve<T, false><<<dim3((cnt + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->sdiag, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, a0, cnt);
+      border_gsolve<T, false><<<dim3((cnt + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->minv, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, (T*)s->bext, a0, cnt);
   }
   SB_LAUNCH_CHECK();
   return 0;
@@ -1559,17 +1723,18 @@ int qg_solver_border(QgSolver* s, cudaStream_t st) {
 }
 
 template <typename T>
-int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
-  const int ny = s->ny, n = s->nx, np = s->np, nl = s->nl;
+int qg_solver_run(QgSolver* s, const T* q, T* psi, int ring_zero, int keep_ring, cudaStream_t st) {
+  const int ny = s->ny, np = s->np, nl = s->nl;
   if (s->kind == SOMAX_B200_SOLVER_FFT) {
-    if (int rc = qg_solver_rows_fwd<T>(s, q, st)) return rc;
+    if (int rc = qg_solver_rows_fwd<T>(s, q, ring_zero, st)) return rc;
     if (int rc = qg_solver_cols<T>(s, 1, 0, -1, st)) return rc;
     if (int rc = qg_solver_border<T>(s, st)) return rc;
     if (int rc = qg_solver_cols<T>(s, 2, 0, -1, st)) return rc;
-    if (int rc = qg_solver_rows_inv<T>(s, psi, st)) return rc;
+    if (int rc = qg_solver_rows_inv<T>(s, psi, keep_ring, st)) return rc;
   } else {
     const ThomasTab tb = make_tab(s);
     T* S = (T*)s->S;
+    const int n = s->nx + 2;
     const size_t smem = (size_t)nl * n * sizeof(T);
     if (smem > 48 * 1024) {
       SB_CUDA(cudaFuncSetAttribute(rowdst_dense<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1577,11 +1742,11 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
     }
     const int threads = std::min(256, ((n + 31) / 32) * 32);
     prof_begin("rowdst_dense_0", st);
-    rowdst_dense<T, false><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->l2m, (const T*)s->dstmat, q, S, 1.0);
+    rowdst_dense<T, false><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, ring_zero, s->l2m, (const T*)s->dstmat, q, S, 1.0);
     SB_LAUNCH_CHECK();
     if (int rc = launch_solve<T, 0>(s, tb, S, nullptr, st)) return rc;
     prof_begin("rowdst_dense_1", st);
-    rowdst_dense<T, true><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, s->m2l, (const T*)s->dstmat, S, psi, 2.0 / (n + 1));
+    rowdst_dense<T, true><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, !keep_ring, s->m2l, (const T*)s->dstmat, S, psi, 2.0 / (n + 1));
     SB_LAUNCH_CHECK();
   }
   return 0;
@@ -1589,7 +1754,7 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, cudaStream_t st) {
 
 QgSolverView qg_solver_view(const QgSolver* s) {
   QgSolverView v;
-  v.S = s->S; v.part = s->part; v.ghat = s->ghat; v.gvec = s->gvec; v.gvecf = s->gvecf; v.ny = s->ny; v.nx = s->nx; v.np = s->np; v.planes = s->planes;
+  v.S = s->S; v.part = s->part; v.bext = s->bext; v.ghat = s->ghat; v.gvec = s->gvec; v.gvecf = s->gvecf; v.ny = s->ny; v.nx = s->nx; v.np = s->np; v.planes = s->planes;
   v.nstrip = s->np / SP_W; v.ncols = s->ncols; v.kind = s->kind; v.nheavy = s->nheavy;
   return v;
 }
@@ -1605,11 +1770,11 @@ extern "C" int somax_b200_debug_dump(unsigned long long* out, unsigned* n) {
 }
 #endif
 
-template int qg_solver_run<float>(QgSolver*, const float*, float*, cudaStream_t);
-template int qg_solver_run<double>(QgSolver*, const double*, double*, cudaStream_t);
+template int qg_solver_run<float>(QgSolver*, const float*, float*, int, int, cudaStream_t);
+template int qg_solver_run<double>(QgSolver*, const double*, double*, int, int, cudaStream_t);
 #define SB_INST_STAGES(T)                                                  \
-  template int qg_solver_rows_fwd<T>(QgSolver*, const T*, cudaStream_t);   \
-  template int qg_solver_rows_inv<T>(QgSolver*, T*, cudaStream_t);         \
+  template int qg_solver_rows_fwd<T>(QgSolver*, const T*, int, cudaStream_t);   \
+  template int qg_solver_rows_inv<T>(QgSolver*, T*, int, cudaStream_t);         \
   template int qg_solver_cols<T>(QgSolver*, int, int, int, cudaStream_t);  \
   template int qg_solver_border<T>(QgSolver*, cudaStream_t);                \
   template int qg_solver_border_stage<T>(QgSolver*, int, int, int, cudaStream_t);

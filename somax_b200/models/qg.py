@@ -298,8 +298,10 @@ class BarotropicQG(_QGBase):
         self.dtype = np.dtype(dtype)
         self._H0 = 1.0
         one = np.ones((1, 1))
+        # BarotropicQG._invert_pv (qg/barotropic.py:113-121) does not zero the ring of psi
         self._engine = _QGEngine(self.dtype, 1, grid.Ny - 2, grid.Nx - 2, grid.dx, grid.dy, one, one,
-                                 np.zeros(1), self.beta_y, self.wind_forcing, solver, spec)
+                                 np.zeros(1), self.beta_y, self.wind_forcing, solver,
+                                 spec | _lib.SPEC_KEEP_PSI_RING)
 
     def diagnose(self, state):
         psi, u, v, zeta = self._diag_fields(state)

@@ -1,0 +1,122 @@
+"""Oracle parity of stepping and of the raw vector field at sizes where the CUDA path runs its
+production kernels: CTAs of the TMA stencil that do not touch the ring (predicate-free path), the
+radix-8 row FFT at 512 / 1024 and the three-pass register FFT at nx >= 4096, fp64-carry (low-k) and
+plain Thomas strips under stepping - and at BASELINE.json's configurations C2 (3 x 128^2, 100
+steps), C5 (256^2 members of an ensemble) and C3 (shallow water at 256^2).  Tolerances are
+BASELINE.json's: relative L2 <= 1e-5 in fp32, <= 1e-12 in fp64; fp32 results are compared with the
+fp64 oracle.
+"""
+import numpy as np
+import pytest
+
+from test_gpu_parity import TOL, assert_swm_parity, qg_pair, qstate, rel, swm_pair, swm_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nx,ny", [(512, 512), (1024, 1024), (4096, 128)])
+def test_qg_vector_field_and_steps_at_size(nx, ny, dtype):
+    import somax_b200 as sb
+    om, gm = qg_pair(nx, ny, dtype)
+    om.workers = -1
+    q0 = qstate(3, nx, ny, dtype, ring=True)
+    st = sb.BaroclinicQGState(q=q0)
+    q64 = q0.astype(np.float64)
+    # raw vector field and _rhs = vector_field(BC(q)), per layer (the lower layers are not
+    # hidden behind the wind-forced top layer)
+    # fp32: differences of psi over one cell lose ~ nx * eps in ANY fp32 evaluation of the Jacobian
+    # (the reference's included); the oracle run in fp32 measures that floor (as for the
+    # shallow-water momentum tendencies, test_gpu_parity.assert_swm_parity)
+    for got, ref, same in ((gm.vector_field(0.0, st).q, om.rhs(q64), om.rhs(q0)),
+                           (gm.build_terms().vf(0.0, st).q, om.rhs(om.bc(q64)), om.rhs(om.bc(q0)))):
+        for l in range(3):
+            tol = max(2e-5, 1.5 * rel(same[l], ref[l])) if dtype == np.float32 else 1e-11
+            assert rel(got[l], ref[l]) <= tol, l
+    dt = 600.0 * 128 / nx
+    for steps in (1, 10):
+        got = gm.integrate(st, 0.0, steps * dt, dt).ys.q[0]
+        ref = om.integrate(q64, 0.0, steps * dt, dt)
+        assert rel(got, ref) <= TOL[dtype], steps
+        for l in range(3):
+            assert rel(got[l], ref[l]) <= 2 * TOL[dtype], (steps, l)
+        assert rel(gm._invert_pv(got), om.invert_pv(ref)) <= 2 * TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_qg_c2_128_100_steps(dtype):
+    """BASELINE config 2: doublegyre_bc_qg (3 x 128^2, dt = 600 s), 1 and 100 steps, diagnostics."""
+    import somax_b200 as sb
+    om, gm = qg_pair(128, 128, dtype)
+    q0 = qstate(3, 128, 128, dtype, ring=True)
+    for steps in (1, 100):
+        got = gm.integrate(sb.BaroclinicQGState(q=q0), 0.0, steps * 600.0, 600.0).ys.q[0]
+        ref = om.integrate(q0.astype(np.float64), 0.0, steps * 600.0, 600.0)
+        assert rel(got, ref) <= TOL[dtype], steps
+        assert rel(gm._invert_pv(got), om.invert_pv(ref)) <= 2 * TOL[dtype]
+    d, dref = gm.diagnose(sb.BaroclinicQGState(q=got)), om.diagnose(ref)
+    assert np.allclose(d.kinetic_energy, dref["kinetic_energy"], rtol=1e-4)
+    assert np.allclose(d.enstrophy, dref["enstrophy"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_qg_c5_ensemble_of_256_members(dtype):
+    """BASELINE config 5's member shape: 4 members of 3 x 256^2 stepped as one batch, each
+    against the oracle (1 and 10 steps)."""
+    import somax_b200 as sb
+    from oracle.testcases import synthetic_qg_state
+    om, gm = qg_pair(256, 256, dtype)
+    qs = np.stack([synthetic_qg_state(3, 256, 256, seed=10_000 + e, dtype=np.float64) for e in range(4)]).astype(dtype)
+    dt = 300.0
+    for steps in (1, 10):
+        got = gm.integrate(sb.BaroclinicQGState(q=qs), 0.0, steps * dt, dt).ys.q[0]
+        assert got.shape == qs.shape
+        for e in range(4):
+            ref = om.integrate(qs[e].astype(np.float64), 0.0, steps * dt, dt)
+            assert rel(got[e], ref) <= TOL[dtype], (steps, e)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("bc", ["periodic", "wall"])
+def test_swm_c3_256_10_steps(bc, dtype):
+    """BASELINE config 3 (swm_jet) at 256^2: 1 and 10 steps of the factory state."""
+    import somax_b200 as sb
+    om, gm = swm_pair(256, 256, dtype, bc)
+    h, u, v = swm_state(256, 256, dtype, noise=False)
+    dt = 20.0 * 64 / 256
+    for steps in (1, 10):
+        sol = gm.integrate(sb.MultilayerSW2DState(h=h, u=u, v=v), 0.0, steps * dt, dt)
+        ref = om.integrate(*[a.astype(np.float64) for a in (h, u, v)], 0.0, steps * dt, dt)
+        same = om.integrate(h, u, v, 0.0, steps * dt, dt)
+        for name, r, rs in zip("huv", ref, same):
+            assert_swm_parity(getattr(sol.ys, name)[0], r, rs, dtype, name)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_barotropic_keeps_the_ring_of_psi(dtype):
+    """BarotropicQG._invert_pv (qg/barotropic.py:113-121) returns the solver output with its
+    ring; BaroclinicQG zeroes it.  Both solve on the whole array."""
+    from oracle import qg as oqg
+    import somax_b200 as sb
+    rng = np.random.default_rng(2)
+    for nx, ny, solver in ((64, 48, 1), (30, 20, 2), (256, 256, 1)):
+        kw = dict(nx=nx, ny=ny)
+        om = oqg.create_barotropic(**kw)
+        gm = sb.BarotropicQG.create(dtype=np.dtype(dtype).name, solver=solver, **kw)
+        q = (1e-6 * rng.standard_normal((ny + 2, nx + 2))).astype(dtype)
+        psi, ref = gm._invert_pv(q), om.invert_pv(q.astype(np.float64)[None])[0]
+        assert rel(psi, ref) <= (5e-6 if dtype == np.float32 else 1e-12)
+        ring = np.ones_like(ref, bool); ring[1:-1, 1:-1] = False
+        assert np.abs(ref[ring]).max() > 0
+        assert rel(psi[ring], ref[ring]) <= (2e-5 if dtype == np.float32 else 1e-11)
+        dq = gm.vector_field(0.0, sb.BarotropicQGState(q=q)).q
+        assert rel(dq, om.rhs(q.astype(np.float64)[None])[0]) <= (5e-5 if dtype == np.float32 else 1e-10)
+
+
+def test_unsupported_dst_conventions_are_refused():
+    import somax_b200 as sb
+    from somax_b200 import _lib
+    for bit in (_lib.SPEC_DST_CONTINUOUS, _lib.SPEC_DST_INTERIOR):
+        m = sb.BaroclinicQG.create(nx=16, ny=16, spec=_lib.DEFAULT_SPEC | bit)
+        with pytest.raises(_lib.SomaxB200Error, match="only the reference's DST convention"):
+            m._invert_pv(np.zeros((3, 18, 18), np.float32))
