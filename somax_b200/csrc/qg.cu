@@ -816,7 +816,7 @@ static int qg_create_impl(somax_b200_qg_t* out, int dtype, int batch, int nl, in
   auto* h = new somax_b200_qg_s();
   h->dtype = dtype; h->L = make_layout(batch, nl, ny, nx); h->ny = ny; h->nx = nx;
   h->dx = dx; h->dy = dy; h->spec = spec_flags;
-  int rc = qg_solver_create(&h->solver, dtype, batch, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, solver, 1, rows, jo, ylo, yhi);
+  int rc = qg_solver_create(&h->solver, dtype, batch, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, solver, rows > 0 ? 1 : 0, rows, jo, ylo, yhi);
   auto up = [&](const double* src, void** dst, bool* one) {
     return dtype == SOMAX_B200_F32 ? upload_coef<float>(src, (float**)dst, h->L.Ny, h->L.Nx, one)
                                    : upload_coef<double>(src, (double**)dst, h->L.Ny, h->L.Nx, one);

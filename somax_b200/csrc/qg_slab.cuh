@@ -203,9 +203,10 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
       // XG1 / XG2: my slice of ghat (3 columns), then of gvec (2 combinations; + float copy, + border
       // column nx of S for the rank that owns the last strip) -> every other rank
       if (r != p) {
-        for (int i = 0; i < 3; ++i) {
-          const size_t go = (((size_t)pl * 3 + i) * NyS + a0) * sizeof(double);
-          xg1.push_back(Seg{(const char*)vc.ghat + go, (char*)g->peers[r].buf[6] + go, 1u, (unsigned)(na * sizeof(double)), 0, 0});
+        if (pl == 0) {      // ghat is interleaved [row][3 nl (padded)]: my rows are one contiguous block
+          const size_t nvp = (size_t)((3 * planes + 1) & ~1);
+          const size_t go = (size_t)a0 * nvp * sizeof(double);
+          xg1.push_back(Seg{(const char*)vc.ghat + go, (char*)g->peers[r].buf[6] + go, 1u, (unsigned)(na * nvp * sizeof(double)), 0, 0});
         }
         for (int i = 0; i < 2; ++i) {
           const size_t go = (((size_t)pl * 2 + i) * NyS + a0) * sizeof(double);

@@ -59,7 +59,9 @@ struct QgSolver {
   Mix l2m, m2l;
   int nheavy = 0;
   int nseg = 1, seg_len = 0;                        // segmented sweeps (ThomasTab)
+  bool seg_plain = true;                            // false: only the LOWK class is segmented
   double* segbuf = nullptr; double* segprod = nullptr;
+  float* ckpt = nullptr; int nck = 0;               // E checkpoints of the PLAIN fp32 strips (ThomasTab)
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t bytes = 0;
@@ -68,7 +70,6 @@ struct QgSolver {
 // Spectral arrays (S, W) are stored BLOCKED in 64-column strips so that the y-sweeps can move a
 // (rows x 64 columns) tile with a single bulk copy: within a plane, element (row j, column k)
 // lives at ((k / 64) * ny + j) * 64 + (k % 64); the plane stride is ny * np, np = roundup(nx, 64).
-constexpr int GS_ROWS = 8;     // outputs (warps) per CTA of border_gsolve
 constexpr int GS_SMALL_NY = 1024;   // up to here: one thread per output (border_gsolve_small)
 
 // ------------------------------------------------------------------------------------------
@@ -573,8 +574,15 @@ struct ThomasTab {
   // segment k from cin_k = e_{k-1} + p_{k-1} cin_{k-1} (p = product of -c_s over a segment,
   // tabulated on the host) and does the real work.  pass 0 = unsegmented (nseg = 1).
   int nseg, seg_len, pass;
+  bool seg_plain;
   double* segbuf;            // [plane][half][seg][np] end values of pass 1
   const double* segprod;     // [kind: 0 elimination, 1 substitution][half][mode][seg][np]
+  // PLAIN fp32 strips never store the eliminated border right-hand side E of the second solve:
+  // thomas_vec_ckpt keeps one value of the recurrence per column and 16-row block and the KIND 2
+  // substitution recomputes E block by block (the recurrence needs only the shared vector g and the
+  // tabulated coefficients).  ckpt: [plane][strip][half][nck][64] floats, block m covers the
+  // elimination rows [cnt - (m+1) 16, cnt - m 16) of the half and holds the value before its first.
+  float* ckpt; int nck;
 };
 
 
@@ -642,7 +650,7 @@ template <typename T, int KIND, bool TAB> struct ThStages {   // ring depth
   // PLAIN rings are kept small enough that a whole sweep (123 strips x 3 planes x 2 halves at
   // 8192^2) is resident in ONE wave next to the LOWK CTAs: every CTA runs for the whole sweep, so
   // a second wave of a few CTAs would double the kernel time
-  static constexpr int v = TAB ? 3 : (sizeof(T) == 4 ? (KIND == 2 ? 4 : 6) : (KIND == 2 ? 2 : 3));
+  static constexpr int v = TAB ? 3 : (sizeof(T) == 4 ? 6 : (KIND == 2 ? 2 : 3));
 };
 
 // Plain fp32 recurrence over one register block, for the well-conditioned strips of the fp32
@@ -654,7 +662,7 @@ __device__ __forceinline__ void thomas_tile_f32(float (*A)[TH_COLS], const float
                                                 const float (*Ct)[TH_COLS], const float* __restrict__ gv,
                                                 int tid, int nr, int s0, int ilo, int Js, int cnt, int jb,
                                                 bool act, float cfix, float kfix, float dy2, float bs,
-                                                float& carry) {
+                                                float ck, float& carry) {
   constexpr int dj = UP ? 1 : -1;
   float f[TH_RT], cj[TH_RT];
 #pragma unroll
@@ -667,7 +675,22 @@ __device__ __forceinline__ void thomas_tile_f32(float (*A)[TH_COLS], const float
     else cj[r] = (ok && i < Js) ? Ct[i - ilo][tid] : cfix;
     if (FROM_VEC) f[r] = ok ? gv[jb + dj * r] : 0.f;
     else f[r] = ok ? A[ok ? rm : 0][tid] : 0.f;
-    if (KIND == 2) f[r] = fmaf(-bs, ok ? Vt[ok ? rm : 0][tid] : 0.f, f[r]);
+  }
+  if (KIND == 2) {
+    // E of this block, recomputed: the elimination ran over the rows in the opposite order
+    // (r = nr-1 .. 0), from the checkpointed value before the block's first row; same arithmetic
+    // as thomas_vec_ckpt, so the values are the ones that kernel went through
+    (void)Vt;
+    float e = ck;
+#pragma unroll
+    for (int r = TH_RT - 1; r >= 0; --r) {
+      if (MODE != 2 || r < nr) {
+        const int i = cnt - 1 - (s0 + r);
+        const float kc = (MODE == 0 || (MODE == 2 && i >= Js)) ? kfix : cj[r] * dy2;
+        e = fmaf(-cj[r], e, kc * gv[jb + dj * r]);
+        f[r] = fmaf(-bs, e, f[r]);
+      }
+    }
   }
   if (!SUBST) {
 #pragma unroll
@@ -766,10 +789,12 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
              const double* __restrict__ bsig, T* __restrict__ out) {
   constexpr int NS = ThStages<T, KIND, TAB>::v;
   constexpr int RT = ThRows<T, KIND, TAB>::v;
-  constexpr bool COMBINE = KIND == 2;      // a second operand tile (E) travels with the first
+  constexpr bool PLAIN = sizeof(T) == 4 && !TAB;     // fp32 arithmetic, float coefficient rows
+  constexpr bool RECOMP = PLAIN && KIND == 2;        // E is recomputed from checkpoints, not loaded
+  constexpr bool COMBINE = KIND == 2 && !RECOMP;     // a second operand tile (E) travels with the first
+  constexpr bool GVEC = FROM_VEC || RECOMP;          // rows of the shared right-hand side g are staged
   static_assert(SUBST || KIND == 0, "KIND applies to substitution sweeps");
   constexpr bool LOAD = !FROM_VEC;
-  constexpr bool PLAIN = sizeof(T) == 4 && !TAB;     // fp32 arithmetic, float coefficient rows
   static_assert(TH_COLS == SP_W, "one CTA per 64-column strip");
   static_assert(RT % TH_RT == 0, "staged tile = whole register blocks");
   constexpr size_t TILE_B = (size_t)RT * TH_COLS * sizeof(T);
@@ -803,18 +828,18 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
   double* sideG = (FROM_VEC ? tb.dbad1 : tb.dbad) + ((size_t)plane * ny) * tb.KB;   // [j][KB] of this plane
   const double* sideG1 = tb.dbad1 + ((size_t)plane * ny) * tb.KB;
   double* meetW = FROM_VEC ? tb.meet1 : tb.meet;
-  const double bs = (COMBINE && act) ? bsig[c] : 0.0;
+  const double bs = (KIND == 2 && act) ? bsig[c] : 0.0;
   const float cfix_f = (float)cfix, kfix_f = (float)(cfix * tb.dy2), dy2_f = (float)tb.dy2, bs_f = (float)bs;
   float carry_f = 0.f;
   // FROM_VEC: the shared right-hand side g[j] of the tile after next is fetched (one element per
   // thread, coalesced) while the current tile runs, and read back as a shared-memory broadcast
   using GT = typename std::conditional<PLAIN, float, double>::type;
-  __shared__ GT gbuf[2][FROM_VEC ? 2 * RT : 1];      // [buffer][column parity][row of the tile]
+  __shared__ GT gbuf[2][GVEC ? 2 * RT : 1];      // [buffer][column parity][row of the tile]
   const GT* gsrc = nullptr;
-  if (FROM_VEC) {
+  if (GVEC) {
     if constexpr (PLAIN) gsrc = gvecf + (size_t)plane * 2 * ny; else gsrc = gvec + (size_t)plane * 2 * ny;
   }
-  const int gpar = FROM_VEC ? (c & 1) * RT : 0;
+  const int gpar = GVEC ? (c & 1) * RT : 0;
   const int m1 = ny / 2;
   const int cnt = half == 0 ? m1 : ny - m1;
   int j0, dj;
@@ -873,7 +898,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     const double ca = tb.meetc[((size_t)m * 2 + 0) * tb.np + c], cb = tb.meetc[((size_t)m * 2 + 1) * tb.np + c];
     double dm = tb.meet[((size_t)plane * 2 + 0) * tb.np + c];
     double em = tb.meet[((size_t)plane * 2 + 1) * tb.np + c];
-    if (COMBINE) {      // eliminated D - bs E at the meeting rows
+    if (KIND == 2) {      // eliminated D - bs E at the meeting rows
       dm = fma(-bs, tb.meet1[((size_t)plane * 2 + 0) * tb.np + c], dm);
       em = fma(-bs, tb.meet1[((size_t)plane * 2 + 1) * tb.np + c], em);
     }
@@ -892,7 +917,15 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     }
     carry_f = (float)carry;
   }
-  if (FROM_VEC && ntile > 0) {
+  // checkpoint of the tile's E block (RECOMP): block index by the elimination rows it covers
+  const float* ckS = nullptr;
+  auto tile_ck = [&](int t) -> float {
+    const int s1 = sa + t * RT + tile_nr(t);                  // rows [cnt - s1, ...) in elimination order
+    return (s1 >= cnt) ? 0.f : ckS[(size_t)(s1 / RT - 1) * TH_COLS + tid];
+  };
+  if (RECOMP) ckS = tb.ckpt + ((size_t)(plane * tb.nstrip + strip) * 2 + (half == 0 ? 0 : 1)) * tb.nck * TH_COLS;
+  float ck_cur = (RECOMP && worker && ntile > 0) ? tile_ck(0) : 0.f;
+  if (GVEC && ntile > 0) {
     if (worker && tid < tile_nr(0)) {
       gbuf[0][tid] = gsrc[tile_jlo(0) + tid];
       gbuf[0][RT + tid] = gsrc[ny + tile_jlo(0) + tid];
@@ -919,10 +952,11 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     const int nrt = tile_nr(t);
     const int ilot = tile_ilo(t);
     GT gnext = 0, gnext1 = 0;
-    if (FROM_VEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) {
+    if (GVEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) {
       gnext = gsrc[tile_jlo(t + 1) + tid];
       gnext1 = gsrc[ny + tile_jlo(t + 1) + tid];
     }
+    const float ck_next = (RECOMP && worker && t + 1 < ntile) ? tile_ck(t + 1) : 0.f;
     const GT* gvt = gbuf[t & 1] + gpar - tile_jlo(t);      // indexed by the memory row
 #ifdef SB_TH_PHASES
     long long ph0 = clock64();
@@ -952,7 +986,7 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
 #define SB_TILE(UPV, MODEV)                                                                        \
         thomas_tile_f32<SUBST, FROM_VEC, KIND, UPV, MODEV>(                                        \
             reinterpret_cast<float (*)[TH_COLS]>(A), reinterpret_cast<const float (*)[TH_COLS]>(Vt), Ct, (const float*)gvt, \
-            tid, nr, s0, ilo, Js, cnt, jb, act, cfix_f, kfix_f, dy2_f, bs_f, carry_f)
+            tid, nr, s0, ilo, Js, cnt, jb, act, cfix_f, kfix_f, dy2_f, bs_f, ck_cur, carry_f)
         if (dj > 0) {
           if (mode == 0) SB_TILE(true, 0); else if (mode == 1) SB_TILE(true, 1); else SB_TILE(true, 2);
         } else {
@@ -980,10 +1014,11 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     long long ph2 = clock64();
     ph_comp += ph2 - ph1;
 #endif
-    if (FROM_VEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) {
+    if (GVEC && worker && t + 1 < ntile && tid < tile_nr(t + 1)) {
       gbuf[(t + 1) & 1][tid] = gnext;
       gbuf[(t + 1) & 1][RT + tid] = gnext1;
     }
+    ck_cur = ck_next;
     if (worker && !SUBST && !probe && t == ntile - 1 && sb == cnt)
       meetW[((size_t)plane * 2 + half) * tb.np + c] = PLAIN ? (double)carry_f : carry;
     // finished tile -> global (the bulk store reads shared memory through the async proxy)
@@ -1055,49 +1090,115 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
 #endif
 }
 
-// Right-hand sides of the border (Schur) system, r[plane][3][ny]:
+// Elimination of the border right-hand side of the second solve on the PLAIN fp32 strips, WITHOUT
+// storing it: every column runs d_i = (dy^2 g_i - d_{i-1}) c_i over its half (g = gvecf[c & 1], the
+// whole half staged in shared memory) and keeps d_{i-1} whenever (cnt - i) is a multiple of TH_RT -
+// the value the KIND 2 substitution needs to recompute its block of E - plus the last value for the
+// meeting-point solve.  No array transfer at all (the stored version wrote and re-read one).
+__global__ void __launch_bounds__(TH_COLS)
+thomas_vec_ckpt(ThomasTab tb, int strip_first, const float* __restrict__ gvecf) {
+  extern __shared__ float gsh[];                 // [2][cnt] rows of this half, in elimination order
+  const int tid = threadIdx.x, strip = strip_first + blockIdx.x, c = strip * TH_COLS + tid;
+  const int plane = blockIdx.y, m = plane % tb.nl, half = blockIdx.z, ny = tb.ny;
+  const int m1 = ny / 2, cnt = half == 0 ? m1 : ny - m1;
+  const int j0 = half == 0 ? 0 : ny - 1, dj = half == 0 ? 1 : -1;
+  const float* g = gvecf + (size_t)plane * 2 * ny;
+  for (int i = tid; i < cnt; i += TH_COLS) {
+    gsh[i] = g[j0 + dj * i];
+    gsh[cnt + i] = g[ny + j0 + dj * i];
+  }
+  __syncthreads();
+  const float* gs = gsh + (c & 1) * cnt;
+  const double cfix = tb.cinf[(size_t)m * tb.np + c];
+  const float cfix_f = (float)cfix, kfix_f = (float)(cfix * tb.dy2), dy2_f = (float)tb.dy2;
+  const int Js = tb.Jstrip[m * tb.nstrip + strip];
+  const float (*Ct)[TH_COLS] = reinterpret_cast<const float (*)[TH_COLS]>(tb.ctabB + tb.tabOff[m * tb.nstrip + strip]);
+  float* ck = tb.ckpt + ((size_t)(plane * tb.nstrip + strip) * 2 + half) * tb.nck * TH_COLS + tid;
+  float carry = 0.f;
+  int i = 0;
+  // the ragged block first (rows [0, cnt mod TH_RT)), then whole blocks with a checkpoint before each
+  const int r0 = cnt % TH_RT;
+  for (; i < r0; ++i) {
+    const float cj = i < Js ? Ct[i][tid] : cfix_f;
+    carry = fmaf(-cj, carry, (i < Js ? cj * dy2_f : kfix_f) * gs[i]);
+  }
+  for (; i < cnt; i += TH_RT) {
+    ck[(size_t)((cnt - i) / TH_RT - 1) * TH_COLS] = carry;
+    float gg[TH_RT];
+#pragma unroll
+    for (int r = 0; r < TH_RT; ++r) gg[r] = gs[i + r];
+    if (i >= Js) {
+#pragma unroll
+      for (int r = 0; r < TH_RT; ++r) carry = fmaf(-cfix_f, carry, kfix_f * gg[r]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < TH_RT; ++r) {
+        const bool tab = i + r < Js;
+        const float cj = tab ? Ct[i + r][tid] : cfix_f;
+        carry = fmaf(-cj, carry, (tab ? cj * dy2_f : kfix_f) * gg[r]);
+      }
+    }
+  }
+  if (c < tb.np) tb.meet1[((size_t)plane * 2 + half) * tb.np + c] = (double)carry;
+}
+
+// Right-hand sides of the border (Schur) system.  rvec / ghat are interleaved so that one 128-bit
+// load fetches two columns of a row: element (batch b, row j, vector v = 3 * layer + i) lives at
+// (b * ny + j) * NVP + v, NVP = border_nvp(nl).
 //   r0 = f_0 - b v(1),  r1 = f_n - b v(n-1),  r2 = f_{n+1}
 // with v(1) = E + O and v(n-1) = E - O, E / O = sum over the even / odd columns c (odd / even
 // x-wavenumbers k = c + 1) of sig2n[c] x[j][c].  The sums arrive as 2 * nstrip per-warp partials per
 // parity from the KIND 1 substitution sweeps (fixed order: deterministic); f_n sits in the border
 // slot of S, f_0 and f_{n+1} in bext.
+__host__ __device__ inline int border_nvp(int nl) { return (3 * nl + 1) & ~1; }
+
+// Thread (jx, py) of a CTA adds the partials p = py, py + 8, ... of row j0 + jx (loads coalesced over
+// jx), the eight py combine through shared memory in a fixed order.  (One thread per row walked
+// all 2 * 256 partials alone: 0.09 ms at 8192^2 on 99 CTAs.)
 template <typename T>
 __global__ void __launch_bounds__(256)
 border_reduce(const T* __restrict__ S, const T* __restrict__ bext, const T* __restrict__ part,
-              int ny, int np, int ncols, int npart, double b, double* __restrict__ r) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x, plane = blockIdx.y;
-  if (j >= ny) return;
-  const T* pe = part + (size_t)plane * 2 * npart * ny + j;
-  const T* po = pe + (size_t)npart * ny;
+              int ny, int np, int ncols, int npart, int nl, double b, double* __restrict__ r) {
+  __shared__ double red[2][8][32];
+  const int jx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jx, plane = blockIdx.y;
   double ev = 0, od = 0;
+  if (j < ny) {
+    const T* pe = part + (size_t)plane * 2 * npart * ny + j;
+    const T* po = pe + (size_t)npart * ny;
 #pragma unroll 8
-  for (int p = 0; p < npart; ++p) { ev += (double)pe[(size_t)p * ny]; od += (double)po[(size_t)p * ny]; }
-  double* rp = r + (size_t)plane * 3 * ny + j;
+    for (int p = py; p < npart; p += 8) { ev += (double)pe[(size_t)p * ny]; od += (double)po[(size_t)p * ny]; }
+  }
+  red[0][py][jx] = ev; red[1][py][jx] = od;
+  __syncthreads();
+  if (py != 0 || j >= ny) return;
+  ev = 0; od = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { ev += red[0][q][jx]; od += red[1][q][jx]; }
+  const int bm = plane / nl, l = plane - bm * nl;
+  double* rp = r + ((size_t)bm * ny + j) * border_nvp(nl) + 3 * l;
   rp[0] = (double)bext[((size_t)plane * 2 + 0) * ny + j] - b * (ev + od);
-  rp[ny] = (double)S[(size_t)plane * ny * np + sp_off(ny, j, ncols)] - b * (ev - od);
-  rp[2 * ny] = (double)bext[((size_t)plane * 2 + 1) * ny + j];
+  rp[1] = (double)S[(size_t)plane * ny * np + sp_off(ny, j, ncols)] - b * (ev - od);
+  rp[2] = (double)bext[((size_t)plane * 2 + 1) * ny + j];
 }
 
-// Border Schur solve = dense DST-I in y of three columns per plane (length ny, N = ny + 1), brute
-// force in fp64: out_i[a] = sum_{t=1..ny} sin(pi a t / N) in_i[t].  Each thread owns the
-// terms t = t0, t0 + B, t0 + 2B, ... and advances sin/cos(pi a t / N) by the fixed angle
-// pi a B / N with a rotation (4 FMAs, shared by the three columns) instead of gathering from the
-// sine table; the start and step values come exactly from the table.  STAGE_A multiplies by the
-// host-inverted 3 x 3 Schur block of y-mode a; stage B scales by 2/N and writes the results where
-// the sweeps / inverse transform read them: gvec = (g0 + g1, g0 - g1), g1 in the border slot of S,
-// g0 and g2 in bext.
+// Epilogue of the border transforms for output row a (1-based) of one layer's three columns.
+// STAGE_A multiplies by the host-inverted 3 x 3 Schur block of y-mode a; stage B scales by 2/N and
+// writes the results where the sweeps / inverse transform read them: gvec = (g0 + g1, g0 - g1), g1
+// in the border slot of S, g0 and g2 in bext.
 template <typename T, bool STAGE_A>
-__device__ __forceinline__ void border_store(double t0, double t1, double t2, int a, int plane, int m,
+__device__ __forceinline__ void border_store(double t0, double t1, double t2, int a, int bm, int l, int nl,
                                              const double* __restrict__ minv, int ny, int np, int n,
                                              double* __restrict__ out, double* __restrict__ gvec,
                                              float* __restrict__ gvecf, T* __restrict__ S,
                                              T* __restrict__ bext) {
+  const int plane = bm * nl + l;
   if (STAGE_A) {
-    const double* M = minv + ((size_t)m * ny + (a - 1)) * 9;
-    double* o = out + (size_t)plane * 3 * ny + (a - 1);
+    const double* M = minv + ((size_t)l * ny + (a - 1)) * 9;
+    double* o = out + ((size_t)bm * ny + (a - 1)) * border_nvp(nl) + 3 * l;
     o[0] = M[0] * t0 + M[1] * t1 + M[2] * t2;
-    o[ny] = M[3] * t0 + M[4] * t1 + M[5] * t2;
-    o[2 * ny] = M[6] * t0 + M[7] * t1 + M[8] * t2;
+    o[1] = M[3] * t0 + M[4] * t1 + M[5] * t2;
+    o[2] = M[6] * t0 + M[7] * t1 + M[8] * t2;
   } else {
     const double sc = 2.0 / (ny + 1);
     t0 *= sc; t1 *= sc; t2 *= sc;
@@ -1113,85 +1214,146 @@ __device__ __forceinline__ void border_store(double t0, double t1, double t2, in
   }
 }
 
-template <typename T, bool STAGE_A>
-__global__ void __launch_bounds__(32 * GS_ROWS)
-border_gsolve(const double* __restrict__ in, const double* __restrict__ sintab,
-              const double* __restrict__ minv, int ny, int np, int n, int nl,
-              double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
-              T* __restrict__ S, T* __restrict__ bext, int a_first, int a_count) {
-  // one warp per output index a; sintab holds sin(pi k / N) for k < 2N followed by cos(pi k / N)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a = a_first + blockIdx.x * GS_ROWS + warp + 1, plane = blockIdx.y, m = plane % nl;
-  if (a > a_first + a_count) return;
+// Border Schur solve = dense DST-I in y of the 3 nl border columns of a member (length ny, N = ny + 1),
+// brute force in fp64: out_v[a] = sum_{t=1..ny} sin(pi a t / N) in_v[t].
+// A CTA computes GS_OUT = 32 consecutive outputs a for ALL NV columns: lane = output, warp = one of
+// GS_SL interleaved slices of the terms t, so every load of in[t][.] is a warp-wide broadcast and the
+// rotation that advances sin/cos(pi a t / N) by the fixed angle pi a GS_SL / N (4 FMAs; start and step
+// values come exactly from the table) is shared by the NV columns.  The input is folded on the fly by
+// the t <-> N - t symmetry, sin(pi a (N - t) / N) = -(-1)^a sin(pi a t / N): half the terms.  The slices
+// are combined through shared memory in a fixed order.  (The first version ran one warp per
+// (output, layer): every warp re-read its three input columns from L2, 4.7 GB per launch at 8192^2.)
+constexpr int GS_OUT = 32, GS_SL = 8;
+constexpr int GS_U = 8;                  // terms per slice and chunk
+constexpr int GS_CH = GS_SL * GS_U;      // rows of the input per staged chunk
+constexpr int GS_NS = 3;                 // ring depth
+
+template <typename T, int NL, bool STAGE_A>
+__global__ void __launch_bounds__(GS_OUT * GS_SL)
+border_dst(const double* __restrict__ in, const double* __restrict__ sintab,
+           const double* __restrict__ minv, int ny, int np, int n,
+           double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
+           T* __restrict__ S, T* __restrict__ bext, int a_first, int a_count) {
+  constexpr int NV = 3 * NL, NVP = (NV + 1) & ~1;
+  // Input rows t-1 (lo) and N-t-1 (hi) of a chunk of terms are two contiguous blocks of the
+  // interleaved array: one cp.async.bulk each into a GS_NS-stage ring, completion on an mbarrier
+  // (first version: per-term global loads, every one an L2 round trip with no memory-level
+  // parallelism - 0.39 ms per launch at 8192^2, 10 % of the DFMA rate).
+  constexpr size_t TILE_B = sizeof(double) * GS_NS * 2 * GS_CH * NVP, RED_B = sizeof(double) * GS_SL * NV * GS_OUT;
+  __shared__ __align__(128) unsigned char gs_smem[TILE_B > RED_B ? TILE_B : RED_B];
+  __shared__ unsigned long long full[GS_NS];
+  double (*tile)[2][GS_CH][NVP] = reinterpret_cast<double (*)[2][GS_CH][NVP]>(gs_smem);
+  double (*red)[NV][GS_OUT] = reinterpret_cast<double (*)[NV][GS_OUT]>(gs_smem);   // after the last chunk
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5, bm = blockIdx.y;
+  const int a = a_first + blockIdx.x * GS_OUT + lane + 1;      // 1-based output row
+  const bool valid = a <= a_first + a_count;
   const unsigned N = ny + 1, N2 = 2 * N;
   const double* costab = sintab + N2;
-  const unsigned t0 = lane + 1;
-  const unsigned k0 = ((unsigned)a * t0) % N2, kd = ((unsigned)a * 32u) % N2;
+  const unsigned aa = valid ? (unsigned)a : 1u;
+  const unsigned k0 = (unsigned)(((unsigned long long)aa * (unsigned)(sl + 1)) % N2), kd = (aa * (unsigned)GS_SL) % N2;
   double s = sintab[k0], c = costab[k0];
   const double ds = sintab[kd], dc = costab[kd];
-  double acc0 = 0, acc1 = 0, acc2 = 0;
-  const double* x0 = in + (size_t)plane * 3 * ny;
-  const double* x1 = x0 + ny;
-  const double* x2 = x1 + ny;
-  // sin(pi a (N - t) / N) = -(-1)^a sin(pi a t / N): fold the input, half the terms
-  const int half = (N - 1) / 2;
-  const double sgn = (a & 1) ? 1.0 : -1.0;
-  for (int t = t0; t <= half; t += 32) {
-    acc0 = fma(s, fma(sgn, x0[N - t - 1], x0[t - 1]), acc0);
-    acc1 = fma(s, fma(sgn, x1[N - t - 1], x1[t - 1]), acc1);
-    acc2 = fma(s, fma(sgn, x2[N - t - 1], x2[t - 1]), acc2);
-    const double s2 = fma(s, dc, c * ds), c2 = fma(c, dc, -(s * ds));   // rotate by 32 pi a / N
-    s = s2; c = c2;
+  const double sgn = (aa & 1) ? 1.0 : -1.0;
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  const double* x = in + (size_t)bm * ny * NVP;
+  const int half = (N - 1) / 2;                       // terms t = 1..half (folded)
+  const int nchunk = (half + GS_CH - 1) / GS_CH;
+  auto chunk_rows = [&](int ch) { return min(GS_CH, half - ch * GS_CH); };
+  auto load_chunk = [&](int ch) {                     // thread 0 only
+    if (ch >= nchunk) return;
+    const int st = ch % GS_NS, nr = chunk_rows(ch), t0 = ch * GS_CH + 1;
+    const unsigned bytes = (unsigned)(nr * NVP * sizeof(double));
+    mbar_arrive_expect_tx(&full[st], 2 * bytes);
+    bulk_g2s(&tile[st][0][0][0], x + (size_t)(t0 - 1) * NVP, bytes, &full[st]);
+    bulk_g2s(&tile[st][1][0][0], x + (size_t)(N - t0 - nr) * NVP, bytes, &full[st]);   // rows N-t-1, ascending
+  };
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < GS_NS; ++q) mbar_init(&full[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    for (int ch = 0; ch < GS_NS - 1; ++ch) load_chunk(ch);
   }
-  if ((N & 1) == 0 && lane == 0) {
-    const double sm = sintab[(unsigned)(((unsigned long long)a * (N / 2)) % N2)];
-    acc0 = fma(sm, x0[N / 2 - 1], acc0);
-    acc1 = fma(sm, x1[N / 2 - 1], acc1);
-    acc2 = fma(sm, x2[N / 2 - 1], acc2);
+  __syncthreads();
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int st = ch % GS_NS, nr = chunk_rows(ch);
+    if (threadIdx.x == 0) load_chunk(ch + GS_NS - 1);     // its stage was released by the barrier below
+    mbar_wait(&full[st], (unsigned)((ch / GS_NS) & 1));
+    // slice sl takes the rows r = sl, sl + GS_SL, ... of the chunk (terms t = ch GS_CH + 1 + r)
+#pragma unroll 4
+    for (int r = sl; r < nr; r += GS_SL) {
+      const double2* lo = reinterpret_cast<const double2*>(&tile[st][0][r][0]);
+      const double2* hi = reinterpret_cast<const double2*>(&tile[st][1][nr - 1 - r][0]);
+#pragma unroll
+      for (int v2 = 0; v2 < NVP / 2; ++v2) {
+        const double2 l2 = lo[v2], h2 = hi[v2];
+        acc[2 * v2] = fma(s, fma(sgn, h2.x, l2.x), acc[2 * v2]);
+        if (2 * v2 + 1 < NV) acc[2 * v2 + 1] = fma(s, fma(sgn, h2.y, l2.y), acc[2 * v2 + 1]);
+      }
+      const double s2 = fma(s, dc, c * ds), c2 = fma(c, dc, -(s * ds));   // rotate by GS_SL pi a / N
+      s = s2; c = c2;
+    }
+    __syncthreads();      // everyone is done with stage st: it may be refilled
   }
-  for (int sh = 16; sh > 0; sh >>= 1) {
-    acc0 += __shfl_down_sync(0xffffffffu, acc0, sh);
-    acc1 += __shfl_down_sync(0xffffffffu, acc1, sh);
-    acc2 += __shfl_down_sync(0xffffffffu, acc2, sh);
+  if ((N & 1) == 0 && sl == 0) {
+    const double sm = sintab[(unsigned)(((unsigned long long)aa * (N / 2)) % N2)];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = fma(sm, x[(size_t)(N / 2 - 1) * NVP + v], acc[v]);
   }
-  if (lane == 0)
-    border_store<T, STAGE_A>(acc0, acc1, acc2, a, plane, m, minv, ny, np, n, out, gvec, gvecf, S, bext);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) red[sl][v][lane] = acc[v];
+  __syncthreads();
+  // layer l of output `lane` is finished by thread (l, lane)
+  if (sl < NL && valid) {
+    double t3[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double sum = 0;
+#pragma unroll
+      for (int q = 0; q < GS_SL; ++q) sum += red[q][3 * sl + i][lane];
+      t3[i] = sum;
+    }
+    border_store<T, STAGE_A>(t3[0], t3[1], t3[2], a, bm, sl, NL, minv, ny, np, n, out, gvec, gvecf, S, bext);
+  }
 }
 
 // Same transform for short columns (ny <= GS_SMALL_NY, ensembles of small grids): one THREAD per
-// output index, so there is no per-warp set-up or reduction; the input is a warp-uniform
-// (broadcast) load and the rotation advances by pi a / N per term.
+// (output, layer), so there is no set-up or reduction; the input is a warp-uniform (broadcast)
+// load and the rotation advances by pi a / N per term.
 template <typename T, bool STAGE_A>
 __global__ void __launch_bounds__(128)
 border_gsolve_small(const double* __restrict__ in, const double* __restrict__ sintab,
                     const double* __restrict__ minv, int ny, int np, int n, int nl,
                     double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
                     T* __restrict__ S, T* __restrict__ bext, int a_first, int a_count) {
-  const int a = a_first + blockIdx.x * blockDim.x + threadIdx.x + 1, plane = blockIdx.y, m = plane % nl;
+  const int a = a_first + blockIdx.x * blockDim.x + threadIdx.x + 1, plane = blockIdx.y;
+  const int bm = plane / nl, l = plane - bm * nl;
   if (a > a_first + a_count) return;
   const unsigned N = ny + 1, N2 = 2 * N;
+  const int nvp = border_nvp(nl);
   const double* costab = sintab + N2;
   const double ds = sintab[a], dc = costab[a];        // a < N2
   double s = ds, c = dc, acc0 = 0, acc1 = 0, acc2 = 0;
-  const double* x0 = in + (size_t)plane * 3 * ny;
-  const double* x1 = x0 + ny;
-  const double* x2 = x1 + ny;
+  const double* x = in + (size_t)bm * ny * nvp + 3 * l;
   const int half = (N - 1) / 2;
   const double sgn = (a & 1) ? 1.0 : -1.0;
   for (int t = 1; t <= half; ++t) {
-    acc0 = fma(s, fma(sgn, x0[N - t - 1], x0[t - 1]), acc0);
-    acc1 = fma(s, fma(sgn, x1[N - t - 1], x1[t - 1]), acc1);
-    acc2 = fma(s, fma(sgn, x2[N - t - 1], x2[t - 1]), acc2);
+    const double* lo = x + (size_t)(t - 1) * nvp;
+    const double* hi = x + (size_t)(N - t - 1) * nvp;
+    acc0 = fma(s, fma(sgn, hi[0], lo[0]), acc0);
+    acc1 = fma(s, fma(sgn, hi[1], lo[1]), acc1);
+    acc2 = fma(s, fma(sgn, hi[2], lo[2]), acc2);
     const double s2 = fma(s, dc, c * ds), c2 = fma(c, dc, -(s * ds));
     s = s2; c = c2;
   }
   if ((N & 1) == 0) {
     const double sm = sintab[(unsigned)(((unsigned long long)a * (N / 2)) % N2)];
-    acc0 = fma(sm, x0[N / 2 - 1], acc0);
-    acc1 = fma(sm, x1[N / 2 - 1], acc1);
-    acc2 = fma(sm, x2[N / 2 - 1], acc2);
+    const double* mid = x + (size_t)(N / 2 - 1) * nvp;
+    acc0 = fma(sm, mid[0], acc0);
+    acc1 = fma(sm, mid[1], acc1);
+    acc2 = fma(sm, mid[2], acc2);
   }
-  border_store<T, STAGE_A>(acc0, acc1, acc2, a, plane, m, minv, ny, np, n, out, gvec, gvecf, S, bext);
+  border_store<T, STAGE_A>(acc0, acc1, acc2, a, bm, l, nl, minv, ny, np, n, out, gvec, gvecf, S, bext);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1321,6 +1483,13 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
     SB_CUDA(cudaMemset(s->segbuf, 0, sbytes));
     s->bytes += sbytes;
   }
+  if (s->dtype == SOMAX_B200_F32 && s->kind == SOMAX_B200_SOLVER_FFT) {
+    s->nck = (hcap + TH_RT - 1) / TH_RT;
+    const size_t cb = (size_t)s->planes * nstrip * 2 * s->nck * SP_W * sizeof(float);
+    SB_CUDA(cudaMalloc((void**)&s->ckpt, cb));
+    SB_CUDA(cudaMemset(s->ckpt, 0, cb));
+    s->bytes += cb;
+  }
   {
     size_t mb = (size_t)s->planes * 2 * np * 8;
     SB_CUDA(cudaMalloc((void**)&s->meet, mb));
@@ -1441,13 +1610,16 @@ static int build_fft_tables(QgSolver* s, const double* lambdas) {
   if (int rc = dev_upload(minv.data(), minv.size() * 8, (void**)&s->minv, &s->bytes)) return rc;
   if (int rc = dev_upload(sintab.data(), sintab.size() * 8, (void**)&s->sintab, &s->bytes)) return rc;
   size_t vb = (size_t)s->planes * ny * 8;
-  SB_CUDA(cudaMalloc((void**)&s->rvec, 3 * vb));
-  SB_CUDA(cudaMalloc((void**)&s->ghat, 3 * vb));
+  const size_t rb = (size_t)s->batch * ny * border_nvp(nl) * 8;      // <= 4 vb
+  SB_CUDA(cudaMalloc((void**)&s->rvec, rb));
+  SB_CUDA(cudaMemset(s->rvec, 0, rb));
+  SB_CUDA(cudaMalloc((void**)&s->ghat, rb));
+  SB_CUDA(cudaMemset(s->ghat, 0, rb));
   SB_CUDA(cudaMalloc((void**)&s->gvec, 2 * vb));
   SB_CUDA(cudaMalloc((void**)&s->gvecf, vb));
   SB_CUDA(cudaMalloc(&s->bext, 2 * (size_t)s->planes * ny * sizeof(T)));
   SB_CUDA(cudaMemset(s->bext, 0, 2 * (size_t)s->planes * ny * sizeof(T)));
-  s->bytes += 9 * vb + 2 * (size_t)s->planes * ny * sizeof(T);
+  s->bytes += 2 * rb + 3 * vb + 2 * (size_t)s->planes * ny * sizeof(T);
   return 0;
 }
 
@@ -1485,6 +1657,13 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
   s->ny = rows > 0 ? rows : ny + 2; s->jo = rows > 0 ? jo : 0;
   s->ylo = rows > 0 ? ylo : 1; s->yhi = rows > 0 ? yhi : 1;
   ny = s->ny;      // from here on: solver rows
+  // nseg = 0 (a whole grid on one device): the PLAIN sweeps fill the GPU unsegmented, but the
+  // handful of LOWK CTAs are serial chains over ny/2 rows that end up as the critical path of both
+  // solves (0.13 + 0.40 ms against 0.08 + 0.29 ms of the PLAIN class at 8192^2), so THEY are cut
+  // into 8 segments once the columns are long
+  s->seg_plain = nseg != 0;
+  if (nseg == 0) nseg = ny + 2 >= 2048 ? 8 : 1;
+  if (const char* e = getenv("SOMAX_B200_LOWK_NSEG")) { if (!s->seg_plain) nseg = atoi(e); }
   s->nseg = std::max(1, std::min(nseg, 16));
   s->ncols = (kind == SOMAX_B200_SOLVER_FFT) ? nx - 1 : nx + 2;
   s->np = ((std::max(nx, s->ncols) + SP_W - 1) / SP_W) * SP_W; s->planes = batch * nl;
@@ -1532,7 +1711,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
 
 void qg_solver_destroy(QgSolver* s) {
   if (!s) return;
-  void* ptrs[] = {s->segbuf, s->segprod, s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->dbad1, s->meet1, s->part, s->bsig, s->sig2n,
+  void* ptrs[] = {s->ckpt, s->segbuf, s->segprod, s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->dbad1, s->meet1, s->part, s->bsig, s->sig2n,
                   s->minv, s->bext, s->sintab, s->rvec, s->ghat, s->gvec, s->gvecf, s->tw, s->twc, s->twb, s->dstmat, s->meet, s->meetc};
   for (void* p : ptrs) cudaFree(p);
   if (s->aux) cudaStreamDestroy(s->aux);
@@ -1549,9 +1728,14 @@ static int launch_thomas_one(const char* tag, const ThomasTab& tb, int strip_fir
                              const T* in, const T* V, const double* gvec, const float* gvecf,
                              const double* bsig, T* out, cudaStream_t st) {
   if (nstrips <= 0) return 0;
+  if (!TAB && tb.nseg > 1 && !tb.seg_plain) {       // this class runs unsegmented
+    ThomasTab t0 = tb;
+    t0.nseg = 1; t0.seg_plain = true;
+    return launch_thomas_one<T, SUBST, FROM_VEC, KIND, TAB>(tag, t0, strip_first, nstrips, planes, in, V, gvec, gvecf, bsig, out, st);
+  }
   constexpr int NS = ThStages<T, KIND, TAB>::v;
   constexpr int RT = ThRows<T, KIND, TAB>::v;
-  constexpr int NOP = KIND == 2 ? 2 : 1;      // operand tiles (and side tiles) per stage
+  constexpr int NOP = (KIND == 2 && (TAB || sizeof(T) == 8)) ? 2 : 1;      // operand tiles (and side tiles) per stage
   constexpr size_t smem0 = (size_t)NS * RT * TH_COLS * ((TAB ? sizeof(double) : 0) + sizeof(T) * NOP) + NS * 8;
   static_assert(smem0 <= 227 * 1024, "sweep ring exceeds shared memory");
   const size_t smem = smem0 + (TAB ? (size_t)NS * RT * tb.KB * sizeof(double) * NOP : 0);
@@ -1619,9 +1803,26 @@ static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream
     SB_CUDA(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
   }
   if (int rc = launch_thomas_one<T, false, SECOND, 0, true>(tfl, tb, hA, nh, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, st)) return rc;
-  if (int rc = launch_thomas_one<T, false, SECOND, 0, false>(tf, tb, pA, npl, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, pl)) return rc;
+  if constexpr (SECOND && sizeof(T) == 4) {
+    // PLAIN fp32 strips: checkpoints of the eliminated border right-hand side, nothing stored
+    if (npl > 0) {
+      const int hcap = s->ny - s->ny / 2;
+      const size_t smem = (size_t)2 * hcap * sizeof(float);
+      static size_t attr_done = 0;
+      if (smem > 48 * 1024 && attr_done < smem) {
+        SB_CUDA(cudaFuncSetAttribute(thomas_vec_ckpt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = smem;
+      }
+      prof_begin(tf, pl);
+      thomas_vec_ckpt<<<dim3(npl, s->planes, 2), TH_COLS, smem, pl>>>(tb, pA, s->gvecf);
+      SB_LAUNCH_CHECK();
+    }
+  } else {
+    if (int rc = launch_thomas_one<T, false, SECOND, 0, false>(tf, tb, pA, npl, s->planes, fin, nullptr, s->gvec, s->gvecf, nullptr, fout, pl)) return rc;
+  }
   if (int rc = launch_thomas_one<T, true, false, KIND, true>(tbl, tb, hA, nh, s->planes, bin, Vv, nullptr, nullptr, bs, S, st)) return rc;
-  if (int rc = launch_thomas_one<T, true, false, KIND, false>(tbk, tb, pA, npl, s->planes, bin, Vv, nullptr, nullptr, bs, S, pl)) return rc;
+  // (the PLAIN fp32 KIND 2 sweep recomputes E from the shared right-hand side: it reads gvecf)
+  if (int rc = launch_thomas_one<T, true, false, KIND, false>(tbk, tb, pA, npl, s->planes, bin, Vv, s->gvec, s->gvecf, bs, S, pl)) return rc;
   if (two) {
     SB_CUDA(cudaEventRecord(s->ev_join, s->aux));
     SB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
@@ -1638,6 +1839,8 @@ static ThomasTab make_tab(const QgSolver* s) {
   tb.part = s->part; tb.sig2n = s->sig2n; tb.ny = s->ny; tb.np = s->np; tb.ncols = s->ncols; tb.nl = s->nl;
   tb.dy2 = s->dy * s->dy;
   tb.nseg = s->nseg; tb.seg_len = s->seg_len; tb.pass = 0; tb.segbuf = s->segbuf; tb.segprod = s->segprod;
+  tb.seg_plain = s->seg_plain;
+  tb.ckpt = s->ckpt; tb.nck = s->nck;
   return tb;
 }
 
@@ -1689,27 +1892,32 @@ int qg_solver_border_stage(QgSolver* s, int stage, int a0, int a1, cudaStream_t 
   if (stage == 0) {
     const double b = 1.0 / (s->dx * s->dx);
     prof_begin("border_reduce", st);
-    border_reduce<T><<<dim3((ny + 255) / 256, s->planes), 256, 0, st>>>(S, (const T*)s->bext, (const T*)s->part, ny, np, s->ncols, 2 * (np / SP_W), b, s->rvec);
+    border_reduce<T><<<dim3((ny + 31) / 32, s->planes), 256, 0, st>>>(S, (const T*)s->bext, (const T*)s->part, ny, np, s->ncols, 2 * (np / SP_W), nl, b, s->rvec);
     SB_LAUNCH_CHECK();
     return 0;
   }
   if (cnt <= 0) return 0;
-  // one thread per output pays off only when there are enough outputs to fill the GPU with
-  // threads (ensembles of small grids); a single grid keeps one warp per output (ny = 1024,
-  // 3 planes: 10 us against 38 us)
+  // one thread per (output, layer) pays off only when there are enough of them to fill the GPU
+  // (ensembles of small grids); a single grid runs the blocked transform
   const bool small = ny <= GS_SMALL_NY && (long)s->planes * ny >= 65536;
-  if (stage == 1) {
-    prof_begin("border_gsolve_a", st);
-    if (small)
-      border_gsolve_small<T, true><<<dim3((cnt + 127) / 128, s->planes), 128, 0, st>>>(s->rvec, s->sintab, s->minv, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, nullptr, a0, cnt);
-    else
-      border_gsolve<T, true><<<dim3((cnt + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->rvec, s->sintab, s->minv, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, nullptr, a0, cnt);
+  const double* in = stage == 1 ? s->rvec : s->ghat;
+  prof_begin(stage == 1 ? "border_gsolve_a" : "border_gsolve_b", st);
+  if (small) {
+    const dim3 g((cnt + 127) / 128, s->planes);
+    if (stage == 1) border_gsolve_small<T, true><<<g, 128, 0, st>>>(in, s->sintab, s->minv, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, nullptr, a0, cnt);
+    else border_gsolve_small<T, false><<<g, 128, 0, st>>>(in, s->sintab, s->minv, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, (T*)s->bext, a0, cnt);
   } else {
-    prof_begin("border_gsolve_b", st);
-    if (small)
-      border_gsolve_small<T, false><<<dim3((cnt + 127) / 128, s->planes), 128, 0, st>>>(s->ghat, s->sintab, s->minv, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, (T*)s->bext, a0, cnt);
-    else
-      border_gsolve<T, false><<<dim3((cnt + GS_ROWS - 1) / GS_ROWS, s->planes), 32 * GS_ROWS, 0, st>>>(s->ghat, s->sintab, s->minv, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, (T*)s->bext, a0, cnt);
+    const dim3 g((cnt + GS_OUT - 1) / GS_OUT, s->batch);
+#define SB_BDST(NLV)                                                                                         \
+    if (stage == 1) border_dst<T, NLV, true><<<g, GS_OUT * GS_SL, 0, st>>>(in, s->sintab, s->minv, ny, np, n, s->ghat, nullptr, nullptr, nullptr, nullptr, a0, cnt); \
+    else border_dst<T, NLV, false><<<g, GS_OUT * GS_SL, 0, st>>>(in, s->sintab, s->minv, ny, np, n, nullptr, s->gvec, s->gvecf, S, (T*)s->bext, a0, cnt)
+    switch (nl) {
+      case 1: SB_BDST(1); break;
+      case 2: SB_BDST(2); break;
+      case 3: SB_BDST(3); break;
+      default: SB_BDST(4); break;
+    }
+#undef SB_BDST
   }
   SB_LAUNCH_CHECK();
   return 0;

@@ -120,3 +120,39 @@ def test_unsupported_dst_conventions_are_refused():
         m = sb.BaroclinicQG.create(nx=16, ny=16, spec=_lib.DEFAULT_SPEC | bit)
         with pytest.raises(_lib.SomaxB200Error, match="only the reference's DST convention"):
             m._invert_pv(np.zeros((3, 18, 18), np.float32))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_diagnose_fields_match_oracle(dtype):
+    """Every field of the Diagnostics pytrees (qg/baroclinic.py:197-228, qg/barotropic.py:159-183,
+    swm/multilayer.py:225-256), not only the scalar sums."""
+    from oracle import qg as oqg
+    import somax_b200 as sb
+    tol = 5e-6 if dtype == np.float32 else 1e-12
+    om, gm = qg_pair(64, 48, dtype)
+    q = qstate(3, 64, 48, dtype, ring=True)
+    d, r = gm.diagnose(sb.BaroclinicQGState(q=q)), om.diagnose(q.astype(np.float64))
+    assert rel(d.psi, r["psi"]) <= tol
+    # u, v, zeta difference psi over one cell: (n / pi) times the rounding of psi
+    for name, key in (("u", "u"), ("v", "v"), ("relative_vorticity", "relative_vorticity")):
+        assert rel(getattr(d, name), r[key]) <= tol * (400 if key == "relative_vorticity" else 20), name
+    assert np.allclose(d.kinetic_energy, r["kinetic_energy"], rtol=1e-4)
+    assert np.allclose(d.total_enstrophy, r["total_enstrophy"], rtol=1e-4)
+    assert np.allclose(d.rossby_radii, r["rossby_radii"], rtol=1e-12)
+    # barotropic: psi keeps its ring, so u, v, zeta next to the ring see it
+    ob = oqg.create_barotropic(nx=64, ny=64)
+    gb = sb.BarotropicQG.create(nx=64, ny=64, dtype=np.dtype(dtype).name)
+    qb = qstate(1, 64, 64, dtype, ring=True)[0]
+    d, r = gb.diagnose(sb.BarotropicQGState(q=qb)), ob.diagnose(qb.astype(np.float64)[None])
+    assert rel(d.psi, r["psi"][0]) <= tol
+    assert rel(d.u, r["u"][0]) <= 20 * tol and rel(d.v, r["v"][0]) <= 20 * tol
+    assert rel(d.relative_vorticity, r["relative_vorticity"][0]) <= 400 * tol
+    assert np.allclose(d.kinetic_energy, r["kinetic_energy"][0], rtol=1e-4)
+    # shallow water
+    osw, gsw = swm_pair(64, 40, dtype, "wall")
+    h, u, v = swm_state(64, 40, dtype)
+    d = gsw.diagnose(sb.MultilayerSW2DState(h=h, u=u, v=v))
+    r = osw.diagnose(*[a.astype(np.float64) for a in (h, u, v)])
+    for name in ("potential_vorticity", "relative_vorticity", "kinetic_energy_field"):
+        assert rel(getattr(d, name), r[name]) <= (2e-5 if dtype == np.float32 else 1e-12), name
+    assert np.allclose(d.energy, r["energy"], rtol=1e-4) and np.allclose(d.enstrophy, r["enstrophy"], rtol=1e-4)
