@@ -40,6 +40,8 @@ WORKLOADS = {
     "qg3_4096": ("qg", 3, 4096, 4096, 1),
     "qg3_1024": ("qg", 3, 1024, 1024, 1),
     "qg3_128": ("qg", 3, 128, 128, 1),           # BASELINE config 2 (launch-latency bound)
+    "qg1_64": ("qgbt", 1, 64, 64, 1),            # BASELINE config 1: barotropic double gyre (sim-bt-qg)
+    "qg3_8192_f64": ("qg", 3, 8192, 8192, 1),    # the headline grid in fp64 (north-star 1e-12 pipeline)
     "qg3_256_ens1024": ("qg", 3, 256, 256, 1024),  # BASELINE config 5: 1024 members x 3 x 256^2
     "swm2_4096": ("swm", 2, 4096, 4096, 1),      # BASELINE config 3 at its largest size
     "swm2_1024": ("swm", 2, 1024, 1024, 1),
@@ -51,7 +53,10 @@ QG_PARAMS = dict(Lx=4e6, Ly=4e6, f0=9.375e-5, beta=1.754e-11, n_layers=3,
 SWM_PARAMS = dict(Lx=1e6, Ly=1e6, f0=1e-4, beta=1.6e-11, H=(500.0, 4500.0), g_prime=(9.81, 0.025),
                   lateral_viscosity=100.0, bottom_drag=1e-7)        # configs/_authoring/swm_jet.py:21-40
 # algorithmic state-sized transfers per Tsit5 step
-TRANSFERS = {"qg": 79, "swm": 111}
+TRANSFERS = {"qg": 79, "qgbt": 79, "swm": 111}
+DTYPES = {"qg3_8192_f64": "float64"}             # every other workload runs the reference's default, fp32
+BT_PARAMS = dict(Lx=1e6, Ly=1e6, f0=1e-4, beta=1.6e-11, lateral_viscosity=500.0, bottom_drag=1e-7,
+                 wind_amplitude=1e-12)                               # configs/_authoring/doublegyre_bt_qg.py:22-29
 # algorithmic transfers of one launch of each kernel (DESIGN.md "kernels"): arrays it must read+write
 KERNEL_TRANSFERS = {
     "rowdst_fwd_fft": 2.0, "rowdst_inv_fft": 2.0, "thomas_fwd_0": 2.0, "thomas_bwd_0": 1.0,
@@ -157,8 +162,9 @@ class ClockSampler(threading.Thread):
 def oracle_model(kind, nl, nx, ny, workers):
     from oracle import qg as oqg
     from oracle import testcases as ot
-    if kind == "qg":
-        m = oqg.create_baroclinic(nx=nx, ny=ny, **QG_PARAMS)
+    if kind in ("qg", "qgbt"):
+        m = (oqg.create_baroclinic(nx=nx, ny=ny, **QG_PARAMS) if kind == "qg"
+             else oqg.create_barotropic(nx=nx, ny=ny, **BT_PARAMS))
         m.workers = workers
         q0 = ot.synthetic_qg_state(nl, nx, ny, dtype=np.float32)
         return m, (q0,), qg_dt(nx)
@@ -194,9 +200,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "cell_updates_per_s", "value": v, "unit": "Gcell-steps/s",
         "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": el / K * 1e3,
-        "higher_is_better": True, "scaling": "strong" if (args.gpus > 1 and args.decomp == "slab") else "weak",
-        "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": args.workload, "sample_grid": sn},
+        "higher_is_better": True, "scaling": scaling_label(args.workload, args.decomp),
+        "vs_baseline": None, "dtype": "f64" if DTYPES.get(args.workload) == "float64" else "f32",
+        "data": "synthetic", "config": workload_config(args.workload, sn),
         "cpu_baseline": {"value": v, "unit": "Gcell-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Gcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -204,18 +210,36 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def build_gpu_model(kind, nl, nx, ny, members=range(1)):
+def scaling_label(workload, decomp):
+    """'strong' when the total work is the same at every N (one grid in slabs; a fixed member set),
+    'weak' when every GPU gets its own grid - the same label at N = 1 and N > 1."""
+    kind, _nl, _nx, _ny, members = WORKLOADS[workload]
+    return "strong" if (members > 1 or (kind == "qg" and decomp == "slab")) else "weak"
+
+
+def workload_config(workload, sample_grid):
+    """The `config` object both arms print: the workload by name plus the grid of the bounded
+    sample the CPU arm / cpu_baseline is timed on."""
+    kind, nl, nx, ny, members = WORKLOADS[workload]
+    return {"workload": workload, "model": f"{nl}-layer {kind}", "grid": [ny, nx], "members": members,
+            "dt": qg_dt(nx) if kind != "swm" else swm_dt(nx), "cpu_sample_grid": [sample_grid, sample_grid]}
+
+
+def build_gpu_model(kind, nl, nx, ny, members=range(1), dtype="float32"):
     """Model + initial state; for ensembles the state gets a leading member axis and member e
     uses seed 10_000 + e."""
     import somax_b200 as sb
     from somax_b200 import gfd_testcases as g
     members = list(members)
+    if kind == "qgbt":
+        model = sb.BarotropicQG.create(nx=nx, ny=ny, dtype=dtype, **BT_PARAMS)
+        return model, sb.BarotropicQGState(q=g.synthetic_qg_state(1, nx, ny, dtype=dtype)[0]), qg_dt(nx)
     if kind == "qg":
-        model = sb.BaroclinicQG.create(nx=nx, ny=ny, **QG_PARAMS)
+        model = sb.BaroclinicQG.create(nx=nx, ny=ny, dtype=dtype, **QG_PARAMS)
         if len(members) == 1 and members[0] == 0:
-            q0 = g.synthetic_qg_state(nl, nx, ny, dtype="float32")
+            q0 = g.synthetic_qg_state(nl, nx, ny, dtype=dtype)
         else:
-            q0 = np.stack([g.synthetic_qg_state(nl, nx, ny, seed=10_000 + e, dtype="float32") for e in members])
+            q0 = np.stack([g.synthetic_qg_state(nl, nx, ny, seed=10_000 + e, dtype=dtype) for e in members])
         return model, sb.BaroclinicQGState(q=q0), qg_dt(nx)
     model, st = g.baroclinic_instability_swm(nx=nx, ny=ny, **SWM_PARAMS)
     return model, st, swm_dt(nx)
@@ -241,16 +265,18 @@ def run_gpu(args):
     # ensembles: strong scaling over a fixed member set; single grids: one member per rank (weak)
     mine = shard_members(members, rank, world) if members > 1 else range(1)
     nb = len(mine)
-    model, st0, dt = build_gpu_model(kind, nl, nx, ny, mine)
+    dtype = DTYPES.get(args.workload, "float32")
+    model, st0, dt = build_gpu_model(kind, nl, nx, ny, mine, dtype)
+    isqg = kind in ("qg", "qgbt")
     fields = [f for f in ("q", "h", "u", "v") if hasattr(st0, f)]
     dev = {f: torch.as_tensor(getattr(st0, f)).cuda() for f in fields}
     state_bytes = sum(t.numel() * t.element_size() for t in dev.values())
-    handle = model._engine.handle(nb) if kind == "qg" else model._handle(nb)
-    p = (sb.models.qg._params_struct(model.params, model._H0) if kind == "qg" else model._pstruct())
+    handle = model._engine.handle(nb) if isqg else model._handle(nb)
+    p = (sb.models.qg._params_struct(model.params, model._H0) if isqg else model._pstruct())
     stream = torch.cuda.current_stream().cuda_stream
 
     def steps_dev(n):
-        if kind == "qg":
+        if isqg:
             _lib.check(lib.somax_b200_qg_steps(handle, dev["q"].data_ptr(), n, dt, 0.0, C.byref(p), stream))
         else:
             _lib.check(lib.somax_b200_swm_steps(handle, dev["h"].data_ptr(), dev["u"].data_ptr(),
@@ -266,12 +292,12 @@ def run_gpu(args):
     barrier()
 
     # ---- timed region: K steps, device resident, CUDA events on the launching stream ----
-    # Per-launch CUDA events ride inside the timed region, except where the library replays a captured
-    # CUDA graph (small grids, K >= 9): per-launch events would force the eager path, so those
-    # workloads are timed clean and profiled in a second, identical pass of K steps.
+    # Timed CLEAN (no per-launch events); the per-kernel profile comes from a second, identical pass
+    # of K steps with the library's per-launch CUDA events on (small grids replay a captured CUDA
+    # graph in the timed pass and run eagerly in the profiled one).
     graphed = nb * nl * (ny + 2) * (nx + 2) <= (1 << 21) and K >= 9
     lib.somax_b200_profile_reset()
-    lib.somax_b200_profile_enable(0 if graphed else 1)
+    lib.somax_b200_profile_enable(0)
     sampler = ClockSampler(local)
     sampler.start()
     n0 = lib.somax_b200_launch_count()
@@ -284,10 +310,9 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     launches = lib.somax_b200_launch_count() - n0
     clocks = sampler.stop()
-    if graphed:
-        lib.somax_b200_profile_enable(1)
-        steps_dev(K)
-        barrier()
+    lib.somax_b200_profile_enable(1)
+    steps_dev(K)
+    barrier()
     lib.somax_b200_profile_enable(0)
     buf = C.create_string_buffer(1 << 16)
     _lib.check(lib.somax_b200_profile_report(buf, len(buf)))
@@ -332,7 +357,7 @@ def run_gpu(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-    w = 4
+    w = 8 if dtype == "float64" else 4
     padded = nb * nl * (ny + 2) * (nx + 2) * w     # one state-sized array (one field) on this rank
     prof.sort(key=lambda r: -r["total_ms"])
     total_prof = sum(r["total_ms"] for r in prof) or 1.0
@@ -347,8 +372,8 @@ def run_gpu(args):
         "frac": achieved / peak, "traffic": ncu_traffic(args.workload, top["kernel"]), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": k_tr * padded, "avg_launch_ms": per_launch_ms,
         "share_of_step": top["total_ms"] / total_prof,
-        "events": "second pass of K eager steps (the timed region replays a CUDA graph)" if graphed
-                  else "per-launch CUDA events inside the timed region",
+        "events": "per-launch CUDA events in a second, identical pass of K steps (the timed region runs "
+                  "without them" + ("; it replays a CUDA graph)" if graphed else ")"),
         "step": {"algorithmic_bytes": step_alg_bytes, "achieved_gbs": step_alg_bytes / (ms_max / K * 1e-3) / 1e9,
                  "frac": step_frac, "transfers_per_step": TRANSFERS[kind]},
         "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "total_ms": round(r["total_ms"], 3),
@@ -367,14 +392,14 @@ def run_gpu(args):
     line = {
         "metric": "cell_updates_per_s", "value": value, "unit": "Gcell-steps/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
-        "scaling": "strong" if members > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": f"{nl}-layer {kind}", "grid": [ny, nx], "members": members,
-                   "dt": dt, "l2": "working set (>= 7 GB) far larger than the 126 MB L2; no flush needed"
+        "scaling": scaling_label(args.workload, args.decomp), "vs_baseline": None,
+        "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",
+        "config": {**workload_config(args.workload, sn), "l2": "working set (>= 7 GB) far larger than the 126 MB L2; no flush needed"
                    if state_bytes > 5e8 else "small working set: L2 resident by nature of the workload",
                    "parallelism": (f"{members} members sharded by member over {world} GPU(s)" if members > 1 else
                                    ("1 member per GPU (ensemble sharded by member)" if world > 1 else "single GPU")),
-                   "solver": "fft+bordered+thomas" if kind == "qg" else "n/a",
-                   "device_bytes": int(lib.somax_b200_qg_device_bytes(handle) if kind == "qg"
+                   "solver": "fft + 3 border columns + thomas (whole-array DST-I solve)" if isqg else "n/a",
+                   "device_bytes": int(lib.somax_b200_qg_device_bytes(handle) if isqg
                                        else lib.somax_b200_swm_device_bytes(handle))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Gcell-steps/s", "h2d_bytes_per_step": io.h2d_bytes / K,
@@ -428,22 +453,45 @@ def run_gpu_slab(args):
         torch.cuda.synchronize()
 
     slab_model.advance_slab(dev, W, dt)
-    slab_model.check_peers()
+    barrier()
+    # ---- correctness carried by the line: the same W steps on ONE device (the single-GPU model on the
+    # whole grid, rank 0), compared on rank 0's window - outside the timed region.  The run fails above
+    # the fp32 tolerance of BASELINE.json.
+    rel = torch.zeros(1, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        full0 = torch.as_tensor(g.synthetic_qg_state(nl, nx, ny, dtype="float32")).cuda()
+        ref = model.integrate(sb.BaroclinicQGState(q=full0), 0.0, W * dt, dt, max_steps=None).ys.q[0][:, win, :]
+        rel[0] = (torch.linalg.vector_norm((dev.double() - ref.double()).flatten()) /
+                  torch.linalg.vector_norm(ref.double().flatten()))
+        del full0, ref
+        model._engine.close()
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.broadcast(rel, 0)
+    slab_rel = float(rel.item())
+    if not (slab_rel <= 1e-5):
+        sys.stderr.write(f"slab decomposition disagrees with the single-GPU model: relL2 = {slab_rel}\n")
+        raise SystemExit(3)
     barrier()
     lib.somax_b200_profile_reset()
-    lib.somax_b200_profile_enable(1)
+    lib.somax_b200_profile_enable(0)
     sampler = ClockSampler(local)
     sampler.start()
     n0 = lib.somax_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    slab_model.advance_slab(dev, K, dt)
+    slab_model.advance_slab(dev, K, dt, check=False)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.somax_b200_launch_count() - n0
     clocks = sampler.stop()
+    slab_model.check_peers()
+    # per-kernel profile: a second, identical pass of K steps with per-launch events on
+    lib.somax_b200_profile_enable(1)
+    slab_model.advance_slab(dev, K, dt, check=False)
+    barrier()
     lib.somax_b200_profile_enable(0)
     slab_model.check_peers()
     buf = C.create_string_buffer(1 << 16)
@@ -461,7 +509,7 @@ def run_gpu_slab(args):
     barrier()
     t0 = time.perf_counter()
     dev.copy_(host, non_blocking=True)
-    slab_model.advance_slab(dev, K, dt)
+    slab_model.advance_slab(dev, K, dt, check=False)
     out_host.copy_(dev, non_blocking=True)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -492,10 +540,12 @@ def run_gpu_slab(args):
             "metric": "cell_updates_per_s", "value": value, "unit": "Gcell-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "model": f"{nl}-layer qg", "grid": [ny, nx], "members": 1, "dt": dt,
+            "slab_vs_single_relL2": slab_rel,
+            "config": {**workload_config(args.workload, min(nx, 1024)),
                        "parallelism": f"one grid in {world} y-slab(s), distributed DST by peer-memory transposes over NVLink",
                        "l2": "per-rank working set far larger than the 126 MB L2; no flush needed",
-                       "solver": "fft+bordered+thomas (row stages on the slab, column stages on wavenumber strips)"},
+                       "solver": "fft + 3 border columns + thomas (row stages on the slab, column stages on wavenumber strips)",
+                       "slab_check": f"{W} steps, slabs vs the single-GPU model on rank 0's window, fails above 1e-5"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gcell-steps/s", "h2d_bytes_per_step": hb / K, "d2h_bytes_per_step": hb / K,
                     "steps_per_call": K, "nonfinite": float(t_e[1].item()),

@@ -127,6 +127,12 @@ int somax_b200_qg_rhs(somax_b200_qg_t h, const void* q, void* dq, void* psi_out,
  * re-projected, as in the reference). */
 int somax_b200_qg_steps(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt_last,
                         const somax_b200_params* p, void* stream);
+/* The same integration CONTINUED from a state an earlier *_steps / *_resume call returned: no
+ * boundary conditions on the initial state.  diffrax projects state0 once (core/model.py:62) and
+ * the states it saves at intermediate `SaveAt(ts=...)` times are un-projected (core/model.py:75-88);
+ * stepping from one save time to the next is one resume call. */
+int somax_b200_qg_resume(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt_last,
+                         const somax_b200_params* p, void* stream);
 
 /* Scalars of BaroclinicQG.diagnose (qg/baroclinic.py:197-228) plus the non-finite guard of the
  * runner (cli/_run.py:671-683).  out (DEVICE, double): batch * (2*nl + 1) values per member:
@@ -195,6 +201,9 @@ int somax_b200_swm_rhs(somax_b200_swm_t h, const void* hh, const void* u, const 
 /* SomaxModel.integrate (core/model.py:53-88) for the shallow-water state, in place. */
 int somax_b200_swm_steps(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps, double dt,
                          double dt_last, const somax_b200_params* p, void* stream);
+/* As somax_b200_qg_resume: continue without boundary conditions on the initial state. */
+int somax_b200_swm_resume(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps, double dt,
+                          double dt_last, const somax_b200_params* p, void* stream);
 
 /* Scalars of MultilayerShallowWater2D.diagnose (swm/multilayer.py:225-256): out (DEVICE,
  * double) batch * (3*nl + 1): ke_sum[nl], sum(h^2)[nl] (PE = 0.5 g'_k * this), potential

@@ -52,6 +52,7 @@ SIGNATURES = {
     "somax_b200_qg_invert": (_I, [_P, _P, _P, _P]),
     "somax_b200_qg_rhs": (_I, [_P, _P, _P, _P, _PP, _I, _P]),
     "somax_b200_qg_steps": (_I, [_P, _P, _L, _D, _D, _PP, _P]),
+    "somax_b200_qg_resume": (_I, [_P, _P, _L, _D, _D, _PP, _P]),
     "somax_b200_qg_diag": (_I, [_P, _P, _P, _P]),
     "somax_b200_qgs_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _I, _I, _I, _U]),
     "somax_b200_qgs_destroy": (_I, [_P]),
@@ -67,6 +68,7 @@ SIGNATURES = {
     "somax_b200_swm_apply_bc": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "somax_b200_swm_rhs": (_I, [_P, _P, _P, _P, _P, _P, _P, _PP, _I, _P]),
     "somax_b200_swm_steps": (_I, [_P, _P, _P, _P, _L, _D, _D, _PP, _P]),
+    "somax_b200_swm_resume": (_I, [_P, _P, _P, _P, _L, _D, _D, _PP, _P]),
     "somax_b200_swm_diag": (_I, [_P, _P, _P, _P, _P, _P]),
 }
 

@@ -424,6 +424,7 @@ def _integrate_and_write(spec: RunSpec, output_dir: Path, *, mode: str, initial_
             metrics_path.write_text(json.dumps(metrics, indent=2, sort_keys=True))
         dump_yaml(spec, str(output_dir / "resolved.yaml"))
     except Exception as exc:
+        _rmtree(tmp_snap)       # no artifacts on failure, the scratch snapshot store included
         run_log.stop(f"FAILED postflight: {type(exc).__name__}: {exc}")
         raise
     run_log.stop("finished cleanly")

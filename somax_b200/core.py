@@ -315,6 +315,16 @@ def step_plan(t0: float, t1: float, dt: float):
     return n, rem
 
 
+def _own_host(state):
+    """Copy of ``state`` whose host torch tensors are owned: the pinned staging buffer a model
+    returns is reused by its next call, so several save times would otherwise alias one buffer."""
+    kw = {}
+    for f in fields(state):
+        v = getattr(state, f.name)
+        kw[f.name] = v.clone() if (torch is not None and isinstance(v, torch.Tensor) and not v.is_cuda) else v
+    return type(state)(**kw)
+
+
 def _stack_states(cls, states):
     names = [f.name for f in fields(cls)]
     vals = {}
@@ -341,8 +351,10 @@ class SomaxModel(abc.ABC):
         ...
 
     @abc.abstractmethod
-    def _advance(self, state, n_steps: int, dt: float, dt_last: float):
-        """Tsit5-advance ``state`` (BC applied to it first) on the device."""
+    def _advance(self, state, n_steps: int, dt: float, dt_last: float, resume: bool = False):
+        """Tsit5-advance ``state`` on the device.  ``resume=False``: boundary conditions are applied
+        to it first (the start of an integration); ``resume=True``: continue from a state an
+        earlier call returned, un-projected."""
 
     def build_terms(self) -> ODETerm:
         def _rhs(t, state, args=None):
@@ -352,8 +364,14 @@ class SomaxModel(abc.ABC):
         return ODETerm(_rhs)
 
     def integrate(self, state0, t0: float, t1: float, dt: float, **kw) -> Solution:
-        """Forward integration (core/model.py:53-88).  Supports ``saveat`` (t1 / ts),
-        ``max_steps``; ``solver`` must be Tsit5 and ``stepsize_controller`` constant."""
+        """Forward integration (core/model.py:53-88).  Supports ``saveat`` (``t0`` / ``ts`` / ``t1``),
+        ``max_steps``; ``solver`` must be Tsit5 and ``stepsize_controller`` constant.
+
+        As in the reference, the boundary conditions are applied to ``state0`` once
+        (core/model.py:62) and afterwards only inside the right-hand side: the states saved at
+        intermediate times carry the drifting ghost ring, and stepping continues from them
+        un-projected.  diffrax reaches save times that are not on the step grid ``t0 + k dt`` by
+        dense-output interpolation, which the CUDA path does not implement: such ``ts`` raise."""
         solver = kw.pop("solver", None)
         if solver is not None and type(solver).__name__ != "Tsit5":
             raise NotImplementedError("the CUDA path implements diffrax.Tsit5 only")
@@ -364,26 +382,39 @@ class SomaxModel(abc.ABC):
         max_steps = kw.pop("max_steps", 4096)
         if kw:
             raise TypeError(f"unsupported integrate() arguments: {sorted(kw)}")
-        ts_attr = getattr(saveat, "ts", None)
-        if ts_attr is None and hasattr(saveat, "subs"):  # a real diffrax.SaveAt
-            ts_attr = saveat.subs.ts
-        save_ts = [float(t) for t in (np.asarray(ts_attr).tolist() if ts_attr is not None else [])]
-        if ts_attr is None:
-            save_ts = [float(t1)]
+        sub = getattr(saveat, "subs", None)          # a real diffrax.SaveAt keeps its fields in .subs
+        src = sub if (sub is not None and not isinstance(sub, (list, tuple))) else saveat
+        ts_attr = getattr(src, "ts", None)
+        want_t0, want_t1 = bool(getattr(src, "t0", False)), bool(getattr(src, "t1", False))
+        ts_list = [float(t) for t in (np.asarray(ts_attr).reshape(-1).tolist() if ts_attr is not None else [])]
+        if ts_attr is None and not (want_t0 or want_t1):
+            want_t1 = True
+        t0, t1, dt = float(t0), float(t1), float(dt)
         n_total, rem_total = step_plan(t0, t1, dt)
         if max_steps is not None and n_total + (1 if rem_total > 0 else 0) > max_steps:
             raise RuntimeError(
                 f"max_steps ({max_steps}) reached: {n_total + (rem_total > 0)} steps are needed")
+        prev = t0
+        for t in ts_list:
+            k = (t - t0) / dt
+            on_grid = abs(k - round(k)) <= 1e-9 * max(1.0, abs(k)) or abs(t - t1) <= 1e-9 * max(abs(t1), abs(dt))
+            if t < prev or t > t1 * (1 + 1e-12) + 1e-300 or not on_grid:
+                raise ValueError(
+                    f"saveat.ts must be increasing, inside [t0, t1] and on the step grid t0 + k*dt (or t1): {t} is "
+                    "not; diffrax interpolates such times from its dense output, the CUDA path does not")
+            prev = t
+        save_ts = ([t0] if want_t0 else []) + ts_list + ([t1] if want_t1 else [])
         outs = []
-        cur, tcur = state0, float(t0)
-        first = True
+        cur, tcur, started = state0, t0, False
+        many = len(save_ts) > 1
         for ts_ in save_ts:
             n, rem = step_plan(tcur, ts_, dt)
-            if first or n > 0 or rem > 0:
-                cur = self._advance(cur, n, float(dt), rem)
-                first = False
+            if not started or n > 0 or rem > 0:
+                # the first call applies the BCs to state0 (also when it takes no step: SaveAt(t0=True))
+                cur = self._advance(cur, n, dt, rem, resume=started)
+                started = True
             tcur = ts_
-            outs.append(cur)
+            outs.append(_own_host(cur) if many else cur)
         ys = _stack_states(type(outs[0]), outs)
         return Solution(ts=np.asarray(save_ts), ys=ys, stats={"num_steps": n_total + (rem_total > 0)})
 

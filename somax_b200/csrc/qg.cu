@@ -658,7 +658,7 @@ int qg_bc_inplace(somax_b200_qg_t h, void* q, cudaStream_t s) {
 
 template <typename T>
 int qg_steps_impl(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt_last,
-                  const somax_b200_params* p, cudaStream_t caller) {
+                  const somax_b200_params* p, bool bc0, cudaStream_t caller) {
   const Layout& L = h->L;
   const long total = n_steps + (dt_last > 0 ? 1 : 0);
   // launch-bound grids: replay two-step CUDA graphs on an internal stream
@@ -672,7 +672,8 @@ int qg_steps_impl(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt
   }
   void *y = h->y, *Yc = h->Ya, *Yn = h->Yb;
   if (int rc = pack_field<T>((const T*)q, (T*)y, L, s)) return rc;
-  if (int rc = qg_bc_inplace<T>(h, y, s)) return rc;   // integrate(): BC on state0
+  if (bc0)
+    if (int rc = qg_bc_inplace<T>(h, y, s)) return rc;   // integrate(): BC on state0 (not when resuming)
   if (total > 0) {
     QgArgs<T> A = make_qargs<T>(h, p, 1);
     auto step_dt = [&](long i) { return (i < n_steps) ? dt : dt_last; };
@@ -882,7 +883,14 @@ int somax_b200_qg_steps(somax_b200_qg_t h, void* q, long n_steps, double dt, dou
                         const somax_b200_params* p, void* stream) {
   if (!h || !q || !p) return fail(SOMAX_B200_ERR_INVALID, "null argument");
   if (n_steps < 0 || !(dt > 0) || dt_last < 0) return fail(SOMAX_B200_ERR_INVALID, "need n_steps>=0, dt>0, dt_last>=0");
-  return SB_DISPATCH(h, qg_steps_impl, h, q, n_steps, dt, dt_last, p, (cudaStream_t)stream);
+  return SB_DISPATCH(h, qg_steps_impl, h, q, n_steps, dt, dt_last, p, true, (cudaStream_t)stream);
+}
+
+int somax_b200_qg_resume(somax_b200_qg_t h, void* q, long n_steps, double dt, double dt_last,
+                         const somax_b200_params* p, void* stream) {
+  if (!h || !q || !p) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  if (n_steps < 0 || !(dt > 0) || dt_last < 0) return fail(SOMAX_B200_ERR_INVALID, "need n_steps>=0, dt>0, dt_last>=0");
+  return SB_DISPATCH(h, qg_steps_impl, h, q, n_steps, dt, dt_last, p, false, (cudaStream_t)stream);
 }
 
 int somax_b200_qg_diag(somax_b200_qg_t h, const void* q, double* out, void* stream) {

@@ -72,7 +72,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // Barrier across the ranks of one slab group: thread t publishes `epoch` in rank t's slot for
 // this rank and waits for rank t's epoch in its own slot.  Everything this rank stored to peer
 // memory earlier in the stream is complete (stream order) and fenced before the flag is released.
-__global__ void slab_barrier_kernel(FlagPtrs F, int me, int nranks, unsigned epoch, unsigned* err) {
+__global__ void slab_barrier_kernel(FlagPtrs F, int me, int nranks, unsigned epoch, unsigned* err,
+                                    unsigned long long timeout_ns) {
   const int t = threadIdx.x;
   if (t >= nranks || t == me) return;
   __threadfence_system();
@@ -83,7 +84,7 @@ __global__ void slab_barrier_kernel(FlagPtrs F, int me, int nranks, unsigned epo
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(F.p[me] + t) : "memory");
     if ((int)(v - epoch) >= 0) break;
-    if (gtimer() - t0 > 20000000000ull) { *err = 1u; break; }   // 20 s: report instead of hanging the GPU
+    if (gtimer() - t0 > timeout_ns) { *err = 1u; break; }   // report instead of hanging the GPU
   }
 }
 
@@ -280,7 +281,15 @@ int qgs_barrier(somax_b200_qgs_s* g, cudaStream_t s) {
   for (int r = 0; r < QGS_MAX_RANKS; ++r) F.p[r] = r < g->nranks ? (unsigned*)g->peers[r].buf[5] : nullptr;
   ++g->epoch;
   prof_begin("slab_barrier", s);
-  slab_barrier_kernel<<<1, 32, 0, s>>>(F, R.rank, g->nranks, g->epoch, R.flags + QGS_MAX_RANKS);
+  // a peer that does not show up within the watchdog time (default 20 s, SOMAX_B200_SLAB_TIMEOUT_S)
+  // sets the error word: the data of this call is then invalid and somax_b200_qgs_status reports it
+  // (the host wrapper checks it after every call)
+  static const unsigned long long timeout_ns = [] {
+    const char* e = getenv("SOMAX_B200_SLAB_TIMEOUT_S");
+    const double sec = e ? atof(e) : 20.0;
+    return (unsigned long long)((sec > 0 ? sec : 20.0) * 1e9);
+  }();
+  slab_barrier_kernel<<<1, 32, 0, s>>>(F, R.rank, g->nranks, g->epoch, R.flags + QGS_MAX_RANKS, timeout_ns);
   SB_LAUNCH_CHECK();
   return 0;
 }

@@ -663,7 +663,7 @@ int bc_inplace(somax_b200_swm_t h, void* const f[3], cudaStream_t s) {
 
 template <typename T>
 int swm_steps_impl(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps, double dt,
-                   double dt_last, const somax_b200_params* p, cudaStream_t caller) {
+                   double dt_last, const somax_b200_params* p, bool bc0, cudaStream_t caller) {
   const Layout& L = h->L;
   const long total = n_steps + (dt_last > 0 ? 1 : 0);
   const bool use_graph = !prof_enabled() && L.count() <= GRAPH_MAX_CELLS && n_steps >= 9 &&
@@ -679,7 +679,8 @@ int swm_steps_impl(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps,
   for (int f = 0; f < 3; ++f) { y[f] = h->y[f]; Yc[f] = h->Ya[f]; Yn[f] = h->Yb[f]; }
   for (int f = 0; f < 3; ++f)
     if (int rc = pack_field<T>((const T*)ext[f], (T*)y[f], L, s)) return rc;
-  if (int rc = bc_inplace<T>(h, y, s)) return rc;   // integrate(): BC on state0
+  if (bc0)
+    if (int rc = bc_inplace<T>(h, y, s)) return rc;   // integrate(): BC on state0 (not when resuming)
   if (total > 0) {
     SwmArgs<T> A = make_args<T>(h, p, 1);
     auto step_dt = [&](long i) { return (i < n_steps) ? dt : dt_last; };
@@ -888,7 +889,14 @@ int somax_b200_swm_steps(somax_b200_swm_t h, void* hh, void* u, void* v, long n_
                          double dt_last, const somax_b200_params* p, void* stream) {
   if (!h || !hh || !u || !v || !p) return fail(SOMAX_B200_ERR_INVALID, "null argument");
   if (n_steps < 0 || !(dt > 0) || dt_last < 0) return fail(SOMAX_B200_ERR_INVALID, "need n_steps>=0, dt>0, dt_last>=0");
-  return SB_DISPATCH(h, swm_steps_impl, h, hh, u, v, n_steps, dt, dt_last, p, (cudaStream_t)stream);
+  return SB_DISPATCH(h, swm_steps_impl, h, hh, u, v, n_steps, dt, dt_last, p, true, (cudaStream_t)stream);
+}
+
+int somax_b200_swm_resume(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps, double dt,
+                          double dt_last, const somax_b200_params* p, void* stream) {
+  if (!h || !hh || !u || !v || !p) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  if (n_steps < 0 || !(dt > 0) || dt_last < 0) return fail(SOMAX_B200_ERR_INVALID, "need n_steps>=0, dt>0, dt_last>=0");
+  return SB_DISPATCH(h, swm_steps_impl, h, hh, u, v, n_steps, dt, dt_last, p, false, (cudaStream_t)stream);
 }
 
 int somax_b200_swm_diag(somax_b200_swm_t h, const void* hh, const void* u, const void* v,

@@ -247,9 +247,41 @@ def save_dataset(ds: Dataset, path, *, mode: str = "w") -> None:
         _write_chunks(adir, var)
 
 
+def _gunzip(raw: bytes, nbytes: int) -> bytes:
+    import zlib
+    return zlib.decompress(raw, wbits=31)
+
+
+def _unzstd(raw: bytes, nbytes: int) -> bytes:
+    """zstd frames as zarr-python's default v3 compressor writes them (what `ds.to_zarr(...,
+    zarr_format=3)` produces when no encoding is given).  The standard library has no zstd before
+    Python 3.14; pyarrow (in this image) or the `zstandard` package decode it."""
+    try:
+        from compression import zstd          # Python >= 3.14
+        return zstd.decompress(raw)
+    except ImportError:
+        pass
+    try:
+        import zstandard
+        return zstandard.ZstdDecompressor().decompress(raw, max_output_size=nbytes)
+    except ImportError:
+        pass
+    try:
+        import pyarrow as pa
+        return pa.decompress(raw, decompressed_size=nbytes, codec="zstd").to_pybytes()
+    except ImportError as e:       # pragma: no cover
+        raise ValueError("this store is zstd-compressed and neither compression.zstd, zstandard nor pyarrow "
+                         "is importable; rewrite it with encoding={var: {'compressors': None}}") from e
+
+
+# bytes -> bytes codecs of the zarr v3 chain the reader can undo
+_DECODERS = {"gzip": _gunzip, "zstd": _unzstd}
+
+
 def load_dataset(path) -> Dataset:
-    """Open a zarr v3 store written by `save_dataset` (or by xarray with the same options and no
-    compression) as a Dataset (io/xarray.py:252-266)."""
+    """Open a zarr v3 store as a Dataset (io/xarray.py:252-266): the ones `save_dataset` writes
+    (uncompressed) and the ones xarray / zarr-python write with their default zstd (or a gzip)
+    compressor, e.g. a `final_state.zarr` of the reference's own somax-sim."""
     path = Path(path)
     meta_p = path / "zarr.json"
     if not meta_p.exists():
@@ -263,8 +295,12 @@ def load_dataset(path) -> Dataset:
         if m.get("node_type") != "array":
             continue
         codecs = [c["name"] for c in m.get("codecs", [])]
-        if codecs != ["bytes"]:
-            raise ValueError(f"{adir}: only the uncompressed 'bytes' codec is supported, got {codecs}")
+        if not codecs or codecs[0] != "bytes" or any(c not in _DECODERS for c in codecs[1:]):
+            raise ValueError(
+                f"{adir}: codec chain {codecs} is not supported (supported: 'bytes' optionally followed by "
+                f"{sorted(_DECODERS)}).  Write the store with xarray's "
+                "`ds.to_zarr(path, zarr_format=3, encoding={var: {'compressors': None} for var in ds.variables})`, "
+                "or with a zstd / gzip compressor")
         endian = m["codecs"][0].get("configuration", {}).get("endian", "little")
         dt = np.dtype(m["data_type"]).newbyteorder("<" if endian == "little" else ">")
         shape = tuple(m["shape"])
@@ -277,7 +313,11 @@ def load_dataset(path) -> Dataset:
             p = adir / key
             if not p.exists():
                 continue
-            block = np.fromfile(p, dtype=dt).reshape(cshape)
+            raw = p.read_bytes()
+            nbytes = int(np.prod(cshape, dtype=np.int64)) * dt.itemsize
+            for cname in reversed(codecs[1:]):      # bytes -> bytes codecs are undone last to first
+                raw = _DECODERS[cname](raw, nbytes)
+            block = np.frombuffer(raw, dtype=dt).reshape(cshape)
             sl = tuple(slice(i * c, min((i + 1) * c, n)) for i, c, n in zip(idx, cshape, shape))
             out[sl] = block[tuple(slice(0, s.stop - s.start) for s in sl)]
         dims = tuple(m.get("dimension_names") or [f"dim{i}" for i in range(len(shape))])

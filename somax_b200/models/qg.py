@@ -180,11 +180,11 @@ class _QGBase(SomaxModel):
         out, _ = self._call_q(state, run)
         return self._state_cls(q=out)
 
-    def _advance(self, state, n_steps, dt, dt_last):
+    def _advance(self, state, n_steps, dt, dt_last, resume=False):
         def run(h, q, io):
             p = _params_struct(self.params, self._H0)
-            _lib.check(_lib.lib().somax_b200_qg_steps(h, q.data_ptr(), int(n_steps), float(dt),
-                                                      float(dt_last), C.byref(p), stream_ptr()))
+            fn = _lib.lib().somax_b200_qg_resume if resume else _lib.lib().somax_b200_qg_steps
+            _lib.check(fn(h, q.data_ptr(), int(n_steps), float(dt), float(dt_last), C.byref(p), stream_ptr()))
             return io.from_device(q)
 
         out, io = self._call_q(state, run)

@@ -158,12 +158,12 @@ class _SWMBase(SomaxModel):
                                                       stream_ptr()))
         return self._state_cls(h=io.from_device(ho), u=io.from_device(uo), v=io.from_device(vo))
 
-    def _advance(self, state, n_steps, dt, dt_last):
+    def _advance(self, state, n_steps, dt, dt_last, resume=False):
         io, h, u, v, hd = self._dev(state)
         p = self._pstruct()
-        _lib.check(_lib.lib().somax_b200_swm_steps(hd, h.data_ptr(), u.data_ptr(), v.data_ptr(),
-                                                   int(n_steps), float(dt), float(dt_last),
-                                                   C.byref(p), stream_ptr()))
+        fn = _lib.lib().somax_b200_swm_resume if resume else _lib.lib().somax_b200_swm_steps
+        _lib.check(fn(hd, h.data_ptr(), u.data_ptr(), v.data_ptr(), int(n_steps), float(dt), float(dt_last),
+                      C.byref(p), stream_ptr()))
         self.last_io = io
         return self._state_cls(h=io.from_device(h), u=io.from_device(u), v=io.from_device(v))
 

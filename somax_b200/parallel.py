@@ -227,17 +227,20 @@ class SlabQG:
         halo rows valid) in place.  Collective over the slab group."""
         from .core import step_plan
         n, rem = step_plan(t0, t1, dt)
-        self.advance_slab(slab, n, dt, rem)
-        if check:
-            self.check_peers()
+        self.advance_slab(slab, n, dt, rem, check=check)
         return slab
 
-    def advance_slab(self, slab, n_steps, dt, dt_last=0.0):
+    def advance_slab(self, slab, n_steps, dt, dt_last=0.0, check=True):
+        """``check`` (default): synchronise the stream afterwards and raise if a flag barrier gave up
+        waiting for a peer (the watchdog sets an error word instead of hanging the GPU; the data
+        of such a call is invalid).  ``check=False`` leaves that to a later ``check_peers()``."""
         if self.local:
             raise RuntimeError("advance_slab() is for one-slab-per-process groups")
         if not (slab.is_cuda and slab.is_contiguous()):
             raise ValueError("slab must be a contiguous CUDA tensor")
         self._steps([slab], n_steps, dt, dt_last)
+        if check:
+            self.check_peers()
 
     def close(self):
         from . import _lib

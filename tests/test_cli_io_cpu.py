@@ -253,8 +253,9 @@ def test_cli_discovery_and_shipped_configs(capsys):
     out = capsys.readouterr().out
     assert "  - BaroclinicQG" in out and "  - MultilayerShallowWater2D" in out
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cfgs = sorted(glob.glob(os.path.join(root, "configs", "*.yaml")))
-    assert len(cfgs) >= 3
+    cfgs = sorted(glob.glob(os.path.join(root, "configs", "simulation", "*.yaml")) +
+                  glob.glob(os.path.join(root, "configs", "short", "*.yaml")))
+    assert len(cfgs) >= 8
     for c in cfgs:
         sp = S.load_yaml(c)
         dbg = sp.with_debug_applied()
@@ -413,9 +414,54 @@ def test_spinup_config_disables_outputs_and_production_enables():
     """tests/test_configs.py:74-90."""
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spin = S.load_yaml(os.path.join(root, "configs", "doublegyre_bc_qg_spinup.yaml"))
+    spin = S.load_yaml(os.path.join(root, "configs", "simulation", "spinup_bc_qg.yaml"))
     assert spin.output.write_snapshots is False and spin.output.write_metrics is False
     for name in ("doublegyre_bt_qg", "doublegyre_bc_qg", "swm_jet"):
-        sp = S.load_yaml(os.path.join(root, "configs", name + ".yaml"))
+        sp = S.load_yaml(os.path.join(root, "configs", "simulation", name + ".yaml"))
         assert sp.output.write_snapshots and sp.output.write_metrics
         assert S.RunSpec.from_dict(sp.to_dict()).to_dict() == sp.to_dict()
+
+
+def test_shipped_configs_carry_the_reference_run_parameters():
+    """configs/simulation/*.yaml are the reference's runs (configs/_authoring/*.py of the reference):
+    the values that set the physics and the run length are pinned here."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    load = lambda n: S.load_yaml(os.path.join(root, "configs", "simulation", n + ".yaml"))  # noqa: E731
+    jet = load("swm_jet")
+    assert jet.testcase.params["lateral_viscosity"] == 1000.0 and jet.timestepping.t1 == 2592000.0
+    assert jet.assertions["cfl"]["wave_speed_m_per_s"] == 221.0
+    bt = load("doublegyre_bt_qg")
+    assert bt.timestepping.t1 == 31557600.0 and bt.assertions["bounded_metric"]["name"] == "kinetic_energy"
+    bc = load("doublegyre_bc_qg")
+    assert bc.timestepping.t1 == 31557600.0 and bc.testcase.grid["nx"] == 128
+    assert load("spinup_bc_qg").timestepping.t1 == 94672800.0
+
+
+def test_reader_decodes_zstd_and_gzip_chunks(tmp_path):
+    """A store as zarr-python writes it by default (zstd after the bytes codec) - what the reference's
+    `ds.to_zarr(path, zarr_format=3)` produces (io/xarray.py:235-249) - is readable for restart."""
+    import gzip
+    import json
+    import pyarrow as pa
+    from somax_b200 import io
+    q = np.arange(2 * 3 * 6 * 6, dtype=np.float32).reshape(2, 3, 6, 6)
+    ds = io.Dataset({"q": (("time", "layer", "y", "x"), q)}, {"time": (("time",), np.array([0.0, 600.0]))},
+                    {"state_class": "BaroclinicQGState", "state_module": "somax_b200.models.qg"})
+    for codec, enc in (("zstd", lambda b: pa.compress(b, codec="zstd", asbytes=True)), ("gzip", gzip.compress)):
+        store = tmp_path / f"s_{codec}.zarr"
+        io.save_dataset(ds, store)
+        for adir in (store / "q", store / "time"):
+            m = json.loads((adir / "zarr.json").read_text())
+            m["codecs"].append({"name": codec, "configuration": {"level": 0}})
+            (adir / "zarr.json").write_text(json.dumps(m))
+            for f in adir.rglob("*"):
+                if f.is_file() and f.name != "zarr.json":
+                    f.write_bytes(enc(f.read_bytes()))
+        back = io.load_dataset(store)
+        assert np.array_equal(back["q"].values, q) and back["time"].values.tolist() == [0.0, 600.0]
+    m = json.loads((store / "q" / "zarr.json").read_text())
+    m["codecs"][-1]["name"] = "blosc"
+    (store / "q" / "zarr.json").write_text(json.dumps(m))
+    with pytest.raises(ValueError, match="compressors"):
+        io.load_dataset(store)

@@ -156,3 +156,36 @@ def test_diagnose_fields_match_oracle(dtype):
     for name in ("potential_vorticity", "relative_vorticity", "kinetic_energy_field"):
         assert rel(getattr(d, name), r[name]) <= (2e-5 if dtype == np.float32 else 1e-12), name
     assert np.allclose(d.energy, r["energy"], rtol=1e-4) and np.allclose(d.enstrophy, r["enstrophy"], rtol=1e-4)
+
+
+def test_saveat_semantics_follow_diffrax():
+    """SaveAt(ts=...) (core/model.py:75-88): BCs on state0 only - stepping continues from the
+    un-projected saved states, so the last save equals the plain t1 run bit for bit; host tensors of
+    different save times do not alias; SaveAt(t0=True) returns BC(state0); off-grid ts raise."""
+    import torch
+    import somax_b200 as sb
+    om, gm = qg_pair(32, 32, np.float64)
+    q0 = qstate(3, 32, 32, np.float64, ring=True)
+    st = sb.BaroclinicQGState(q=q0)
+    one = gm.integrate(st, 0.0, 3600.0, 600.0).ys.q[0]
+    sol = gm.integrate(st, 0.0, 3600.0, 600.0, saveat=sb.SaveAt(ts=[1200.0, 2400.0, 3600.0]))
+    assert sol.ys.q.shape[0] == 3 and np.array_equal(sol.ys.q[2], one)
+    assert rel(sol.ys.q[0], om.integrate(q0, 0.0, 1200.0, 600.0)) <= 1e-12
+    assert rel(sol.ys.q[2], om.integrate(q0, 0.0, 3600.0, 600.0)) <= 1e-12
+    # the ring of an intermediate save is NOT projected (wind forcing drifts it)
+    assert np.abs(sol.ys.q[0][0, 0, :]).max() > 0
+    pin = torch.as_tensor(q0).pin_memory()
+    solp = gm.integrate(sb.BaroclinicQGState(q=pin), 0.0, 3600.0, 600.0, saveat=sb.SaveAt(ts=[1200.0, 3600.0]))
+    assert np.array_equal(solp.ys.q[0].numpy(), sol.ys.q[0]) and np.array_equal(solp.ys.q[1].numpy(), one)
+    s0 = gm.integrate(st, 0.0, 1200.0, 600.0, saveat=sb.SaveAt(t0=True, t1=True))
+    assert s0.ys.q.shape[0] == 2 and np.array_equal(s0.ys.q[0], om.bc(q0)) and np.array_equal(s0.ys.q[1], sol.ys.q[0])
+    with pytest.raises(ValueError, match="step grid"):
+        gm.integrate(st, 0.0, 3600.0, 600.0, saveat=sb.SaveAt(ts=[900.0]))
+    # shallow water: same continuation rule
+    osw, gsw = swm_pair(32, 32, np.float64, "wall")
+    h, u, v = swm_state(32, 32, np.float64)
+    sw = sb.MultilayerSW2DState(h=h, u=u, v=v)
+    a = gsw.integrate(sw, 0.0, 80.0, 20.0).ys
+    b = gsw.integrate(sw, 0.0, 80.0, 20.0, saveat=sb.SaveAt(ts=[40.0, 80.0])).ys
+    for f in "huv":
+        assert np.array_equal(getattr(b, f)[1], getattr(a, f)[0]), f

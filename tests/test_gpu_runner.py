@@ -103,13 +103,13 @@ def test_swm_finite_run_and_divergence_guard(tmp_path):
 
 
 def test_cli_run_debug_config_and_assertions(tmp_path):
-    """`somax-sim run --config configs/swm_jet.yaml --debug` end to end; a violated CFL assertion
+    """`somax-sim run --config configs/short/swm_jet.yaml --debug` end to end; a violated CFL assertion
     stops the run before any stepping."""
     import os
     from somax_b200 import io
     from somax_b200.cli import AssertionFailedError, app, load_yaml, simulate
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cfg = os.path.join(root, "configs", "swm_jet.yaml")
+    cfg = os.path.join(root, "configs", "short", "swm_jet.yaml")
     assert app.main(["run", "--config", cfg, "--output-dir", str(tmp_path / "o"), "--debug",
                      "--diagnostics-per-save", "2"]) == 0
     snaps = io.load_dataset(tmp_path / "o" / "snapshots.zarr")
