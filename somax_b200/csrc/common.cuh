@@ -58,6 +58,8 @@ constexpr size_t GRAPH_MAX_CELLS = (size_t)1 << 21;
   } while (0)
 
 int require_device();
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device (per device, mutex-guarded).
+int ensure_dyn_smem(const void* fn, size_t bytes);
 
 // ---------------------------------------------------------------------------------------
 // HBM layout of a field inside a handle ("padded layout").

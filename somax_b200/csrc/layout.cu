@@ -1,6 +1,10 @@
 // Error plumbing, launch accounting and reference<->padded layout conversion.
 #include "common.cuh"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include <string.h>
 
 #include <vector>
@@ -83,6 +87,23 @@ void prof_end() {
   if (!g_prof.open) return;
   cudaEventRecord(g_prof.recs.back().b, g_prof.stream);
   g_prof.open = false;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (kernel, DEVICE): a process that
+// drives several devices (one host thread per device, as jax.ffi does) must set it on each of
+// them, and two threads may arrive here at once.  Largest size set so far per (kernel, device).
+int ensure_dyn_smem(const void* fn, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  int dev = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = done[std::make_pair(fn, dev)];
+  if (cur >= bytes) return 0;
+  SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  cur = bytes;
+  return 0;
 }
 
 int require_device() {

@@ -604,12 +604,7 @@ bool qg_launch_tma(somax_b200_qg_t h, const QgArgs<float>& A, const Stage<float>
       M.f[jj] = ef->epi;
     }
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(qg_rhs_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)QG_TMA_SMEM) != cudaSuccess) { cudaGetLastError(); return false; }
-    attr_done = true;
-  }
+  if (ensure_dyn_smem((const void*)qg_rhs_kernel_tma, QG_TMA_SMEM) != 0) { cudaGetLastError(); return false; }
   const Layout& L = h->L;
   dim3 block(QTXG, QTY);
   dim3 grid((L.groups() + QTXG - 1) / QTXG, (L.Ny + QFY - 1) / QFY, L.batch * L.nl);

@@ -8,16 +8,18 @@
 // unknown (oracle/elliptic.py), so for the solve the edge ranks also own their ring row: rank r
 // holds the solver rows [slab_r0(r), slab_r1(r)) of the Ny = ny + 2.  One right-hand-side evaluation:
 //
-//   rows_fwd   layer->mode mix + DST-I in x of the slab's rows            (local, R)
-//   X1         transpose: strips of R -> the owning rank's column array S  (peer stores, NVLink)
+//   rows_fwd   layer->mode mix + DST-I in x of the slab's rows; the transform kernel stores every
+//   + X1       spectral row segment STRAIGHT into the column array S of the rank that owns its strip
+//              of x-wavenumbers (peer memory over NVLink): compute and transpose are one kernel
 //   cols(1)    first Thomas solve in y on the rank's x-wavenumber strips
 //   X2         border row-sum partials -> every rank                       (peer stores)
 //   border     fixed-order reduction of all partials (replicated, cheap), then the Schur solve
 //              (two dense fp64 DSTs in y) with the OUTPUT rows split over the ranks: slices of
 //              ghat, then of gvec / the border column, are pushed to the peers (XG1, XG2);
 //              bitwise the single-GPU result
-//   cols(2)    second Thomas solve on the rank's strips
-//   X3         transpose back: row blocks of S -> the owning rank's R      (peer stores)
+//   cols(2)    second Thomas solve on the rank's strips; its last sweep stores every finished tile
+//   + X3       (cp.async.bulk, shared -> peer memory) STRAIGHT into the row array R of the rank that
+//              owns the rows: again no transpose kernel
 //   rows_inv   inverse transform + mode->layer mix -> psi slab
 //   X4         psi halo rows -> neighbours                                 (peer stores)
 //   stencil    fused Arakawa / viscosity / wind / drag + Tsit5 epilogue on the slab
@@ -94,7 +96,7 @@ struct SlabRank {
   int rank = 0, s0 = 0, s1 = 0;
   void* inbox = nullptr;            // [2][planes][pitch]: halo rows of the newest stage state from below / above
   unsigned* flags = nullptr;        // [QGS_MAX_RANKS] barrier slots + [QGS_MAX_RANKS] error word
-  SegTable x1, xb, x2, x3, xpsi, xstate[3], xin[3], xg1, xg2, xg2f, xring;
+  SegTable xb, x2, xpsi, xstate[3], xin[3], xg1, xg2, xg2f, xring;
 };
 
 struct SlabPeer { void* buf[QGS_NBUF]; };
@@ -161,40 +163,34 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
   const int NyS = vc.ny;                                 // solver rows of the whole grid (ny + 2)
   const int my0 = slab_r0(g, p), my1 = slab_r1(g, p), myrows = my1 - my0;      // == vr.ny
   const Layout& L = R.core->L;
-  char* Rl = (char*)vr.S;
   char* Sl = (char*)vc.S;
-  const size_t blk = (size_t)myrows * SP_W * es;       // one strip of my rows
-  const size_t col = (size_t)NyS * SP_W * es;          // one strip of the whole grid
-  std::vector<Seg> x1, xb, x2, x3, xpsi, xg1, xg2, xg2f, xring;
+  std::vector<Seg> xb, x2, xpsi, xg1, xg2, xg2f, xring;
   // BarotropicQG keeps the ring of psi: the solved border columns 0 and nx+1 of my rows (my slice of
   // the border-system outputs) go from the column solver's bext to the row solver's (local copy)
   for (int pl = 0; pl < planes; ++pl)
     for (int w = 0; w < 2; ++w)
-      xring.push_back(Seg{(const char*)vc.bext + (((size_t)pl * 2 + w) * NyS + my0) * es,
-                          (char*)vr.bext + ((size_t)pl * 2 + w) * myrows * es, 1u, (unsigned)(myrows * es), 0, 0});
+      xring.push_back(Seg{(const char*)vc.bext + (((size_t)pl * 3 + w) * NyS + my0) * es,
+                          (char*)vr.bext + ((size_t)pl * 3 + w) * myrows * es, 1u, (unsigned)(myrows * es), 0, 0});
+  // fused exchanges: rows_fwd scatters into the peers' column arrays, cols(2) pushes into their row arrays
+  {
+    void* peerS[QGS_MAX_RANKS]; void* peerR[QGS_MAX_RANKS]; int row0[QGS_MAX_RANKS + 1];
+    for (int r = 0; r < P; ++r) { peerS[r] = g->peers[r].buf[0]; peerR[r] = g->peers[r].buf[2]; row0[r] = slab_r0(g, r); }
+    row0[P] = NyS;
+    qg_solver_set_scatter(R.core->solver, peerS, P, spr, my0, NyS);
+    qg_solver_set_push(R.cols, peerR, P, row0);
+  }
   const int last_owner = (nstrip - 1) / spr;
   const int a0 = my0, na = myrows;                       // my slice of the border-system outputs
   for (int r = 0; r < P; ++r) {
     char* Sr = (char*)g->peers[r].buf[0];
     char* partr = (char*)g->peers[r].buf[1];
-    char* Rr = (char*)g->peers[r].buf[2];
     char* bextr = (char*)g->peers[r].buf[9];
-    const int r0 = slab_r0(g, r), rrows = slab_r1(g, r) - r0;
-    const size_t blkr = (size_t)rrows * SP_W * es;
     for (int pl = 0; pl < planes; ++pl) {
-      // X1: my rows of rank r's strips -> its column array
-      x1.push_back(Seg{Rl + ((size_t)pl * nstrip + (size_t)r * spr) * blk,
-                       Sr + ((size_t)pl * nstrip + (size_t)r * spr) * col + (size_t)my0 * SP_W * es,
-                       (unsigned)spr, (unsigned)blk, blk, col});
-      // raw border columns of my rows -> every rank (each one reduces the border system): column nx
-      // (slot ncols of S; its strip's owner gets it with X1), columns 0 and nx+1 (bext)
-      if (r != last_owner)
-        xb.push_back(Seg{Rl + ((size_t)pl * myrows * np + sp_off(myrows, 0, vc.ncols)) * es,
-                         Sr + ((size_t)pl * NyS * np + sp_off(NyS, my0, vc.ncols)) * es,
-                         (unsigned)myrows, (unsigned)es, SP_W * es, SP_W * es});
-      for (int w = 0; w < 2; ++w)
-        xb.push_back(Seg{(const char*)vr.bext + ((size_t)pl * 2 + w) * myrows * es,
-                         bextr + (((size_t)pl * 2 + w) * NyS + my0) * es, 1u, (unsigned)(myrows * es), 0, 0});
+      // raw border columns 0, nx+1 and nx of my rows (bext of the row stage) -> every rank (each one
+      // reduces the border system)
+      for (int w = 0; w < 3; ++w)
+        xb.push_back(Seg{(const char*)vr.bext + ((size_t)pl * 3 + w) * myrows * es,
+                         bextr + (((size_t)pl * 3 + w) * NyS + my0) * es, 1u, (unsigned)(myrows * es), 0, 0});
       // X2: border partial sums (even / odd columns) of my strips -> every other rank
       if (r != p)
         for (int par = 0; par < 2; ++par) {
@@ -222,10 +218,6 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
           xg2f.push_back(Seg{Sl + so, Sr + so, (unsigned)na, (unsigned)es, SP_W * es, SP_W * es});
         }
       }
-      // X3: rank r's rows of my strips -> its row array
-      x3.push_back(Seg{Sl + ((size_t)pl * nstrip + (size_t)R.s0) * col + (size_t)r0 * SP_W * es,
-                       Rr + ((size_t)pl * nstrip + (size_t)R.s0) * blkr,
-                       (unsigned)spr, (unsigned)blkr, col, blkr});
     }
   }
   // halo rows: my first owned row (1) -> rank p-1's top halo row; my last owned row -> rank p+1's row 0
@@ -245,10 +237,8 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
   };
   halo((const char*)R.core->psi, 3, false, xpsi);
   void* st[3] = {R.core->y, R.core->Ya, R.core->Yb};
-  if (int rc = seg_upload(R.x1, x1, &g->bytes)) return rc;
   if (int rc = seg_upload(R.xb, xb, &g->bytes)) return rc;
   if (int rc = seg_upload(R.x2, x2, &g->bytes)) return rc;
-  if (int rc = seg_upload(R.x3, x3, &g->bytes)) return rc;
   if (int rc = seg_upload(R.xpsi, xpsi, &g->bytes)) return rc;
   if (int rc = seg_upload(R.xg1, xg1, &g->bytes)) return rc;
   if (int rc = seg_upload(R.xg2, xg2, &g->bytes)) return rc;
@@ -306,10 +296,8 @@ int qgs_eval(somax_b200_qgs_s* g, const somax_b200_params* p, int in_b, int y_b,
   auto bufp = [](SlabRank& R, int b) -> void* { return b == 0 ? R.core->y : (b == 1 ? R.core->Ya : R.core->Yb); };
   for (SlabRank& R : g->local)
     if (int rc = qg_solver_rows_fwd<T>(R.core->solver, (const T*)bufp(R, in_b), 1, s)) return rc;
-  for (SlabRank& R : g->local) {
-    if (int rc = seg_launch("slab_x1_transpose", R.x1, s)) return rc;
+  for (SlabRank& R : g->local)
     if (int rc = seg_launch("slab_x1_border", R.xb, s)) return rc;
-  }
   if (int rc = qgs_barrier(g, s)) return rc;
   for (SlabRank& R : g->local) {
     // halo rows of Yin pushed by the neighbours after the previous evaluation
@@ -335,8 +323,6 @@ int qgs_eval(somax_b200_qgs_s* g, const somax_b200_params* p, int in_b, int y_b,
   if (int rc = qgs_barrier(g, s)) return rc;
   for (SlabRank& R : g->local)
     if (int rc = qg_solver_cols<T>(R.cols, 2, R.s0, R.s1, s)) return rc;
-  for (SlabRank& R : g->local)
-    if (int rc = seg_launch("slab_x3_transpose", R.x3, s)) return rc;
   if (int rc = qgs_barrier(g, s)) return rc;
   for (SlabRank& R : g->local) {
     const int keep = keep_psi_ring(R.core);
@@ -496,7 +482,7 @@ int somax_b200_qgs_destroy(somax_b200_qgs_t g) {
   cudaDeviceSynchronize();
   for (void* p : g->ipc_opened) cudaIpcCloseMemHandle(p);
   for (SlabRank& R : g->local) {
-    SegTable* ts[] = {&R.x1, &R.xb, &R.x2, &R.x3, &R.xpsi, &R.xstate[0], &R.xstate[1], &R.xstate[2],
+    SegTable* ts[] = {&R.xb, &R.x2, &R.xpsi, &R.xstate[0], &R.xstate[1], &R.xstate[2],
                       &R.xin[0], &R.xin[1], &R.xin[2], &R.xg1, &R.xg2, &R.xg2f, &R.xring};
     for (SegTable* t : ts) cudaFree(t->dev);
     cudaFree(R.inbox); cudaFree(R.flags);

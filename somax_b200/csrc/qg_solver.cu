@@ -52,7 +52,12 @@ struct QgSolver {
   double* ctab = nullptr; long long* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
   int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0, KBs = 2; double* dbad = nullptr; double* dbad1 = nullptr; double* meet1 = nullptr; void* part = nullptr;
   double* bsig = nullptr; void* sig2n = nullptr; double* minv = nullptr; double* sintab = nullptr;
-  void* bext = nullptr;                             // [plane][2][ny]: border columns 0 and nx+1
+  void* bext = nullptr;                             // [plane][3][ny]: border columns 0, nx+1 and (raw, forward only) nx
+  // slab-distributed model: the row stage stores its spectral rows straight into the column arrays
+  // of the ranks that own the strips (scatter), the last sweep stores its tiles straight into the
+  // row arrays of the ranks that own the rows (push) - peer memory over NVLink, no transpose kernels
+  void* sc_peer[16] = {nullptr}; int sc_lgspr = -1, sc_row0 = 0, sc_ny = 0;
+  void* ps_peer[16] = {nullptr}; int ps_row0[17] = {0}; int ps_n = 0;
   double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; float* gvecf = nullptr; double* meet = nullptr; double* meetc = nullptr;
   void* tw = nullptr; void* twc = nullptr; void* twb = nullptr; void* dstmat = nullptr;
   FftPlan plan;
@@ -97,9 +102,15 @@ struct RowArgsCT {
   // jo + j.  ylo / yhi: solver row 0 / ny-1 is a physical ring row.  ringmode: FWD = the ring of the
   // input is to be read as zero (boundary condition applied on load); INV = the ring of psi is not
   // written (BaroclinicQG zeroes it, qg/baroclinic.py:157-158; it stays at its initial zero).
-  // bext: [plane][2][ny] border columns 0 and nx+1 (raw mixed right-hand side in, solution out).
+  // bext: [plane][3][ny] border columns 0 and nx+1 (raw mixed right-hand side in, solution out) and
+  // the raw column nx (FWD).
+  // Scatter (FWD, slab-distributed model, lgspr >= 0): spectral element (row j, slot p) goes to the
+  // column array of the rank that owns strip p / 64, peer[(p >> 6) >> lgspr], at row prow0 + j of its
+  // pny rows - a store into peer memory over NVLink - instead of this solver's own array.
   int ny, np, nl, nrows, jo, ylo, yhi, ringmode;
   T* bext;
+  T* peer[16];
+  int lgspr, prow0, pny;
   T mix[QG_MAX_NL][QG_MAX_NL];
   const C2<T>* tw;    // exp(-i pi t / n), t = 0..2n-1 (real-odd split)
   const C2<T>* twc;   // compact per-pass butterfly twiddles (fft.cuh: twc_offset)
@@ -118,6 +129,14 @@ __device__ __forceinline__ void fft_passes_ct(C2<T>* s, int lt, const C2<T>* __r
   }
 }
 
+// Destination of spectral element (row j, slot p) of plane `plane` in the forward transform.
+template <typename T>
+__device__ __forceinline__ T* fwd_dst(const RowArgsCT<T>& A, T* out, int plane, int j, int p) {
+  if (A.lgspr >= 0)
+    return A.peer[(p >> 6) >> A.lgspr] + (size_t)plane * A.pny * A.np + sp_off(A.pny, A.prow0 + j, p);
+  return out + (size_t)plane * A.ny * A.np + sp_off(A.ny, j, p);
+}
+
 // Border columns 0 (which = 0) and nx+1 (which = 1) of one row, handled by two threads of the row:
 // FWD mixes the layers' raw values into bext (zero when the input ring is read as zero); INV mixes
 // the solved modal values of bext into psi unless the ring of psi is left alone.
@@ -126,18 +145,18 @@ __device__ __forceinline__ void row_border_cols(const RowArgsCT<T>& A, const T* 
                                                 T* __restrict__ out, int b, int a, int j, int fj,
                                                 int which, int n) {
   if (A.ringmode) {
-    if (!INV) A.bext[(((size_t)b * A.nl + a) * 2 + which) * A.ny + j] = T(0);
+    if (!INV) A.bext[(((size_t)b * A.nl + a) * 3 + which) * A.ny + j] = T(0);
     return;
   }
   const int col = which ? n + 1 : 0;
   T acc = 0;
   for (int c = 0; c < A.nl; ++c) {
-    const T v = INV ? A.bext[(((size_t)b * A.nl + c) * 2 + which) * A.ny + j]
+    const T v = INV ? A.bext[(((size_t)b * A.nl + c) * 3 + which) * A.ny + j]
                     : in[(((size_t)b * A.nl + c) * A.L.Ny + fj) * A.L.pitch + OFF + col];
     acc += A.mix[a][c] * v;
   }
   if (INV) out[(((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + col] = acc;
-  else A.bext[(((size_t)b * A.nl + a) * 2 + which) * A.ny + j] = acc;
+  else A.bext[(((size_t)b * A.nl + a) * 3 + which) * A.ny + j] = acc;
 }
 
 template <typename T, int LGN, bool INV>
@@ -163,9 +182,10 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
                : in + (((size_t)b * A.nl + c) * A.L.Ny + fj) * A.L.pitch + OFF + 1 + p;
   };
   auto dst = [&](int a, int p) -> T* {
-    return INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + 1 + p
-               : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, p);
+    if (INV) return out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + 1 + p;
+    return fwd_dst<T>(A, out, b * A.nl + a, j, p);
   };
+  auto raw_border = [&](int a) -> T* { return A.bext + (((size_t)b * A.nl + a) * 3 + 2) * A.ny + j; };
   const bool ring_row = valid && A.ringmode && ((j == 0 && A.ylo) || (j == A.ny - 1 && A.yhi));
   if (ring_row) {
     // FWD: a ring row of the boundary-conditioned input is zero, so is its transform;
@@ -173,7 +193,7 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
     if (!INV)
       for (int a = 0; a < A.nl; ++a) {
         for (int p = lt; p < n; p += G) *dst(a, p) = T(0);
-        if (lt < 2) A.bext[(((size_t)b * A.nl + a) * 2 + lt) * A.ny + j] = T(0);
+        if (lt < 3) A.bext[(((size_t)b * A.nl + a) * 3 + lt) * A.ny + j] = T(0);
       }
   }
   const bool work = valid && !ring_row;    // (block-wide barriers below are reached by everyone)
@@ -204,7 +224,8 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (t + u < n) { z[zi(t + u)] = vals[u]; z[zi(2 * n - t - u)] = -vals[u]; }
-            else *dst(a, n - 1) = vals[u];        // border column (x index n)
+            else if (INV) *dst(a, n - 1) = vals[u];        // border column (x index n)
+            else *raw_border(a) = vals[u];
           }
         }
       } else {
@@ -215,7 +236,8 @@ rowdst_fft_ct(RowArgsCT<T> A, const T* __restrict__ in, T* __restrict__ out) {
           for (int c = 0; c < A.nl; ++c) val += A.mix[a][c] * *src(c, p);
           const int t = p + 1;
           if (t < n) { z[zi(t)] = val; z[zi(2 * n - t)] = -val; }
-          else *dst(a, n - 1) = val;
+          else if (INV) *dst(a, n - 1) = val;
+          else *raw_border(a) = val;
         }
       }
       if (lt == 0) { z[zi(0)] = 0; z[zi(n)] = 0; }
@@ -242,11 +264,7 @@ template <typename T, int LGN, bool INV>
 static int launch_rowdst_ct(const RowArgsCT<T>& A, const T* in, T* out, cudaStream_t st) {
   using Cfg = RowCfg<LGN>;
   constexpr size_t smem = (size_t)fft_padded_len(Cfg::n) * sizeof(C2<T>) * Cfg::RPB;
-  static bool attr_done = false;
-  if (smem > 48 * 1024 && !attr_done) {
-    SB_CUDA(cudaFuncSetAttribute(rowdst_fft_ct<T, LGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)rowdst_fft_ct<T, LGN, INV>, smem)) return rc;
   const int blocks = (A.nrows + Cfg::RPB - 1) / Cfg::RPB;
   prof_begin(INV ? "rowdst_inv_fft" : "rowdst_fwd_fft", st);
   rowdst_fft_ct<T, LGN, INV><<<blocks, Cfg::threads, smem, st>>>(A, in, out);
@@ -301,9 +319,8 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
     // INV: the ring of psi is left alone
     if (!INV)
       for (int a = 0; a < A.nl; ++a) {
-        float* orow = out + ((size_t)b * A.nl + a) * A.ny * A.np;
-        for (int p = lt; p < n; p += G) orow[sp_off(A.ny, j, p)] = 0.f;
-        if (lt < 2) A.bext[(((size_t)b * A.nl + a) * 2 + lt) * A.ny + j] = 0.f;
+        for (int p = lt; p < n; p += G) *fwd_dst<float>(A, out, b * A.nl + a, j, p) = 0.f;
+        if (lt < 3) A.bext[(((size_t)b * A.nl + a) * 3 + lt) * A.ny + j] = 0.f;
       }
     return;
   }
@@ -344,7 +361,7 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
         if (i == n / 4 - 1) {
           // x_n is the border column, not part of the transform: z_n = 0
           *(INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + n
-                : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, n - 1)) = acc[e].w;
+                : A.bext + (((size_t)b * A.nl + a) * 3 + 2) * A.ny + j) = acc[e].w;
           hi = 0.f;
         } else if (lane == 31) {
           z[4 * i + 4] = acc[e].w;           // x_{4(i+1)} for lane 0 of the next warp
@@ -447,8 +464,13 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
           const C O = {0.5f * (Ak.y + Bk.y), -0.5f * (Ak.x - Bk.x)};
           const C wO = cmul(w[u], O);
           const float Xk = -0.5f * (E.y + wO.y), Xnk = 0.5f * (E.y - wO.y);
-          pk[(m0 + u) * dstride] = INV ? A.scale * Xk : Xk;
-          pnk[-(m0 + u) * dstride] = INV ? A.scale * Xnk : Xnk;
+          if (!INV && A.lgspr >= 0) {       // slab model: straight into the strip owners' column arrays
+            *fwd_dst<float>(A, out, b * A.nl + a, j, k - 1) = Xk;
+            *fwd_dst<float>(A, out, b * A.nl + a, j, n - k - 1) = Xnk;
+          } else {
+            pk[(m0 + u) * dstride] = INV ? A.scale * Xk : Xk;
+            pnk[-(m0 + u) * dstride] = INV ? A.scale * Xnk : Xnk;
+          }
         }
       }
     }
@@ -460,11 +482,7 @@ template <int LGN, bool INV>
 static int launch_rowdst_big(const RowArgsCT<float>& A, const float* in, float* out, cudaStream_t st) {
   using Cfg = BigCfg<LGN>;
   constexpr size_t smem = (size_t)Cfg::slen * sizeof(C2<float>);
-  static bool attr_done = false;
-  if (!attr_done) {
-    SB_CUDA(cudaFuncSetAttribute(rowdst_fft_big<LGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)rowdst_fft_big<LGN, INV>, smem)) return rc;
   prof_begin(INV ? "rowdst_inv_fft" : "rowdst_fwd_fft", st);
   rowdst_fft_big<LGN, INV><<<A.nrows, Cfg::G, smem, st>>>(A, in, out);
   SB_LAUNCH_CHECK();
@@ -583,6 +601,10 @@ struct ThomasTab {
   // tabulated coefficients).  ckpt: [plane][strip][half][nck][64] floats, block m covers the
   // elimination rows [cnt - (m+1) 16, cnt - m 16) of the half and holds the value before its first.
   float* ckpt; int nck;
+  // Push (slab-distributed model, KIND 2 only): the finished tiles go straight into the row arrays
+  // of the ranks that own the rows - rank r holds rows [prow[r], prow[r+1]) as
+  // [plane][strip][prow[r+1] - prow[r]][64] at ppeer[r] (peer memory over NVLink) - instead of `out`.
+  void* ppeer[16]; int prow[17]; int pn;
 };
 
 
@@ -1053,7 +1075,17 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
     ph_sync += clock64() - ph2;
 #endif
     if (issuer) {
-      if (KIND != 1 && !probe)
+      if (KIND == 2 && !probe && tb.pn > 0) {
+        // rows [jlo, jlo + nrt) of the tile, cut at the row ownership boundaries
+        const int jlo = tile_jlo(t);
+        for (int r = 0; r < tb.pn; ++r) {
+          const int a0 = max(jlo, tb.prow[r]), a1 = min(jlo + nrt, tb.prow[r + 1]);
+          if (a1 <= a0) continue;
+          const int rr = tb.prow[r + 1] - tb.prow[r];
+          T* d = reinterpret_cast<T*>(tb.ppeer[r]) + (((size_t)plane * tb.nstrip + strip) * rr + (a0 - tb.prow[r])) * SP_W;
+          bulk_s2g(d, &tileA[st][a0 - jlo][0], (unsigned)((a1 - a0) * TH_COLS * sizeof(T)));
+        }
+      } else if (KIND != 1 && !probe)
         bulk_s2g(out + strip0 + (size_t)tile_jlo(t) * SP_W, &tileA[st][0][0], (unsigned)(nrt * TH_COLS * sizeof(T)));
       if (TAB && !SUBST && strip_bad && !probe)
         bulk_s2g(sideG + (size_t)tile_jlo(t) * tb.KB, tileD + (size_t)st * RT * tb.KB,
@@ -1177,9 +1209,9 @@ border_reduce(const T* __restrict__ S, const T* __restrict__ bext, const T* __re
   for (int q = 0; q < 8; ++q) { ev += red[0][q][jx]; od += red[1][q][jx]; }
   const int bm = plane / nl, l = plane - bm * nl;
   double* rp = r + ((size_t)bm * ny + j) * border_nvp(nl) + 3 * l;
-  rp[0] = (double)bext[((size_t)plane * 2 + 0) * ny + j] - b * (ev + od);
-  rp[1] = (double)S[(size_t)plane * ny * np + sp_off(ny, j, ncols)] - b * (ev - od);
-  rp[2] = (double)bext[((size_t)plane * 2 + 1) * ny + j];
+  rp[0] = (double)bext[((size_t)plane * 3 + 0) * ny + j] - b * (ev + od);
+  rp[1] = (double)bext[((size_t)plane * 3 + 2) * ny + j] - b * (ev - od);
+  rp[2] = (double)bext[((size_t)plane * 3 + 1) * ny + j];
 }
 
 // Epilogue of the border transforms for output row a (1-based) of one layer's three columns.
@@ -1209,8 +1241,8 @@ __device__ __forceinline__ void border_store(double t0, double t1, double t2, in
       gf[0] = (float)(t0 + t1); gf[ny] = (float)(t0 - t1);
     }
     S[(size_t)plane * ny * np + sp_off(ny, a - 1, n - 1)] = (T)t1;
-    bext[((size_t)plane * 2 + 0) * ny + (a - 1)] = (T)t0;
-    bext[((size_t)plane * 2 + 1) * ny + (a - 1)] = (T)t2;
+    bext[((size_t)plane * 3 + 0) * ny + (a - 1)] = (T)t0;
+    bext[((size_t)plane * 3 + 1) * ny + (a - 1)] = (T)t2;
   }
 }
 
@@ -1617,8 +1649,8 @@ static int build_fft_tables(QgSolver* s, const double* lambdas) {
   SB_CUDA(cudaMemset(s->ghat, 0, rb));
   SB_CUDA(cudaMalloc((void**)&s->gvec, 2 * vb));
   SB_CUDA(cudaMalloc((void**)&s->gvecf, vb));
-  SB_CUDA(cudaMalloc(&s->bext, 2 * (size_t)s->planes * ny * sizeof(T)));
-  SB_CUDA(cudaMemset(s->bext, 0, 2 * (size_t)s->planes * ny * sizeof(T)));
+  SB_CUDA(cudaMalloc(&s->bext, 3 * (size_t)s->planes * ny * sizeof(T)));
+  SB_CUDA(cudaMemset(s->bext, 0, 3 * (size_t)s->planes * ny * sizeof(T)));
   s->bytes += 2 * rb + 3 * vb + 2 * (size_t)s->planes * ny * sizeof(T);
   return 0;
 }
@@ -1721,6 +1753,19 @@ void qg_solver_destroy(QgSolver* s) {
 }
 
 size_t qg_solver_bytes(const QgSolver* s) { return s ? s->bytes : 0; }
+
+void qg_solver_set_scatter(QgSolver* s, void* const* peerS, int nranks, int spr, int row0, int ny_cols) {
+  for (int r = 0; r < 16; ++r) s->sc_peer[r] = r < nranks ? peerS[r] : nullptr;
+  int lg = 0;
+  while ((1 << lg) < spr) ++lg;
+  s->sc_lgspr = lg; s->sc_row0 = row0; s->sc_ny = ny_cols;
+}
+
+void qg_solver_set_push(QgSolver* s, void* const* peerR, int nranks, const int* row0) {
+  for (int r = 0; r < 16; ++r) s->ps_peer[r] = r < nranks ? peerR[r] : nullptr;
+  for (int r = 0; r <= nranks; ++r) s->ps_row0[r] = row0[r];
+  s->ps_n = nranks;
+}
 int qg_solver_kind(const QgSolver* s) { return s->kind; }
 
 template <typename T, bool SUBST, bool FROM_VEC, int KIND, bool TAB>
@@ -1741,12 +1786,7 @@ static int launch_thomas_one(const char* tag, const ThomasTab& tb, int strip_fir
   const size_t smem = smem0 + (TAB ? (size_t)NS * RT * tb.KB * sizeof(double) * NOP : 0);
   if (smem > 227 * 1024)
     return fail(SOMAX_B200_ERR_UNSUPPORTED, "too many indefinite Helmholtz columns for the staged side buffer");
-  static size_t attr_done = 0;
-  if (smem > 48 * 1024 && attr_done < smem) {
-    SB_CUDA(cudaFuncSetAttribute(thomas_sweep<T, SUBST, FROM_VEC, KIND, TAB>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = smem;
-  }
+  if (int rc = ensure_dyn_smem((const void*)thomas_sweep<T, SUBST, FROM_VEC, KIND, TAB>, smem)) return rc;
   if (tb.nseg > 1) {
     ThomasTab t1 = tb;
     t1.pass = 1;
@@ -1808,11 +1848,7 @@ static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream
     if (npl > 0) {
       const int hcap = s->ny - s->ny / 2;
       const size_t smem = (size_t)2 * hcap * sizeof(float);
-      static size_t attr_done = 0;
-      if (smem > 48 * 1024 && attr_done < smem) {
-        SB_CUDA(cudaFuncSetAttribute(thomas_vec_ckpt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = smem;
-      }
+      if (int rc = ensure_dyn_smem((const void*)thomas_vec_ckpt, smem)) return rc;
       prof_begin(tf, pl);
       thomas_vec_ckpt<<<dim3(npl, s->planes, 2), TH_COLS, smem, pl>>>(tb, pA, s->gvecf);
       SB_LAUNCH_CHECK();
@@ -1841,6 +1877,9 @@ static ThomasTab make_tab(const QgSolver* s) {
   tb.nseg = s->nseg; tb.seg_len = s->seg_len; tb.pass = 0; tb.segbuf = s->segbuf; tb.segprod = s->segprod;
   tb.seg_plain = s->seg_plain;
   tb.ckpt = s->ckpt; tb.nck = s->nck;
+  for (int r = 0; r < 16; ++r) tb.ppeer[r] = s->ps_peer[r];
+  for (int r = 0; r < 17; ++r) tb.prow[r] = s->ps_row0[r];
+  tb.pn = s->ps_n;
   return tb;
 }
 
@@ -1848,6 +1887,8 @@ template <typename T>
 static void make_row_args(const QgSolver* s, RowArgsCT<T>& Af, RowArgsCT<T>& Ai) {
   Af.L = s->L; Af.ny = s->ny; Af.np = s->np; Af.nl = s->nl; Af.nrows = s->batch * s->ny;
   Af.jo = s->jo; Af.ylo = s->ylo; Af.yhi = s->yhi; Af.ringmode = 0; Af.bext = (T*)s->bext;
+  for (int r = 0; r < 16; ++r) Af.peer[r] = (T*)s->sc_peer[r];
+  Af.lgspr = s->sc_lgspr; Af.prow0 = s->sc_row0; Af.pny = s->sc_ny;
   Af.tw = (const C2<T>*)s->tw; Af.twc = (const C2<T>*)s->twc; Af.twb = (const C2<T>*)s->twb; Af.scale = (T)1;
   Ai = Af; Ai.scale = (T)(2.0 / s->nx);
   for (int a = 0; a < QG_MAX_NL; ++a)
@@ -1944,10 +1985,8 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, int ring_zero, int keep_ring,
     T* S = (T*)s->S;
     const int n = s->nx + 2;
     const size_t smem = (size_t)nl * n * sizeof(T);
-    if (smem > 48 * 1024) {
-      SB_CUDA(cudaFuncSetAttribute(rowdst_dense<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      SB_CUDA(cudaFuncSetAttribute(rowdst_dense<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    if (int rc = ensure_dyn_smem((const void*)rowdst_dense<T, false>, smem)) return rc;
+    if (int rc = ensure_dyn_smem((const void*)rowdst_dense<T, true>, smem)) return rc;
     const int threads = std::min(256, ((n + 31) / 32) * 32);
     prof_begin("rowdst_dense_0", st);
     rowdst_dense<T, false><<<s->batch * ny, threads, smem, st>>>(s->L, ny, n, np, nl, ring_zero, s->l2m, (const T*)s->dstmat, q, S, 1.0);

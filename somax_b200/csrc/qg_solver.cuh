@@ -23,6 +23,15 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
                      int solver_kind, int nseg = 1, int rows = -1, int jo = 0, int ylo = 1, int yhi = 1);
 void qg_solver_destroy(QgSolver* s);
 size_t qg_solver_bytes(const QgSolver* s);
+// Slab-distributed model, fused compute + exchange (no transpose kernels):
+//   scatter: rows_fwd of this (row-stage) solver stores spectral element (row j, strip st) into
+//            peerS[st / spr], the column array (ny_cols rows per strip) of the rank that owns the
+//            strip, at row row0 + j;
+//   push:    the last sweep of cols(2) of this (column-stage) solver stores its tiles into peerR[r],
+//            the row array of the rank that owns rows [row0[r], row0[r+1]).
+// Pointers may be peer memory (CUDA IPC over NVLink); spr must be a power of two.
+void qg_solver_set_scatter(QgSolver* s, void* const* peerS, int nranks, int spr, int row0, int ny_cols);
+void qg_solver_set_push(QgSolver* s, void* const* peerR, int nranks, const int* row0);
 int qg_solver_kind(const QgSolver* s);
 
 // psi = Cm2l . Helm^-1 . Cl2m . q on padded planes (batch, nl, Ny, pitch), every point of the
@@ -49,8 +58,8 @@ template <typename T> int qg_solver_border(QgSolver* s, cudaStream_t stream);
 template <typename T> int qg_solver_border_stage(QgSolver* s, int stage, int a0, int a1, cudaStream_t stream);
 
 // Raw view of the spectral storage: S is [plane][strip][ny][64] (strip = 64 x-wavenumbers, ny =
-// solver rows), part is [plane][2][2 * nstrip][ny], bext is [plane][2][ny] (border columns 0 and
-// nx+1); ncols is the slot of border column nx in a row of S.
+// solver rows), part is [plane][2][2 * nstrip][ny], bext is [plane][3][ny] (border columns 0, nx+1
+// and the raw column nx); ncols is the slot of border column nx in a row of S.
 struct QgSolverView {
   void* S; void* part; void* bext;
   double* ghat; double* gvec; float* gvecf;   // border system: ghat [plane][3][ny], gvec / gvecf [plane][2][ny]

@@ -626,11 +626,7 @@ int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A, const Stage<T>& st_in, c
   if (h->f1d && h->wx1d && h->wy1d) {
     // fp32: per-thread shared slots for the prefetched epilogue operands
     const size_t dyn = sizeof(T) == 4 ? (size_t)3 * (MAX_PREV + 1) * TXG * TY * 4 * sizeof(T) : 0;
-    static bool attr_done = false;
-    if (dyn > 0 && !attr_done) {
-      SB_CUDA(cudaFuncSetAttribute(swm_rhs_kernel_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-      attr_done = true;
-    }
+    if (int rc = ensure_dyn_smem((const void*)swm_rhs_kernel_fast<T>, dyn)) return rc;
     swm_rhs_kernel_fast<T><<<grid, block, dyn, s>>>(A, st);
   }
   else swm_rhs_kernel<T><<<grid, block, 0, s>>>(A, st);
