@@ -14,7 +14,9 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "lib" / "libsomax_b200.so"
-SOURCES = ["layout.cu", "swm.cu", "qg_solver.cu", "qg.cu"]
+SOURCES = ["layout.cu", "swm.cu", "swm_f64.cu", "qg_solver.cu", "qg.cu"]
+# per-source extra flags: the fp64 shallow-water kernel keeps the reference's rounding (no FMA contraction)
+EXTRA_FLAGS = {"swm_f64.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-O3", "-std=c++17"]
 
@@ -91,7 +93,7 @@ def build_library(verbose: bool = False) -> Path:
         obj = objdir / (src.stem + ".o")
         deps = [str(src)] + hdrs
         if extra or not obj.exists() or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
-            cmd = [nvcc] + flags + extra + ["-c", "-o", str(obj), str(src)]
+            cmd = [nvcc] + flags + EXTRA_FLAGS.get(src.name, []) + extra + ["-c", "-o", str(obj), str(src)]
             if verbose:
                 print(" ".join(cmd))
             jobs.append((cmd, subprocess.Popen(cmd)))

