@@ -187,11 +187,26 @@ int somax_b200_swm_create(somax_b200_swm_t* out, int dtype, int batch, int nl, i
                           const double* f_field, const double* wind_x, const double* wind_y,
                           unsigned spec_flags);
 int somax_b200_swm_destroy(somax_b200_swm_t h);
+/* Turns the handle into the reparameterized QG model (ReparameterizedQG, qg/reparameterized.py:66-189:
+ * a MultilayerShallowWater2D whose apply_boundary_conditions also projects the state onto the
+ * geostrophic manifold, P = G (Q G)^-1 Q).  From then on every entry point that applies the boundary
+ * conditions (apply_bc, rhs with apply_bc != 0, steps) applies shallow-water BCs + projection; rhs
+ * with apply_bc == 0 stays the plain shallow-water vector field (reparameterized.py:179-183).
+ * H (nl) layer thicknesses; Cl2m, Cm2l (nl*nl), eigenvalues (nl) = ModalTransform fields;
+ * lambdas (nl) = helmholtz_lambdas = f0^2 * eigenvalues as the model holds them.  Needs BC_WALL. */
+int somax_b200_swm_set_projection(somax_b200_swm_t h, double f0, const double* H, const double* Cl2m,
+                                  const double* Cm2l, const double* eigenvalues, const double* lambdas,
+                                  int solver);
 size_t somax_b200_swm_device_bytes(somax_b200_swm_t h);
 
 /* MultilayerShallowWater2D.apply_boundary_conditions (swm/multilayer.py:203-223, 383-410). */
 int somax_b200_swm_apply_bc(somax_b200_swm_t h, const void* hh, const void* u, const void* v,
                             void* hh_out, void* u_out, void* v_out, void* stream);
+
+/* ReparameterizedQG.project (qg/reparameterized.py:142-177): (h, u, v) -> the geostrophically balanced
+ * state, no boundary conditions applied first.  Needs somax_b200_swm_set_projection. */
+int somax_b200_swm_project(somax_b200_swm_t h, const void* hh, const void* u, const void* v,
+                           void* hh_out, void* u_out, void* v_out, void* stream);
 
 /* MultilayerShallowWater2D.vector_field (swm/multilayer.py:150-201). */
 int somax_b200_swm_rhs(somax_b200_swm_t h, const void* hh, const void* u, const void* v,

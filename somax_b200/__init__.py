@@ -19,6 +19,7 @@ from .models.swm import (  # noqa: F401
     MultilayerSW2DPhysConsts, MultilayerSW2DState, NonlinearShallowWater2D,
     NonlinearSW2DDiagnostics, NonlinearSW2DParams, NonlinearSW2DPhysConsts, NonlinearSW2DState,
 )
+from .models.reparam import ReparameterizedQG, ReparamQGDiagnostics  # noqa: F401
 from . import gfd_testcases  # noqa: F401
 
 __version__ = "0.1.0"

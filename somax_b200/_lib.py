@@ -66,8 +66,10 @@ SIGNATURES = {
     "somax_b200_qgs_status": (_I, [_P, C.POINTER(_I)]),
     "somax_b200_swm_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _D, _D, _I, _P, _P, _P, _P, _U]),
     "somax_b200_swm_destroy": (_I, [_P]),
+    "somax_b200_swm_set_projection": (_I, [_P, _D, _P, _P, _P, _P, _P, _I]),
     "somax_b200_swm_device_bytes": (C.c_size_t, [_P]),
     "somax_b200_swm_apply_bc": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "somax_b200_swm_project": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "somax_b200_swm_rhs": (_I, [_P, _P, _P, _P, _P, _P, _P, _PP, _I, _P]),
     "somax_b200_swm_steps": (_I, [_P, _P, _P, _P, _L, _D, _D, _PP, _P]),
     "somax_b200_swm_resume": (_I, [_P, _P, _P, _P, _L, _D, _D, _PP, _P]),

@@ -12,8 +12,66 @@
 #include <vector>
 
 #include "swm_kernels.cuh"
+#include "qg_solver.cuh"
 
 namespace sb {
+
+// ------------------------------------------------------------------------------------------
+// Geostrophic projection of the reparameterized QG model, P = G . (Q.G)^-1 . Q
+// (reference qg/reparameterized.py:142-189), applied by its apply_boundary_conditions after the
+// shallow-water BCs.  Q and G are two small stencil kernels around the PV-inversion solver of the
+// QG models (qg_solver.cu).
+// ------------------------------------------------------------------------------------------
+struct ProjArgs {
+  double f0;
+  double H[SWM_MAX_NL];
+  double A[SWM_MAX_NL][SWM_MAX_NL];   // Cm2l . diag(eigenvalues) . Cl2m
+};
+
+// Q: q = curl(u, v) - f0 (h - H_k) / H_k on the whole array; the curl is finitevolx's
+// relative_vorticity (interior only, zero ring), h - H_k is taken everywhere (reparameterized.py:160-164).
+template <typename T>
+__global__ void rqg_q_kernel(const T* __restrict__ h, const T* __restrict__ u, const T* __restrict__ v,
+                             T* __restrict__ q, Layout L, int bc, int apply_bc, ProjArgs P, T dx, T dy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, plane = blockIdx.z;
+  if (i >= L.Nx) return;
+  const int k = plane % L.nl, Ny = L.Ny, Nx = L.Nx, pitch = L.pitch;
+  const size_t po = (size_t)plane * L.plane();
+  auto val = [&](const T* f, int kind, int jj, int ii) -> T {
+    return apply_bc ? swm_bc_value(f + po, kind, bc, jj, ii, Ny, Nx, pitch) : f[po + (size_t)jj * pitch + OFF + ii];
+  };
+  T zeta = 0;
+  if (j >= 1 && j <= Ny - 2 && i >= 1 && i <= Nx - 2)
+    zeta = (val(v, FV, j, i + 1) - val(v, FV, j, i)) / dx - (val(u, FU, j + 1, i) - val(u, FU, j, i)) / dy;
+  const T Hk = (T)P.H[k];
+  const T eta = val(h, FH, j, i) - Hk;
+  q[po + (size_t)j * pitch + OFF + i] = zeta - ((T)P.f0 * eta) / Hk;
+}
+
+// G: (u_g, v_g) = grad_perp(psi) = (-d psi/dy at U points, d psi/dx at V points), interior only with
+// a zero ring; h_g = H_k (1 + f0 (A psi)_k), A psi = Cm2l (eigenvalues * (Cl2m psi)), everywhere
+// (reparameterized.py:169-177).
+template <typename T>
+__global__ void rqg_g_kernel(const T* __restrict__ psi, T* __restrict__ hg, T* __restrict__ ug,
+                             T* __restrict__ vg, Layout L, ProjArgs P, T dx, T dy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, plane = blockIdx.z;
+  if (i >= L.Nx) return;
+  const int b = plane / L.nl, k = plane - b * L.nl, Ny = L.Ny, Nx = L.Nx, pitch = L.pitch;
+  const size_t o = (size_t)j * pitch + OFF + i;
+  const size_t po = (size_t)plane * L.plane();
+  T uu = 0, vv = 0;
+  if (j >= 1 && j <= Ny - 2 && i >= 1 && i <= Nx - 2) {
+    const T pc = psi[po + o];
+    uu = -((pc - psi[po + o - pitch]) / dy);
+    vv = (pc - psi[po + o - 1]) / dx;
+  }
+  T ap = 0;
+  for (int c = 0; c < L.nl; ++c) ap += (T)P.A[k][c] * psi[((size_t)b * L.nl + c) * L.plane() + o];
+  const T Hk = (T)P.H[k];
+  hg[po + o] = Hk * (T(1) + (T)P.f0 * ap);
+  ug[po + o] = uu;
+  vg[po + o] = vv;
+}
 
 // Fast variant (f, wind_x, wind_y depend on y only - every reference factory): 128-bit tile
 // loads, per-thread 3x6 register windows filled with 128-bit shared reads + warp shuffles,
@@ -385,6 +443,11 @@ struct somax_b200_swm_s {
   void* F[5][3] = {};
   StepGraph graph;
   size_t bytes = 0;
+  // geostrophic projection (reparameterized QG): Helmholtz solver, PV / streamfunction planes and the
+  // projected state the right-hand side is evaluated at
+  QgSolver* proj = nullptr;
+  ProjArgs pargs;
+  void* pq = nullptr; void* ppsi = nullptr; void* P[3] = {0, 0, 0};
 };
 
 namespace {
@@ -405,10 +468,39 @@ SwmArgs<T> make_args(somax_b200_swm_t h, const somax_b200_params* p, int apply_b
   return A;
 }
 
+// out = project(BC(in)) (apply_bc) or project(in); in / out are triples of padded planes.
 template <typename T>
-int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A, const Stage<T>& st_in, cudaStream_t s) {
+int project_state(somax_b200_swm_t h, const T* const in[3], T* const out[3], int apply_bc, cudaStream_t s) {
+  const Layout& L = h->L;
+  dim3 b(128), g((L.Nx + 127) / 128, L.Ny, L.batch * L.nl);
+  prof_begin("rqg_q_kernel", s);
+  rqg_q_kernel<T><<<g, b, 0, s>>>(in[0], in[1], in[2], (T*)h->pq, L, h->bc, apply_bc, h->pargs, (T)h->dx, (T)h->dy);
+  SB_LAUNCH_CHECK();
+  // the PV carries its ring (-f0 eta / H there): the solve takes it as it is, psi's ring is zeroed
+  if (int rc = qg_solver_run<T>(h->proj, (const T*)h->pq, (T*)h->ppsi, 0, 0, s)) return rc;
+  prof_begin("rqg_g_kernel", s);
+  rqg_g_kernel<T><<<g, b, 0, s>>>((const T*)h->ppsi, out[0], out[1], out[2], L, h->pargs, (T)h->dx, (T)h->dy);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A_in, const Stage<T>& st_in, cudaStream_t s) {
   const Layout& L = h->L;
   Stage<T> st = st_in;
+  SwmArgs<T> A = A_in;
+  if (h->proj && A.apply_bc) {
+    // ReparameterizedQG._rhs = swm.vector_field(project(swm_bc(Y))): the right-hand side is evaluated
+    // at the projected state, the Runge-Kutta combination still starts from the un-projected one
+    const T* in[3] = {st.Yin[0], st.Yin[1], st.Yin[2]};
+    T* out[3] = {(T*)h->P[0], (T*)h->P[1], (T*)h->P[2]};
+    if (int rc = project_state<T>(h, in, out, 1, s)) return rc;
+    for (int f = 0; f < 3; ++f) {
+      if (!st.y[f]) st.y[f] = st.Yin[f];
+      st.Yin[f] = (const T*)h->P[f];
+    }
+    A.apply_bc = 0;
+  }
   stage_finalize(st, (double)st.dt);
   dim3 block(TXG, TY);
   dim3 grid((L.groups() + TXG - 1) / TXG, (L.Ny + TY - 1) / TY, L.batch);
@@ -447,6 +539,14 @@ int bc_inplace(somax_b200_swm_t h, void* const f[3], cudaStream_t s) {
   prof_begin("swm_bc_kernel", s);
   swm_bc_kernel<T><<<g, b, 0, s>>>((T*)f[0], (T*)f[1], (T*)f[2], L, h->bc);
   SB_LAUNCH_CHECK();
+  if (h->proj) {
+    // ReparameterizedQG.apply_boundary_conditions: the shallow-water BCs, then the projection
+    const T* in[3] = {(const T*)f[0], (const T*)f[1], (const T*)f[2]};
+    T* out[3] = {(T*)h->P[0], (T*)h->P[1], (T*)h->P[2]};
+    if (int rc = project_state<T>(h, in, out, 0, s)) return rc;
+    const size_t nb = L.count() * sizeof(T);
+    for (int k = 0; k < 3; ++k) SB_CUDA(cudaMemcpyAsync(f[k], h->P[k], nb, cudaMemcpyDeviceToDevice, s));
+  }
   return 0;
 }
 
@@ -455,7 +555,7 @@ int swm_steps_impl(somax_b200_swm_t h, void* hh, void* u, void* v, long n_steps,
                    double dt_last, const somax_b200_params* p, bool bc0, cudaStream_t caller) {
   const Layout& L = h->L;
   const long total = n_steps + (dt_last > 0 ? 1 : 0);
-  const bool use_graph = !prof_enabled() && L.count() <= GRAPH_MAX_CELLS && n_steps >= 9 &&
+  const bool use_graph = !prof_enabled() && L.count() <= GRAPH_MAX_CELLS && n_steps >= 9 && !h->proj &&
                          h->graph.init() == 0;
   cudaStream_t s = caller;
   if (use_graph) {
@@ -582,6 +682,22 @@ int swm_bc_impl(somax_b200_swm_t h, const void* hh, const void* u, const void* v
 }
 
 template <typename T>
+int swm_project_impl(somax_b200_swm_t h, const void* hh, const void* u, const void* v, void* ho,
+                     void* uo, void* vo, cudaStream_t s) {
+  const Layout& L = h->L;
+  const void* in[3] = {hh, u, v};
+  void* out[3] = {ho, uo, vo};
+  for (int f = 0; f < 3; ++f)
+    if (int rc = pack_field<T>((const T*)in[f], (T*)h->Ya[f], L, s)) return rc;
+  const T* pin[3] = {(const T*)h->Ya[0], (const T*)h->Ya[1], (const T*)h->Ya[2]};
+  T* pout[3] = {(T*)h->P[0], (T*)h->P[1], (T*)h->P[2]};
+  if (int rc = project_state<T>(h, pin, pout, 0, s)) return rc;
+  for (int f = 0; f < 3; ++f)
+    if (int rc = unpack_field<T>((const T*)h->P[f], (T*)out[f], L, s)) return rc;
+  return 0;
+}
+
+template <typename T>
 int swm_diag_impl(somax_b200_swm_t h, const void* hh, const void* u, const void* v, double* out,
                   cudaStream_t s) {
   const Layout& L = h->L;
@@ -653,10 +769,45 @@ int somax_b200_swm_destroy(somax_b200_swm_t h) {
   h->graph.destroy();
   cudaFree(h->f); cudaFree(h->wx); cudaFree(h->wy);
   for (int f = 0; f < 3; ++f) {
-    cudaFree(h->y[f]); cudaFree(h->Ya[f]); cudaFree(h->Yb[f]);
+    cudaFree(h->y[f]); cudaFree(h->Ya[f]); cudaFree(h->Yb[f]); cudaFree(h->P[f]);
     for (int j = 0; j < 5; ++j) cudaFree(h->F[j][f]);
   }
+  cudaFree(h->pq); cudaFree(h->ppsi);
+  qg_solver_destroy(h->proj);
   delete h;
+  return 0;
+}
+
+int somax_b200_swm_set_projection(somax_b200_swm_t h, double f0, const double* H, const double* Cl2m,
+                                  const double* Cm2l, const double* eigenvalues, const double* lambdas,
+                                  int solver) {
+  if (!h || !H || !Cl2m || !Cm2l || !eigenvalues || !lambdas) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  if (h->bc != SOMAX_B200_BC_WALL)
+    return fail(SOMAX_B200_ERR_INVALID, "the geostrophic projection needs wall boundary conditions");
+  if (h->proj) return fail(SOMAX_B200_ERR_INVALID, "projection already set");
+  const Layout& L = h->L;
+  const int nl = L.nl;
+  if (nl > 4) return fail(SOMAX_B200_ERR_UNSUPPORTED, "projection supports nl <= 4");
+  if (int rc = qg_solver_create(&h->proj, h->dtype, L.batch, nl, h->ny, h->nx, h->dx, h->dy, Cl2m, Cm2l, lambdas,
+                                solver, 0)) return rc;
+  h->pargs.f0 = f0;
+  for (int k = 0; k < nl; ++k) {
+    h->pargs.H[k] = H[k];
+    for (int c = 0; c < nl; ++c) {
+      double a = 0;
+      for (int m = 0; m < nl; ++m) a += Cm2l[k * nl + m] * eigenvalues[m] * Cl2m[m * nl + c];
+      h->pargs.A[k][c] = a;
+    }
+  }
+  const size_t fb = L.count() * (h->dtype == SOMAX_B200_F32 ? 4 : 8);
+  void** bufs[] = {&h->pq, &h->ppsi, &h->P[0], &h->P[1], &h->P[2]};
+  for (void** bp : bufs) {
+    cudaError_t e = cudaMalloc(bp, fb);
+    if (e != cudaSuccess) return fail(SOMAX_B200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cudaMemset(*bp, 0, fb);
+    h->bytes += fb;
+  }
+  h->bytes += qg_solver_bytes(h->proj);
   return 0;
 }
 
@@ -666,6 +817,13 @@ int somax_b200_swm_apply_bc(somax_b200_swm_t h, const void* hh, const void* u, c
                             void* ho, void* uo, void* vo, void* stream) {
   if (!h || !hh || !u || !v || !ho || !uo || !vo) return fail(SOMAX_B200_ERR_INVALID, "null argument");
   return SB_DISPATCH(h, swm_bc_impl, h, hh, u, v, ho, uo, vo, (cudaStream_t)stream);
+}
+
+int somax_b200_swm_project(somax_b200_swm_t h, const void* hh, const void* u, const void* v,
+                           void* ho, void* uo, void* vo, void* stream) {
+  if (!h || !hh || !u || !v || !ho || !uo || !vo) return fail(SOMAX_B200_ERR_INVALID, "null argument");
+  if (!h->proj) return fail(SOMAX_B200_ERR_INVALID, "no projection on this handle (somax_b200_swm_set_projection)");
+  return SB_DISPATCH(h, swm_project_impl, h, hh, u, v, ho, uo, vo, (cudaStream_t)stream);
 }
 
 int somax_b200_swm_rhs(somax_b200_swm_t h, const void* hh, const void* u, const void* v, void* dh,

@@ -2,7 +2,8 @@
 
 Mirror of somax/_src/models/gfd_testcases.py for the four ``somax-sim`` test cases
 (cli/_factories.py:153-158): barotropic_jet_instability (:120-181), doublegyre_qg (:184-228),
-doublegyre_baroclinic_qg (:231-287), baroclinic_instability_swm (:290-362).  States are numpy
+doublegyre_baroclinic_qg (:231-287), baroclinic_instability_swm (:290-362), and
+doublegyre_reparameterized_qg (:365-428).  States are numpy
 arrays in the model dtype (pass them, or CUDA tensors, to ``model.integrate``).
 """
 from __future__ import annotations
@@ -10,6 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 from .models.qg import BaroclinicQG, BaroclinicQGState, BarotropicQG, BarotropicQGState
+from .models.reparam import ReparameterizedQG
 from .models.swm import (MultilayerShallowWater2D, MultilayerSW2DState, NonlinearShallowWater2D,
                          NonlinearSW2DState)
 
@@ -73,6 +75,23 @@ def baroclinic_instability_swm(nx=64, ny=64, Lx=1e6, Ly=1e6, f0=1e-4, beta=1.6e-
     return model, MultilayerSW2DState(h=h0.astype(dt), u=u0.astype(dt), v=v0.astype(dt))
 
 
+def doublegyre_reparameterized_qg(nx=128, ny=128, Lx=4e6, Ly=4e6, f0=9.375e-5, beta=1.754e-11, n_layers=3,
+                                  H=(400.0, 1100.0, 2600.0), g_prime=(9.81, 0.025, 0.0125),
+                                  lateral_viscosity=15.0, bottom_drag=3.6e-8, wind_amplitude=8e-5,
+                                  dtype="float32"):
+    """Wind-driven multilayer double gyre solved in (u, v, h) with the geostrophic projection
+    (gfd_testcases.py:365-428): state at rest, h = H."""
+    model = ReparameterizedQG.create(nx=nx, ny=ny, Lx=Lx, Ly=Ly, f0=f0, beta=beta, n_layers=n_layers, H=H,
+                                     g_prime=g_prime, lateral_viscosity=lateral_viscosity,
+                                     bottom_drag=bottom_drag, wind_amplitude=wind_amplitude,
+                                     wind_profile="doublegyre", bc="wall", dtype=dtype)
+    nl, g = model.consts.n_layers, model.grid
+    dt = np.dtype(dtype)
+    h0 = (np.ones((nl, g.Ny, g.Nx)) * np.asarray(model.strat.H)[:, None, None]).astype(dt)
+    z = np.zeros((nl, g.Ny, g.Nx), dt)
+    return model, MultilayerSW2DState(h=h0, u=z, v=z.copy())
+
+
 def synthetic_qg_state(nl, nx, ny, seed=1234, amps=(4e-6, 2e-6, 1e-6), nmodes=8, dtype="float32"):
     """Seeded low-wavenumber sine superposition used by bench.py and the parity tests
     (SURVEY section 8d): the factory state q0 = 0 is degenerate.  Ghost ring = 0."""
@@ -94,4 +113,5 @@ TEST_CASES = {
     "doublegyre_qg": doublegyre_qg,
     "doublegyre_baroclinic_qg": doublegyre_baroclinic_qg,
     "baroclinic_instability_swm": baroclinic_instability_swm,
+    "doublegyre_reparameterized_qg": doublegyre_reparameterized_qg,
 }

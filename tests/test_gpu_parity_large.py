@@ -274,3 +274,57 @@ def test_energy_enstrophy_series_over_a_full_chunk():
         d = gsw.diagnose(sb.MultilayerSW2DState(h=sol.ys.h[i], u=sol.ys.u[i], v=sol.ys.v[i]))
         assert np.allclose(d.energy, dref["energy"], rtol=1e-4), i
         assert np.allclose(d.enstrophy, dref["enstrophy"], rtol=1e-4), i
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_reparameterized_qg_parity(dtype):
+    """ReparameterizedQG (qg/reparameterized.py:66-330): project, apply_boundary_conditions, the
+    `_rhs` of build_terms, 1 and 20 Tsit5 steps and the diagnostics against the oracle; the reference's
+    property tests (tests/models/test_qg_reparameterized.py) on the CUDA path."""
+    import somax_b200 as sb
+    from oracle.reparam import create_reparameterized
+    kw = dict(nx=64, ny=48, lateral_viscosity=15.0, bottom_drag=3.6e-8, wind_amplitude=8e-5)
+    om = create_reparameterized(**kw)
+    gm = sb.ReparameterizedQG.create(dtype=np.dtype(dtype).name, **kw)
+    assert isinstance(gm.swm, sb.MultilayerShallowWater2D)
+    rng = np.random.default_rng(4)
+    H = np.asarray(om.swm.H)[:, None, None]
+    h = (H * (1.0 + 1e-3 * rng.standard_normal((3, 50, 66)))).astype(dtype)
+    u = (0.05 * rng.standard_normal(h.shape)).astype(dtype)
+    v = (0.05 * rng.standard_normal(h.shape)).astype(dtype)
+    st = sb.MultilayerSW2DState(h=h, u=u, v=v)
+    f64 = [a.astype(np.float64) for a in (h, u, v)]
+    tol = 2e-5 if dtype == np.float32 else 1e-10
+    for got, ref in ((gm.project(st), om.project(*f64)), (gm.apply_boundary_conditions(st), om.bc(*f64))):
+        for name, r in zip("huv", ref):
+            assert rel(getattr(got, name), r) <= tol, name
+    # vector_field is the plain shallow-water one; _rhs evaluates it at the projected state
+    t = gm.vector_field(0.0, st)
+    for name, r, rs in zip("huv", om.rhs(*f64), om.rhs(h, u, v)):
+        assert_swm_parity(getattr(t, name), r, rs, dtype, name)
+    t = gm.build_terms().vf(0.0, st)
+    for name, r in zip("huv", om.rhs(*om.bc(*f64))):
+        assert rel(getattr(t, name), r) <= (1e-3 if dtype == np.float32 else 1e-9), name
+    dt = 200.0
+    for steps in (1, 20):
+        sol = gm.integrate(st, 0.0, steps * dt, dt)
+        ref = om.integrate(*f64, 0.0, steps * dt, dt)
+        same = om.integrate(h, u, v, 0.0, steps * dt, dt) if dtype == np.float32 else ref
+        for name, r, rs in zip("huv", ref, same):
+            # fp32: the shallow-water momentum tendencies sit on a rounding floor (assert_swm_parity)
+            lim = max(1e-5, 1.5 * rel(rs, r)) if dtype == np.float32 else 1e-10
+            assert rel(getattr(sol.ys, name)[0], r) <= lim, (steps, name)
+    last = sb.MultilayerSW2DState(h=sol.ys.h[0], u=sol.ys.u[0], v=sol.ys.v[0])
+    d, dref = gm.diagnose(last), om.diagnose(*ref)
+    assert isinstance(d, sb.ReparamQGDiagnostics)
+    assert rel(d.psi, dref["psi"]) <= tol * 50
+    assert rel(d.u_ageostrophic, dref["u_ageostrophic"]) <= tol * 500
+    assert np.allclose(d.energy, dref["energy"], rtol=1e-4)
+    # rest state: fixed point of the projection, zero tendency (test_qg_reparameterized.py:60-125)
+    m2, st0 = sb.gfd_testcases.doublegyre_reparameterized_qg(nx=32, ny=32, wind_amplitude=0.0, dtype=np.dtype(dtype).name)
+    p = m2.project(st0)
+    assert np.allclose(p.h, st0.h, atol=1e-3 if dtype == np.float32 else 1e-6) and np.abs(p.u).max() < 1e-10
+    tend = m2.build_terms().vf(0.0, st0)
+    assert max(np.abs(tend.h).max(), np.abs(tend.u).max(), np.abs(tend.v).max()) < 1e-10
+    with pytest.raises(ValueError, match="wall"):
+        sb.ReparameterizedQG.create(nx=16, ny=16, bc="periodic")

@@ -198,3 +198,45 @@ def test_tsit5_tableau_and_exponential_decay():  # tests/core/test_model.py:12-7
     assert y[0] == pytest.approx(np.exp(-1.0), rel=1e-10)
     assert tsit5.step_plan(0.0, 1.0, 0.3) == (3, pytest.approx(0.1))
     assert tsit5.step_plan(0.0, 86400.0 * 30, 600.0) == (4320, 0.0)
+
+
+# ---------------------------------------------------------------- reparameterized QG
+def _reparam(nl=2, **kw):
+    from oracle.reparam import create_reparameterized
+    args = dict(nx=16, ny=16, n_layers=2, H=(500.0, 500.0), g_prime=(9.81, 0.02))
+    if nl == 3:
+        args = dict(nx=16, ny=16)
+    args.update(kw)
+    m = create_reparameterized(**args)
+    h = np.ones((m.swm.nl, 18, 18)) * m.swm.H[:, None, None]
+    return m, h, np.zeros_like(h), np.zeros_like(h)
+
+
+def test_reparameterized_qg_reference_properties():
+    """tests/models/test_qg_reparameterized.py:60-135: rest state is a fixed point of the projection
+    and of the flow; the projection is (nearly) idempotent and produces geostrophic velocities;
+    curl(grad_perp(psi)) is the 5-point Laplacian, which is what makes (Q G)^-1 the Helmholtz solve."""
+    from oracle import operators as op
+    from oracle.reparam import grad_perp
+    m, h, u, v = _reparam()
+    ph, pu, pv = m.project(h, u, v)
+    assert np.abs(ph - h).max() < 1e-6 and np.abs(pu).max() < 1e-10 and np.abs(pv).max() < 1e-10
+    assert all(np.abs(a).max() < 1e-10 for a in m.rhs(*m.bc(h, u, v)))
+    h2 = h.copy()
+    h2[0, 9, 9] += 1.0
+    p1 = m.project(h2, u, v)
+    p2 = m.project(*p1)
+    assert all(np.abs(a - b).max() < 0.1 for a, b in zip(p1, p2))
+    assert np.abs(p1[1]).max() > 0 and np.abs(p1[2]).max() > 0 and all(np.isfinite(a).all() for a in p1)
+    psi = np.random.default_rng(0).standard_normal((2, 18, 18))
+    ug, vg = grad_perp(psi, m.swm.dx, m.swm.dy)
+    lap = op.laplacian(psi, m.swm.dx, m.swm.dy)
+    s = (slice(None), slice(2, -2), slice(2, -2))       # away from the zero ring of u_g, v_g
+    assert np.allclose(op.curl(ug, vg, m.swm.dx, m.swm.dy)[s], lap[s], rtol=1e-10, atol=1e-22)
+    out = m.integrate(h2, u, v, 0.0, 600.0, 60.0)
+    assert all(np.isfinite(a).all() for a in out)
+    m3, h3, u3, v3 = _reparam(nl=3, wind_amplitude=8e-5, lateral_viscosity=15.0)
+    out = m3.integrate(h3, u3, v3, 0.0, 600.0, 60.0)
+    assert all(np.isfinite(a).all() for a in out) and np.abs(out[1][0]).max() > 0
+    with pytest.raises(ValueError, match="wall"):
+        _reparam(bc="periodic")
