@@ -226,6 +226,31 @@ int somax_b200_swm_resume(somax_b200_swm_t h, void* hh, void* u, void* v, long n
 int somax_b200_swm_diag(somax_b200_swm_t h, const void* hh, const void* u, const void* v,
                         double* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Slab-distributed shallow water: ONE grid partitioned in y-slabs over `nranks` GPUs, halo exchange
+ * only (no elliptic solve).  Same model as somax_b200_swm_* with batch = 1; replaces the same
+ * reference functions (swm/multilayer.py:150-223 under core/model.py:47-88).  Rank r owns rows
+ * [r*ny/nranks, (r+1)*ny/nranks) and works on the window (nl, ny/nranks + 2, Nx) of the global
+ * arrays starting at global row r*ny/nranks.  Periodic basins: ranks 0 and nranks-1 are neighbours
+ * (the y wrap-around of enforce_periodic is the halo exchange).  Needs ny % nranks == 0.
+ * nlocal as for somax_b200_qgs_create.  f_field, wind_x, wind_y: the GLOBAL (Ny, Nx) host arrays.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct somax_b200_swms_s* somax_b200_swms_t;
+
+int somax_b200_swms_create(somax_b200_swms_t* out, int dtype, int nl, int ny, int nx, double dx, double dy,
+                           int bc, const double* g_prime, const double* f_field, const double* wind_x,
+                           const double* wind_y, int nranks, int rank_first, int nlocal, unsigned spec_flags);
+int somax_b200_swms_destroy(somax_b200_swms_t g);
+size_t somax_b200_swms_device_bytes(somax_b200_swms_t g);
+size_t somax_b200_swms_export_bytes(void);
+int somax_b200_swms_export(somax_b200_swms_t g, void* blob);
+int somax_b200_swms_attach(somax_b200_swms_t g, const void* blobs);
+/* SomaxModel.integrate on the slabs, in place: h/u/v_slabs[v] (DEVICE) are local slab v's windows
+ * (nl, ny/nranks + 2, Nx), halo rows valid on entry and on return.  Collective over the group. */
+int somax_b200_swms_steps(somax_b200_swms_t g, void* const* h_slabs, void* const* u_slabs, void* const* v_slabs,
+                          long n_steps, double dt, double dt_last, const somax_b200_params* p, void* stream);
+int somax_b200_swms_status(somax_b200_swms_t g, int* barrier_timeouts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,14 @@ SIGNATURES = {
     "somax_b200_qgs_attach": (_I, [_P, _P]),
     "somax_b200_qgs_steps": (_I, [_P, _P, _L, _D, _D, _PP, _P]),
     "somax_b200_qgs_status": (_I, [_P, C.POINTER(_I)]),
+    "somax_b200_swms_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _D, _D, _I, _P, _P, _P, _P, _I, _I, _I, _U]),
+    "somax_b200_swms_destroy": (_I, [_P]),
+    "somax_b200_swms_device_bytes": (C.c_size_t, [_P]),
+    "somax_b200_swms_export_bytes": (C.c_size_t, []),
+    "somax_b200_swms_export": (_I, [_P, _P]),
+    "somax_b200_swms_attach": (_I, [_P, _P]),
+    "somax_b200_swms_steps": (_I, [_P, _P, _P, _P, _L, _D, _D, _PP, _P]),
+    "somax_b200_swms_status": (_I, [_P, C.POINTER(_I)]),
     "somax_b200_swm_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _D, _D, _I, _P, _P, _P, _P, _U]),
     "somax_b200_swm_destroy": (_I, [_P]),
     "somax_b200_swm_set_projection": (_I, [_P, _D, _P, _P, _P, _P, _P, _I]),

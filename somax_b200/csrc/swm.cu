@@ -102,7 +102,7 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
   // row / column interior flags of the 3 x 6 window
   bool rin[3], cin[6];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) rin[d] = (j - 1 + d >= 1) && (j - 1 + d <= Ny - 2);
+  for (int d = 0; d < 3; ++d) rin[d] = swm_row_interior(j - 1 + d, Ny, A.ylo, A.yhi);
 #pragma unroll
   for (int w = 0; w < 6; ++w) cin[w] = (i0 - 1 + w >= 1) && (i0 - 1 + w <= Nx - 2);
   // Coriolis at the X points of rows j-1 and j: f depends on y only, so
@@ -132,6 +132,11 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
     const T* ph = st.Yin[FH] + plane_off;
     const T* pu = st.Yin[FU] + plane_off;
     const T* pv = st.Yin[FV] + plane_off;
+    // periodic basin in slabs: source rows of the physical ghost rows (SwmArgs::lo_src / hi_src)
+    const size_t ro = ((size_t)b * L.nl + k) * pitch;
+    const T* loh = A.lo_src[FH] ? A.lo_src[FH] + ro : nullptr; const T* hih = A.hi_src[FH] ? A.hi_src[FH] + ro : nullptr;
+    const T* lou = A.lo_src[FU] ? A.lo_src[FU] + ro : nullptr; const T* hiu = A.hi_src[FU] ? A.hi_src[FU] + ro : nullptr;
+    const T* lov = A.lo_src[FV] ? A.lo_src[FV] + ro : nullptr; const T* hiv = A.hi_src[FV] ? A.hi_src[FV] + ro : nullptr;
     if (STAGE_EPI) {
       if (epi_valid) {
         const size_t eidx = plane_off + (size_t)j * pitch + (size_t)g * 4;
@@ -158,7 +163,7 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
       if (jj >= 0 && jj < Ny && gg >= 0 && gg < ngroups) {
         const int ib = gg * 4 - OFF;
         const bool plain = !A.apply_bc ||
-                           (jj >= 1 && jj <= Ny - 3 && ib >= 1 && ib + 3 <= Nx - 3);
+                           (jj >= (A.ylo ? 1 : 0) && jj <= (A.yhi ? Ny - 3 : Ny - 1) && ib >= 1 && ib + 3 <= Nx - 3);
         if (plain) {
           const size_t o = (size_t)jj * pitch + (size_t)gg * 4;
           vh = ld4(ph + o); vu = ld4(pu + o); vv = ld4(pv + o);
@@ -169,9 +174,9 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
             const int ii = ib + q;
             th[q] = tu[q] = tv[q] = T(0);
             if (ii >= 0 && ii < Nx) {
-              th[q] = swm_bc_value(ph, FH, A.bc, jj, ii, Ny, Nx, pitch);
-              tu[q] = swm_bc_value(pu, FU, A.bc, jj, ii, Ny, Nx, pitch);
-              tv[q] = swm_bc_value(pv, FV, A.bc, jj, ii, Ny, Nx, pitch);
+              th[q] = swm_bc_value(ph, FH, A.bc, jj, ii, Ny, Nx, pitch, A.ylo, A.yhi, loh, hih);
+              tu[q] = swm_bc_value(pu, FU, A.bc, jj, ii, Ny, Nx, pitch, A.ylo, A.yhi, lou, hiu);
+              tv[q] = swm_bc_value(pv, FV, A.bc, jj, ii, Ny, Nx, pitch, A.ylo, A.yhi, lov, hiv);
             }
           }
           vh = Vec4<T>{th[0], th[1], th[2], th[3]};
@@ -293,7 +298,7 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
           dv = -qV * uhV - (P10 - P00) * idy_;
           bool wr = true;
           if (A.spec & SOMAX_B200_SPEC_ADVECTION_REGION2)
-            wr = (j >= 2 && j <= Ny - 3 && i >= 2 && i <= Nx - 3);
+            wr = (j >= (A.ylo ? 2 : 0) && j <= (A.yhi ? Ny - 3 : Ny - 1) && i >= 2 && i <= Nx - 3);
           if (wr) dh = -((fe[w] - fe[w - 1]) * idx_ + (fn0[w] - fnm[w]) * idy_);
         }
         if (k == 0) { du = du + windx; dv = dv + windy; }
@@ -353,21 +358,21 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
 // In-place apply_boundary_conditions on padded planes.
 template <typename T>
 __global__ void swm_bc_kernel(T* __restrict__ h, T* __restrict__ u, T* __restrict__ v, Layout L,
-                              int bc) {
+                              int bc, int ylo, int yhi) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int j = blockIdx.y;
   int p = blockIdx.z;
   if (i >= L.Nx) return;
-  bool ring = (j == 0 || j == L.Ny - 1 || i == 0 || i == L.Nx - 1);
+  bool ring = ((j == 0 && ylo) || (j == L.Ny - 1 && yhi) || i == 0 || i == L.Nx - 1);
   bool near_u = (bc == SOMAX_B200_BC_WALL) && (i == L.Nx - 2);
-  bool near_v = (bc == SOMAX_B200_BC_WALL) && (j == L.Ny - 2);
+  bool near_v = (bc == SOMAX_B200_BC_WALL) && yhi && (j == L.Ny - 2);
   if (!ring && !near_u && !near_v) return;
   size_t po = (size_t)p * L.plane();
   size_t o = po + (size_t)j * L.pitch + OFF + i;
   // every value is computed from cells the kernel never writes (see swm_bc_value)
-  if (ring) h[o] = swm_bc_value(h + po, FH, bc, j, i, L.Ny, L.Nx, L.pitch);
-  if (ring || near_u) u[o] = swm_bc_value(u + po, FU, bc, j, i, L.Ny, L.Nx, L.pitch);
-  if (ring || near_v) v[o] = swm_bc_value(v + po, FV, bc, j, i, L.Ny, L.Nx, L.pitch);
+  if (ring) h[o] = swm_bc_value(h + po, FH, bc, j, i, L.Ny, L.Nx, L.pitch, ylo, yhi);
+  if (ring || near_u) u[o] = swm_bc_value(u + po, FU, bc, j, i, L.Ny, L.Nx, L.pitch, ylo, yhi);
+  if (ring || near_v) v[o] = swm_bc_value(v + po, FV, bc, j, i, L.Ny, L.Nx, L.pitch, ylo, yhi);
 }
 
 // Diagnostics on the reference layout (state as given, no BC): swm/multilayer.py:225-256.
@@ -443,6 +448,7 @@ struct somax_b200_swm_s {
   void* F[5][3] = {};
   StepGraph graph;
   size_t bytes = 0;
+  int bc_ylo = 1, bc_yhi = 1;   // physical ghost rows (a slab of the distributed model clears them)
   // geostrophic projection (reparameterized QG): Helmholtz solver, PV / streamfunction planes and the
   // projected state the right-hand side is evaluated at
   QgSolver* proj = nullptr;
@@ -455,7 +461,8 @@ namespace {
 template <typename T>
 SwmArgs<T> make_args(somax_b200_swm_t h, const somax_b200_params* p, int apply_bc) {
   SwmArgs<T> A;
-  A.L = h->L; A.bc = h->bc; A.spec = h->spec; A.apply_bc = apply_bc;
+  A.L = h->L; A.bc = h->bc; A.spec = h->spec; A.apply_bc = apply_bc; A.ylo = h->bc_ylo; A.yhi = h->bc_yhi;
+  for (int f = 0; f < 3; ++f) { A.lo_src[f] = nullptr; A.hi_src[f] = nullptr; }
   A.dx = (T)h->dx; A.dy = (T)h->dy; A.dx2 = (T)(h->dx * h->dx); A.dy2 = (T)(h->dy * h->dy);
   A.idx = (T)(1.0 / h->dx); A.idy = (T)(1.0 / h->dy); A.idx2 = (T)(1.0 / (h->dx * h->dx));
   A.idy2 = (T)(1.0 / (h->dy * h->dy)); A.iH0 = (T)(1.0 / p->H0);
@@ -537,7 +544,7 @@ int bc_inplace(somax_b200_swm_t h, void* const f[3], cudaStream_t s) {
   const Layout& L = h->L;
   dim3 b(256), g((L.Nx + 255) / 256, L.Ny, L.batch * L.nl);
   prof_begin("swm_bc_kernel", s);
-  swm_bc_kernel<T><<<g, b, 0, s>>>((T*)f[0], (T*)f[1], (T*)f[2], L, h->bc);
+  swm_bc_kernel<T><<<g, b, 0, s>>>((T*)f[0], (T*)f[1], (T*)f[2], L, h->bc, h->bc_ylo, h->bc_yhi);
   SB_LAUNCH_CHECK();
   if (h->proj) {
     // ReparameterizedQG.apply_boundary_conditions: the shallow-water BCs, then the projection
@@ -853,3 +860,5 @@ int somax_b200_swm_diag(somax_b200_swm_t h, const void* hh, const void* u, const
 }
 
 }  // extern "C"
+
+#include "swm_slab.cuh"

@@ -17,6 +17,17 @@ struct SwmArgs {
   int bc;
   unsigned spec;
   int apply_bc;
+  // ylo / yhi: row 0 / row Ny-1 of these arrays is the physical ghost row.  A y-slab of the
+  // distributed model clears the flag on the side where a neighbouring slab continues: that row is
+  // then a halo row holding the neighbour's data - no boundary condition on it, and "interior"
+  // for the interior-only operators.
+  int ylo, yhi;
+  // Periodic basin in slabs: the data of the physical ghost rows after apply_boundary_conditions
+  // (row 0 <- global row Ny-2, row Ny-1 <- global row 1) lives on the opposite edge rank; it arrives
+  // in the halo inbox and is read from there: lo_src[f] / hi_src[f] = rows [plane][pitch] of field f,
+  // or null (one device: the rows are taken from the array itself).
+  const T* lo_src[3];
+  const T* hi_src[3];
   T dx, dy, dx2, dy2;
   T idx, idy, idx2, idy2, iH0;   // reciprocals (fast kernel)
   const T* f;  int f_cp, f_xs;
@@ -30,22 +41,32 @@ enum { FH = 0, FU = 1, FV = 2 };
 
 // Value of field `kind` at (j,i) after apply_boundary_conditions, read from the raw plane.
 // Periodic: enforce_periodic (rows then columns).  Wall: swm/multilayer.py:386-408.
+// is row jj inside the region finitevolx's interior-only operators write?
+__device__ __forceinline__ bool swm_row_interior(int jj, int Ny, int ylo, int yhi) {
+  return jj >= (ylo ? 1 : 0) && jj <= (yhi ? Ny - 2 : Ny - 1);
+}
+
 template <typename T>
 __device__ __forceinline__ T swm_bc_value(const T* __restrict__ plane, int kind, int bc, int j,
-                                          int i, int Ny, int Nx, int pitch) {
+                                          int i, int Ny, int Nx, int pitch, int ylo = 1, int yhi = 1,
+                                          const T* __restrict__ lo_row = nullptr,
+                                          const T* __restrict__ hi_row = nullptr) {
+  const bool lo = ylo && j == 0, hi = yhi && j == Ny - 1;
   if (bc == SOMAX_B200_BC_PERIODIC) {
-    int jj = (j == 0) ? Ny - 2 : (j == Ny - 1 ? 1 : j);
+    int jj = lo ? Ny - 2 : (hi ? 1 : j);
     int ii = (i == 0) ? Nx - 2 : (i == Nx - 1 ? 1 : i);
+    if (lo && lo_row) return lo_row[OFF + ii];
+    if (hi && hi_row) return hi_row[OFF + ii];
     return plane[(size_t)jj * pitch + OFF + ii];
   }
-  int jj = (j == 0) ? 1 : (j == Ny - 1 ? Ny - 2 : j);
+  int jj = lo ? 1 : (hi ? Ny - 2 : j);
   int ii = (i == 0) ? 1 : (i == Nx - 1 ? Nx - 2 : i);
   if (kind == FU) {
     if (i == 0 || i >= Nx - 2) return T(0);
     return plane[(size_t)jj * pitch + OFF + i];
   }
   if (kind == FV) {
-    if (j == 0 || j >= Ny - 2) return T(0);
+    if (lo || (yhi && j >= Ny - 2)) return T(0);
     return plane[(size_t)j * pitch + OFF + ii];
   }
   return plane[(size_t)jj * pitch + OFF + ii];
@@ -85,9 +106,10 @@ swm_rhs_kernel(SwmArgs<T> A, Stage<T> st) {
       T vh = 0, vu = 0, vv = 0;
       if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
         if (A.apply_bc) {
-          vh = swm_bc_value(ph, FH, A.bc, jj, ii, Ny, Nx, pitch);
-          vu = swm_bc_value(pu, FU, A.bc, jj, ii, Ny, Nx, pitch);
-          vv = swm_bc_value(pv, FV, A.bc, jj, ii, Ny, Nx, pitch);
+          const size_t ro = ((size_t)b * L.nl + k) * pitch;
+          vh = swm_bc_value(ph, FH, A.bc, jj, ii, Ny, Nx, pitch, A.ylo, A.yhi, A.lo_src[FH] ? A.lo_src[FH] + ro : nullptr, A.hi_src[FH] ? A.hi_src[FH] + ro : nullptr);
+          vu = swm_bc_value(pu, FU, A.bc, jj, ii, Ny, Nx, pitch, A.ylo, A.yhi, A.lo_src[FU] ? A.lo_src[FU] + ro : nullptr, A.hi_src[FU] ? A.hi_src[FU] + ro : nullptr);
+          vv = swm_bc_value(pv, FV, A.bc, jj, ii, Ny, Nx, pitch, A.ylo, A.yhi, A.lo_src[FV] ? A.lo_src[FV] + ro : nullptr, A.hi_src[FV] ? A.hi_src[FV] + ro : nullptr);
         } else {
           size_t o = (size_t)jj * pitch + OFF + ii;
           vh = ph[o]; vu = pu[o]; vv = pv[o];
@@ -113,7 +135,7 @@ swm_rhs_kernel(SwmArgs<T> A, Stage<T> st) {
         auto P = [&](int dr, int dc) { return s_p[r + dr][c + dc]; };
         auto inI = [&](int dr, int dc) {
           int jj = j + dr, ii = i + dc;
-          return jj >= 1 && jj <= Ny - 2 && ii >= 1 && ii <= Nx - 2;
+          return swm_row_interior(jj, Ny, A.ylo, A.yhi) && ii >= 1 && ii <= Nx - 2;
         };
         auto Fc = [&](int dr, int dc) {
           return A.f[(size_t)(j + dr) * A.f_cp + (size_t)(i + dc) * A.f_xs];
@@ -163,7 +185,7 @@ swm_rhs_kernel(SwmArgs<T> A, Stage<T> st) {
           };
           bool wr = true;
           if (A.spec & SOMAX_B200_SPEC_ADVECTION_REGION2)
-            wr = (j >= 2 && j <= Ny - 3 && i >= 2 && i <= Nx - 3);
+            wr = (j >= (A.ylo ? 2 : 0) && j <= (A.yhi ? Ny - 3 : Ny - 1) && i >= 2 && i <= Nx - 3);
           if (wr) dh = -((fe(0, 0) - fe(0, -1)) / A.dx + (fn(0, 0) - fn(-1, 0)) / A.dy);
         }
         // --- wind (top layer, FULL grid incl. ring) ---

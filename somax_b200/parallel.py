@@ -253,3 +253,135 @@ class SlabQG:
             self.close()
         except Exception:
             pass
+
+
+class SlabSWM:
+    """A `MultilayerShallowWater2D` / `NonlinearShallowWater2D` model stepped on y-slabs over several
+    GPUs (`libsomax_b200`'s `somax_b200_swms_*`; reference path: core/model.py:53-88 over
+    swm/multilayer.py:150-223).  Halo exchange only: one row of (h, u, v) per neighbour and
+    right-hand-side evaluation, pushed into the neighbour's memory (CUDA IPC over NVLink).
+
+    Same two uses as `SlabQG`: one slab per process inside a torchrun job (`advance_slab` /
+    `integrate_slab` on this rank's windows), or `local=True` with every slab in this process on the
+    current GPU (validation; `integrate` takes and returns the global arrays).
+    """
+
+    def __init__(self, model, world: int, local: bool = False, rank: int | None = None):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _lib
+        self.model, self.world, self.local = model, int(world), bool(local)
+        self.dtype = np.dtype(model.dtype)
+        g = model.grid
+        self.nl, self.ny, self.nx = model._nl, g.Ny - 2, g.Nx - 2
+        if model._base_ndim != 3 and model._nl != 1:
+            raise ValueError("unexpected model layout")
+        if local:
+            self.rank, first, nlocal = 0, 0, self.world
+        else:
+            import torch.distributed as dist
+            if rank is None:
+                rank = dist.get_rank() if dist.is_initialized() else 0
+            self.rank, first, nlocal = int(rank), int(rank), 1
+        h = C.c_void_p()
+        L = _lib.lib()
+        _lib.check(L.somax_b200_swms_create(
+            C.byref(h), _lib.F32 if self.dtype == np.float32 else _lib.F64, self.nl, self.ny, self.nx, g.dx, g.dy,
+            _lib.BC_PERIODIC if model._bc == "periodic" else _lib.BC_WALL, model._g.ctypes.data,
+            model._f.ctypes.data, model._wx.ctypes.data, model._wy.ctypes.data, self.world, first, nlocal,
+            model._spec))
+        self._h = h
+        if not local:
+            nb = int(L.somax_b200_swms_export_bytes())
+            mine = (C.c_ubyte * nb)()
+            _lib.check(L.somax_b200_swms_export(self._h, mine))
+            raw = gather_blobs(bytes(mine), self.world)
+            buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+            _lib.check(L.somax_b200_swms_attach(self._h, buf))
+
+    def window(self):
+        return slab_window(self.ny, self.rank, self.world)
+
+    def _steps(self, hs, us, vs, n_steps, dt, dt_last):
+        import ctypes as C
+
+        from . import _lib
+        from .core import stream_ptr
+        p = self.model._pstruct()
+        arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
+        _lib.check(_lib.lib().somax_b200_swms_steps(self._h, arr(hs), arr(us), arr(vs), int(n_steps), float(dt),
+                                                    float(dt_last), C.byref(p), stream_ptr()))
+
+    def check_peers(self):
+        """Synchronise and raise if a barrier gave up waiting for a peer."""
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+        torch.cuda.current_stream().synchronize()
+        n = C.c_int(0)
+        _lib.check(_lib.lib().somax_b200_swms_status(self._h, C.byref(n)))
+        if n.value:
+            raise _lib.SomaxB200Error(f"slab group: {n.value} barrier(s) timed out waiting for a peer")
+
+    def integrate(self, state0, t0, t1, dt):
+        """local=True: Tsit5-advance the global (h, u, v) arrays from t0 to t1; returns a state of
+        the same class (numpy in -> numpy out)."""
+        import numpy as np
+        import torch
+
+        from .core import step_plan, torch_dtype
+        if not self.local:
+            raise RuntimeError("integrate() takes the global arrays: use local=True, or integrate_slab()")
+        n, rem = step_plan(t0, t1, dt)
+        was_numpy = not isinstance(state0.h, torch.Tensor)
+        single = np.ndim(state0.h) == 2
+        parts = []
+        for f in ("h", "u", "v"):
+            a = getattr(state0, f)
+            t = torch.as_tensor(np.asarray(a) if was_numpy else a).to("cuda", dtype=torch_dtype(self.dtype))
+            if single:
+                t = t[None]
+            parts.append([s.contiguous().clone() for s in split_slabs(t, self.world)])
+        self._steps(parts[0], parts[1], parts[2], n, dt, rem)
+        self.check_peers()
+        outs = []
+        for p in parts:
+            o = merge_slabs(p)
+            if single:
+                o = o[0]
+            outs.append(o.cpu().numpy() if was_numpy else o)
+        return type(state0)(h=outs[0], u=outs[1], v=outs[2])
+
+    def advance_slab(self, h, u, v, n_steps, dt, dt_last=0.0, check=True):
+        """One process per GPU: advance this rank's windows (contiguous CUDA tensors
+        (nl, ny/world + 2, Nx), halo rows valid) in place.  Collective over the slab group."""
+        if self.local:
+            raise RuntimeError("advance_slab() is for one-slab-per-process groups")
+        for t in (h, u, v):
+            if not (t.is_cuda and t.is_contiguous()):
+                raise ValueError("slabs must be contiguous CUDA tensors")
+        self._steps([h], [u], [v], n_steps, dt, dt_last)
+        if check:
+            self.check_peers()
+
+    def integrate_slab(self, h, u, v, t0, t1, dt, check=True):
+        from .core import step_plan
+        n, rem = step_plan(t0, t1, dt)
+        self.advance_slab(h, u, v, n, dt, rem, check=check)
+        return h, u, v
+
+    def close(self):
+        from . import _lib
+        if getattr(self, "_h", None) is not None:
+            _lib.lib().somax_b200_swms_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,169 @@
+"""GPU: the y-slab decomposition of ONE shallow-water grid (halo exchange only) against the
+single-GPU path and the CPU oracle.
+
+* all slabs in one process on one device (`local=True`): same kernels, same exchange tables;
+* one process per GPU over CUDA IPC + flag barriers (needs >= 2 GPUs: `gpurun --gpus 2`).
+
+Every owned cell is computed by the same kernel from the same operands as on one GPU (the slab
+kernels are told which of their first / last rows are physical), so the comparison with the
+single-GPU result is bit-exact in fp64; in fp32 the edge / interior instantiations of the fast
+kernel differ in FMA contraction by an ulp where a slab boundary moves a CTA between them.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ARGS = dict(Lx=1e6, Ly=1e6, f0=1e-4, beta=1.6e-11, n_layers=2, H=(500.0, 4500.0), g_prime=(9.81, 0.025),
+            lateral_viscosity=100.0, bottom_drag=1e-7, wind_amplitude=1e-6)
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def swm_state(nx, ny, dtype):
+    from oracle.testcases import baroclinic_instability_swm
+    _, (h, u, v) = baroclinic_instability_swm(nx=nx, ny=ny, dtype=np.float64)
+    rng = np.random.default_rng(5)          # noise everywhere, ghost ring included: BCs are applied per slab
+    h = h + 0.5 * rng.standard_normal(h.shape)
+    u = u + 0.05 * rng.standard_normal(u.shape)
+    v = v + 0.05 * rng.standard_normal(v.shape)
+    return h.astype(dtype), u.astype(dtype), v.astype(dtype)
+
+
+def assert_same(got, one, dtype):
+    for f in "huv":
+        a, b = getattr(got, f), getattr(one, f)
+        if np.dtype(dtype) == np.float64:
+            assert np.array_equal(a, b), (f, rel(a, b))
+        else:
+            assert rel(a, b) <= 2e-6, (f, rel(a, b))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("bc", ["periodic", "wall"])
+@pytest.mark.parametrize("nx,ny,world,steps", [(64, 48, 2, 3), (130, 96, 4, 3), (256, 256, 8, 12), (32, 24, 1, 2)])
+def test_local_slabs_match_single_gpu_and_oracle(nx, ny, world, steps, bc, dtype):
+    import somax_b200 as sb
+    from oracle import swm as oswm
+    from somax_b200.parallel import SlabSWM
+    gm = sb.MultilayerShallowWater2D.create(nx=nx, ny=ny, bc=bc, dtype=np.dtype(dtype).name, **ARGS)
+    h, u, v = swm_state(nx, ny, dtype)
+    st = sb.MultilayerSW2DState(h=h, u=u, v=v)
+    dt = 20.0 * 64 / max(nx, 64)
+    t1 = steps * dt + 0.37 * dt               # a clipped last step as well
+    sol = gm.integrate(st, 0.0, t1, dt).ys
+    one = sb.MultilayerSW2DState(h=sol.h[0], u=sol.u[0], v=sol.v[0])
+    sl = SlabSWM(gm, world, local=True)
+    got = sl.integrate(st, 0.0, t1, dt)
+    sl.close()
+    assert got.h.shape == one.h.shape and got.h.dtype == one.h.dtype
+    assert_same(got, one, dtype)
+    if dtype == np.float64:
+        ref = oswm.create_multilayer(nx=nx, ny=ny, bc=bc, **ARGS).integrate(h, u, v, 0.0, t1, dt)
+        for f, r in zip("huv", ref):
+            assert rel(getattr(got, f), r) <= 1e-12, f
+
+
+def test_local_slabs_single_layer_and_chained_calls():
+    """NonlinearShallowWater2D (nl = 1); the windows come back with valid halo rows, so a second
+    call continues from them."""
+    import torch
+    import somax_b200 as sb
+    from somax_b200.parallel import SlabSWM, merge_slabs, split_slabs
+    gm, st = sb.gfd_testcases.barotropic_jet_instability(nx=64, ny=64, dtype="float64")
+    sl = SlabSWM(gm, 4, local=True)
+    parts = [[s.contiguous().clone() for s in split_slabs(torch.as_tensor(getattr(st, f))[None].cuda(), 4)] for f in "huv"]
+    sl._steps(parts[0], parts[1], parts[2], 3, 20.0, 0.0)
+    sl.check_peers()
+    for p in parts:       # halo rows agree with the neighbours' owned rows
+        assert torch.equal(p[0][:, -1], p[1][:, 1]) and torch.equal(p[1][:, 0], p[0][:, -2])
+        assert torch.equal(p[2][:, -1], p[3][:, 1]) and torch.equal(p[3][:, 0], p[2][:, -2])
+    sl._steps(parts[0], parts[1], parts[2], 3, 20.0, 0.0)
+    sl.check_peers()
+    got = [merge_slabs(p)[0].cpu().numpy() for p in parts]
+    sl.close()
+    mid = gm.integrate(st, 0.0, 60.0, 20.0).ys
+    two = gm.integrate(type(st)(h=mid.h[0], u=mid.u[0], v=mid.v[0]), 0.0, 60.0, 20.0).ys
+    # whole arrays: the physical ghost rows of the periodic basin drift exactly as on one device
+    for a, f in zip(got, "huv"):
+        assert np.array_equal(a, getattr(two, f)[0]), f
+
+
+def test_slab_create_rejects_bad_shapes():
+    import somax_b200 as sb
+    from somax_b200._lib import SomaxB200Error
+    from somax_b200.parallel import SlabSWM
+    gm = sb.MultilayerShallowWater2D.create(nx=64, ny=63, **ARGS)
+    with pytest.raises((SomaxB200Error, ValueError)):
+        SlabSWM(gm, 2, local=True)
+
+
+def _mp_worker(rank, world, port, nx, ny, steps, dtype_name, bc, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import somax_b200 as sb
+    from somax_b200.parallel import SlabSWM, slab_owned, slab_window
+    dtype = np.dtype(dtype_name)
+    gm = sb.MultilayerShallowWater2D.create(nx=nx, ny=ny, bc=bc, dtype=dtype_name, **ARGS)
+    h, u, v = swm_state(nx, ny, dtype.type)
+    dt = 20.0 * 64 / max(nx, 64)
+    sl = SlabSWM(gm, world)
+    w = slab_window(ny, rank, world)
+    win = [torch.as_tensor(a[:, w, :]).cuda().contiguous() for a in (h, u, v)]
+    sl.integrate_slab(*win, 0.0, steps * dt, dt)
+    own = slab_owned(ny, rank, world)
+    q.put((rank, own.start, own.stop, [t[:, own.start - w.start:own.stop - w.start].cpu().numpy() for t in win]))
+    dist.barrier()
+    sl.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bc", ["periodic", "wall"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_multi_process_slabs_match_single_gpu(dtype, bc):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = 4 if world >= 4 else 2
+    import somax_b200 as sb
+    nx, ny, steps = 256, 192, 6
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_mp_worker, args=(r, world, port, nx, ny, steps, np.dtype(dtype).name, bc, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = sorted((out.get(timeout=300) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    gm = sb.MultilayerShallowWater2D.create(nx=nx, ny=ny, bc=bc, dtype=np.dtype(dtype).name, **ARGS)
+    h, u, v = swm_state(nx, ny, dtype)
+    dt = 20.0 * 64 / max(nx, 64)
+    one = gm.integrate(sb.MultilayerSW2DState(h=h, u=u, v=v), 0.0, steps * dt, dt).ys
+    for fi, f in enumerate("huv"):
+        ref = getattr(one, f)[0]
+        got = np.empty_like(ref)
+        for _, lo, hi, arrs in parts:
+            got[:, lo:hi] = arrs[fi]
+        if np.dtype(dtype) == np.float64:
+            assert np.array_equal(got, ref), (f, rel(got, ref))
+        else:
+            assert rel(got, ref) <= 2e-6, f
