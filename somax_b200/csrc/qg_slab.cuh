@@ -114,12 +114,12 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
       for (int w = 0; w < 3; ++w)
         xb.push_back(Seg{(const char*)vr.bext + ((size_t)pl * 3 + w) * myrows * es,
                          bextr + (((size_t)pl * 3 + w) * NyS + my0) * es, 1u, (unsigned)(myrows * es), 0, 0});
-      // X2: border partial sums (even / odd columns) of my strips -> every other rank
-      if (r != p)
-        for (int par = 0; par < 2; ++par) {
-          const size_t o = (((size_t)pl * 2 + par) * 2 * nstrip + 2 * (size_t)R.s0) * NyS * es;
-          x2.push_back(Seg{(char*)vc.part + o, partr + o, 1u, (unsigned)(2 * (size_t)spr * NyS * es), 0, 0});
-        }
+      // X2: the pre-summed border partials of my strips (my slot of pvec: planes x 2 vectors) -> every
+      // other rank
+      if (r != p && pl == 0) {
+        const size_t o = (size_t)p * planes * 2 * NyS * sizeof(double);
+        x2.push_back(Seg{(const char*)vc.pvec + o, partr + o, 1u, (unsigned)((size_t)planes * 2 * NyS * sizeof(double)), 0, 0});
+      }
       // XG1 / XG2: my slice of ghat (3 columns), then of gvec (2 combinations; + float copy, + border
       // column nx of S for the rank that owns the last strip) -> every other rank
       if (r != p) {
@@ -183,7 +183,7 @@ int qgs_build_tables(somax_b200_qgs_s* g, SlabRank& R) {
 
 void qgs_local_ptrs(const SlabRank& R, void** out) {
   const QgSolverView vr = qg_solver_view(R.core->solver), vc = qg_solver_view(R.cols);
-  out[0] = vc.S; out[1] = vc.part; out[2] = vr.S; out[3] = R.core->psi; out[4] = R.inbox; out[5] = R.flags;
+  out[0] = vc.S; out[1] = vc.pvec; out[2] = vr.S; out[3] = R.core->psi; out[4] = R.inbox; out[5] = R.flags;
   out[6] = vc.ghat; out[7] = vc.gvec; out[8] = vc.gvecf ? (void*)vc.gvecf : (void*)vc.gvec; out[9] = vc.bext;
 }
 
@@ -227,6 +227,8 @@ int qgs_eval(somax_b200_qgs_s* g, const somax_b200_params* p, int in_b, int y_b,
     if (int rc = seg_launch("slab_halo_in", R.xin[in_b], s)) return rc;
     if (int rc = qg_solver_cols<T>(R.cols, 1, R.s0, R.s1, s)) return rc;
   }
+  for (SlabRank& R : g->local)
+    if (int rc = qg_solver_border_stage<T>(R.cols, -1, 0, -1, s)) return rc;
   for (SlabRank& R : g->local)
     if (int rc = seg_launch("slab_x2_partials", R.x2, s)) return rc;
   if (int rc = qgs_barrier(g, s)) return rc;
@@ -379,6 +381,8 @@ int somax_b200_qgs_create(somax_b200_qgs_t* out, int dtype, int nl, int ny, int 
     if (rc) break;
     R.core->bc_ylo = R.rank == 0; R.core->bc_yhi = R.rank == nranks - 1;
     rc = qg_solver_create(&R.cols, dtype, 1, nl, ny, nx, dx, dy, Cl2m, Cm2l, lambdas, SOMAX_B200_SOLVER_FFT, g->nseg);
+    if (rc) break;
+    rc = qg_solver_set_rank_reduce(R.cols, nranks, R.rank, R.s0, R.s1);
     if (rc) break;
     const size_t ib = 2 * (size_t)nl * R.core->L.pitch * es;
     if (cudaMalloc(&R.inbox, ib) != cudaSuccess || cudaMemset(R.inbox, 0, ib) != cudaSuccess ||

@@ -52,12 +52,16 @@ struct QgSolver {
   double* ctab = nullptr; long long* coff = nullptr; int* krow = nullptr; double* cinf = nullptr;
   int kbad[QG_MAX_NL] = {0, 0, 0, 0}; int KB = 0, KBs = 2; double* dbad = nullptr; double* dbad1 = nullptr; double* meet1 = nullptr; void* part = nullptr;
   double* bsig = nullptr; void* sig2n = nullptr; double* minv = nullptr; double* sintab = nullptr;
+  double* zpart = nullptr; unsigned* zcount = nullptr;   // border_dst: partial sums of term-split CTAs
   void* bext = nullptr;                             // [plane][3][ny]: border columns 0, nx+1 and (raw, forward only) nx
   // slab-distributed model: the row stage stores its spectral rows straight into the column arrays
   // of the ranks that own the strips (scatter), the last sweep stores its tiles straight into the
   // row arrays of the ranks that own the rows (push) - peer memory over NVLink, no transpose kernels
   void* sc_peer[16] = {nullptr}; int sc_lgspr = -1, sc_row0 = 0, sc_ny = 0;
   void* ps_peer[16] = {nullptr}; int ps_row0[17] = {0}; int ps_n = 0;
+  // slab-distributed model: the border partial sums of a rank's strips are pre-summed on the rank
+  // (pvec[rank][plane][2][ny], fp64) and only those vectors are exchanged
+  double* pvec = nullptr; int pv_n = 0, pv_me = 0, pv_s0 = 0, pv_s1 = 0;
   double* rvec = nullptr; double* ghat = nullptr; double* gvec = nullptr; float* gvecf = nullptr; double* meet = nullptr; double* meetc = nullptr;
   void* tw = nullptr; void* twc = nullptr; void* twb = nullptr; void* dstmat = nullptr;
   FftPlan plan;
@@ -67,6 +71,7 @@ struct QgSolver {
   bool seg_plain = true;                            // false: only the LOWK class is segmented
   double* segbuf = nullptr; double* segprod = nullptr;
   float* ckpt = nullptr; int nck = 0;               // E checkpoints of the PLAIN fp32 strips (ThomasTab)
+  int* vwarm = nullptr; int vwarm_max = 0;
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t bytes = 0;
@@ -601,6 +606,7 @@ struct ThomasTab {
   // tabulated coefficients).  ckpt: [plane][strip][half][nck][64] floats, block m covers the
   // elimination rows [cnt - (m+1) 16, cnt - m 16) of the half and holds the value before its first.
   float* ckpt; int nck;
+  const int* vwarm;          // [mode][strip] warm-up rows of a thomas_vec_ckpt segment (multiple of TH_RT)
   // Push (slab-distributed model, KIND 2 only): the finished tiles go straight into the row arrays
   // of the ranks that own the rows - rank r holds rows [prow[r], prow[r+1]) as
   // [plane][strip][prow[r+1] - prow[r]][64] at ppeer[r] (peer memory over NVLink) - instead of `out`.
@@ -1123,39 +1129,56 @@ thomas_sweep(ThomasTab tb, int strip_first, const T* __restrict__ in, const T* _
 }
 
 // Elimination of the border right-hand side of the second solve on the PLAIN fp32 strips, WITHOUT
-// storing it: every column runs d_i = (dy^2 g_i - d_{i-1}) c_i over its half (g = gvecf[c & 1], the
-// whole half staged in shared memory) and keeps d_{i-1} whenever (cnt - i) is a multiple of TH_RT -
-// the value the KIND 2 substitution needs to recompute its block of E - plus the last value for the
-// meeting-point solve.  No array transfer at all (the stored version wrote and re-read one).
+// storing it: every column runs d_i = (dy^2 g_i - d_{i-1}) c_i over its half (g = gvecf[c & 1], staged
+// in shared memory) and keeps d_{i-1} whenever (cnt - i) is a multiple of TH_RT - the value the
+// KIND 2 substitution needs to recompute its block of E - plus the last value for the meeting-point
+// solve.  No array transfer at all (the stored version wrote and re-read one).
+//
+// The half is cut into VC_NSEG segments run by different CTAs.  The recurrence forgets its start
+// like |c|^rows and the PLAIN strips have |c| <= ~0.9, so a segment starts from zero `warm` rows
+// early (warm = rows until |c_max|^rows < 1e-13, per strip, tabulated on the host; a segment whose
+// warm-up reaches the start of the half starts there, exactly): what is left of the wrong start is far
+// below fp32 rounding, and the serial chain is VC_NSEG times shorter (it sits on the critical path
+// of the slab-distributed model: 0.066 ms per evaluation at 8192^2 on 8 GPUs, unsegmented).
+constexpr int VC_NSEG = 8;
+
 __global__ void __launch_bounds__(TH_COLS)
-thomas_vec_ckpt(ThomasTab tb, int strip_first, const float* __restrict__ gvecf) {
-  extern __shared__ float gsh[];                 // [2][cnt] rows of this half, in elimination order
+thomas_vec_ckpt(ThomasTab tb, int strip_first, const float* __restrict__ gvecf, int nseg) {
+  extern __shared__ float gsh[];                 // [2][rows of this segment incl. warm-up], elimination order
   const int tid = threadIdx.x, strip = strip_first + blockIdx.x, c = strip * TH_COLS + tid;
-  const int plane = blockIdx.y, m = plane % tb.nl, half = blockIdx.z, ny = tb.ny;
+  const int plane = blockIdx.y, m = plane % tb.nl, half = blockIdx.z & 1, seg = blockIdx.z >> 1, ny = tb.ny;
   const int m1 = ny / 2, cnt = half == 0 ? m1 : ny - m1;
   const int j0 = half == 0 ? 0 : ny - 1, dj = half == 0 ? 1 : -1;
+  // segment boundaries sit on the checkpoint grid: (cnt - sa) is a multiple of TH_RT; segment 0 also
+  // takes the ragged rows [0, cnt mod TH_RT)
+  const int r0 = cnt % TH_RT, nblk = (cnt - r0) / TH_RT;
+  const int sa = seg == 0 ? 0 : r0 + TH_RT * (int)((long long)seg * nblk / nseg);
+  const int sb = r0 + TH_RT * (int)((long long)(seg + 1) * nblk / nseg);
+  if (sb <= sa) return;
+  const int warm = tb.vwarm[m * tb.nstrip + strip];
+  const int i0 = (seg == 0 || sa - warm <= r0) ? 0 : sa - warm;      // warm is a multiple of TH_RT
+  const int nrow = sb - i0;
   const float* g = gvecf + (size_t)plane * 2 * ny;
-  for (int i = tid; i < cnt; i += TH_COLS) {
-    gsh[i] = g[j0 + dj * i];
-    gsh[cnt + i] = g[ny + j0 + dj * i];
+  for (int i = tid; i < nrow; i += TH_COLS) {
+    gsh[i] = g[j0 + dj * (i0 + i)];
+    gsh[nrow + i] = g[ny + j0 + dj * (i0 + i)];
   }
   __syncthreads();
-  const float* gs = gsh + (c & 1) * cnt;
+  const float* gs = gsh + (c & 1) * nrow - i0;     // indexed by the elimination row
   const double cfix = tb.cinf[(size_t)m * tb.np + c];
   const float cfix_f = (float)cfix, kfix_f = (float)(cfix * tb.dy2), dy2_f = (float)tb.dy2;
   const int Js = tb.Jstrip[m * tb.nstrip + strip];
   const float (*Ct)[TH_COLS] = reinterpret_cast<const float (*)[TH_COLS]>(tb.ctabB + tb.tabOff[m * tb.nstrip + strip]);
   float* ck = tb.ckpt + ((size_t)(plane * tb.nstrip + strip) * 2 + half) * tb.nck * TH_COLS + tid;
   float carry = 0.f;
-  int i = 0;
-  // the ragged block first (rows [0, cnt mod TH_RT)), then whole blocks with a checkpoint before each
-  const int r0 = cnt % TH_RT;
-  for (; i < r0; ++i) {
-    const float cj = i < Js ? Ct[i][tid] : cfix_f;
-    carry = fmaf(-cj, carry, (i < Js ? cj * dy2_f : kfix_f) * gs[i]);
-  }
-  for (; i < cnt; i += TH_RT) {
-    ck[(size_t)((cnt - i) / TH_RT - 1) * TH_COLS] = carry;
+  int i = i0;
+  if (i0 == 0)
+    for (; i < r0; ++i) {      // the ragged block first
+      const float cj = i < Js ? Ct[i][tid] : cfix_f;
+      carry = fmaf(-cj, carry, (i < Js ? cj * dy2_f : kfix_f) * gs[i]);
+    }
+  for (; i < sb; i += TH_RT) {
+    if (i >= sa) ck[(size_t)((cnt - i) / TH_RT - 1) * TH_COLS] = carry;      // (not during the warm-up)
     float gg[TH_RT];
 #pragma unroll
     for (int r = 0; r < TH_RT; ++r) gg[r] = gs[i + r];
@@ -1171,7 +1194,7 @@ thomas_vec_ckpt(ThomasTab tb, int strip_first, const float* __restrict__ gvecf) 
       }
     }
   }
-  if (c < tb.np) tb.meet1[((size_t)plane * 2 + half) * tb.np + c] = (double)carry;
+  if (sb == cnt && c < tb.np) tb.meet1[((size_t)plane * 2 + half) * tb.np + c] = (double)carry;
 }
 
 // Right-hand sides of the border (Schur) system.  rvec / ghat are interleaved so that one 128-bit
@@ -1207,6 +1230,48 @@ border_reduce(const T* __restrict__ S, const T* __restrict__ bext, const T* __re
   ev = 0; od = 0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) { ev += red[0][q][jx]; od += red[1][q][jx]; }
+  const int bm = plane / nl, l = plane - bm * nl;
+  double* rp = r + ((size_t)bm * ny + j) * border_nvp(nl) + 3 * l;
+  rp[0] = (double)bext[((size_t)plane * 3 + 0) * ny + j] - b * (ev + od);
+  rp[1] = (double)bext[((size_t)plane * 3 + 2) * ny + j] - b * (ev - od);
+  rp[2] = (double)bext[((size_t)plane * 3 + 1) * ny + j];
+}
+
+// Slab-distributed model: the per-warp partials of the strips [s0, s1) a rank owns, summed per
+// (plane, parity, row) into the rank's slot of pvec (fixed order), so that 2 * planes vectors leave
+// the rank instead of 4 * (s1 - s0) * planes; border_reduce_ranks then adds the ranks' vectors in rank
+// order.  (All partials to every rank: 44 MB per rank and evaluation at 8192^2 on 8 GPUs.)
+template <typename T>
+__global__ void __launch_bounds__(256)
+border_presum(const T* __restrict__ part, int ny, int npart, int p0, int p1, double* __restrict__ pv) {
+  __shared__ double red[8][32];
+  const int jx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jx, pp = blockIdx.y;            // pp = plane * 2 + parity
+  double acc = 0;
+  if (j < ny) {
+    const T* src = part + (size_t)pp * npart * ny + j;
+    for (int p = p0 + py; p < p1; p += 8) acc += (double)src[(size_t)p * ny];
+  }
+  red[py][jx] = acc;
+  __syncthreads();
+  if (py != 0 || j >= ny) return;
+  acc = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc += red[q][jx];
+  pv[(size_t)pp * ny + j] = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+border_reduce_ranks(const T* __restrict__ bext, const double* __restrict__ pvec, int nranks, int planes,
+                    int ny, int nl, double b, double* __restrict__ r) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, plane = blockIdx.y;
+  if (j >= ny) return;
+  double ev = 0, od = 0;
+  for (int q = 0; q < nranks; ++q) {
+    const double* pv = pvec + ((size_t)q * planes + plane) * 2 * ny + j;
+    ev += pv[0]; od += pv[ny];
+  }
   const int bm = plane / nl, l = plane - bm * nl;
   double* rp = r + ((size_t)bm * ny + j) * border_nvp(nl) + 3 * l;
   rp[0] = (double)bext[((size_t)plane * 3 + 0) * ny + j] - b * (ev + od);
@@ -1259,14 +1324,20 @@ constexpr int GS_OUT = 32, GS_SL = 8;
 constexpr int GS_U = 8;                  // terms per slice and chunk
 constexpr int GS_CH = GS_SL * GS_U;      // rows of the input per staged chunk
 constexpr int GS_NS = 3;                 // ring depth
+constexpr int GS_ZMAX = 8;               // at most this many term-split CTAs per output block
 
 template <typename T, int NL, bool STAGE_A>
 __global__ void __launch_bounds__(GS_OUT * GS_SL)
 border_dst(const double* __restrict__ in, const double* __restrict__ sintab,
            const double* __restrict__ minv, int ny, int np, int n,
            double* __restrict__ out, double* __restrict__ gvec, float* __restrict__ gvecf,
-           T* __restrict__ S, T* __restrict__ bext, int a_first, int a_count) {
+           T* __restrict__ S, T* __restrict__ bext, int a_first, int a_count,
+           double* __restrict__ zpart, unsigned* __restrict__ zcount) {
   constexpr int NV = 3 * NL, NVP = (NV + 1) & ~1;
+  // gridDim.z > 1: the terms are split over gridDim.z CTAs per output block (few output blocks - a
+  // rank of the slab model computes a slice of the outputs - would leave most SMs idle and every
+  // CTA with the full-length chain); partial sums meet in `zpart`, the CTA that arrives last adds
+  // them in z order (deterministic) and runs the epilogue.
   // Input rows t-1 (lo) and N-t-1 (hi) of a chunk of terms are two contiguous blocks of the
   // interleaved array: one cp.async.bulk each into a GS_NS-stage ring, completion on an mbarrier
   // (first version: per-term global loads, every one an L2 round trip with no memory-level
@@ -1282,20 +1353,23 @@ border_dst(const double* __restrict__ in, const double* __restrict__ sintab,
   const unsigned N = ny + 1, N2 = 2 * N;
   const double* costab = sintab + N2;
   const unsigned aa = valid ? (unsigned)a : 1u;
-  const unsigned k0 = (unsigned)(((unsigned long long)aa * (unsigned)(sl + 1)) % N2), kd = (aa * (unsigned)GS_SL) % N2;
+  const double* x = in + (size_t)bm * ny * NVP;
+  const int half = (N - 1) / 2;                       // terms t = 1..half (folded)
+  const int nchunk_all = (half + GS_CH - 1) / GS_CH;
+  const int nz = gridDim.z, z = blockIdx.z;
+  const int ch_first = (int)((long long)z * nchunk_all / nz), nchunk = (int)((long long)(z + 1) * nchunk_all / nz);
+  const unsigned k0 = (unsigned)(((unsigned long long)aa * (unsigned)(ch_first * GS_CH + sl + 1)) % N2);
+  const unsigned kd = (aa * (unsigned)GS_SL) % N2;
   double s = sintab[k0], c = costab[k0];
   const double ds = sintab[kd], dc = costab[kd];
   const double sgn = (aa & 1) ? 1.0 : -1.0;
   double acc[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-  const double* x = in + (size_t)bm * ny * NVP;
-  const int half = (N - 1) / 2;                       // terms t = 1..half (folded)
-  const int nchunk = (half + GS_CH - 1) / GS_CH;
   auto chunk_rows = [&](int ch) { return min(GS_CH, half - ch * GS_CH); };
   auto load_chunk = [&](int ch) {                     // thread 0 only
     if (ch >= nchunk) return;
-    const int st = ch % GS_NS, nr = chunk_rows(ch), t0 = ch * GS_CH + 1;
+    const int st = (ch - ch_first) % GS_NS, nr = chunk_rows(ch), t0 = ch * GS_CH + 1;
     const unsigned bytes = (unsigned)(nr * NVP * sizeof(double));
     mbar_arrive_expect_tx(&full[st], 2 * bytes);
     bulk_g2s(&tile[st][0][0][0], x + (size_t)(t0 - 1) * NVP, bytes, &full[st]);
@@ -1304,13 +1378,13 @@ border_dst(const double* __restrict__ in, const double* __restrict__ sintab,
   if (threadIdx.x == 0) {
     for (int q = 0; q < GS_NS; ++q) mbar_init(&full[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    for (int ch = 0; ch < GS_NS - 1; ++ch) load_chunk(ch);
+    for (int ch = ch_first; ch < ch_first + GS_NS - 1; ++ch) load_chunk(ch);
   }
   __syncthreads();
-  for (int ch = 0; ch < nchunk; ++ch) {
-    const int st = ch % GS_NS, nr = chunk_rows(ch);
+  for (int ch = ch_first; ch < nchunk; ++ch) {
+    const int st = (ch - ch_first) % GS_NS, nr = chunk_rows(ch);
     if (threadIdx.x == 0) load_chunk(ch + GS_NS - 1);     // its stage was released by the barrier below
-    mbar_wait(&full[st], (unsigned)((ch / GS_NS) & 1));
+    mbar_wait(&full[st], (unsigned)(((ch - ch_first) / GS_NS) & 1));
     // slice sl takes the rows r = sl, sl + GS_SL, ... of the chunk (terms t = ch GS_CH + 1 + r)
 #pragma unroll 4
     for (int r = sl; r < nr; r += GS_SL) {
@@ -1327,7 +1401,7 @@ border_dst(const double* __restrict__ in, const double* __restrict__ sintab,
     }
     __syncthreads();      // everyone is done with stage st: it may be refilled
   }
-  if ((N & 1) == 0 && sl == 0) {
+  if ((N & 1) == 0 && sl == 0 && z == 0) {
     const double sm = sintab[(unsigned)(((unsigned long long)aa * (N / 2)) % N2)];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = fma(sm, x[(size_t)(N / 2 - 1) * NVP + v], acc[v]);
@@ -1336,8 +1410,8 @@ border_dst(const double* __restrict__ in, const double* __restrict__ sintab,
   for (int v = 0; v < NV; ++v) red[sl][v][lane] = acc[v];
   __syncthreads();
   // layer l of output `lane` is finished by thread (l, lane)
-  if (sl < NL && valid) {
-    double t3[3];
+  double t3[3] = {0.0, 0.0, 0.0};
+  if (sl < NL) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       double sum = 0;
@@ -1345,8 +1419,34 @@ border_dst(const double* __restrict__ in, const double* __restrict__ sintab,
       for (int q = 0; q < GS_SL; ++q) sum += red[q][3 * sl + i][lane];
       t3[i] = sum;
     }
-    border_store<T, STAGE_A>(t3[0], t3[1], t3[2], a, bm, sl, NL, minv, ny, np, n, out, gvec, gvecf, S, bext);
   }
+  if (nz > 1) {
+    __shared__ unsigned last_flag;
+    const size_t blk = (size_t)bm * gridDim.x + blockIdx.x;
+    double* zp = zpart + blk * nz * (NV * GS_OUT);
+    if (sl < NL) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) zp[(size_t)z * (NV * GS_OUT) + (3 * sl + i) * GS_OUT + lane] = t3[i];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_flag = (atomicAdd(&zcount[blk], 1u) == (unsigned)(nz - 1));
+    __syncthreads();
+    if (!last_flag) return;
+    __threadfence();
+    if (threadIdx.x == 0) zcount[blk] = 0u;      // ready for the next launch
+    if (sl < NL) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double sum = 0;
+        for (int q = 0; q < nz; ++q)
+          sum += reinterpret_cast<volatile double*>(zp)[(size_t)q * (NV * GS_OUT) + (3 * sl + i) * GS_OUT + lane];
+        t3[i] = sum;
+      }
+    }
+  }
+  if (sl < NL && valid)
+    border_store<T, STAGE_A>(t3[0], t3[1], t3[2], a, bm, sl, NL, minv, ny, np, n, out, gvec, gvecf, S, bext);
 }
 
 // Same transform for short columns (ny <= GS_SMALL_NY, ensembles of small grids): one THREAD per
@@ -1505,6 +1605,30 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
   if (ctab.empty()) ctab.push_back(0.0);
   if (int rc = dev_upload(ctab.data(), ctab.size() * 8, (void**)&s->ctab, &s->bytes)) return rc;
   if (int rc = dev_upload(Jstrip.data(), Jstrip.size() * 4, (void**)&s->krow, &s->bytes)) return rc;
+  {
+    // warm-up rows of a thomas_vec_ckpt segment: |c_max|^rows < 1e-13 over the strip's columns
+    // (indefinite / near-singular columns never decay: their strips are LOWK and not run by it)
+    std::vector<int> vwarm((size_t)nl * nstrip, hcap);
+    s->vwarm_max = 0;
+    for (int m = 0; m < nl; ++m)
+      for (int st = 0; st < nstrip; ++st) {
+        double cmax = 0.0;
+        for (int cl = 0; cl < SP_W; ++cl) {
+          const int c = st * SP_W + cl;
+          if (c >= nc) continue;
+          const double ci = fabs(cinf[(size_t)m * np + c]);
+          cmax = std::max(cmax, ci > 0.0 ? ci : 1.0);
+        }
+        int w = hcap;
+        if (cmax > 0.0 && cmax < 1.0) {
+          const double rows = log(1e-13) / log(cmax) + Jstrip[(size_t)m * nstrip + st];
+          if (rows < (double)hcap) w = ((int)ceil(rows) + TH_RT - 1) / TH_RT * TH_RT;
+        }
+        vwarm[(size_t)m * nstrip + st] = w;
+        if (st >= 0) s->vwarm_max = std::max(s->vwarm_max, std::min(w, hcap));
+      }
+    if (int rc = dev_upload(vwarm.data(), vwarm.size() * 4, (void**)&s->vwarm, &s->bytes)) return rc;
+  }
   if (int rc = dev_upload(tabOff.data(), tabOff.size() * 8, (void**)&s->coff, &s->bytes)) return rc;
   if (int rc = dev_upload(cinf.data(), cinf.size() * 8, (void**)&s->cinf, &s->bytes)) return rc;
   if (int rc = dev_upload(meetc.data(), meetc.size() * 8, (void**)&s->meetc, &s->bytes)) return rc;
@@ -1649,6 +1773,14 @@ static int build_fft_tables(QgSolver* s, const double* lambdas) {
   SB_CUDA(cudaMemset(s->ghat, 0, rb));
   SB_CUDA(cudaMalloc((void**)&s->gvec, 2 * vb));
   SB_CUDA(cudaMalloc((void**)&s->gvecf, vb));
+  if (!(ny <= GS_SMALL_NY && (long)s->planes * ny >= 65536)) {      // the blocked border transform is in use
+    const size_t nblk = (size_t)s->batch * ((ny + GS_OUT - 1) / GS_OUT);
+    const size_t zb = nblk * GS_ZMAX * 12 * GS_OUT * sizeof(double);
+    SB_CUDA(cudaMalloc((void**)&s->zpart, zb));
+    SB_CUDA(cudaMalloc((void**)&s->zcount, nblk * sizeof(unsigned)));
+    SB_CUDA(cudaMemset(s->zcount, 0, nblk * sizeof(unsigned)));
+    s->bytes += zb + nblk * sizeof(unsigned);
+  }
   SB_CUDA(cudaMalloc(&s->bext, 3 * (size_t)s->planes * ny * sizeof(T)));
   SB_CUDA(cudaMemset(s->bext, 0, 3 * (size_t)s->planes * ny * sizeof(T)));
   s->bytes += 2 * rb + 3 * vb + 2 * (size_t)s->planes * ny * sizeof(T);
@@ -1743,7 +1875,7 @@ int qg_solver_create(QgSolver** out, int dtype, int batch, int nl, int ny, int n
 
 void qg_solver_destroy(QgSolver* s) {
   if (!s) return;
-  void* ptrs[] = {s->ckpt, s->segbuf, s->segprod, s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->dbad1, s->meet1, s->part, s->bsig, s->sig2n,
+  void* ptrs[] = {s->zpart, s->zcount, s->vwarm, s->pvec, s->ckpt, s->segbuf, s->segprod, s->S, s->W, s->ctab, s->coff, s->krow, s->cinf, s->dbad, s->dbad1, s->meet1, s->part, s->bsig, s->sig2n,
                   s->minv, s->bext, s->sintab, s->rvec, s->ghat, s->gvec, s->gvecf, s->tw, s->twc, s->twb, s->dstmat, s->meet, s->meetc};
   for (void* p : ptrs) cudaFree(p);
   if (s->aux) cudaStreamDestroy(s->aux);
@@ -1759,6 +1891,15 @@ void qg_solver_set_scatter(QgSolver* s, void* const* peerS, int nranks, int spr,
   int lg = 0;
   while ((1 << lg) < spr) ++lg;
   s->sc_lgspr = lg; s->sc_row0 = row0; s->sc_ny = ny_cols;
+}
+
+int qg_solver_set_rank_reduce(QgSolver* s, int nranks, int me, int s0, int s1) {
+  const size_t nb = (size_t)nranks * s->planes * 2 * s->ny * sizeof(double);
+  SB_CUDA(cudaMalloc((void**)&s->pvec, nb));
+  SB_CUDA(cudaMemset(s->pvec, 0, nb));
+  s->bytes += nb;
+  s->pv_n = nranks; s->pv_me = me; s->pv_s0 = s0; s->pv_s1 = s1;
+  return 0;
 }
 
 void qg_solver_set_push(QgSolver* s, void* const* peerR, int nranks, const int* row0) {
@@ -1847,10 +1988,11 @@ static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream
     // PLAIN fp32 strips: checkpoints of the eliminated border right-hand side, nothing stored
     if (npl > 0) {
       const int hcap = s->ny - s->ny / 2;
-      const size_t smem = (size_t)2 * hcap * sizeof(float);
+      const int vseg = hcap >= 1024 ? VC_NSEG : 1;
+      const size_t smem = (size_t)2 * hcap * sizeof(float);      // upper bound: a segment plus its warm-up
       if (int rc = ensure_dyn_smem((const void*)thomas_vec_ckpt, smem)) return rc;
       prof_begin(tf, pl);
-      thomas_vec_ckpt<<<dim3(npl, s->planes, 2), TH_COLS, smem, pl>>>(tb, pA, s->gvecf);
+      thomas_vec_ckpt<<<dim3(npl, s->planes, 2 * vseg), TH_COLS, smem, pl>>>(tb, pA, s->gvecf, vseg);
       SB_LAUNCH_CHECK();
     }
   } else {
@@ -1876,7 +2018,7 @@ static ThomasTab make_tab(const QgSolver* s) {
   tb.dy2 = s->dy * s->dy;
   tb.nseg = s->nseg; tb.seg_len = s->seg_len; tb.pass = 0; tb.segbuf = s->segbuf; tb.segprod = s->segprod;
   tb.seg_plain = s->seg_plain;
-  tb.ckpt = s->ckpt; tb.nck = s->nck;
+  tb.ckpt = s->ckpt; tb.nck = s->nck; tb.vwarm = s->vwarm;
   for (int r = 0; r < 16; ++r) tb.ppeer[r] = s->ps_peer[r];
   for (int r = 0; r < 17; ++r) tb.prow[r] = s->ps_row0[r];
   tb.pn = s->ps_n;
@@ -1930,6 +2072,23 @@ int qg_solver_border_stage(QgSolver* s, int stage, int a0, int a1, cudaStream_t 
   T* S = (T*)s->S;
   if (a1 < 0) a1 = ny;
   const int cnt = a1 - a0;
+  if (stage == -1) {      // slab model: pre-sum the partials of this rank's strips into its slot of pvec
+    if (!s->pvec) return fail(SOMAX_B200_ERR_INVALID, "rank reduction not configured");
+    prof_begin("border_presum", st);
+    border_presum<T><<<dim3((ny + 31) / 32, s->planes * 2), 256, 0, st>>>(
+        (const T*)s->part, ny, 2 * (np / SP_W), 2 * s->pv_s0, 2 * s->pv_s1,
+        s->pvec + (size_t)s->pv_me * s->planes * 2 * ny);
+    SB_LAUNCH_CHECK();
+    return 0;
+  }
+  if (stage == 0 && s->pvec) {
+    const double b = 1.0 / (s->dx * s->dx);
+    prof_begin("border_reduce", st);
+    border_reduce_ranks<T><<<dim3((ny + 255) / 256, s->planes), 256, 0, st>>>(
+        (const T*)s->bext, s->pvec, s->pv_n, s->planes, ny, nl, b, s->rvec);
+    SB_LAUNCH_CHECK();
+    return 0;
+  }
   if (stage == 0) {
     const double b = 1.0 / (s->dx * s->dx);
     prof_begin("border_reduce", st);
@@ -1948,10 +2107,15 @@ int qg_solver_border_stage(QgSolver* s, int stage, int a0, int a1, cudaStream_t 
     if (stage == 1) border_gsolve_small<T, true><<<g, 128, 0, st>>>(in, s->sintab, s->minv, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, nullptr, a0, cnt);
     else border_gsolve_small<T, false><<<g, 128, 0, st>>>(in, s->sintab, s->minv, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, (T*)s->bext, a0, cnt);
   } else {
-    const dim3 g((cnt + GS_OUT - 1) / GS_OUT, s->batch);
+    const int nblk = (cnt + GS_OUT - 1) / GS_OUT;
+    const int nchunk_all = ((ny + 1 - 1) / 2 + GS_CH - 1) / GS_CH;
+    // enough CTAs for two per SM: split the terms when there are few output blocks
+    int nz = (2 * 148 + nblk * s->batch - 1) / (nblk * s->batch);
+    nz = std::max(1, std::min(std::min(nz, GS_ZMAX), nchunk_all));
+    const dim3 g(nblk, s->batch, nz);
 #define SB_BDST(NLV)                                                                                         \
-    if (stage == 1) border_dst<T, NLV, true><<<g, GS_OUT * GS_SL, 0, st>>>(in, s->sintab, s->minv, ny, np, n, s->ghat, nullptr, nullptr, nullptr, nullptr, a0, cnt); \
-    else border_dst<T, NLV, false><<<g, GS_OUT * GS_SL, 0, st>>>(in, s->sintab, s->minv, ny, np, n, nullptr, s->gvec, s->gvecf, S, (T*)s->bext, a0, cnt)
+    if (stage == 1) border_dst<T, NLV, true><<<g, GS_OUT * GS_SL, 0, st>>>(in, s->sintab, s->minv, ny, np, n, s->ghat, nullptr, nullptr, nullptr, nullptr, a0, cnt, s->zpart, s->zcount); \
+    else border_dst<T, NLV, false><<<g, GS_OUT * GS_SL, 0, st>>>(in, s->sintab, s->minv, ny, np, n, nullptr, s->gvec, s->gvecf, S, (T*)s->bext, a0, cnt, s->zpart, s->zcount)
     switch (nl) {
       case 1: SB_BDST(1); break;
       case 2: SB_BDST(2); break;
@@ -2001,7 +2165,7 @@ int qg_solver_run(QgSolver* s, const T* q, T* psi, int ring_zero, int keep_ring,
 
 QgSolverView qg_solver_view(const QgSolver* s) {
   QgSolverView v;
-  v.S = s->S; v.part = s->part; v.bext = s->bext; v.ghat = s->ghat; v.gvec = s->gvec; v.gvecf = s->gvecf; v.ny = s->ny; v.nx = s->nx; v.np = s->np; v.planes = s->planes;
+  v.S = s->S; v.part = s->part; v.pvec = s->pvec; v.bext = s->bext; v.ghat = s->ghat; v.gvec = s->gvec; v.gvecf = s->gvecf; v.ny = s->ny; v.nx = s->nx; v.np = s->np; v.planes = s->planes;
   v.nstrip = s->np / SP_W; v.ncols = s->ncols; v.kind = s->kind; v.nheavy = s->nheavy;
   return v;
 }

@@ -32,6 +32,10 @@ size_t qg_solver_bytes(const QgSolver* s);
 // Pointers may be peer memory (CUDA IPC over NVLink); spr must be a power of two.
 void qg_solver_set_scatter(QgSolver* s, void* const* peerS, int nranks, int spr, int row0, int ny_cols);
 void qg_solver_set_push(QgSolver* s, void* const* peerR, int nranks, const int* row0);
+// rank reduce: border stage -1 pre-sums the partials of strips [s0, s1) into slot `me` of
+// pvec[nranks][planes][2][ny] (fp64); the slots of the other ranks arrive by exchange; border stage 0
+// then adds the slots in rank order instead of walking every strip's partials.
+int qg_solver_set_rank_reduce(QgSolver* s, int nranks, int me, int s0, int s1);
 int qg_solver_kind(const QgSolver* s);
 
 // psi = Cm2l . Helm^-1 . Cl2m . q on padded planes (batch, nl, Ny, pitch), every point of the
@@ -61,7 +65,7 @@ template <typename T> int qg_solver_border_stage(QgSolver* s, int stage, int a0,
 // solver rows), part is [plane][2][2 * nstrip][ny], bext is [plane][3][ny] (border columns 0, nx+1
 // and the raw column nx); ncols is the slot of border column nx in a row of S.
 struct QgSolverView {
-  void* S; void* part; void* bext;
+  void* S; void* part; double* pvec; void* bext;
   double* ghat; double* gvec; float* gvecf;   // border system: ghat [plane][3][ny], gvec / gvecf [plane][2][ny]
   int ny, nx, np, planes, nstrip, ncols, kind, nheavy;
 };
