@@ -18,10 +18,15 @@ and cannot be imported in this image (no jax/jaxlib wheels, no network):
 Their published algorithms are restated here and anchored
 on the reference's own call sites and property tests.
 
-PARITY UNPINNED: the reference holds no golden vectors for this path
- and cannot be executed here, so this oracle is pinned
-only by the reference's property / known-answer tests (ported in
-``tests/test_oracle_*.py``).  Every unverified operator choice is one field of
-``oracle.operators.OperatorSpec``; ``tools/capture_reference.py`` regenerates
-the golden fixtures from the real reference on a machine that has JAX.
+PINNED BY THE REFERENCE'S OWN PRINTED OUTPUTS: the reference holds no golden vectors for this path
+and cannot be executed here, but it ships EXECUTED tutorial notebooks whose stored cell outputs
+are numbers the real implementation printed (Poisson / Helmholtz errors and maxima to 6-7 digits,
+the extrema and corner values of a 56 031-step shallow-water spin-up, `eqx.filter_grad` values after
+1121 steps).  ``tools/extract_notebook_outputs.py`` copies them into
+``tests/golden/reference_notebook_outputs.json``; ``tests/test_oracle_reference_pins.py`` checks
+this oracle against them and shows that the other settings of ``oracle.operators.OperatorSpec`` do
+not reproduce them.  Still unpinned: ``Difference2D.grad_perp`` (oracle/reparam.py only) and the
+mode ordering of ``decompose_vertical_modes`` (mode matrices are inputs on both sides).
+``tools/capture_reference.py`` regenerates the ``.npz`` fixtures from the real reference on a machine
+that has JAX.
 """

@@ -1,6 +1,6 @@
 """Layer coupling matrix and vertical-mode transform (setup-time, host only).
 
-Test infrastructure only.  PARITY UNPINNED.
+Test infrastructure only.  UNPINNED (mode ordering / normalisation): the mode matrices are inputs on both sides.
 ref: somax/_src/core/transforms.py:172-224 (ModalTransform.from_physics, to_modal, to_layer);
 finitevolx.build_coupling_matrix / decompose_vertical_modes restated per SURVEY App. B.7
 (MQGeometry convention).

@@ -1,6 +1,7 @@
 """Multilayer / single-layer nonlinear shallow water (vector-invariant form).
 
-Test infrastructure only.  PARITY UNPINNED (see oracle/__init__.py).
+Test infrastructure only.  Operator conventions pinned by the reference's printed tutorial outputs
+(step17_shallow_water_2d.ipynb; tests/test_oracle_reference_pins.py; see oracle/__init__.py).
 ref: somax/_src/models/swm/multilayer.py:150-256,313-410; swm/nonlinear_2d.py:132-234.
 """
 from __future__ import annotations

@@ -96,8 +96,8 @@ def test_jax_ffi_shim_compiles_against_the_stub_header_and_covers_the_abi():
     assert sorted(handlers) == ["SomaxB200QgDiag", "SomaxB200QgInvert", "SomaxB200QgRhs", "SomaxB200QgSteps",
                                 "SomaxB200SwmDiag", "SomaxB200SwmRhs", "SomaxB200SwmSteps"]
     for sym in header_symbols():
-        if "_qgs_" in sym or sym.endswith(("_destroy", "_device_bytes", "_apply_bc", "_abi_version",
+        if "_qgs_" in sym or "_swms_" in sym or sym.endswith(("_destroy", "_device_bytes", "_apply_bc", "_abi_version",
                                            "_launch_count", "_set_projection", "_swm_project")) or "_profile_" in sym:
-            continue        # slab group and the reparameterized-QG projection: host wrapper only;
+            continue        # slab groups and the reparameterized-QG projection: host wrapper only;
                             # housekeeping; BC is applied inside *_rhs / *_steps
         assert sym + "(" in text, sym
