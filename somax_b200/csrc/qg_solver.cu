@@ -303,6 +303,12 @@ template <int LGN> struct BigCfg {
   static constexpr int P2 = n / R3 + 1;
   static constexpr int slen = (R3 * P2 > n + (n >> LG1) + 1) ? R3 * P2 : n + (n >> LG1) + 1;
   static constexpr int minblocks = LGN >= 14 ? 1 : 2;
+  // PAIR (n = 8192, 16384): every thread runs a pass-3 butterfly AND its mirror (frequencies k and
+  // n - k), so the real-odd split happens in registers and the results leave for global memory
+  // straight from there: the line is crossed 6 times per transform instead of 8 (the kernel is
+  // bound by shared-memory wavefronts).  Needs two butterflies per thread in
+  // pass 3 and R1 = 32 = one warp of pass-1 digits.
+  static constexpr bool PAIR = (B3 == 2) && (R1 == 32);
 };
 
 template <int LGN, bool INV>
@@ -416,11 +422,84 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
         for (int jj = 0; jj < LG2; ++jj) wp[jj] = tw2[jj * R3 + pos];
         fft_reg_twiddle<float, R2>(u[i], wp);
 #pragma unroll
-        for (int q = 0; q < R2; ++q) s[pos * P2 + b2 * R2 + q] = u[i][fft_reg_pos<R2>(q)];
+        for (int q = 0; q < R2; ++q)
+          s[pos * P2 + (Cfg::PAIR ? q * R1 + b2 : b2 * R2 + q)] = u[i][fft_reg_pos<R2>(q)];
       }
     }
     __syncthreads();
 
+    // destination of X_k (element p = k - 1 of the spectral row / field column k of the psi row)
+    auto store_out = [&](int k, float val) {
+      if (INV) out[(((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + k] = A.scale * val;
+      else *fwd_dst<float>(A, out, b * A.nl + a, j, k - 1) = val;
+    };
+    auto split_pair = [&](int k, const C& Ak, const C& Bk, const C& wk) {
+      const C E = {0.5f * (Ak.x + Bk.x), 0.5f * (Ak.y - Bk.y)};
+      const C O = {0.5f * (Ak.y + Bk.y), -0.5f * (Ak.x - Bk.x)};
+      const C wO = cmul(wk, O);
+      store_out(k, -0.5f * (E.y + wO.y));
+      store_out(n - k, 0.5f * (E.y - wO.y));
+    };
+    if constexpr (Cfg::PAIR) {
+      // ---- pass 3 on a butterfly (b3, q2) = (lane, warp) and its mirror (32 - lane, R2 - 1 - warp):
+      // outputs k = b3 + R1 (q2 + R2 q) and n - k = b3' + R1 (q2' + R2 (R3 - 1 - q)).  Pass 2 stored
+      // its output with b fastest, so both reads are conflict-free (consecutive / reversed words).
+      const int w = lt >> 5, l = lt & 31;
+      const int cola = w * R1 + l, colb = (R2 - 1 - w) * R1 + ((R1 - l) & (R1 - 1));
+      C ua[R3], ub[R3];
+#pragma unroll
+      for (int q = 0; q < R3; ++q) { ua[q] = s[q * P2 + cola]; ub[q] = s[q * P2 + colb]; }
+      __syncthreads();
+      fft_reg<float, R3>(ua);
+      fft_reg<float, R3>(ub);
+      // lane 0 holds the frequencies k = R1 m, m = q2 + R2 q, whose mirrors R1 (R2 R3 - m) sit in
+      // lane 0 of OTHER warps: those M = R2 R3 values meet in shared memory
+      constexpr int M = R2 * R3;
+      if (l == 0) {
+#pragma unroll
+        for (int q = 0; q < R3; ++q) {
+          s[w + R2 * q] = ua[fft_reg_pos<R3>(q)];
+          s[(R2 - 1 - w) + R2 * q] = ub[fft_reg_pos<R3>(q)];
+        }
+      } else {
+        constexpr int KB = 8;
+        // X_k of consecutive q sit a constant stride apart (R1 R2 columns = R1 R2 / 64 strips) unless
+        // the row is scattered over the strip owners of the slab model
+        const bool strided = INV || A.lgspr < 0;
+        const int kk0 = l + R1 * w;
+        float* pk = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + kk0
+                        : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, kk0 - 1);
+        float* pnk = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + (n - kk0)
+                         : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, n - kk0 - 1);
+        const ptrdiff_t dstride = INV ? (ptrdiff_t)(R1 * R2) : (ptrdiff_t)(R1 * R2 / SP_W) * A.ny * SP_W;
+#pragma unroll
+        for (int q0 = 0; q0 < R3; q0 += KB) {
+          C wk[KB];
+#pragma unroll
+          for (int u = 0; u < KB; ++u) wk[u] = A.tw[kk0 + R1 * R2 * (q0 + u)];
+#pragma unroll
+          for (int u = 0; u < KB; ++u) {
+            const int q = q0 + u, k = kk0 + R1 * R2 * q;
+            if (strided) {
+              const C Ak = ua[fft_reg_pos<R3>(q)], Bk = ub[fft_reg_pos<R3>(R3 - 1 - q)];
+              const C E = {0.5f * (Ak.x + Bk.x), 0.5f * (Ak.y - Bk.y)};
+              const C O = {0.5f * (Ak.y + Bk.y), -0.5f * (Ak.x - Bk.x)};
+              const C wO = cmul(wk[u], O);
+              const float Xk = -0.5f * (E.y + wO.y), Xnk = 0.5f * (E.y - wO.y);
+              pk[q * dstride] = INV ? A.scale * Xk : Xk;
+              pnk[-q * dstride] = INV ? A.scale * Xnk : Xnk;
+            } else {
+              split_pair(k, ua[fft_reg_pos<R3>(q)], ub[fft_reg_pos<R3>(R3 - 1 - q)], wk[u]);
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (lt < M / 2) {      // pairs (R1 m, R1 (M - m)), m = 1 .. M/2 (m = M/2 pairs with itself: both stores agree)
+        const int m = lt + 1, k = R1 * m;
+        split_pair(k, s[m], s[M - m], A.tw[k]);
+      }
+    } else {
     // ---- pass 3
     {
       C u[Cfg::B3][R3];
@@ -444,15 +523,9 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
     }
     __syncthreads();
 
-    // ---- real-odd split, pairs (k, n-k), k = 1 + lt + G m.  X_k is element p = k-1 of the
-    // destination row; both destinations move by a constant stride per m (G columns = G/64 strips)
+    // ---- real-odd split, pairs (k, n-k), k = 1 + lt + G m, read from the line in natural order
     {
-      float* orow = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF
-                        : out + ((size_t)b * A.nl + a) * A.ny * A.np;
       const int k1 = 1 + lt;
-      float* pk = INV ? orow + k1 : orow + sp_off(A.ny, j, k1 - 1);
-      float* pnk = INV ? orow + (n - k1) : orow + sp_off(A.ny, j, n - k1 - 1);
-      const ptrdiff_t dstride = INV ? (ptrdiff_t)G : (ptrdiff_t)(G / SP_W) * A.ny * SP_W;
       constexpr int NK = (n / 2) / G;      // k = n/2 (thread G-1, last m) pairs with itself: both stores agree
       constexpr int KB = 8;
 #pragma unroll 1
@@ -463,21 +536,10 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
 #pragma unroll
         for (int u = 0; u < KB; ++u) {
           const int k = k1 + (m0 + u) * G;
-          const C Ak = s[k + (k >> LG1)];
-          const C Bk = s[(n - k) + ((n - k) >> LG1)];
-          const C E = {0.5f * (Ak.x + Bk.x), 0.5f * (Ak.y - Bk.y)};
-          const C O = {0.5f * (Ak.y + Bk.y), -0.5f * (Ak.x - Bk.x)};
-          const C wO = cmul(w[u], O);
-          const float Xk = -0.5f * (E.y + wO.y), Xnk = 0.5f * (E.y - wO.y);
-          if (!INV && A.lgspr >= 0) {       // slab model: straight into the strip owners' column arrays
-            *fwd_dst<float>(A, out, b * A.nl + a, j, k - 1) = Xk;
-            *fwd_dst<float>(A, out, b * A.nl + a, j, n - k - 1) = Xnk;
-          } else {
-            pk[(m0 + u) * dstride] = INV ? A.scale * Xk : Xk;
-            pnk[-(m0 + u) * dstride] = INV ? A.scale * Xnk : Xnk;
-          }
+          split_pair(k, s[k + (k >> LG1)], s[(n - k) + ((n - k) >> LG1)], w[u]);
         }
       }
+    }
     }
     __syncthreads();
   }
