@@ -12,7 +12,7 @@ done
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/${R}_bench_reference.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file gpurun_out/${R}_qg3_8192_launches.csv python bench.py --steps 2 --warmup 1 > /dev/null 2>&1
-timeout 900 ncu --set full --clock-control none -c 24 -o gpurun_out/${R}_qg3_8192_full -f \
+timeout 900 ncu --set full --clock-control none -c 40 -o gpurun_out/${R}_qg3_8192_full -f \
   python tools/prof_run.py qg3_8192 1 > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:qg_rhs -c 6 -o gpurun_out/${R}_qg3_8192_full_rhs -f \
   python tools/prof_run.py qg3_8192 1 > /dev/null 2>&1
