@@ -26,6 +26,8 @@ template <typename T>
 __host__ __device__ __forceinline__ C2<T> cmul(C2<T> a, C2<T> b) {
   return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
 }
+template <typename T>
+__host__ __device__ __forceinline__ C2<T> cscale(C2<T> a, T h) { return {h * a.x, h * a.y}; }
 // multiply by -i
 template <typename T>
 __host__ __device__ __forceinline__ C2<T> mul_mi(C2<T> a) { return {a.y, -a.x}; }
@@ -48,7 +50,29 @@ __device__ __forceinline__ C2<float> csub(C2<float> a, C2<float> b) {
   unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c2_pack(a)), "l"(c2_pack(b)));
   return c2_unpack(r);
 }
+__device__ __forceinline__ C2<float> cscale(C2<float> a, float h) {
+  const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(h, h));
+  return {r.x, r.y};
+}
+// complex products as FMUL2 + FFMA2 (two instructions instead of four; ptxas folds the half swaps,
+// scalar broadcasts and single-half negations into operand modifiers: .LO_HI, .F32, .NP).  Same
+// roundings as the contracted scalar form: re = fma(a.x, b.x, -(a.y b.y)), im = fma(a.x, b.y, a.y b.x).
+__device__ __forceinline__ C2<float> cmul(C2<float> a, C2<float> b) {
+  const float2 t = __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x));
+  const float2 r = __ffma2_rn(make_float2(a.x, a.x), make_float2(b.x, b.y), make_float2(-t.x, t.y));
+  return {r.x, r.y};
+}
+// a * (c - i sn) with real scalars c, sn
+__device__ __forceinline__ C2<float> cmul_cs(C2<float> a, float c, float sn) {
+  const float2 t = __fmul2_rn(make_float2(a.y, a.x), make_float2(sn, sn));
+  const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(c, c), make_float2(t.x, -t.y));
+  return {r.x, r.y};
+}
 #endif
+template <typename T>
+__host__ __device__ __forceinline__ C2<T> cmul_cs(C2<T> a, T c, T sn) {
+  return {a.x * c + a.y * sn, a.y * c - a.x * sn};
+}
 
 // complex index -> padded complex index.  Three-level padding (one slot per 16, per 128 and per
 // 1024 elements) keeps both the natural-stride butterfly accesses and the digit-reversed reads
@@ -104,9 +128,12 @@ __host__ __device__ __forceinline__ void fft8(C2<T>* v) {
   fft4(v[0], v[2], v[4], v[6]);
   fft4(v[1], v[3], v[5], v[7]);
   const T h = (T)0.70710678118654752440;
-  C2<T> o1 = {h * (v[3].x + v[3].y), h * (v[3].y - v[3].x)};       // * exp(-i pi/4)
-  C2<T> o2 = mul_mi(v[5]);                                          // * -i
-  C2<T> o3 = {h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y)};      // * exp(-3i pi/4)
+  // * exp(-i pi/4), * -i, * exp(-3i pi/4): (v - i v) h and (-i v - v) h, one packed add + one packed multiply
+  C2<T> o1 = cadd(v[3], mul_mi(v[3]));
+  o1 = cscale(o1, h);
+  C2<T> o2 = mul_mi(v[5]);
+  C2<T> o3 = csub(mul_mi(v[7]), v[7]);
+  o3 = cscale(o3, h);
   C2<T> e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
   v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
   v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
@@ -283,8 +310,7 @@ __host__ __device__ __forceinline__ C2<T> cmul_w32(C2<T> a, int m) {
   if (m == 8) return mul_mi(a);
   if (m == 16) return {-a.x, -a.y};
   if (m == 24) return {-a.y, a.x};
-  const T c = (T)COS32[m], sn = (T)SIN32[m];
-  return {a.x * c + a.y * sn, a.y * c - a.x * sn};
+  return cmul_cs(a, (T)COS32[m], (T)SIN32[m]);
 }
 
 // In-register DIF FFT of R = 4 * Rb points (R = 8, 16, 32), natural-order input in v[0..R-1].

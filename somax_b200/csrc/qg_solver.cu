@@ -472,22 +472,41 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
         float* pnk = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + (n - kk0)
                          : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, n - kk0 - 1);
         const ptrdiff_t dstride = INV ? (ptrdiff_t)(R1 * R2) : (ptrdiff_t)(R1 * R2 / SP_W) * A.ny * SP_W;
+        // split twiddles w_k = exp(-i pi k / n), k = kk0 + R1 R2 q: one load, then the 16 rotations
+        // exp(-i pi q / R3) are compile-time constants (the table load per k was 10 % of the
+        // kernel's LSU wavefronts, which bound it)
+        static_assert(R3 == 16, "rotation table");
+        constexpr float RC[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                                  0.70710678118654752f, 0.55557023301960218f, 0.38268343236508978f,
+                                  0.19509032201612825f, 0.f, -0.19509032201612825f, -0.38268343236508978f,
+                                  -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
+                                  -0.92387953251128674f, -0.98078528040323043f};
+        constexpr float RS[16] = {0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+                                  0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f,
+                                  0.98078528040323043f, 1.f, 0.98078528040323043f, 0.92387953251128674f,
+                                  0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
+                                  0.38268343236508978f, 0.19509032201612825f};
+        const C w0 = A.tw[kk0];
+        const float qs = INV ? 0.25f * A.scale : 0.25f;
 #pragma unroll
         for (int q0 = 0; q0 < R3; q0 += KB) {
           C wk[KB];
 #pragma unroll
-          for (int u = 0; u < KB; ++u) wk[u] = A.tw[kk0 + R1 * R2 * (q0 + u)];
+          for (int u = 0; u < KB; ++u) {     // w0 * (RC - i RS)
+            const int q = q0 + u;
+            wk[u] = cmul_cs(w0, RC[q], RS[q]);
+          }
 #pragma unroll
           for (int u = 0; u < KB; ++u) {
             const int q = q0 + u, k = kk0 + R1 * R2 * q;
             if (strided) {
+              // (X_k, X_{n-k}) = (-(e + o) / 4, (e - o) / 4), e = A.y - B.y, o = w.y (A.y + B.y) - w.x (A.x - B.x)
               const C Ak = ua[fft_reg_pos<R3>(q)], Bk = ub[fft_reg_pos<R3>(R3 - 1 - q)];
-              const C E = {0.5f * (Ak.x + Bk.x), 0.5f * (Ak.y - Bk.y)};
-              const C O = {0.5f * (Ak.y + Bk.y), -0.5f * (Ak.x - Bk.x)};
-              const C wO = cmul(wk[u], O);
-              const float Xk = -0.5f * (E.y + wO.y), Xnk = 0.5f * (E.y - wO.y);
-              pk[q * dstride] = INV ? A.scale * Xk : Xk;
-              pnk[-q * dstride] = INV ? A.scale * Xnk : Xnk;
+              const float2 p = __fadd2_rn(make_float2(Ak.y, Ak.y), make_float2(-Bk.y, Bk.y));
+              const float o = fmaf(wk[u].y, p.y, -(wk[u].x * (Ak.x - Bk.x)));
+              const float2 X = __fmul2_rn(__fadd2_rn(make_float2(p.x, p.x), make_float2(o, -o)), make_float2(-qs, qs));
+              pk[q * dstride] = X.x;
+              pnk[-q * dstride] = X.y;
             } else {
               split_pair(k, ua[fft_reg_pos<R3>(q)], ub[fft_reg_pos<R3>(R3 - 1 - q)], wk[u]);
             }
@@ -1229,6 +1248,7 @@ thomas_vec_ckpt(ThomasTab tb, int strip_first, const float* __restrict__ gvecf, 
   const float* gs = gsh + (c & 1) * nrow - i0;     // indexed by the elimination row
   const double cfix = tb.cinf[(size_t)m * tb.np + c];
   const float cfix_f = (float)cfix, kfix_f = (float)(cfix * tb.dy2), dy2_f = (float)tb.dy2;
+  const float kinv_f = kfix_f != 0.f ? 1.f / kfix_f : 0.f;      // (padding columns have c = 0)
   const int Js = tb.Jstrip[m * tb.nstrip + strip];
   const float (*Ct)[TH_COLS] = reinterpret_cast<const float (*)[TH_COLS]>(tb.ctabB + tb.tabOff[m * tb.nstrip + strip]);
   float* ck = tb.ckpt + ((size_t)(plane * tb.nstrip + strip) * 2 + half) * tb.nck * TH_COLS + tid;
@@ -1245,8 +1265,11 @@ thomas_vec_ckpt(ThomasTab tb, int strip_first, const float* __restrict__ gvecf, 
 #pragma unroll
     for (int r = 0; r < TH_RT; ++r) gg[r] = gs[i + r];
     if (i >= Js) {
+      // constant coefficient: u = carry / k runs u' = g - c u, one FMA per row on the chain
+      float u = carry * kinv_f;
 #pragma unroll
-      for (int r = 0; r < TH_RT; ++r) carry = fmaf(-cfix_f, carry, kfix_f * gg[r]);
+      for (int r = 0; r < TH_RT; ++r) u = fmaf(-cfix_f, u, gg[r]);
+      carry = u * kfix_f;
     } else {
 #pragma unroll
       for (int r = 0; r < TH_RT; ++r) {
@@ -1687,7 +1710,7 @@ static int build_thomas_tables(QgSolver* s, const double* lambdas, int Nx_eig) {
           if (rows < (double)hcap) w = ((int)ceil(rows) + TH_RT - 1) / TH_RT * TH_RT;
         }
         vwarm[(size_t)m * nstrip + st] = w;
-        if (st >= 0) s->vwarm_max = std::max(s->vwarm_max, std::min(w, hcap));
+        if (st >= s->nheavy) s->vwarm_max = std::max(s->vwarm_max, std::min(w, hcap));   // PLAIN strips only
       }
     if (int rc = dev_upload(vwarm.data(), vwarm.size() * 4, (void**)&s->vwarm, &s->bytes)) return rc;
   }
@@ -2051,7 +2074,9 @@ static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream
     if (npl > 0) {
       const int hcap = s->ny - s->ny / 2;
       const int vseg = hcap >= 1024 ? VC_NSEG : 1;
-      const size_t smem = (size_t)2 * hcap * sizeof(float);      // upper bound: a segment plus its warm-up
+      // a segment plus its warm-up (6 CTAs / SM and six waves when sized for a whole half)
+      const int seg_rows = TH_RT * ((hcap / TH_RT + vseg - 1) / vseg + 1) + TH_RT;
+      const size_t smem = (size_t)2 * std::min(hcap, seg_rows + s->vwarm_max) * sizeof(float);
       if (int rc = ensure_dyn_smem((const void*)thomas_vec_ckpt, smem)) return rc;
       prof_begin(tf, pl);
       thomas_vec_ckpt<<<dim3(npl, s->planes, 2 * vseg), TH_COLS, smem, pl>>>(tb, pA, s->gvecf, vseg);

@@ -79,13 +79,13 @@ __global__ void rqg_g_kernel(const T* __restrict__ psi, T* __restrict__ hg, T* _
 // multiplies for the constant divisors.
 constexpr int SSW = TXG * 4 + 8;   // shared row: 4 | 128 | 4 (halo columns at [3] and [132])
 
-template <typename T>
-__global__ void __launch_bounds__(TXG* TY, (sizeof(T) == 4 ? 2 : 1))
-swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
-  __shared__ __align__(32) T s_h[TY + 2][SSW];
-  __shared__ __align__(32) T s_u[TY + 2][SSW];
-  __shared__ __align__(32) T s_v[TY + 2][SSW];
-  __shared__ __align__(32) T s_p[TY + 2][SSW];
+// EDGE = false: the CTA's tile and its halo lie inside the region where every load is a plain load,
+// every window cell is interior and every output is written - 97 % of the CTAs of a 4096^2 grid; that
+// instance carries no ring / range predicates at all (they were a quarter of the instructions of a
+// kernel that is issue bound, not HBM bound).
+template <typename T, bool EDGE>
+__device__ __forceinline__ void swm_rhs_body(const SwmArgs<T>& A, const Stage<T>& st, T (*s_h)[SSW], T (*s_u)[SSW],
+                                             T (*s_v)[SSW], T (*s_p)[SSW]) {
   const Layout& L = A.L;
   const int Ny = L.Ny, Nx = L.Nx, pitch = L.pitch, ngroups = L.groups();
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TXG + tx;
@@ -102,20 +102,20 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
   // row / column interior flags of the 3 x 6 window
   bool rin[3], cin[6];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) rin[d] = swm_row_interior(j - 1 + d, Ny, A.ylo, A.yhi);
+  for (int d = 0; d < 3; ++d) rin[d] = !EDGE || swm_row_interior(j - 1 + d, Ny, A.ylo, A.yhi);
 #pragma unroll
-  for (int w = 0; w < 6; ++w) cin[w] = (i0 - 1 + w >= 1) && (i0 - 1 + w <= Nx - 2);
+  for (int w = 0; w < 6; ++w) cin[w] = !EDGE || ((i0 - 1 + w >= 1) && (i0 - 1 + w <= Nx - 2));
   // Coriolis at the X points of rows j-1 and j: f depends on y only, so
   // T_to_X(f) = 0.25*(f[j] + f[j] + f[j+1] + f[j+1]) in the reference's summation order
   T fX[2];
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
-    int ja = j - 1 + d; ja = ja < 0 ? 0 : (ja > Ny - 1 ? Ny - 1 : ja);
-    int jb = ja + 1 > Ny - 1 ? Ny - 1 : ja + 1;
+    int ja = j - 1 + d, jb = ja + 1;
+    if (EDGE) { ja = ja < 0 ? 0 : (ja > Ny - 1 ? Ny - 1 : ja); jb = ja + 1 > Ny - 1 ? Ny - 1 : ja + 1; }
     const T fa = A.f[ja], fb = A.f[jb];
     fX[d] = T(0.25) * (((fa + fa) + fb) + fb);
   }
-  const int jc = j < Ny ? j : Ny - 1;
+  const int jc = (!EDGE || j < Ny) ? j : Ny - 1;
   const T windx = (A.tau0 * A.wx[jc]) * A.iH0, windy = (A.tau0 * A.wy[jc]) * A.iH0;
 
   // fp32: the Tsit5 epilogue operands of this layer (step-start state and previous stage
@@ -125,7 +125,7 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
   constexpr bool STAGE_EPI = sizeof(T) == 4;
   extern __shared__ __align__(16) unsigned char swm_dyn[];
   T (*s_epi)[TXG * TY][4] = reinterpret_cast<T (*)[TXG * TY][4]>(swm_dyn);     // [3 * (MAX_PREV + 1)]
-  const bool epi_valid = j < Ny && g < ngroups && st.Yout[FH] != nullptr;
+  const bool epi_valid = (!EDGE || (j < Ny && g < ngroups)) && st.Yout[FH] != nullptr;
 
   for (int k = 0; k < L.nl; ++k) {
     const size_t plane_off = ((size_t)b * L.nl + k) * L.plane();
@@ -160,9 +160,9 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
       const int rr = e / (TXG + 2), gs = e - rr * (TXG + 2);
       const int jj = j0 - 1 + rr, gg = g0 - 1 + gs;
       Vec4<T> vh{0, 0, 0, 0}, vu{0, 0, 0, 0}, vv{0, 0, 0, 0};
-      if (jj >= 0 && jj < Ny && gg >= 0 && gg < ngroups) {
+      if (!EDGE || (jj >= 0 && jj < Ny && gg >= 0 && gg < ngroups)) {
         const int ib = gg * 4 - OFF;
-        const bool plain = !A.apply_bc ||
+        const bool plain = !EDGE || !A.apply_bc ||
                            (jj >= (A.ylo ? 1 : 0) && jj <= (A.yhi ? Ny - 3 : Ny - 1) && ib >= 1 && ib + 3 <= Nx - 3);
         if (plain) {
           const size_t o = (size_t)jj * pitch + (size_t)gg * 4;
@@ -191,7 +191,7 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
       st4(&s_p[rr][gs * 4], pp);
     }
     __syncthreads();
-    if (j >= Ny) continue;     // warp-uniform
+    if (EDGE && j >= Ny) continue;     // warp-uniform
     // ---- 3 x 6 register windows: columns i0-1 .. i0+4, rows j-1 .. j+1 ----
     T H[3][6], U[3][6], V[3][6];
 #pragma unroll
@@ -218,7 +218,7 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
       const Vec4<T> c4 = ld4(&s_p[r + 1][cs]);
       P1[0] = c4.x; P1[1] = c4.y; P1[2] = c4.z; P1[3] = c4.w;
     }
-    if (g >= ngroups) continue;
+    if (EDGE && g >= ngroups) continue;
     // window index helpers: row d (0..2 <-> dr = d-1), column w (0..5 <-> dc = w-1 from cell 0)
     // ---- potential vorticity at X points: rows dr = -1 (w 1..4) and 0 (w 0..4) ----
     T qm[6], q0[6];
@@ -284,7 +284,7 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
     for (int e = 0; e < 4; ++e) {
       const int i = i0 + e, w = e + 1;
       T dh = 0, du = 0, dv = 0;
-      if (i >= 0 && i < Nx) {
+      if (!EDGE || (i >= 0 && i < Nx)) {
         const bool interior = rin[1] && cin[w];
         if (interior) {
           const T qU = T(0.5) * (q0[w] + qm[w]);
@@ -297,7 +297,7 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
           du = qU * vhU - (P01 - P00) * idx_;
           dv = -qV * uhV - (P10 - P00) * idy_;
           bool wr = true;
-          if (A.spec & SOMAX_B200_SPEC_ADVECTION_REGION2)
+          if (EDGE && (A.spec & SOMAX_B200_SPEC_ADVECTION_REGION2))
             wr = (j >= (A.ylo ? 2 : 0) && j <= (A.yhi ? Ny - 3 : Ny - 1) && i >= 2 && i <= Nx - 3);
           if (wr) dh = -((fe[w] - fe[w - 1]) * idx_ + (fn0[w] - fnm[w]) * idy_);
         }
@@ -353,6 +353,25 @@ swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
       }
     }
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TXG* TY, (sizeof(T) == 4 ? 2 : 1))
+swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
+  __shared__ __align__(32) T s_h[TY + 2][SSW];
+  __shared__ __align__(32) T s_u[TY + 2][SSW];
+  __shared__ __align__(32) T s_v[TY + 2][SSW];
+  __shared__ __align__(32) T s_p[TY + 2][SSW];
+  // the tile rows j0-1 .. j0+TY and column groups g0-1 .. g0+TXG (halo included): all plain loads
+  // (two cells inside a physical boundary, which also covers the [2:-2] write region of the
+  // advection), all in range
+  const int Ny = A.L.Ny, Nx = A.L.Nx;
+  const int jlo = (int)blockIdx.y * TY - 1, jhi = jlo + TY + 1;
+  const int ilo = ((int)blockIdx.x * TXG - 1) * 4 - OFF, ihi = ((int)blockIdx.x * TXG + TXG) * 4 - OFF + 3;
+  const bool inner = jlo >= (A.ylo ? 1 : 0) && jhi <= (A.yhi ? Ny - 3 : Ny - 1) && ilo >= 1 && ihi <= Nx - 3 &&
+                     (int)blockIdx.x * TXG + TXG < A.L.groups();
+  if (inner) swm_rhs_body<T, false>(A, st, s_h, s_u, s_v, s_p);
+  else swm_rhs_body<T, true>(A, st, s_h, s_u, s_v, s_p);
 }
 
 // In-place apply_boundary_conditions on padded planes.
