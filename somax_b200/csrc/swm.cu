@@ -84,12 +84,12 @@ constexpr int SSW = TXG * 4 + 8;   // shared row: 4 | 128 | 4 (halo columns at [
 // instance carries no ring / range predicates at all (they were a quarter of the instructions of a
 // kernel that is issue bound, not HBM bound).
 template <typename T, bool EDGE>
-__device__ __forceinline__ void swm_rhs_body(const SwmArgs<T>& A, const Stage<T>& st, T (*s_h)[SSW], T (*s_u)[SSW],
-                                             T (*s_v)[SSW], T (*s_p)[SSW]) {
+__device__ __forceinline__ void swm_rhs_body(const SwmArgs<T>& A, const Stage<T>& st, int j0, T (*s_h)[SSW],
+                                             T (*s_u)[SSW], T (*s_v)[SSW], T (*s_p)[SSW]) {
   const Layout& L = A.L;
   const int Ny = L.Ny, Nx = L.Nx, pitch = L.pitch, ngroups = L.groups();
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TXG + tx;
-  const int g0 = blockIdx.x * TXG, j0 = blockIdx.y * TY;
+  const int g0 = blockIdx.x * TXG;
   const int b = blockIdx.z;
   const int j = j0 + ty, g = g0 + tx;
   const int r = ty + 1, cs = 4 * (tx + 1);
@@ -355,23 +355,261 @@ __device__ __forceinline__ void swm_rhs_body(const SwmArgs<T>& A, const Stage<T>
   }
 }
 
-template <typename T>
+// Interior CTAs (97 % at 4096^2): no predicate, and a software pipeline over the CTA's work items
+// (tile t of the CTA's column of `ntile` row tiles, layer k): the h/u/v halo tile of item it+1 is
+// fetched with 16-byte cp.async into the other half of a double buffer while item `it` is computed,
+// next to the Tsit5 epilogue operands of item `it` (per-thread slots).  Commit groups retire in
+// order, so "all but the newest group" = tile `it` has landed.  The layer pressure sum lives in
+// registers (the general path keeps a fourth shared tile for it).  Before: tile load -> barrier ->
+// stencil per layer, the load latency covered only by the SM's other CTA.
+// NPREV (stored stage derivatives entering the Runge-Kutta combination) and FLUX (flux-form
+// diffusion) are compile-time: the kernel is issue bound, and the `jj < nprev` / `spec &` tests of
+// the generic path were a tenth of its instructions.
+__device__ __forceinline__ float swm_div(float a, float b) { return __fdividef(a, b); }     // <= 2 ulp
+__device__ __forceinline__ double swm_div(double a, double b) { return a / b; }
+
+template <typename T, int NPREV, bool FLUX>
+__device__ __forceinline__ void swm_rhs_inner(const SwmArgs<T>& A, const Stage<T>& st, int jt0, int ntile,
+                                              T* __restrict__ tiles, T (*s_epi)[TXG * TY][4]) {
+  constexpr int TSZ = (TY + 2) * SSW;            // one field's tile
+  const Layout& L = A.L;
+  const int pitch = L.pitch, nl = L.nl;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TXG + tx;
+  const int g0 = blockIdx.x * TXG, g = g0 + tx, b = blockIdx.z;
+  const int r = ty + 1, cs = 4 * (tx + 1);
+  const T idx_ = A.idx, idy_ = A.idy;
+  const int nitems = ntile * nl;
+  const bool want_y = st.Yout[FH] != nullptr;
+
+  // the (TY+2) x (TXG+2) vectors of a tile over the 256 threads: elements tid and tid + 256
+  // (the second one for the first 84 threads); offsets relative to the tile's first vector
+  constexpr int NE = (TY + 2) * (TXG + 2);
+  const int e1 = tid + TXG * TY;
+  const int rr0 = tid / (TXG + 2), gs0 = tid - rr0 * (TXG + 2);
+  const int rr1 = e1 / (TXG + 2), gs1 = e1 - rr1 * (TXG + 2);
+  const unsigned goff0 = (unsigned)(rr0 * pitch + gs0 * 4), goff1 = (unsigned)(rr1 * pitch + gs1 * 4);
+  const unsigned tiles_sa = (unsigned)__cvta_generic_to_shared(tiles);
+  const unsigned soff0 = (unsigned)((rr0 * SSW + gs0 * 4) * sizeof(T)), soff1 = (unsigned)((rr1 * SSW + gs1 * 4) * sizeof(T));
+  const unsigned epi_sa = (unsigned)__cvta_generic_to_shared(&s_epi[0][tid][0]);
+  constexpr unsigned EPI_STRIDE = TXG * TY * 4 * sizeof(T);
+
+  auto issue_tile = [&](int it) {
+    const int t = it / nl, k = it - t * nl;
+    const size_t base = ((size_t)b * nl + k) * L.plane() + (size_t)(jt0 + t * TY - 1) * pitch + (size_t)(g0 - 1) * 4;
+    const unsigned sb = tiles_sa + (unsigned)((it & 1) * 3 * TSZ * sizeof(T));
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      const T* src = st.Yin[f] + base;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sb + soff0 + f * TSZ * (unsigned)sizeof(T)), "l"(src + goff0) : "memory");
+      if (e1 < NE)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sb + soff1 + f * TSZ * (unsigned)sizeof(T)), "l"(src + goff1) : "memory");
+    }
+  };
+  auto issue_epi = [&](size_t eidx) {
+    if (!want_y) return;
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      const T* base = (st.y[f] ? st.y[f] : st.Yin[f]) + eidx;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(epi_sa + (f * (MAX_PREV + 1) + MAX_PREV) * EPI_STRIDE), "l"(base) : "memory");
+#pragma unroll
+      for (int jj = 0; jj < NPREV; ++jj)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(epi_sa + (f * (MAX_PREV + 1) + jj) * EPI_STRIDE), "l"(st.Fprev[jj][f] + eidx) : "memory");
+    }
+  };
+
+  issue_tile(0);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  T P0[5], P1[4], fX[2], windx = 0, windy = 0;
+  for (int it = 0; it < nitems; ++it) {
+    const int t = it / nl, k = it - t * nl;
+    const int j = jt0 + t * TY + ty;
+    const size_t idx = ((size_t)b * nl + k) * L.plane() + (size_t)j * pitch + (size_t)g * 4;
+    // row constants of a new tile: loaded here, used after the barrier that hides their latency
+    T fr[3] = {0, 0, 0}, wxr = 0, wyr = 0;
+    if (k == 0) { fr[0] = A.f[j - 1]; fr[1] = A.f[j]; fr[2] = A.f[j + 1]; wxr = A.wx[j]; wyr = A.wy[j]; }
+    issue_epi(idx);
+    if (it + 1 < nitems) issue_tile(it + 1);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    __syncthreads();
+    if (k == 0) {
+      // Coriolis at the X points of rows j-1 and j (f depends on y only; reference summation order)
+#pragma unroll
+      for (int d = 0; d < 2; ++d) fX[d] = T(0.25) * (((fr[d] + fr[d]) + fr[d + 1]) + fr[d + 1]);
+      windx = (A.tau0 * wxr) * A.iH0; windy = (A.tau0 * wyr) * A.iH0;
+#pragma unroll
+      for (int e = 0; e < 5; ++e) P0[e] = T(0);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) P1[e] = T(0);
+    }
+    // ---- 3 x 6 register windows: columns i0-1 .. i0+4, rows j-1 .. j+1 ----
+    const T* bh = tiles + (it & 1) * 3 * TSZ;
+    T H[3][6], U[3][6], V[3][6];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const T* rowp = bh + (r - 1 + d) * SSW + cs;
+      const Vec4<T> a = ld4(rowp);
+      const Vec4<T> bq = ld4(rowp + TSZ);
+      const Vec4<T> c4 = ld4(rowp + 2 * TSZ);
+      T al = __shfl_up_sync(0xffffffffu, a.w, 1), ar = __shfl_down_sync(0xffffffffu, a.x, 1);
+      T bl = __shfl_up_sync(0xffffffffu, bq.w, 1), br = __shfl_down_sync(0xffffffffu, bq.x, 1);
+      T cl = __shfl_up_sync(0xffffffffu, c4.w, 1), cr = __shfl_down_sync(0xffffffffu, c4.x, 1);
+      if (tx == 0) { al = rowp[-1]; bl = rowp[TSZ - 1]; cl = rowp[2 * TSZ - 1]; }
+      if (tx == TXG - 1) { ar = rowp[4]; br = rowp[TSZ + 4]; cr = rowp[2 * TSZ + 4]; }
+      H[d][0] = al; H[d][1] = a.x; H[d][2] = a.y; H[d][3] = a.z; H[d][4] = a.w; H[d][5] = ar;
+      U[d][0] = bl; U[d][1] = bq.x; U[d][2] = bq.y; U[d][3] = bq.z; U[d][4] = bq.w; U[d][5] = br;
+      V[d][0] = cl; V[d][1] = c4.x; V[d][2] = c4.y; V[d][3] = c4.z; V[d][4] = c4.w; V[d][5] = cr;
+    }
+    __syncthreads();      // the buffer may be refilled (by the tile issued at the top of the next item)
+    // pressure sum at (j, i..i+4) and (j+1, i..i+3)
+    {
+      const T gk = A.gprime[k];
+#pragma unroll
+      for (int e = 0; e < 5; ++e) P0[e] = P0[e] + gk * H[1][1 + e];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) P1[e] = P1[e] + gk * H[2][1 + e];
+    }
+    // ---- potential vorticity at X points: rows dr = -1 (w 1..4) and 0 (w 0..4) ----
+    T qm[6], q0[6];
+#pragma unroll
+    for (int w = 0; w < 5; ++w) {
+      {
+        const T zeta = (V[1][w + 1] - V[1][w]) * idx_ - (U[2][w] - U[1][w]) * idy_;
+        const T hX = T(0.25) * (((H[1][w] + H[1][w + 1]) + H[2][w]) + H[2][w + 1]);
+        q0[w] = swm_div(zeta + fX[1], hX);
+      }
+      if (w >= 1) {
+        const T zeta = (V[0][w + 1] - V[0][w]) * idx_ - (U[1][w] - U[0][w]) * idy_;
+        const T hX = T(0.25) * (((H[0][w] + H[0][w + 1]) + H[1][w]) + H[1][w + 1]);
+        qm[w] = swm_div(zeta + fX[0], hX);
+      }
+    }
+    // ---- mass fluxes: vh at rows -1,0 (w 1..5); uh at rows 0,1 (w 0..4) ----
+    T vhm[6], vh0[6], uh0[6], uh1[6];
+#pragma unroll
+    for (int w = 0; w < 6; ++w) {
+      vhm[w] = (T(0.5) * (H[0][w] + H[1][w])) * V[0][w];
+      vh0[w] = (T(0.5) * (H[1][w] + H[2][w])) * V[1][w];
+      if (w < 5) {
+        uh0[w] = (T(0.5) * (H[1][w] + H[1][w + 1])) * U[1][w];
+        uh1[w] = (T(0.5) * (H[2][w] + H[2][w + 1])) * U[2][w];
+      }
+    }
+    // ---- kinetic energy: row 0 (w 1..5), row +1 (w 1..4) ----
+    T ke0[6], ke1[6];
+#pragma unroll
+    for (int w = 1; w < 6; ++w) {
+      {
+        const T u2 = T(0.5) * (U[1][w] * U[1][w] + U[1][w - 1] * U[1][w - 1]);
+        const T v2 = T(0.5) * (V[1][w] * V[1][w] + V[0][w] * V[0][w]);
+        ke0[w] = T(0.5) * (u2 + v2);
+      }
+      if (w < 5) {
+        const T u2 = T(0.5) * (U[2][w] * U[2][w] + U[2][w - 1] * U[2][w - 1]);
+        const T v2 = T(0.5) * (V[2][w] * V[2][w] + V[1][w] * V[1][w]);
+        ke1[w] = T(0.5) * (u2 + v2);
+      }
+    }
+    // ---- upwind mass fluxes: fe at row 0 (w 0..4), fn at rows -1, 0 (w 1..4) ----
+    T fe[6], fnm[6], fn0[6];
+#pragma unroll
+    for (int w = 0; w < 5; ++w) {
+      const T uu = U[1][w];
+      fe[w] = uu * (uu > T(0) ? H[1][w] : H[1][w + 1]);
+      const T vv = V[1][w];
+      fn0[w] = vv * (vv > T(0) ? H[1][w] : H[2][w]);
+      const T vm = V[0][w];
+      fnm[w] = vm * (vm > T(0) ? H[0][w] : H[1][w]);
+    }
+    Vec4<T> Fv[3];
+    {
+      T out_h[4], out_u[4], out_v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int w = e + 1;
+        const T qU = T(0.5) * (q0[w] + qm[w]);
+        const T qV = T(0.5) * (q0[w] + q0[w - 1]);
+        const T vhU = T(0.25) * (((vh0[w] + vh0[w + 1]) + vhm[w]) + vhm[w + 1]);
+        const T uhV = T(0.25) * (((uh0[w] + uh1[w]) + uh0[w - 1]) + uh1[w - 1]);
+        const T P00 = ke0[w] + P0[e];
+        const T P01 = ke0[w + 1] + P0[e + 1];
+        const T P10 = ke1[w] + P1[e];
+        T du = qU * vhU - (P01 - P00) * idx_;
+        T dv = -qV * uhV - (P10 - P00) * idy_;
+        const T dh = -((fe[w] - fe[w - 1]) * idx_ + (fn0[w] - fnm[w]) * idy_);
+        if (k == 0) { du = du + windx; dv = dv + windy; }
+        T lu, lv;
+        if (FLUX) {
+          auto fxf = [&](const T (&X)[3][6], int d, int ww) -> T { return A.nu * ((X[d][ww + 1] - X[d][ww]) * idx_); };
+          auto fyf = [&](const T (&X)[3][6], int d, int ww) -> T { return A.nu * ((X[d + 1][ww] - X[d][ww]) * idy_); };
+          lu = (fxf(U, 1, w) - fxf(U, 1, w - 1)) * idx_ + (fyf(U, 1, w) - fyf(U, 0, w)) * idy_;
+          lv = (fxf(V, 1, w) - fxf(V, 1, w - 1)) * idx_ + (fyf(V, 1, w) - fyf(V, 0, w)) * idy_;
+        } else {
+          lu = A.nu * ((U[1][w + 1] - T(2) * U[1][w] + U[1][w - 1]) * A.idx2 +
+                       (U[2][w] - T(2) * U[1][w] + U[0][w]) * A.idy2);
+          lv = A.nu * ((V[1][w + 1] - T(2) * V[1][w] + V[1][w - 1]) * A.idx2 +
+                       (V[2][w] - T(2) * V[1][w] + V[0][w]) * A.idy2);
+        }
+        du = du + lu; dv = dv + lv;
+        if (k == nl - 1) { du = du + (-A.kappa * U[1][w]); dv = dv + (-A.kappa * V[1][w]); }
+        out_h[e] = dh; out_u[e] = du; out_v[e] = dv;
+      }
+      Fv[0] = Vec4<T>{out_h[0], out_h[1], out_h[2], out_h[3]};
+      Fv[1] = Vec4<T>{out_u[0], out_u[1], out_u[2], out_u[3]};
+      Fv[2] = Vec4<T>{out_v[0], out_v[1], out_v[2], out_v[3]};
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      const Vec4<T> F = Fv[f];
+      if (st.Fout[f]) st4(st.Fout[f] + idx, F);
+      if (!st.Yout[f]) continue;
+      Vec4<T> acc = ld4(&s_epi[f * (MAX_PREV + 1) + MAX_PREV][tid][0]);
+#pragma unroll
+      for (int jj = 0; jj < NPREV; ++jj) {
+        const Vec4<T> kk = ld4(&s_epi[f * (MAX_PREV + 1) + jj][tid][0]);
+        acc.x = fma(st.adt[jj], kk.x, acc.x); acc.y = fma(st.adt[jj], kk.y, acc.y);
+        acc.z = fma(st.adt[jj], kk.z, acc.z); acc.w = fma(st.adt[jj], kk.w, acc.w);
+      }
+      acc.x = fma(st.adt_new, F.x, acc.x); acc.y = fma(st.adt_new, F.y, acc.y);
+      acc.z = fma(st.adt_new, F.z, acc.z); acc.w = fma(st.adt_new, F.w, acc.w);
+      st4(st.Yout[f] + idx, acc);
+    }
+  }
+}
+
+template <typename T, int NPREV, bool FLUX>
 __global__ void __launch_bounds__(TXG* TY, (sizeof(T) == 4 ? 2 : 1))
-swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st) {
-  __shared__ __align__(32) T s_h[TY + 2][SSW];
-  __shared__ __align__(32) T s_u[TY + 2][SSW];
-  __shared__ __align__(32) T s_v[TY + 2][SSW];
-  __shared__ __align__(32) T s_p[TY + 2][SSW];
-  // the tile rows j0-1 .. j0+TY and column groups g0-1 .. g0+TXG (halo included): all plain loads
-  // (two cells inside a physical boundary, which also covers the [2:-2] write region of the
-  // advection), all in range
+swm_rhs_kernel_fast(SwmArgs<T> A, Stage<T> st, int ntile) {
+  constexpr int TSZ = (TY + 2) * SSW;
+  __shared__ __align__(32) T tiles[2 * 3 * TSZ];      // inner: double-buffered h, u, v; edge: h, u, v, p
+  extern __shared__ __align__(16) unsigned char swm_dyn[];
+  // A tile is `inner` when its rows j0-1 .. j0+TY and column groups g0-1 .. g0+TXG (halo included)
+  // are all plain loads (two cells inside a physical boundary, which also covers the [2:-2] write
+  // region of the advection) and all in range.  Runs of inner tiles go through the pipeline.
   const int Ny = A.L.Ny, Nx = A.L.Nx;
-  const int jlo = (int)blockIdx.y * TY - 1, jhi = jlo + TY + 1;
+  const int jt0 = (int)blockIdx.y * ntile * TY;
   const int ilo = ((int)blockIdx.x * TXG - 1) * 4 - OFF, ihi = ((int)blockIdx.x * TXG + TXG) * 4 - OFF + 3;
-  const bool inner = jlo >= (A.ylo ? 1 : 0) && jhi <= (A.yhi ? Ny - 3 : Ny - 1) && ilo >= 1 && ihi <= Nx - 3 &&
-                     (int)blockIdx.x * TXG + TXG < A.L.groups();
-  if (inner) swm_rhs_body<T, false>(A, st, s_h, s_u, s_v, s_p);
-  else swm_rhs_body<T, true>(A, st, s_h, s_u, s_v, s_p);
+  const bool cols_inner = ilo >= 1 && ihi <= Nx - 3 && (int)blockIdx.x * TXG + TXG < A.L.groups();
+  auto tile_inner = [&](int t) {
+    const int j0 = jt0 + t * TY;
+    return cols_inner && j0 - 1 >= (A.ylo ? 1 : 0) && j0 + TY <= (A.yhi ? Ny - 3 : Ny - 1);
+  };
+  T (*s_h)[SSW] = reinterpret_cast<T (*)[SSW]>(tiles);
+  for (int t = 0; t < ntile;) {
+    const int j0 = jt0 + t * TY;
+    if (j0 >= Ny) break;
+    if (t) __syncthreads();      // the previous tile's windows have been read
+    if (tile_inner(t)) {
+      int n = 1;
+      while (t + n < ntile && tile_inner(t + n)) ++n;
+      swm_rhs_inner<T, NPREV, FLUX>(A, st, j0, n, tiles, reinterpret_cast<T (*)[TXG * TY][4]>(swm_dyn));
+      t += n;
+    } else {
+      swm_rhs_body<T, true>(A, st, j0, s_h, s_h + (TY + 2), s_h + 2 * (TY + 2), s_h + 3 * (TY + 2));
+      ++t;
+    }
+  }
 }
 
 // In-place apply_boundary_conditions on padded planes.
@@ -510,6 +748,29 @@ int project_state(somax_b200_swm_t h, const T* const in[3], T* const out[3], int
   return 0;
 }
 
+template <typename T, int NPREV, bool FLUX>
+static int launch_fast_one(const SwmArgs<T>& A, const Stage<T>& st, int ntile, dim3 grid, dim3 block, size_t dyn,
+                           cudaStream_t s) {
+  if (int rc = ensure_dyn_smem((const void*)swm_rhs_kernel_fast<T, NPREV, FLUX>, dyn)) return rc;
+  swm_rhs_kernel_fast<T, NPREV, FLUX><<<grid, block, dyn, s>>>(A, st, ntile);
+  return 0;
+}
+
+template <typename T>
+static int launch_fast(const SwmArgs<T>& A, const Stage<T>& st, int ntile, dim3 grid, dim3 block, size_t dyn,
+                       cudaStream_t s) {
+  const bool flux = (A.spec & SOMAX_B200_SPEC_DIFFUSION_FLUX) != 0;
+#define SB_SWM_CASE(N)                                                                        \
+  case N:                                                                                     \
+    return flux ? launch_fast_one<T, N, true>(A, st, ntile, grid, block, dyn, s)              \
+                : launch_fast_one<T, N, false>(A, st, ntile, grid, block, dyn, s);
+  switch (st.nprev) {
+    SB_SWM_CASE(0) SB_SWM_CASE(1) SB_SWM_CASE(2) SB_SWM_CASE(3) SB_SWM_CASE(4) SB_SWM_CASE(5)
+  }
+#undef SB_SWM_CASE
+  return SOMAX_B200_ERR_INVALID;
+}
+
 template <typename T>
 int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A_in, const Stage<T>& st_in, cudaStream_t s) {
   const Layout& L = h->L;
@@ -530,6 +791,9 @@ int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A_in, const Stage<T>& st_in
   stage_finalize(st, (double)st.dt);
   dim3 block(TXG, TY);
   dim3 grid((L.groups() + TXG - 1) / TXG, (L.Ny + TY - 1) / TY, L.batch);
+  // fast kernel: a CTA walks `ntile` row tiles (software pipeline over tiles and layers) on grids
+  // large enough to keep every SM busy with whole columns
+  const int ntile = (int)grid.y >= 128 ? 4 : 1;
   prof_begin("swm_rhs_kernel", s);
   if constexpr (sizeof(T) == 8) {
     // fp64 = the validation pipeline: reference operation order, no FMA contraction (swm_f64.cu)
@@ -537,8 +801,8 @@ int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A_in, const Stage<T>& st_in
   } else if (h->f1d && h->wx1d && h->wy1d) {
     // fp32: per-thread shared slots for the prefetched epilogue operands
     const size_t dyn = sizeof(T) == 4 ? (size_t)3 * (MAX_PREV + 1) * TXG * TY * 4 * sizeof(T) : 0;
-    if (int rc = ensure_dyn_smem((const void*)swm_rhs_kernel_fast<T>, dyn)) return rc;
-    swm_rhs_kernel_fast<T><<<grid, block, dyn, s>>>(A, st);
+    dim3 gridf(grid.x, (grid.y + ntile - 1) / ntile, grid.z);
+    if (int rc = launch_fast<T>(A, st, ntile, gridf, block, dyn, s)) return rc;
   }
   else swm_rhs_kernel<T><<<grid, block, 0, s>>>(A, st);
   SB_LAUNCH_CHECK();
