@@ -378,6 +378,7 @@ __device__ __forceinline__ void swm_rhs_inner(const SwmArgs<T>& A, const Stage<T
   const int g0 = blockIdx.x * TXG, g = g0 + tx, b = blockIdx.z;
   const int r = ty + 1, cs = 4 * (tx + 1);
   const T idx_ = A.idx, idy_ = A.idy;
+  const T nux = A.nu * idx_, nuy = A.nu * idy_;
   const int nitems = ntile * nl;
   const bool want_y = st.Yout[FH] != nullptr;
 
@@ -393,9 +394,7 @@ __device__ __forceinline__ void swm_rhs_inner(const SwmArgs<T>& A, const Stage<T
   const unsigned epi_sa = (unsigned)__cvta_generic_to_shared(&s_epi[0][tid][0]);
   constexpr unsigned EPI_STRIDE = TXG * TY * 4 * sizeof(T);
 
-  auto issue_tile = [&](int it) {
-    const int t = it / nl, k = it - t * nl;
-    const size_t base = ((size_t)b * nl + k) * L.plane() + (size_t)(jt0 + t * TY - 1) * pitch + (size_t)(g0 - 1) * 4;
+  auto issue_tile = [&](int it, size_t base) {
     const unsigned sb = tiles_sa + (unsigned)((it & 1) * 3 * TSZ * sizeof(T));
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
@@ -417,18 +416,23 @@ __device__ __forceinline__ void swm_rhs_inner(const SwmArgs<T>& A, const Stage<T
     }
   };
 
-  issue_tile(0);
+  // (tile, layer) of the item, its tile base and this thread's output vector, advanced incrementally
+  const size_t plane = L.plane();
+  const size_t tile_step = (size_t)TY * pitch - (size_t)(nl - 1) * plane;      // last layer -> layer 0 of the next tile
+  size_t tb = (size_t)b * nl * plane + (size_t)(jt0 - 1) * pitch + (size_t)(g0 - 1) * 4;
+  size_t idx = (size_t)b * nl * plane + (size_t)(jt0 + ty) * pitch + (size_t)g * 4;
+  int k = 0, j = jt0 + ty;
+  issue_tile(0, tb);
   asm volatile("cp.async.commit_group;\n" ::: "memory");
   T P0[5], P1[4], fX[2], windx = 0, windy = 0;
   for (int it = 0; it < nitems; ++it) {
-    const int t = it / nl, k = it - t * nl;
-    const int j = jt0 + t * TY + ty;
-    const size_t idx = ((size_t)b * nl + k) * L.plane() + (size_t)j * pitch + (size_t)g * 4;
+    const bool last_layer = k == nl - 1;
+    const size_t tbn = tb + (last_layer ? tile_step : plane);
     // row constants of a new tile: loaded here, used after the barrier that hides their latency
     T fr[3] = {0, 0, 0}, wxr = 0, wyr = 0;
     if (k == 0) { fr[0] = A.f[j - 1]; fr[1] = A.f[j]; fr[2] = A.f[j + 1]; wxr = A.wx[j]; wyr = A.wy[j]; }
     issue_epi(idx);
-    if (it + 1 < nitems) issue_tile(it + 1);
+    if (it + 1 < nitems) issue_tile(it + 1, tbn);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     __syncthreads();
@@ -484,30 +488,33 @@ __device__ __forceinline__ void swm_rhs_inner(const SwmArgs<T>& A, const Stage<T
         qm[w] = swm_div(zeta + fX[0], hX);
       }
     }
-    // ---- mass fluxes: vh at rows -1,0 (w 1..5); uh at rows 0,1 (w 0..4) ----
+    // Factors 1/2 and 1/4 are exact in binary floating point, so they are collected: twice the mass
+    // fluxes, four times the kinetic energy and twice the interpolated q are carried, and one
+    // power-of-two constant per use restores the scale - bit-identical to scaling every term.
+    // ---- 2 x mass fluxes: vh at rows -1,0 (w 1..5); uh at rows 0,1 (w 0..4) ----
     T vhm[6], vh0[6], uh0[6], uh1[6];
 #pragma unroll
     for (int w = 0; w < 6; ++w) {
-      vhm[w] = (T(0.5) * (H[0][w] + H[1][w])) * V[0][w];
-      vh0[w] = (T(0.5) * (H[1][w] + H[2][w])) * V[1][w];
+      vhm[w] = (H[0][w] + H[1][w]) * V[0][w];
+      vh0[w] = (H[1][w] + H[2][w]) * V[1][w];
       if (w < 5) {
-        uh0[w] = (T(0.5) * (H[1][w] + H[1][w + 1])) * U[1][w];
-        uh1[w] = (T(0.5) * (H[2][w] + H[2][w + 1])) * U[2][w];
+        uh0[w] = (H[1][w] + H[1][w + 1]) * U[1][w];
+        uh1[w] = (H[2][w] + H[2][w + 1]) * U[2][w];
       }
     }
-    // ---- kinetic energy: row 0 (w 1..5), row +1 (w 1..4) ----
+    // ---- 4 x kinetic energy: row 0 (w 1..5), row +1 (w 1..4) ----
     T ke0[6], ke1[6];
 #pragma unroll
     for (int w = 1; w < 6; ++w) {
       {
-        const T u2 = T(0.5) * (U[1][w] * U[1][w] + U[1][w - 1] * U[1][w - 1]);
-        const T v2 = T(0.5) * (V[1][w] * V[1][w] + V[0][w] * V[0][w]);
-        ke0[w] = T(0.5) * (u2 + v2);
+        const T u2 = U[1][w] * U[1][w] + U[1][w - 1] * U[1][w - 1];
+        const T v2 = V[1][w] * V[1][w] + V[0][w] * V[0][w];
+        ke0[w] = u2 + v2;
       }
       if (w < 5) {
-        const T u2 = T(0.5) * (U[2][w] * U[2][w] + U[2][w - 1] * U[2][w - 1]);
-        const T v2 = T(0.5) * (V[2][w] * V[2][w] + V[1][w] * V[1][w]);
-        ke1[w] = T(0.5) * (u2 + v2);
+        const T u2 = U[2][w] * U[2][w] + U[2][w - 1] * U[2][w - 1];
+        const T v2 = V[2][w] * V[2][w] + V[1][w] * V[1][w];
+        ke1[w] = u2 + v2;
       }
     }
     // ---- upwind mass fluxes: fe at row 0 (w 0..4), fn at rows -1, 0 (w 1..4) ----
@@ -527,21 +534,22 @@ __device__ __forceinline__ void swm_rhs_inner(const SwmArgs<T>& A, const Stage<T
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int w = e + 1;
-        const T qU = T(0.5) * (q0[w] + qm[w]);
-        const T qV = T(0.5) * (q0[w] + q0[w - 1]);
-        const T vhU = T(0.25) * (((vh0[w] + vh0[w + 1]) + vhm[w]) + vhm[w + 1]);
-        const T uhV = T(0.25) * (((uh0[w] + uh1[w]) + uh0[w - 1]) + uh1[w - 1]);
-        const T P00 = ke0[w] + P0[e];
-        const T P01 = ke0[w + 1] + P0[e + 1];
-        const T P10 = ke1[w] + P1[e];
+        const T qU = q0[w] + qm[w];                                   // 2 qU
+        const T qV = q0[w] + q0[w - 1];                               // 2 qV
+        const T vhU = T(0.0625) * (((vh0[w] + vh0[w + 1]) + vhm[w]) + vhm[w + 1]);      // vhU / 2
+        const T uhV = T(0.0625) * (((uh0[w] + uh1[w]) + uh0[w - 1]) + uh1[w - 1]);      // uhV / 2
+        const T P00 = fma(T(0.25), ke0[w], P0[e]);
+        const T P01 = fma(T(0.25), ke0[w + 1], P0[e + 1]);
+        const T P10 = fma(T(0.25), ke1[w], P1[e]);
         T du = qU * vhU - (P01 - P00) * idx_;
         T dv = -qV * uhV - (P10 - P00) * idy_;
         const T dh = -((fe[w] - fe[w - 1]) * idx_ + (fn0[w] - fnm[w]) * idy_);
         if (k == 0) { du = du + windx; dv = dv + windy; }
         T lu, lv;
         if (FLUX) {
-          auto fxf = [&](const T (&X)[3][6], int d, int ww) -> T { return A.nu * ((X[d][ww + 1] - X[d][ww]) * idx_); };
-          auto fyf = [&](const T (&X)[3][6], int d, int ww) -> T { return A.nu * ((X[d + 1][ww] - X[d][ww]) * idy_); };
+          // (nu / dx rounded once: <= 1 ulp from nu * (d / dx), like the other constant divisors)
+          auto fxf = [&](const T (&X)[3][6], int d, int ww) -> T { return (X[d][ww + 1] - X[d][ww]) * nux; };
+          auto fyf = [&](const T (&X)[3][6], int d, int ww) -> T { return (X[d + 1][ww] - X[d][ww]) * nuy; };
           lu = (fxf(U, 1, w) - fxf(U, 1, w - 1)) * idx_ + (fyf(U, 1, w) - fyf(U, 0, w)) * idy_;
           lv = (fxf(V, 1, w) - fxf(V, 1, w - 1)) * idx_ + (fyf(V, 1, w) - fyf(V, 0, w)) * idy_;
         } else {
@@ -551,7 +559,7 @@ __device__ __forceinline__ void swm_rhs_inner(const SwmArgs<T>& A, const Stage<T
                        (V[2][w] - T(2) * V[1][w] + V[0][w]) * A.idy2);
         }
         du = du + lu; dv = dv + lv;
-        if (k == nl - 1) { du = du + (-A.kappa * U[1][w]); dv = dv + (-A.kappa * V[1][w]); }
+        if (last_layer) { du = du + (-A.kappa * U[1][w]); dv = dv + (-A.kappa * V[1][w]); }
         out_h[e] = dh; out_u[e] = du; out_v[e] = dv;
       }
       Fv[0] = Vec4<T>{out_h[0], out_h[1], out_h[2], out_h[3]};
@@ -575,6 +583,10 @@ __device__ __forceinline__ void swm_rhs_inner(const SwmArgs<T>& A, const Stage<T
       acc.z = fma(st.adt_new, F.z, acc.z); acc.w = fma(st.adt_new, F.w, acc.w);
       st4(st.Yout[f] + idx, acc);
     }
+    tb = tbn;
+    idx += last_layer ? tile_step : plane;
+    j += last_layer ? TY : 0;
+    k = last_layer ? 0 : k + 1;
   }
 }
 
