@@ -1398,12 +1398,14 @@ __device__ __forceinline__ void border_store(double t0, double t1, double t2, in
 
 // Border Schur solve = dense DST-I in y of the 3 nl border columns of a member (length ny, N = ny + 1),
 // brute force in fp64: out_v[a] = sum_{t=1..ny} sin(pi a t / N) in_v[t].
-// A CTA computes GS_OUT = 32 consecutive outputs a for ALL NV columns: lane = output, warp = one of
-// GS_SL interleaved slices of the terms t, so every load of in[t][.] is a warp-wide broadcast and the
-// rotation that advances sin/cos(pi a t / N) by the fixed angle pi a GS_SL / N (4 FMAs; start and step
-// values come exactly from the table) is shared by the NV columns.  The input is folded on the fly by
-// the t <-> N - t symmetry, sin(pi a (N - t) / N) = -(-1)^a sin(pi a t / N): half the terms.  The slices
-// are combined through shared memory in a fixed order.  (The first version ran one warp per
+// A CTA computes GS_OUT = 32 outputs a OF ONE PARITY (a, a + 2, ...) for ALL NV columns: lane = output,
+// warp = one of GS_SL interleaved slices of the terms t, so every load of in[t][.] is a warp-wide
+// broadcast and the rotation that advances sin/cos(pi a t / N) by the fixed angle pi a GS_SL / N
+// (4 FMAs; start and step values come exactly from the table) is shared by the NV columns.  The
+// input is folded by the t <-> N - t symmetry, sin(pi a (N - t) / N) = -(-1)^a sin(pi a t / N): half
+// the terms, and because the sign is the same for the whole CTA the fold x[t] -+ x[N-t] is done once
+// per staged chunk in shared memory (13 fp64 operations per output and term instead of 22 when every
+// lane folded for itself).  The slices are combined through shared memory in a fixed order.  (The first version ran one warp per
 // (output, layer): every warp re-read its three input columns from L2, 4.7 GB per launch at 8192^2.)
 constexpr int GS_OUT = 32, GS_SL = 8;
 constexpr int GS_U = 8;                  // terms per slice and chunk
@@ -1433,7 +1435,7 @@ border_dst(const double* __restrict__ in, const double* __restrict__ sintab,
   double (*tile)[2][GS_CH][NVP] = reinterpret_cast<double (*)[2][GS_CH][NVP]>(gs_smem);
   double (*red)[NV][GS_OUT] = reinterpret_cast<double (*)[NV][GS_OUT]>(gs_smem);   // after the last chunk
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5, bm = blockIdx.y;
-  const int a = a_first + blockIdx.x * GS_OUT + lane + 1;      // 1-based output row
+  const int a = a_first + ((int)blockIdx.x >> 1) * (2 * GS_OUT) + 2 * lane + ((int)blockIdx.x & 1) + 1;      // 1-based output row
   const bool valid = a <= a_first + a_count;
   const unsigned N = ny + 1, N2 = 2 * N;
   const double* costab = sintab + N2;
@@ -1447,7 +1449,7 @@ border_dst(const double* __restrict__ in, const double* __restrict__ sintab,
   const unsigned kd = (aa * (unsigned)GS_SL) % N2;
   double s = sintab[k0], c = costab[k0];
   const double ds = sintab[kd], dc = costab[kd];
-  const double sgn = (aa & 1) ? 1.0 : -1.0;
+  const double sgn = ((a_first + ((int)blockIdx.x & 1) + 1) & 1) ? 1.0 : -1.0;      // the CTA's parity (also of its invalid lanes)
   double acc[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = 0.0;
@@ -1468,24 +1470,32 @@ border_dst(const double* __restrict__ in, const double* __restrict__ sintab,
   __syncthreads();
   for (int ch = ch_first; ch < nchunk; ++ch) {
     const int st = (ch - ch_first) % GS_NS, nr = chunk_rows(ch);
-    if (threadIdx.x == 0) load_chunk(ch + GS_NS - 1);     // its stage was released by the barrier below
     mbar_wait(&full[st], (unsigned)(((ch - ch_first) / GS_NS) & 1));
+    // fold in place: lo[r] += sgn hi[nr-1-r]
+    for (int e = threadIdx.x; e < nr * NVP; e += GS_OUT * GS_SL) {
+      const int r = e / NVP, v = e - r * NVP;
+      tile[st][0][r][v] = fma(sgn, tile[st][1][nr - 1 - r][v], tile[st][0][r][v]);
+    }
+    __syncthreads();      // the fold is visible; everyone is also done with the previous chunk's stage,
+    if (threadIdx.x == 0) {                               // which is the one this load refills
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // (it was written by the fold: generic proxy)
+      load_chunk(ch + GS_NS - 1);
+    }
     // slice sl takes the rows r = sl, sl + GS_SL, ... of the chunk (terms t = ch GS_CH + 1 + r)
 #pragma unroll 4
     for (int r = sl; r < nr; r += GS_SL) {
       const double2* lo = reinterpret_cast<const double2*>(&tile[st][0][r][0]);
-      const double2* hi = reinterpret_cast<const double2*>(&tile[st][1][nr - 1 - r][0]);
 #pragma unroll
       for (int v2 = 0; v2 < NVP / 2; ++v2) {
-        const double2 l2 = lo[v2], h2 = hi[v2];
-        acc[2 * v2] = fma(s, fma(sgn, h2.x, l2.x), acc[2 * v2]);
-        if (2 * v2 + 1 < NV) acc[2 * v2 + 1] = fma(s, fma(sgn, h2.y, l2.y), acc[2 * v2 + 1]);
+        const double2 l2 = lo[v2];
+        acc[2 * v2] = fma(s, l2.x, acc[2 * v2]);
+        if (2 * v2 + 1 < NV) acc[2 * v2 + 1] = fma(s, l2.y, acc[2 * v2 + 1]);
       }
       const double s2 = fma(s, dc, c * ds), c2 = fma(c, dc, -(s * ds));   // rotate by GS_SL pi a / N
       s = s2; c = c2;
     }
-    __syncthreads();      // everyone is done with stage st: it may be refilled
   }
+  __syncthreads();        // all slices are done with the ring: `red` aliases it
   if ((N & 1) == 0 && sl == 0 && z == 0) {
     const double sm = sintab[(unsigned)(((unsigned long long)aa * (N / 2)) % N2)];
 #pragma unroll
@@ -1859,7 +1869,7 @@ static int build_fft_tables(QgSolver* s, const double* lambdas) {
   SB_CUDA(cudaMalloc((void**)&s->gvec, 2 * vb));
   SB_CUDA(cudaMalloc((void**)&s->gvecf, vb));
   if (!(ny <= GS_SMALL_NY && (long)s->planes * ny >= 65536)) {      // the blocked border transform is in use
-    const size_t nblk = (size_t)s->batch * ((ny + GS_OUT - 1) / GS_OUT);
+    const size_t nblk = (size_t)s->batch * (2 * ((ny + 2 * GS_OUT - 1) / (2 * GS_OUT)));
     const size_t zb = nblk * GS_ZMAX * 12 * GS_OUT * sizeof(double);
     SB_CUDA(cudaMalloc((void**)&s->zpart, zb));
     SB_CUDA(cudaMalloc((void**)&s->zcount, nblk * sizeof(unsigned)));
@@ -2194,7 +2204,7 @@ int qg_solver_border_stage(QgSolver* s, int stage, int a0, int a1, cudaStream_t 
     if (stage == 1) border_gsolve_small<T, true><<<g, 128, 0, st>>>(in, s->sintab, s->minv, ny, np, n, nl, s->ghat, nullptr, nullptr, nullptr, nullptr, a0, cnt);
     else border_gsolve_small<T, false><<<g, 128, 0, st>>>(in, s->sintab, s->minv, ny, np, n, nl, nullptr, s->gvec, s->gvecf, S, (T*)s->bext, a0, cnt);
   } else {
-    const int nblk = (cnt + GS_OUT - 1) / GS_OUT;
+    const int nblk = 2 * ((cnt + 2 * GS_OUT - 1) / (2 * GS_OUT));      // blocks of 32 outputs of one parity
     const int nchunk_all = ((ny + 1 - 1) / 2 + GS_CH - 1) / GS_CH;
     // enough CTAs for two per SM: split the terms when there are few output blocks
     int nz = (2 * 148 + nblk * s->batch - 1) / (nblk * s->batch);
