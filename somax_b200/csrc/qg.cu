@@ -380,7 +380,12 @@ qg_rhs_kernel_tma(const __grid_constant__ QgTmaps M, const QgArgs<float> A, cons
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(qsm + 2 * QG_TMA_HALO_B + (MAX_PREV + 1) * QG_TMA_EPI_B);
   const Layout& L = A.L;
   const int tid = threadIdx.y * QTXG + threadIdx.x;
-  const int g0 = blockIdx.x * QTXG, j0 = blockIdx.y * QFY;
+  // Tiles start at the first interior cell (row 1, column 1 = group 1), so a grid whose interior is a
+  // multiple of the tile (every power-of-two grid: 256^2 members, 8192^2) splits into whole,
+  // predicate-free tiles; row 0 and column 0 - and the last row / column when no tile reaches them -
+  // are written by qg_ring_kernel.  (With the origin at row 0 / group 0 a 256^2 member took 3 x 17
+  // tiles, every one of them on the predicated path, instead of 2 x 16.)
+  const int g0 = 1 + blockIdx.x * QTXG, j0 = 1 + blockIdx.y * QFY;
   const int plane = blockIdx.z;
   const int k = L.nl == 1 ? 0 : plane - (int)__umulhi((unsigned)plane, A.nl_magic) * L.nl;
   if (tid == 0) {
@@ -409,21 +414,55 @@ qg_rhs_kernel_tma(const __grid_constant__ QgTmaps M, const QgArgs<float> A, cons
                    "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(ba) : "memory");
     }
   }
-  // CTAs whose halo tile touches the domain ring (row 0 / Ny-1, column 0 / Nx-1) or overhangs
-  const int gR = (L.Nx - 1 + OFF) >> 2;
-  const bool edge = blockIdx.x == 0 || g0 + QTXG >= gR || blockIdx.y == 0 || j0 + QFY >= L.Ny - 1;
-  if (edge) {
-    if (A.apply_bc) {
-      for (int e = tid; e < QHR * QHW; e += QTXG * QTY) {
-        const int r = e / QHW, cidx = e - r * QHW;
-        const int jj = j0 - 1 + r, i = 4 * (g0 - 1) + cidx - OFF;
-        if ((jj == 0 && A.bc_ylo) || (jj == L.Ny - 1 && A.bc_yhi) || i == 0 || i == L.Nx - 1) s_q[r][cidx] = 0.f;
-      }
+  // boundary condition on load: ring cells of q inside the halo tile are zero
+  if (A.apply_bc) {
+    const int rtop = L.Ny - 1 - (j0 - 1);                         // tile row of domain row Ny-1
+    const int cright = L.Nx - 1 + OFF - 4 * (g0 - 1);             // tile column of domain column Nx-1
+    const bool r0 = blockIdx.y == 0 && A.bc_ylo, r1 = rtop < QHR && A.bc_yhi;
+    const bool c0 = blockIdx.x == 0, c1 = cright < QHW;
+    if (r0 | r1 | c0 | c1) {
+      if (r0 && tid < QHW) s_q[0][tid] = 0.f;
+      if (r1 && tid < QHW) s_q[rtop][tid] = 0.f;
+      if (c0 && tid < QHR) s_q[tid][OFF] = 0.f;
+      if (c1 && tid < QHR) s_q[tid][cright] = 0.f;
       __syncthreads();
     }
-    qg_tma_compute<true>(A, st, s_q, s_p, s_epi, g0, j0, plane, k);
+  }
+  // tiles that reach past the last interior row / column take the predicated path
+  const bool edge = 4 * g0 + 4 * QTXG - 4 > L.Nx - 2 || j0 + QFY - 1 > L.Ny - 2;
+  if (edge) qg_tma_compute<true>(A, st, s_q, s_p, s_epi, g0, j0, plane, k);
+  else qg_tma_compute<false>(A, st, s_q, s_p, s_epi, g0, j0, plane, k);
+}
+
+// Ring cells no tile of qg_rhs_kernel_tma covers: row 0 and column 0 always, row Ny-1 / column Nx-1
+// when the interior is a whole number of tiles in that direction.  Nothing but the wind acts there
+// (same arithmetic as the predicated path of the tile kernel).  blockIdx.y: 0 = row 0, 1 = column 0,
+// 2 = row Ny-1, 3 = column Nx-1; rows take the corners.
+__global__ void qg_ring_kernel(const QgArgs<float> A, const Stage<float> st, int do_top, int do_right) {
+  const Layout& L = A.L;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, which = blockIdx.y, plane = blockIdx.z;
+  int j, i;
+  if (which == 0 || which == 2) {
+    if (which == 2 && !do_top) return;
+    j = which == 0 ? 0 : L.Ny - 1; i = t;
+    if (i >= L.Nx) return;
   } else {
-    qg_tma_compute<false>(A, st, s_q, s_p, s_epi, g0, j0, plane, k);
+    if (which == 3 && !do_right) return;
+    i = which == 1 ? 0 : L.Nx - 1; j = 1 + t;
+    if (j > (do_top ? L.Ny - 2 : L.Ny - 1)) return;
+  }
+  const int k = L.nl == 1 ? 0 : plane % L.nl;
+  float F = 0.f;
+  if (k == 0) F = F + (A.tau0 * A.wind[j]) * A.iH0;
+  const size_t idx = (size_t)plane * L.plane() + (size_t)j * L.pitch + OFF + i;
+  if (st.Fout[0]) st.Fout[0][idx] = F;
+  if (st.Yout[0]) {
+    float acc = (st.y[0] ? st.y[0] : st.Yin[0])[idx];
+#pragma unroll
+    for (int jj = 0; jj < MAX_PREV; ++jj)
+      if (jj < st.nprev) acc = fmaf(st.adt[jj], st.Fprev[jj][0][idx], acc);
+    acc = fmaf(st.adt_new, F, acc);
+    st.Yout[0][idx] = acc;
   }
 }
 
@@ -607,9 +646,18 @@ bool qg_launch_tma(somax_b200_qg_t h, const QgArgs<float>& A, const Stage<float>
   if (ensure_dyn_smem((const void*)qg_rhs_kernel_tma, QG_TMA_SMEM) != 0) { cudaGetLastError(); return false; }
   const Layout& L = h->L;
   dim3 block(QTXG, QTY);
-  dim3 grid((L.groups() + QTXG - 1) / QTXG, (L.Ny + QFY - 1) / QFY, L.batch * L.nl);
+  // tiles over the interior rows 1 .. Ny-2 and the groups 1 .. gI of the interior columns
+  const int gI = (L.Nx - 2 + OFF) >> 2, gR = (L.Nx - 1 + OFF) >> 2;
+  const int gx = (gI + QTXG - 1) / QTXG, gy = (L.Ny - 2 + QFY - 1) / QFY;
+  dim3 grid(gx, gy, L.batch * L.nl);
   prof_begin("qg_rhs_kernel", s);
   qg_rhs_kernel_tma<<<grid, block, QG_TMA_SMEM, s>>>(M, A, st);
+  const int do_top = QFY * gy < L.Ny - 1, do_right = gR > QTXG * gx;
+  const int nmax = L.Nx > L.Ny ? L.Nx : L.Ny;
+  prof_end();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  prof_begin("qg_ring_kernel", s);
+  qg_ring_kernel<<<dim3((nmax + 255) / 256, 4, L.batch * L.nl), 256, 0, s>>>(A, st, do_top, do_right);
   return true;
 }
 
