@@ -753,7 +753,10 @@ constexpr int TH_RT = 16;   // rows per register block of the recurrence
 // CTAs exist and each is a serial chain over ny/2 rows.  PLAIN (TAB = false): everything else, in
 // the pipeline's own precision, coefficients (needed for the first rows only) read from L2.
 template <typename T, int KIND, bool TAB> struct ThRows {      // rows per staged tile
-  static constexpr int v = TAB ? ((sizeof(T) == 4 && KIND != 2) ? 64 : 32) : TH_RT;
+  // (LOWK fp32 used 64-row tiles when a sweep was a handful of unsegmented CTAs; with 8 segments there
+  // are 240 of them and a 150 KB ring left room for only three PLAIN CTAs beside it on an SM, so the
+  // PLAIN launch spilled into a second wave)
+  static constexpr int v = TAB ? 32 : TH_RT;
 };
 template <typename T, int KIND, bool TAB> struct ThStages {   // ring depth
   // PLAIN rings are kept small enough that a whole sweep (123 strips x 3 planes x 2 halves at
