@@ -254,7 +254,8 @@ qg_rhs_kernel_fast(QgArgs<T> A, const T* __restrict__ psi, Stage<T> st) {
 // arrive in shared memory through 3-D tensor maps over the padded (pitch, Ny, plane) arrays --
 // out-of-range boxes are zero-filled by the hardware, so the loader has no per-thread address
 // arithmetic or bounds checks at all.  Each thread computes 2 rows x 4 columns from a 4 x 6
-// register window; CTAs that touch the domain ring take the predicated EDGE path (~3% of CTAs).
+// register window; only tiles that reach past the last interior row / column take the predicated
+// EDGE path (none on a power-of-two grid: the tile grid starts at the first interior cell).
 // Same arithmetic (operation order) as qg_rhs_kernel_fast.
 // ------------------------------------------------------------------------------------------
 constexpr int QFR = 2;                    // rows per thread
