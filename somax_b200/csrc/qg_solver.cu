@@ -596,304 +596,9 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
   }
 }
 
-// Pipelined variant for the mirror-paired configurations (n = 8192, 16384), persistent CTAs.
-// The kernel above waits for the 24 128-bit loads of a mode's three layers in front of every
-// transform (15 % of its stall samples: all warps of a CTA are in the same phase, only the SM's
-// other CTA covers).  Here the raw layers of the NEXT item - the next mode of the row, or the first
-// mode of the CTA's next row - are fetched with 16-byte cp.async while the current mode's last pass
-// runs: layers 0 .. nl-2 into the line itself (free between the pass-3 reads and the next staging,
-// now that the lane-0 exchange has its own 2 KB), the last layer into a side buffer that is reused
-// by all modes of the row.  Every thread copies exactly the vectors it mixes later, so the copies
-// need no barrier of their own.  (Layers that do not fit - nl = 4 - are read from global memory.)
-template <int LGN, bool INV>
-__global__ void __launch_bounds__(BigCfg<LGN>::G, BigCfg<LGN>::minblocks)
-rowdst_fft_pipe(RowArgsCT<float> A, const float* __restrict__ in, float* __restrict__ out) {
-  using Cfg = BigCfg<LGN>;
-  using C = C2<float>;
-  static_assert(Cfg::PAIR, "mirror-paired configurations only");
-  constexpr int n = Cfg::n, G = Cfg::G, R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3;
-  constexpr int LG1 = Cfg::LG1, LG2 = Cfg::LG2, LG3 = Cfg::LG3, P2 = Cfg::P2;
-  constexpr int NV = n / 4 / G;
-  constexpr int LINE = R3 * P2;                    // complex words of the line (no natural-order layout here)
-  static_assert(2 * LINE >= 2 * n, "two raw layers fit the line");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  C* s = reinterpret_cast<C*>(smem_raw);
-  float* z = reinterpret_cast<float*>(s);
-  C* tw1 = s + LINE;                               // [LG1][G]: exp(-2 pi i lt 2^jj / n)
-  C* tw2 = tw1 + LG1 * G;                          // [LG2][R3]: exp(-2 pi i pos 2^jj / G)
-  C* tw0 = tw2 + LG2 * R3;                         // [G]: split twiddle exp(-i pi lt / n)
-  C* xch = tw0 + G;                                // [R2 R3]: lane-0 frequencies of pass 3
-  float* side = reinterpret_cast<float*>(xch + R2 * R3);      // [n]: raw last layer of the row
-  const int lt = threadIdx.x, lane = lt & 31;
-  const int nline = A.nl - 1 < 2 ? A.nl - 1 : 2;   // layers 0 .. nline-1 travel through the line
-  const int cside = nline;                          // layer in the side buffer (the others: global memory)
-
-  auto src_of = [&](int b, int j, int c) -> const float* {
-    return INV ? in + ((size_t)b * A.nl + c) * A.ny * A.np + sp_off(A.ny, j, 4 * lt)
-               : in + (((size_t)b * A.nl + c) * A.L.Ny + (A.jo + j)) * A.L.pitch + OFF + 1 + 4 * lt;
-  };
-  const size_t estride = INV ? (size_t)(4 * G / SP_W) * A.ny * SP_W : (size_t)4 * G;
-  const unsigned z_sa = (unsigned)__cvta_generic_to_shared(z) + 16u * lt;
-  const unsigned side_sa = (unsigned)__cvta_generic_to_shared(side) + 16u * lt;
-  auto ring_row = [&](int j) { return A.ringmode && ((j == 0 && A.ylo) || (j == A.ny - 1 && A.yhi)); };
-  // raw layers of row r: the line layers always, the side layer when r is a new row
-  auto prefetch = [&](int r, bool with_side) {
-    const int b = r / A.ny, j = r - b * A.ny;
-    if (ring_row(j)) return;
-    for (int c = 0; c < nline; ++c) {
-      const float* src = src_of(b, j, c);
-#pragma unroll
-      for (int e = 0; e < NV; ++e)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(z_sa + (unsigned)((c * n + 4 * e * G) * 4)), "l"(src + e * estride) : "memory");
-    }
-    if (with_side) {
-      const float* src = src_of(b, j, cside);
-#pragma unroll
-      for (int e = 0; e < NV; ++e)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(side_sa + (unsigned)(4 * e * G * 4)), "l"(src + e * estride) : "memory");
-    }
-  };
-
-  int row = blockIdx.x;
-  if (row < A.nrows) prefetch(row, true);
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
-#pragma unroll
-  for (int jj = 0; jj < LG1; ++jj) tw1[jj * G + lt] = A.twb[jj * G + lt];
-  if (lt < LG2 * R3) tw2[lt] = A.twb[LG1 * G + lt];
-  tw0[lt] = A.tw[lt];
-  // (visible after the barrier that follows the staging of the first mode)
-
-  for (; row < A.nrows; row += gridDim.x) {
-    const int b = row / A.ny, j = row - b * A.ny, fj = A.jo + j;
-    if (ring_row(j)) {
-      // FWD: a ring row of the boundary-conditioned input is zero, so is its transform;
-      // INV: the ring of psi is left alone.  Nothing was fetched for it: fetch the next row.
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-      __syncthreads();
-      if (row + (int)gridDim.x < A.nrows) prefetch(row + (int)gridDim.x, true);
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-      if (!INV)
-        for (int a = 0; a < A.nl; ++a) {
-          for (int p = lt; p < n; p += G) *fwd_dst<float>(A, out, b * A.nl + a, j, p) = 0.f;
-          if (lt < 3) A.bext[(((size_t)b * A.nl + a) * 3 + lt) * A.ny + j] = 0.f;
-        }
-      continue;
-    }
-    for (int a = 0; a < A.nl; ++a) {
-      if (lt < 2) row_border_cols<float, INV>(A, in, out, b, a, j, fj, lt, n);
-      // ---- mix the layers (own vectors: visible after the thread's own wait)
-      Vec4<float> acc[NV];
-#pragma unroll
-      for (int e = 0; e < NV; ++e) acc[e] = Vec4<float>{0.f, 0.f, 0.f, 0.f};
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-      for (int c = 0; c < A.nl; ++c) {
-        const float mx = A.mix[a][c];
-        Vec4<float> w[NV];
-        if (c < nline) {
-#pragma unroll
-          for (int e = 0; e < NV; ++e) w[e] = ld4(z + c * n + 4 * (lt + e * G));
-        } else if (c == cside) {
-#pragma unroll
-          for (int e = 0; e < NV; ++e) w[e] = ld4(side + 4 * (lt + e * G));
-        } else {
-          const float* src = src_of(b, j, c);
-#pragma unroll
-          for (int e = 0; e < NV; ++e) w[e] = ld4(src + e * estride);
-        }
-#pragma unroll
-        for (int e = 0; e < NV; ++e) {
-          acc[e].x = fmaf(mx, w[e].x, acc[e].x); acc[e].y = fmaf(mx, w[e].y, acc[e].y);
-          acc[e].z = fmaf(mx, w[e].z, acc[e].z); acc[e].w = fmaf(mx, w[e].w, acc[e].w);
-        }
-      }
-      __syncthreads();      // everyone has read its raw vectors: the line becomes z
-      // ---- stage the odd-extended row: z_t at word t of the line (128-bit, conflict-free; see above)
-      {
-#pragma unroll
-        for (int e = 0; e < NV; ++e) {
-          const int i = lt + e * G;
-          const float lo = __shfl_up_sync(0xffffffffu, acc[e].w, 1);
-          float hi = -acc[e].w;
-          if (i == n / 4 - 1) {
-            // x_n is the border column, not part of the transform: z_n = 0
-            *(INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + n
-                  : A.bext + (((size_t)b * A.nl + a) * 3 + 2) * A.ny + j) = acc[e].w;
-            hi = 0.f;
-          } else if (lane == 31) {
-            z[4 * i + 4] = acc[e].w;           // x_{4(i+1)} for lane 0 of the next warp
-          }
-          if (lane == 0) {
-            if (i == 0) z[0] = 0.f;            // z_0
-            z[4 * i + 1] = acc[e].x; z[4 * i + 2] = acc[e].y; z[4 * i + 3] = acc[e].z;
-          } else {
-            st4(z + 4 * i, Vec4<float>{lo, acc[e].x, acc[e].y, acc[e].z});
-          }
-          st4(z + 2 * n - 4 * i - 4, Vec4<float>{hi, -acc[e].z, -acc[e].y, -acc[e].x});
-        }
-      }
-      __syncthreads();
-      // ---- pass 1
-      C v[R1];
-  #pragma unroll
-      for (int q = 0; q < R1; ++q) v[q] = s[lt + G * q];
-      __syncthreads();
-      fft_reg<float, R1>(v);
-      {
-        C wp[LG1];
-  #pragma unroll
-        for (int jj = 0; jj < LG1; ++jj) wp[jj] = tw1[jj * G + lt];
-        fft_reg_twiddle<float, R1>(v, wp);
-      }
-  #pragma unroll
-      for (int q = 0; q < R1; ++q) s[q * G + lt] = v[fft_reg_pos<R1>(q)];
-      __syncthreads();
-
-      // ---- pass 2
-      {
-        C u[Cfg::B2][R2];
-  #pragma unroll
-        for (int i = 0; i < Cfg::B2; ++i) {
-          const int t2 = lt + G * i, b2 = t2 >> LG3, pos = t2 & (R3 - 1);
-  #pragma unroll
-          for (int q = 0; q < R2; ++q) u[i][q] = s[b2 * G + pos + R3 * q];
-        }
-        __syncthreads();
-  #pragma unroll
-        for (int i = 0; i < Cfg::B2; ++i) {
-          const int t2 = lt + G * i, b2 = t2 >> LG3, pos = t2 & (R3 - 1);
-          fft_reg<float, R2>(u[i]);
-          C wp[LG2];
-  #pragma unroll
-          for (int jj = 0; jj < LG2; ++jj) wp[jj] = tw2[jj * R3 + pos];
-          fft_reg_twiddle<float, R2>(u[i], wp);
-  #pragma unroll
-          for (int q = 0; q < R2; ++q)
-            s[pos * P2 + (Cfg::PAIR ? q * R1 + b2 : b2 * R2 + q)] = u[i][fft_reg_pos<R2>(q)];
-        }
-      }
-      __syncthreads();
-
-      // destination of X_k (element p = k - 1 of the spectral row / field column k of the psi row)
-      auto store_out = [&](int k, float val) {
-        if (INV) out[(((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + k] = A.scale * val;
-        else *fwd_dst<float>(A, out, b * A.nl + a, j, k - 1) = val;
-      };
-      auto split_pair = [&](int k, const C& Ak, const C& Bk, const C& wk) {
-        const C E = {0.5f * (Ak.x + Bk.x), 0.5f * (Ak.y - Bk.y)};
-        const C O = {0.5f * (Ak.y + Bk.y), -0.5f * (Ak.x - Bk.x)};
-        const C wO = cmul(wk, O);
-        store_out(k, -0.5f * (E.y + wO.y));
-        store_out(n - k, 0.5f * (E.y - wO.y));
-      };
-      // ---- pass 3 on a butterfly (b3, q2) = (lane, warp) and its mirror (32 - lane, R2 - 1 - warp):
-      // outputs k = b3 + R1 (q2 + R2 q) and n - k = b3' + R1 (q2' + R2 (R3 - 1 - q)).  Pass 2 stored
-      // its output with b fastest, so both reads are conflict-free (consecutive / reversed words).
-      const int w = lt >> 5, l = lt & 31;
-      const int cola = w * R1 + l, colb = (R2 - 1 - w) * R1 + ((R1 - l) & (R1 - 1));
-      C ua[R3], ub[R3];
-#pragma unroll
-      for (int q = 0; q < R3; ++q) { ua[q] = s[q * P2 + cola]; ub[q] = s[q * P2 + colb]; }
-      __syncthreads();
-      // the line is free until the next staging: the raw layers of the next item arrive in it
-      // (and, before a new row, in the side buffer) while the butterflies and the stores run
-      if (a + 1 < A.nl) prefetch(row, false);
-      else if (row + (int)gridDim.x < A.nrows) prefetch(row + (int)gridDim.x, true);
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-      fft_reg<float, R3>(ua);
-      fft_reg<float, R3>(ub);
-      // lane 0 holds the frequencies k = R1 m, m = q2 + R2 q, whose mirrors R1 (R2 R3 - m) sit in
-      // lane 0 of OTHER warps: those M = R2 R3 values meet in shared memory
-      constexpr int M = R2 * R3;
-      if (l == 0) {
-#pragma unroll
-        for (int q = 0; q < R3; ++q) {
-          xch[w + R2 * q] = ua[fft_reg_pos<R3>(q)];
-          xch[(R2 - 1 - w) + R2 * q] = ub[fft_reg_pos<R3>(q)];
-        }
-      } else {
-        constexpr int KB = 8;
-        // X_k of consecutive q sit a constant stride apart (R1 R2 columns = R1 R2 / 64 strips) unless
-        // the row is scattered over the strip owners of the slab model
-        const bool strided = INV || A.lgspr < 0;
-        const int kk0 = l + R1 * w;
-        float* pk = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + kk0
-                        : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, kk0 - 1);
-        float* pnk = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + (n - kk0)
-                         : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, n - kk0 - 1);
-        const ptrdiff_t dstride = INV ? (ptrdiff_t)(R1 * R2) : (ptrdiff_t)(R1 * R2 / SP_W) * A.ny * SP_W;
-        // split twiddles w_k = exp(-i pi k / n), k = kk0 + R1 R2 q: one load, then the 16 rotations
-        // exp(-i pi q / R3) are compile-time constants (the table load per k was 10 % of the
-        // kernel's LSU wavefronts, which bound it)
-        static_assert(R3 == 16, "rotation table");
-        constexpr float RC[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
-                                  0.70710678118654752f, 0.55557023301960218f, 0.38268343236508978f,
-                                  0.19509032201612825f, 0.f, -0.19509032201612825f, -0.38268343236508978f,
-                                  -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
-                                  -0.92387953251128674f, -0.98078528040323043f};
-        constexpr float RS[16] = {0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
-                                  0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f,
-                                  0.98078528040323043f, 1.f, 0.98078528040323043f, 0.92387953251128674f,
-                                  0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
-                                  0.38268343236508978f, 0.19509032201612825f};
-        const C w0 = tw0[kk0];
-        const float qs = INV ? 0.25f * A.scale : 0.25f;
-#pragma unroll
-        for (int q0 = 0; q0 < R3; q0 += KB) {
-          C wk[KB];
-#pragma unroll
-          for (int u = 0; u < KB; ++u) {     // w0 * (RC - i RS)
-            const int q = q0 + u;
-            wk[u] = cmul_cs(w0, RC[q], RS[q]);
-          }
-#pragma unroll
-          for (int u = 0; u < KB; ++u) {
-            const int q = q0 + u, k = kk0 + R1 * R2 * q;
-            if (strided) {
-              // (X_k, X_{n-k}) = (-(e + o) / 4, (e - o) / 4), e = A.y - B.y, o = w.y (A.y + B.y) - w.x (A.x - B.x)
-              const C Ak = ua[fft_reg_pos<R3>(q)], Bk = ub[fft_reg_pos<R3>(R3 - 1 - q)];
-              const float2 p = __fadd2_rn(make_float2(Ak.y, Ak.y), make_float2(-Bk.y, Bk.y));
-              const float o = fmaf(wk[u].y, p.y, -(wk[u].x * (Ak.x - Bk.x)));
-              const float2 X = __fmul2_rn(__fadd2_rn(make_float2(p.x, p.x), make_float2(o, -o)), make_float2(-qs, qs));
-              pk[q * dstride] = X.x;
-              pnk[-q * dstride] = X.y;
-            } else {
-              split_pair(k, ua[fft_reg_pos<R3>(q)], ub[fft_reg_pos<R3>(R3 - 1 - q)], wk[u]);
-            }
-          }
-        }
-      }
-      __syncthreads();
-      if (lt < M / 2) {      // pairs (R1 m, R1 (M - m)), m = 1 .. M/2 (m = M/2 pairs with itself: both stores agree)
-        const int m = lt + 1, k = R1 * m;
-        split_pair(k, xch[m], xch[M - m], A.tw[k]);
-      }
-
-      // (no barrier here: the next shared-memory writes are the stage after the mix barrier)
-    }
-  }
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-}
-
 template <int LGN, bool INV>
 static int launch_rowdst_big(const RowArgsCT<float>& A, const float* in, float* out, cudaStream_t st) {
   using Cfg = BigCfg<LGN>;
-  if constexpr (Cfg::PAIR) {
-    const bool nopipe = getenv("SOMAX_B200_ROWFFT_NOPIPE") != nullptr;      // (A/B switch of the tests)
-    if (!nopipe) {
-      constexpr size_t smem = (size_t)(Cfg::R3 * Cfg::P2 + Cfg::LG1 * Cfg::G + Cfg::LG2 * Cfg::R3 + Cfg::G + Cfg::R2 * Cfg::R3) * sizeof(C2<float>) +
-                              (size_t)Cfg::n * sizeof(float);
-      static_assert(Cfg::minblocks * (smem + 1024) <= 228 * 1024, "pipelined row transform: shared memory");
-      if (int rc = ensure_dyn_smem((const void*)rowdst_fft_pipe<LGN, INV>, smem)) return rc;
-      int dev = 0, nsm = 148;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-      const int grid = std::min(A.nrows, Cfg::minblocks * nsm);
-      prof_begin(INV ? "rowdst_inv_fft" : "rowdst_fwd_fft", st);
-      rowdst_fft_pipe<LGN, INV><<<grid, Cfg::G, smem, st>>>(A, in, out);
-      SB_LAUNCH_CHECK();
-      return 0;
-    }
-  }
   constexpr size_t smem = (size_t)(Cfg::slen + Cfg::LG1 * Cfg::G + Cfg::LG2 * Cfg::R3 + Cfg::G) * sizeof(C2<float>);
   if (int rc = ensure_dyn_smem((const void*)rowdst_fft_big<LGN, INV>, smem)) return rc;
   prof_begin(INV ? "rowdst_inv_fft" : "rowdst_fwd_fft", st);

@@ -328,44 +328,3 @@ def test_reparameterized_qg_parity(dtype):
     assert max(np.abs(tend.h).max(), np.abs(tend.u).max(), np.abs(tend.v).max()) < 1e-10
     with pytest.raises(ValueError, match="wall"):
         sb.ReparameterizedQG.create(nx=16, ny=16, bc="periodic")
-
-
-@pytest.mark.parametrize("nl", [1, 2, 3, 4])
-def test_row_fft_pipeline_is_bitwise_the_plain_kernel(nl, monkeypatch):
-    """n = 8192 rows go through the persistent, cp.async-pipelined row transform (raw layers of the
-    next mode / row fetched into the line and a side buffer during the last pass).  Same arithmetic
-    as the one-row-per-CTA kernel it replaces (SOMAX_B200_ROWFFT_NOPIPE selects that one): the PV
-    inversion and two steps must agree bit for bit, with several rows per CTA (702 rows on 296
-    CTAs) and for every layer count (nl = 4: one layer does not fit the staging and is read from
-    global memory)."""
-    import somax_b200 as sb
-    import torch
-    nx, ny = 8192, 700
-    if nl == 1:
-        mk = lambda: sb.BarotropicQG.create(nx=nx, ny=ny, Lx=4e6, Ly=4e6 * ny / nx, dtype="float32",
-                                            lateral_viscosity=15.0, bottom_drag=1e-7, wind_amplitude=1.3e-10)
-    else:
-        H = (400.0, 1100.0, 2600.0, 900.0)[:nl]
-        gp = (9.81, 0.025, 0.0125, 0.01)[:nl]
-        mk = lambda: sb.BaroclinicQG.create(nx=nx, ny=ny, Lx=4e6, Ly=4e6 * ny / nx, n_layers=nl, H=H, g_prime=gp,
-                                            dtype="float32", lateral_viscosity=15.0, bottom_drag=1e-7,
-                                            wind_amplitude=1.3e-10)
-    g = torch.Generator(device="cuda").manual_seed(11 + nl)
-    q = 1e-6 * torch.randn((nl, ny + 2, nx + 2), generator=g, device="cuda", dtype=torch.float32)
-    m = mk()
-    dt = 0.25 * m.grid.dx / 2.0
-    State = sb.BarotropicQGState if nl == 1 else sb.BaroclinicQGState
-    q_in = q[0] if nl == 1 else q
-
-    def run():
-        psi = m._invert_pv(q_in.clone())
-        out = m.integrate(State(q=q_in.clone()), 0.0, 2 * dt, dt).ys.q[0]
-        return psi.clone(), torch.as_tensor(out).clone()
-
-    monkeypatch.delenv("SOMAX_B200_ROWFFT_NOPIPE", raising=False)
-    psi_p, q_p = run()
-    monkeypatch.setenv("SOMAX_B200_ROWFFT_NOPIPE", "1")
-    psi_r, q_r = run()
-    assert torch.isfinite(psi_p).all() and float(psi_p.abs().max()) > 0
-    assert torch.equal(psi_p, psi_r)
-    assert torch.equal(q_p, q_r)
