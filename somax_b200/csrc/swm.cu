@@ -9,6 +9,8 @@
 // predicate on the global index.
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "swm_kernels.cuh"
@@ -83,6 +85,9 @@ constexpr int SSW = TXG * 4 + 8;   // shared row: 4 | 128 | 4 (halo columns at [
 // every window cell is interior and every output is written - 97 % of the CTAs of a 4096^2 grid; that
 // instance carries no ring / range predicates at all (they were a quarter of the instructions of a
 // kernel that is issue bound, not HBM bound).
+__device__ __forceinline__ float swm_div(float a, float b) { return __fdividef(a, b); }     // <= 2 ulp
+__device__ __forceinline__ double swm_div(double a, double b) { return a / b; }
+
 template <typename T, bool EDGE>
 __device__ __forceinline__ void swm_rhs_body(const SwmArgs<T>& A, const Stage<T>& st, int j0, T (*s_h)[SSW],
                                              T (*s_u)[SSW], T (*s_v)[SSW], T (*s_p)[SSW]) {
@@ -95,6 +100,7 @@ __device__ __forceinline__ void swm_rhs_body(const SwmArgs<T>& A, const Stage<T>
   const int r = ty + 1, cs = 4 * (tx + 1);
   const int i0 = g * 4 - OFF;                    // column of this thread's first cell
   const T idx_ = A.idx, idy_ = A.idy;
+  const T nux = A.nu * idx_, nuy = A.nu * idy_;      // as in swm_rhs_inner: the two paths agree bit for bit
 
   for (int e = tid; e < (TY + 2) * (SSW / 4); e += TXG * TY)
     st4(&s_p[0][0] + 4 * e, Vec4<T>{0, 0, 0, 0});
@@ -228,12 +234,12 @@ __device__ __forceinline__ void swm_rhs_body(const SwmArgs<T>& A, const Stage<T>
       if (rin[1] && cin[w]) {
         const T zeta = (V[1][w + 1] - V[1][w]) * idx_ - (U[2][w] - U[1][w]) * idy_;
         const T hX = T(0.25) * (((H[1][w] + H[1][w + 1]) + H[2][w]) + H[2][w + 1]);
-        q0[w] = (zeta + fX[1]) / hX;
+        q0[w] = swm_div(zeta + fX[1], hX);
       }
       if (w >= 1 && rin[0] && cin[w]) {
         const T zeta = (V[0][w + 1] - V[0][w]) * idx_ - (U[1][w] - U[0][w]) * idy_;
         const T hX = T(0.25) * (((H[0][w] + H[0][w + 1]) + H[1][w]) + H[1][w + 1]);
-        qm[w] = (zeta + fX[0]) / hX;
+        qm[w] = swm_div(zeta + fX[0], hX);
       }
     }
     // ---- mass fluxes: vh at rows -1,0 (w 1..5); uh at rows 0,1 (w 0..4) ----
@@ -306,9 +312,9 @@ __device__ __forceinline__ void swm_rhs_body(const SwmArgs<T>& A, const Stage<T>
           T lu, lv;
           if (A.spec & SOMAX_B200_SPEC_DIFFUSION_FLUX) {
             auto fxf = [&](const T (&X)[3][6], int d, int ww) -> T {
-              return (rin[d] && cin[ww]) ? A.nu * ((X[d][ww + 1] - X[d][ww]) * idx_) : T(0); };
+              return (rin[d] && cin[ww]) ? (X[d][ww + 1] - X[d][ww]) * nux : T(0); };
             auto fyf = [&](const T (&X)[3][6], int d, int ww) -> T {
-              return (rin[d] && cin[ww]) ? A.nu * ((X[d + 1][ww] - X[d][ww]) * idy_) : T(0); };
+              return (rin[d] && cin[ww]) ? (X[d + 1][ww] - X[d][ww]) * nuy : T(0); };
             lu = (fxf(U, 1, w) - fxf(U, 1, w - 1)) * idx_ + (fyf(U, 1, w) - fyf(U, 0, w)) * idy_;
             lv = (fxf(V, 1, w) - fxf(V, 1, w - 1)) * idx_ + (fyf(V, 1, w) - fyf(V, 0, w)) * idy_;
           } else {
@@ -365,9 +371,6 @@ __device__ __forceinline__ void swm_rhs_body(const SwmArgs<T>& A, const Stage<T>
 // NPREV (stored stage derivatives entering the Runge-Kutta combination) and FLUX (flux-form
 // diffusion) are compile-time: the kernel is issue bound, and the `jj < nprev` / `spec &` tests of
 // the generic path were a tenth of its instructions.
-__device__ __forceinline__ float swm_div(float a, float b) { return __fdividef(a, b); }     // <= 2 ulp
-__device__ __forceinline__ double swm_div(double a, double b) { return a / b; }
-
 template <typename T, int NPREV, bool FLUX>
 __device__ __forceinline__ void swm_rhs_inner(const SwmArgs<T>& A, const Stage<T>& st, int jt0, int ntile,
                                               T* __restrict__ tiles, T (*s_epi)[TXG * TY][4]) {
@@ -805,7 +808,8 @@ int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A_in, const Stage<T>& st_in
   dim3 grid((L.groups() + TXG - 1) / TXG, (L.Ny + TY - 1) / TY, L.batch);
   // fast kernel: a CTA walks `ntile` row tiles (software pipeline over tiles and layers) on grids
   // large enough to keep every SM busy with whole columns
-  const int ntile = (int)grid.y >= 128 ? 4 : 1;
+  int ntile = (int)grid.y >= 128 ? 4 : 1;
+  if (const char* e = getenv("SOMAX_B200_SWM_NTILE")) ntile = std::max(1, atoi(e));
   prof_begin("swm_rhs_kernel", s);
   if constexpr (sizeof(T) == 8) {
     // fp64 = the validation pipeline: reference operation order, no FMA contraction (swm_f64.cu)

@@ -40,15 +40,15 @@ def swm_state(nx, ny, dtype):
 def assert_same(got, one, dtype):
     for f in "huv":
         a, b = getattr(got, f), getattr(one, f)
-        if np.dtype(dtype) == np.float64:
-            assert np.array_equal(a, b), (f, rel(a, b))
-        else:
-            assert rel(a, b) <= 2e-6, (f, rel(a, b))
+        # fp32 too: the predicate-free interior path and the edge path of the fused kernel use the
+        # same arithmetic, so the result does not depend on which tiles a decomposition makes interior
+        assert np.array_equal(a, b), (f, rel(a, b))
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("bc", ["periodic", "wall"])
-@pytest.mark.parametrize("nx,ny,world,steps", [(64, 48, 2, 3), (130, 96, 4, 3), (256, 256, 8, 12), (32, 24, 1, 2)])
+@pytest.mark.parametrize("nx,ny,world,steps", [(64, 48, 2, 3), (130, 96, 4, 3), (256, 256, 8, 12), (32, 24, 1, 2),
+                                               (512, 96, 4, 3)])
 def test_local_slabs_match_single_gpu_and_oracle(nx, ny, world, steps, bc, dtype):
     import somax_b200 as sb
     from oracle import swm as oswm
