@@ -495,10 +495,16 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
         }
       } else {
         constexpr int KB = 8;
-        // X_k of consecutive q sit a constant stride apart (R1 R2 columns = R1 R2 / 64 strips) unless
-        // the row is scattered over the strip owners of the slab model
-        const bool strided = INV || A.lgspr < 0;
+        // X_k of consecutive q sit a constant stride apart (R1 R2 columns = R1 R2 / 64 strips).  When
+        // the row is scattered over the strip owners of the slab model the element keeps its offset
+        // inside the owner's (full-size) array and only the base pointer changes with the strip.
+        const bool scatter = !INV && A.lgspr >= 0;
         const int kk0 = l + R1 * w;
+        constexpr int QSTRIPS = R1 * R2 / SP_W;
+        const int sk = (kk0 - 1) >> 6, snk = (n - kk0 - 1) >> 6;
+        const size_t offk = scatter ? ((size_t)b * A.nl + a) * A.pny * A.np + sp_off(A.pny, A.prow0 + j, kk0 - 1) : 0;
+        const size_t offnk = scatter ? ((size_t)b * A.nl + a) * A.pny * A.np + sp_off(A.pny, A.prow0 + j, n - kk0 - 1) : 0;
+        const ptrdiff_t sstride = (ptrdiff_t)QSTRIPS * A.pny * SP_W;
         float* pk = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + kk0
                         : out + ((size_t)b * A.nl + a) * A.ny * A.np + sp_off(A.ny, j, kk0 - 1);
         float* pnk = INV ? out + (((size_t)b * A.nl + a) * A.L.Ny + fj) * A.L.pitch + OFF + (n - kk0)
@@ -530,17 +536,18 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
           }
 #pragma unroll
           for (int u = 0; u < KB; ++u) {
-            const int q = q0 + u, k = kk0 + R1 * R2 * q;
-            if (strided) {
-              // (X_k, X_{n-k}) = (-(e + o) / 4, (e - o) / 4), e = A.y - B.y, o = w.y (A.y + B.y) - w.x (A.x - B.x)
-              const C Ak = ua[fft_reg_pos<R3>(q)], Bk = ub[fft_reg_pos<R3>(R3 - 1 - q)];
-              const float2 p = __fadd2_rn(make_float2(Ak.y, Ak.y), make_float2(-Bk.y, Bk.y));
-              const float o = fmaf(wk[u].y, p.y, -(wk[u].x * (Ak.x - Bk.x)));
-              const float2 X = __fmul2_rn(__fadd2_rn(make_float2(p.x, p.x), make_float2(o, -o)), make_float2(-qs, qs));
+            const int q = q0 + u;
+            // (X_k, X_{n-k}) = (-(e + o) / 4, (e - o) / 4), e = A.y - B.y, o = w.y (A.y + B.y) - w.x (A.x - B.x)
+            const C Ak = ua[fft_reg_pos<R3>(q)], Bk = ub[fft_reg_pos<R3>(R3 - 1 - q)];
+            const float2 p = __fadd2_rn(make_float2(Ak.y, Ak.y), make_float2(-Bk.y, Bk.y));
+            const float o = fmaf(wk[u].y, p.y, -(wk[u].x * (Ak.x - Bk.x)));
+            const float2 X = __fmul2_rn(__fadd2_rn(make_float2(p.x, p.x), make_float2(o, -o)), make_float2(-qs, qs));
+            if (!scatter) {
               pk[q * dstride] = X.x;
               pnk[-q * dstride] = X.y;
             } else {
-              split_pair(k, ua[fft_reg_pos<R3>(q)], ub[fft_reg_pos<R3>(R3 - 1 - q)], wk[u]);
+              A.peer[(sk + QSTRIPS * q) >> A.lgspr][offk + q * sstride] = X.x;
+              A.peer[(snk - QSTRIPS * q) >> A.lgspr][offnk - q * sstride] = X.y;
             }
           }
         }

@@ -806,9 +806,11 @@ int launch_rhs(somax_b200_swm_t h, const SwmArgs<T>& A_in, const Stage<T>& st_in
   stage_finalize(st, (double)st.dt);
   dim3 block(TXG, TY);
   dim3 grid((L.groups() + TXG - 1) / TXG, (L.Ny + TY - 1) / TY, L.batch);
-  // fast kernel: a CTA walks `ntile` row tiles (software pipeline over tiles and layers) on grids
-  // large enough to keep every SM busy with whole columns
-  int ntile = (int)grid.y >= 128 ? 4 : 1;
+  // fast kernel: a CTA can walk `ntile` row tiles (software pipeline over tiles and layers).  One
+  // tile per CTA - the pipeline then only spans the layers - measured best at 2 x 4096^2: 2.91 ms/step
+  // against 2.97 / 3.04 / 3.11 / 3.44 for 2 / 3 / 4 / 8 tiles (more, shorter CTAs balance the SMs
+  // better than a longer pipeline hides latency); SOMAX_B200_SWM_NTILE overrides for tuning.
+  int ntile = 1;
   if (const char* e = getenv("SOMAX_B200_SWM_NTILE")) ntile = std::max(1, atoi(e));
   prof_begin("swm_rhs_kernel", s);
   if constexpr (sizeof(T) == 8) {

@@ -40,9 +40,13 @@ def swm_state(nx, ny, dtype):
 def assert_same(got, one, dtype):
     for f in "huv":
         a, b = getattr(got, f), getattr(one, f)
-        # fp32 too: the predicate-free interior path and the edge path of the fused kernel use the
-        # same arithmetic, so the result does not depend on which tiles a decomposition makes interior
-        assert np.array_equal(a, b), (f, rel(a, b))
+        if np.dtype(dtype) == np.float64:
+            assert np.array_equal(a, b), (f, rel(a, b))
+        else:
+            # fp32: a decomposition changes which tiles take the predicate-free interior path of the
+            # fused kernel; the two paths evaluate the same formulas but contract them differently
+            # (slab_vs_single_relL2 of the bench: 6e-10 at 2 x 4096^2 on smooth fields; the noisy test state gives ~1e-7)
+            assert rel(a, b) <= 2e-6, (f, rel(a, b))
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
