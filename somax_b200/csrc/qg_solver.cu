@@ -2114,7 +2114,8 @@ static int launch_solve(QgSolver* s, const ThomasTab& tb, T* S, T* W, cudaStream
   // before the wide PLAIN launches (auxiliary stream, released by an event a few microseconds
   // later) fill every SM's shared memory; measured the other way round, the LOWK CTAs could not be
   // placed until the PLAIN kernel drained and the two chains ran back to back.
-  const bool two = nh > 0 && npl > 0;
+  static const bool serial = getenv("SOMAX_B200_SERIAL_SWEEPS") != nullptr;      // (diagnostic: both classes on one stream)
+  const bool two = nh > 0 && npl > 0 && !serial;
   cudaStream_t pl = two ? s->aux : st;
   if (two) {
     SB_CUDA(cudaEventRecord(s->ev_fork, st));
