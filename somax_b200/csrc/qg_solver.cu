@@ -327,7 +327,7 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
   // memory once per CTA (behind the line) and re-read from there - the global loads in front of
   // passes 1, 2 and the split were 6 % of the kernel's stall samples (L1 / L2 latency no other warp
   // covers: all eight warps of the CTA are in the same phase).
-  C* tw1 = s + Cfg::slen;                          // [LG1][G]: exp(-2 pi i lt 2^jj / n)
+  C* tw1 = s + ((Cfg::slen + 1) & ~1);             // [LG1][G]: exp(-2 pi i lt 2^jj / n); 16-byte aligned
   C* tw2 = tw1 + LG1 * G;                          // [LG2][R3]: exp(-2 pi i pos 2^jj / G)
   C* tw0 = tw2 + LG2 * R3;                         // [G]: split twiddle exp(-i pi lt / n)
   if (A.ringmode && ((j == 0 && A.ylo) || (j == A.ny - 1 && A.yhi))) {
@@ -606,7 +606,7 @@ rowdst_fft_big(RowArgsCT<float> A, const float* __restrict__ in, float* __restri
 template <int LGN, bool INV>
 static int launch_rowdst_big(const RowArgsCT<float>& A, const float* in, float* out, cudaStream_t st) {
   using Cfg = BigCfg<LGN>;
-  constexpr size_t smem = (size_t)(Cfg::slen + Cfg::LG1 * Cfg::G + Cfg::LG2 * Cfg::R3 + Cfg::G) * sizeof(C2<float>);
+  constexpr size_t smem = (size_t)(((Cfg::slen + 1) & ~1) + Cfg::LG1 * Cfg::G + Cfg::LG2 * Cfg::R3 + Cfg::G) * sizeof(C2<float>);
   if (int rc = ensure_dyn_smem((const void*)rowdst_fft_big<LGN, INV>, smem)) return rc;
   prof_begin(INV ? "rowdst_inv_fft" : "rowdst_fwd_fft", st);
   rowdst_fft_big<LGN, INV><<<A.nrows, Cfg::G, smem, st>>>(A, in, out);
